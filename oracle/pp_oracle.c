@@ -1,0 +1,657 @@
+/*
+ * pp_oracle.c -- CPU restatement of the reference's PointPillars pre/post hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This file is the parity checker for the CUDA path and the
+ * "port" CPU baseline that bench.py times beside it.  Nothing in the product package may
+ * import, link or call it; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs do.
+ *
+ * Every function cites the reference file:line (paths relative to the reference checkout)
+ * whose algorithm it follows.  Pinning status (see DESIGN.md "Oracle"):
+ *   - voxelizer, box decode, standup prep, NMS sweep, rotated IoU: pinned against the
+ *     reference's own source executed in the build container (oracle/ref_extract.py,
+ *     tests/golden/ fixtures, tests/test_oracle_vs_reference.py).
+ *   - decoration and scatter: the reference implements them with TensorFlow ops; TensorFlow
+ *     is not installable here, the reference has no tests => "parity unpinned" for those two.
+ *
+ * Build: plain C99, `gcc -O2 -ffp-contract=off -fno-fast-math` (no FMA contraction: the numba
+ * CPU oracle derived from the reference source does not contract either).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define PPO_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------------------------
+ * Grid size: load_data.py:612-615 / 722-731 (np.round == round-half-to-even, then int32).
+ * arith_f32 != 0 reproduces the case where the caller handed python lists, which the wrapper
+ * casts to points.dtype == float32 (load_data.py:726-729).
+ * ------------------------------------------------------------------------------------------ */
+PPO_API void ppo_grid_size(const double voxel_size[3], const double coors_range[6], int arith_f32,
+                           int32_t grid_xyz[3]) {
+    for (int j = 0; j < 3; ++j) {
+        if (arith_f32) {
+            float g = ((float)coors_range[3 + j] - (float)coors_range[j]) / (float)voxel_size[j];
+            grid_xyz[j] = (int32_t)nearbyintf(g);
+        } else {
+            double g = (coors_range[3 + j] - coors_range[j]) / voxel_size[j];
+            grid_xyz[j] = (int32_t)nearbyint(g);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Voxelizer: load_data.py:593-641 (_points_to_voxel_reverse_kernel, reverse_index=True, the
+ * one the reference calls at load_data.py:2966) and 643-692 (_points_to_voxel_kernel).
+ * Wrapper semantics (zeroed outputs, -1 map, slice to voxel_num): load_data.py:695-771.
+ *
+ *   points       [N,D]  float32 (is_f64=0) or float64 (is_f64=1), C-contiguous
+ *   arith_f32    cell arithmetic in float32 (only when points AND params are float32),
+ *                otherwise float64 (numba promotion)
+ *   voxels       [max_voxels,max_points,D] same dtype as points, zero-filled here
+ *   coors        [max_voxels,3] int32 (z,y,x) if reverse_index else (x,y,z)
+ *   num          [max_voxels] int32
+ *   point_slot   optional [N] int32: voxel*max_points+slot for a stored point, -1 otherwise
+ * returns voxel_num.
+ *
+ * NaN coordinates are undefined behaviour in the reference (both comparisons at
+ * load_data.py:623 are false, then NaN is cast to int32).  Defined here, and in the CUDA path,
+ * as "point dropped".
+ * ------------------------------------------------------------------------------------------ */
+PPO_API int ppo_points_to_voxel(const void* points, int is_f64, int64_t N, int D,
+                                const double voxel_size[3], const double coors_range[6],
+                                int arith_f32, int max_points, int max_voxels, int reverse_index,
+                                void* voxels, int32_t* coors, int32_t* num, int32_t* point_slot) {
+    int32_t grid[3];
+    ppo_grid_size(voxel_size, coors_range, arith_f32, grid);
+    const size_t esz = is_f64 ? 8 : 4;
+    const int64_t ncell = (int64_t)grid[0] * grid[1] * grid[2];
+    int32_t* map = (int32_t*)malloc(sizeof(int32_t) * (size_t)(ncell > 0 ? ncell : 1));
+    if (!map) return -1;
+    for (int64_t c = 0; c < ncell; ++c) map[c] = -1;
+    memset(voxels, 0, esz * (size_t)max_voxels * max_points * D);
+    memset(coors, 0, sizeof(int32_t) * 3 * (size_t)max_voxels);
+    memset(num, 0, sizeof(int32_t) * (size_t)max_voxels);
+    if (point_slot)
+        for (int64_t i = 0; i < N; ++i) point_slot[i] = -1;
+
+    const float* pf = (const float*)points;
+    const double* pd = (const double*)points;
+    float lo32[3], vs32[3];
+    for (int j = 0; j < 3; ++j) {
+        lo32[j] = (float)coors_range[j];
+        vs32[j] = (float)voxel_size[j];
+    }
+    int voxel_num = 0;
+    for (int64_t i = 0; i < N; ++i) {
+        int32_t cxyz[3];
+        int failed = 0;
+        for (int j = 0; j < 3; ++j) {
+            double c;
+            if (arith_f32) {
+                c = (double)floorf((pf[i * D + j] - lo32[j]) / vs32[j]);
+            } else {
+                double p = is_f64 ? pd[i * D + j] : (double)pf[i * D + j];
+                c = floor((p - coors_range[j]) / voxel_size[j]);
+            }
+            if (!(c >= 0.0) || !(c < (double)grid[j])) { /* also drops NaN */
+                failed = 1;
+                break;
+            }
+            cxyz[j] = (int32_t)c;
+        }
+        if (failed) continue;
+        /* same cell whichever index order the reference's map uses */
+        const int64_t cell = ((int64_t)cxyz[2] * grid[1] + cxyz[1]) * grid[0] + cxyz[0];
+        int32_t v = map[cell];
+        if (v == -1) {
+            v = voxel_num;
+            if (voxel_num >= max_voxels) break; /* load_data.py:632-633: break, not continue */
+            voxel_num += 1;
+            map[cell] = v;
+            if (reverse_index) {
+                coors[3 * v + 0] = cxyz[2];
+                coors[3 * v + 1] = cxyz[1];
+                coors[3 * v + 2] = cxyz[0];
+            } else {
+                coors[3 * v + 0] = cxyz[0];
+                coors[3 * v + 1] = cxyz[1];
+                coors[3 * v + 2] = cxyz[2];
+            }
+        }
+        int32_t n = num[v];
+        if (n < max_points) {
+            memcpy((char*)voxels + esz * (((size_t)v * max_points + n) * D),
+                   (const char*)points + esz * ((size_t)i * D), esz * D);
+            num[v] = n + 1;
+            if (point_slot) point_slot[i] = v * max_points + n;
+        }
+    }
+    free(map);
+    return voxel_num;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Pillar decoration: model/pointpillars.py:143-203 (constants 121-124, mask 23-49).
+ *   voxels [M,P,D] f32, num_points [M] i32, coors [M,4] i32 (batch,z,y,x)
+ *   out    [M,P,D+5] f32 = concat(voxels, xyz - mean, (x - cx, y - cy)) * (p < num_points)
+ * vx, vy, x_offset, y_offset are python doubles in the reference that TensorFlow converts to
+ * float32 constants; the multiply and the add are separate TF ops (no FMA).
+ * The mean is sum over ALL P slots / num_points (padding slots are zero).  TF's reduction order
+ * is unspecified; this restatement adds slots in order 0..P-1.  PARITY UNPINNED (no TF here).
+ * ------------------------------------------------------------------------------------------ */
+PPO_API void ppo_decorate(const float* voxels, const int32_t* num_points, const int32_t* coors,
+                          int64_t M, int P, int D, double vx, double vy, double x_offset,
+                          double y_offset, float* out) {
+    const float vxf = (float)vx, vyf = (float)vy, xof = (float)x_offset, yof = (float)y_offset;
+    const int Do = D + 5;
+    for (int64_t m = 0; m < M; ++m) {
+        const float* v = voxels + (size_t)m * P * D;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        for (int p = 0; p < P; ++p) {
+            s0 += v[p * D + 0];
+            s1 += v[p * D + 1];
+            s2 += v[p * D + 2];
+        }
+        const float n = (float)num_points[m];
+        const float m0 = s0 / n, m1 = s1 / n, m2 = s2 / n;
+        float ex = (float)coors[4 * m + 3] * vxf;
+        ex = ex + xof;
+        float ey = (float)coors[4 * m + 2] * vyf;
+        ey = ey + yof;
+        for (int p = 0; p < P; ++p) {
+            const float mask = (num_points[m] > p) ? 1.f : 0.f;
+            float* o = out + ((size_t)m * P + p) * Do;
+            for (int d = 0; d < D; ++d) o[d] = v[p * D + d] * mask;
+            o[D + 0] = (v[p * D + 0] - m0) * mask;
+            o[D + 1] = (v[p * D + 1] - m1) * mask;
+            o[D + 2] = (v[p * D + 2] - m2) * mask;
+            o[D + 3] = (v[p * D + 0] - ex) * mask;
+            o[D + 4] = (v[p * D + 1] - ey) * mask;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Scatter: model/pointpillars.py:285-341.  Per batch element b: rows with coords[:,0]==b,
+ * index = y*nx + x (z ignored, line 302), tf.scatter_nd SUMS duplicates (line 317), result
+ * transposed to [C, ny*nx], stacked, reshaped to [B,C,ny,nx] (NCHW).
+ * layout_nhwc != 0 writes [B,ny,nx,C] instead (what the RPN transposes to, voxelnet.py:697).
+ * Rows whose batch index is outside [0,B) are ignored (boolean_mask never selects them).
+ * Duplicates are added in row order.  PARITY UNPINNED (TensorFlow op).
+ * ------------------------------------------------------------------------------------------ */
+PPO_API void ppo_scatter(const float* feats, const int32_t* coords, int64_t M, int C, int B, int ny,
+                         int nx, int layout_nhwc, float* out) {
+    memset(out, 0, sizeof(float) * (size_t)B * C * ny * nx);
+    for (int64_t m = 0; m < M; ++m) {
+        const int b = coords[4 * m + 0], y = coords[4 * m + 2], x = coords[4 * m + 3];
+        if (b < 0 || b >= B) continue;
+        if (y < 0 || y >= ny || x < 0 || x >= nx) continue; /* tf.scatter_nd on GPU drops OOB */
+        for (int c = 0; c < C; ++c) {
+            size_t o = layout_nhwc ? ((((size_t)b * ny + y) * nx + x) * C + c)
+                                   : ((((size_t)b * C + c) * ny + y) * nx + x);
+            out[o] += feats[(size_t)m * C + c];
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Box decode: libraries/eval_helper_functions.py:388-461 (default flags), float32 numpy.
+ * Output order [x,y,z,w,l,h,r].
+ * ------------------------------------------------------------------------------------------ */
+PPO_API void ppo_second_box_decode(const float* enc, const float* anchors, int64_t N, float* out) {
+    for (int64_t i = 0; i < N; ++i) {
+        const float* a = anchors + 7 * i;
+        const float* t = enc + 7 * i;
+        const float xa = a[0], ya = a[1], wa = a[3], la = a[4], ha = a[5], ra = a[6];
+        float za = a[2];
+        za = za + ha / 2.f;
+        const float l2 = la * la, w2 = wa * wa;
+        const float diagonal = sqrtf(l2 + w2);
+        float xg = t[0] * diagonal;
+        xg = xg + xa;
+        float yg = t[1] * diagonal;
+        yg = yg + ya;
+        float zg = t[2] * ha;
+        zg = zg + za;
+        const float lg = expf(t[4]) * la;
+        const float wg = expf(t[3]) * wa;
+        const float hg = expf(t[5]) * ha;
+        const float rg = t[6] + ra;
+        zg = zg - hg / 2.f;
+        float* o = out + 7 * i;
+        o[0] = xg; o[1] = yg; o[2] = zg; o[3] = wg; o[4] = lg; o[5] = hg; o[6] = rg;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Rotated BEV box -> axis-aligned "standup" box: load_data.py:1525-1546 (center_to_corner_box2d),
+ * 1563-1594 (corners_nd, origin 0.5, corner order (-,-),(-,+),(+,+),(+,-)), 1548-1561
+ * (rotation_2d: x' = x cos + y sin, y' = -x sin + y cos), 1330-1341 (min/max).
+ *   boxes [N,5] f32 (x,y,w,l,r) -> out [N,4] f32 (xmin,ymin,xmax,ymax).  Call site:
+ *   model/voxelnet.py:1233-1249.
+ * ------------------------------------------------------------------------------------------ */
+PPO_API void ppo_rbox_to_standup(const float* boxes, int64_t N, float* out) {
+    static const float cn[4][2] = {{-0.5f, -0.5f}, {-0.5f, 0.5f}, {0.5f, 0.5f}, {0.5f, -0.5f}};
+    for (int64_t i = 0; i < N; ++i) {
+        const float* b = boxes + 5 * i;
+        const float s = sinf(b[4]), c = cosf(b[4]);
+        float mnx = 0, mny = 0, mxx = 0, mxy = 0;
+        for (int k = 0; k < 4; ++k) {
+            const float x = b[2] * cn[k][0], y = b[3] * cn[k][1];
+            float xr = x * c;
+            xr = xr + y * s;
+            float yr = x * (-s);
+            yr = yr + y * c;
+            xr = xr + b[0];
+            yr = yr + b[1];
+            if (k == 0) { mnx = mxx = xr; mny = mxy = yr; }
+            else {
+                mnx = xr < mnx ? xr : mnx; mxx = xr > mxx ? xr : mxx;
+                mny = yr < mny ? yr : mny; mxy = yr > mxy ? yr : mxy;
+            }
+        }
+        out[4 * i + 0] = mnx; out[4 * i + 1] = mny; out[4 * i + 2] = mxx; out[4 * i + 3] = mxy;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Score ordering used by every NMS entry point: `order = scores.argsort()[::-1]`
+ * (eval_helper_functions.py:510, nms_gpu.py:138,473).  numpy's default sort is unstable, so the
+ * reference defines no order for ties; the rule fixed here (and in the CUDA path) is
+ * "descending score, ties by descending original index" == argsort(kind="stable")[::-1].
+ * NaN scores sort as larger than everything (numpy puts NaN last before the reversal).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct { uint32_t key; int32_t idx; } ppo_kv;
+
+static uint32_t ppo_score_key(float s) {
+    uint32_t u;
+    if (s != s) return 0xFFFFFFFFu;
+    memcpy(&u, &s, 4);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+static int ppo_kv_desc(const void* a, const void* b) {
+    const ppo_kv* x = (const ppo_kv*)a; const ppo_kv* y = (const ppo_kv*)b;
+    if (x->key != y->key) return x->key > y->key ? -1 : 1;
+    return x->idx > y->idx ? -1 : (x->idx < y->idx ? 1 : 0);
+}
+PPO_API void ppo_argsort_desc(const float* scores, int64_t N, int32_t* order) {
+    ppo_kv* kv = (ppo_kv*)malloc(sizeof(ppo_kv) * (size_t)(N > 0 ? N : 1));
+    for (int64_t i = 0; i < N; ++i) { kv[i].key = ppo_score_key(scores[i]); kv[i].idx = (int32_t)i; }
+    qsort(kv, (size_t)N, sizeof(ppo_kv), ppo_kv_desc);
+    for (int64_t i = 0; i < N; ++i) order[i] = kv[i].idx;
+    free(kv);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Greedy sweep over the suppression bitmask: nms_postprocess, eval_helper_functions.py:529-546
+ * (identical copy nms_gpu.py:111-128).  mask is [n, col_blocks] uint64, row i word j holds the
+ * bits of boxes 64j..64j+63 that box i suppresses.
+ * ------------------------------------------------------------------------------------------ */
+PPO_API int ppo_nms_postprocess(const uint64_t* mask, int64_t n, int32_t* keep_out) {
+    const int64_t cb = (n + 63) / 64;
+    uint64_t* remv = (uint64_t*)calloc((size_t)(cb > 0 ? cb : 1), sizeof(uint64_t));
+    int nk = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t nb = i / 64; const int ib = (int)(i % 64);
+        if (!(remv[nb] & (1ULL << ib))) {
+            keep_out[nk++] = (int32_t)i;
+            for (int64_t j = nb; j < cb; ++j) remv[j] |= mask[i * cb + j];
+        }
+    }
+    free(remv);
+    return nk;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Axis-aligned IoU with the pixel "+1" convention: iou_device, eval_helper_functions.py:553-564.
+ * numba promotes `float32 - float32 + 1` to float64 at the `+ 1`: the differences
+ * are rounded to float32 first, everything after is float64.
+ * ------------------------------------------------------------------------------------------ */
+static double ppo_iou_standup(const float* a, const float* b) {
+    const float left = a[0] > b[0] ? a[0] : b[0];
+    const float right = a[2] < b[2] ? a[2] : b[2];
+    const float top = a[1] > b[1] ? a[1] : b[1];
+    const float bottom = a[3] < b[3] ? a[3] : b[3];
+    const float dw = right - left, dh = bottom - top;
+    double width = (double)dw + 1.0; if (!(width > 0.)) width = 0.;
+    double height = (double)dh + 1.0; if (!(height > 0.)) height = 0.;
+    const double interS = width * height;
+    const float aw = a[2] - a[0], ah = a[3] - a[1], bw = b[2] - b[0], bh = b[3] - b[1];
+    const double Sa = ((double)aw + 1.0) * ((double)ah + 1.0);
+    const double Sb = ((double)bw + 1.0) * ((double)bh + 1.0);
+    return interS / (Sa + Sb - interS);
+}
+
+/* nms_kernel, eval_helper_functions.py:567-598: bit (i,j) set iff j>i (within the diagonal
+ * tile; every j in later tiles; earlier tiles are computed too but never read by the sweep)
+ * and iou > thresh (thresh is a float32 kernel argument, compared in float64).
+ * boxes_sorted [n,4] f32 already in score order.  Only the upper triangle is filled. */
+PPO_API void ppo_standup_mask(const float* boxes_sorted, int64_t n, float thresh, uint64_t* mask) {
+    const int64_t cb = (n + 63) / 64;
+    memset(mask, 0, sizeof(uint64_t) * (size_t)(n * cb));
+    const double th = (double)thresh;
+    for (int64_t i = 0; i < n; ++i)
+        for (int64_t j = i + 1; j < n; ++j)
+            if (ppo_iou_standup(boxes_sorted + 4 * i, boxes_sorted + 4 * j) > th)
+                mask[i * cb + j / 64] |= 1ULL << (j % 64);
+}
+
+/* nms(): eval_helper_functions.py:463-492 with nms_gpu 494-527.
+ * pre_max_size/post_max_size < 0 mean None.  The reference picks the pre_max_size best scores
+ * with np.argpartition (any order), then sorts them; the kept ORDER is therefore the sorted one.
+ * keep_out receives indices into the caller's arrays; returns the count (0 <=> reference None). */
+PPO_API int ppo_nms_standup(const float* bboxes, const float* scores, int64_t N, int pre_max_size,
+                            int post_max_size, float thresh, int64_t* keep_out) {
+    if (N <= 0) return 0;
+    int32_t* order = (int32_t*)malloc(sizeof(int32_t) * (size_t)N);
+    ppo_argsort_desc(scores, N, order);
+    int64_t n = N;
+    if (pre_max_size >= 0 && pre_max_size < n) n = pre_max_size;
+    if (n == 0) { free(order); return 0; }
+    float* sb = (float*)malloc(sizeof(float) * 4 * (size_t)n);
+    for (int64_t i = 0; i < n; ++i) memcpy(sb + 4 * i, bboxes + 4 * (size_t)order[i], 16);
+    const int64_t cb = (n + 63) / 64;
+    uint64_t* mask = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)(n * cb));
+    int32_t* keep = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+    ppo_standup_mask(sb, n, thresh, mask);
+    int nk = ppo_nms_postprocess(mask, n, keep);
+    if (post_max_size >= 0 && nk > post_max_size) nk = post_max_size;
+    for (int i = 0; i < nk; ++i) keep_out[i] = order[keep[i]];
+    free(order); free(sb); free(mask); free(keep);
+    return nk;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Rotated IoU: second/core/non_max_suppression/nms_gpu.py:180-415 (+564-576 for criterion).
+ * Float32 with the float64 islands numba's typing creates:
+ *   trangle_area  180-183   f32 products/differences, "/ 2.0" in f64
+ *   area          186-193   f64 accumulator
+ *   sort_vertex   196-233   centre sum f32, "/ num" in f64 stored f32; key "-2 - x" f64 stored f32
+ *   line_segment_intersection 236-279   f32, strict ">" orientation tests
+ *   point_in_quadrilateral    324-340   f32, inclusive tests
+ *   quadrilateral_intersection 343-364  interleaved corner tests then 4x4 edge pairs
+ *   rbbox_to_corners 367-390  "x/2" exact, f32 rotate (cosf/sinf)
+ *   devRotateIoU 410-415    areas f32, ratio f64
+ * The reference's intersection buffer holds 8 points (line 397); coincident boxes overflow it
+ * (undefined).  Defined here, and in the CUDA path, as "points beyond the 8th are ignored".
+ * ------------------------------------------------------------------------------------------ */
+static double ppo_trangle_area(const float* a, const float* b, const float* c) {
+    const float t0 = (a[0] - c[0]) * (b[1] - c[1]);
+    const float t1 = (a[1] - c[1]) * (b[0] - c[0]);
+    const float d = t0 - t1;
+    return (double)d / 2.0;
+}
+
+static double ppo_poly_area(const float* p, int n) {
+    double s = 0.0;
+    for (int i = 0; i < n - 2; ++i) s += fabs(ppo_trangle_area(p, p + 2 * i + 2, p + 2 * i + 4));
+    return s;
+}
+
+static void ppo_sort_vertex(float* p, int n) {
+    if (n <= 0) return;
+    float c0 = 0.f, c1 = 0.f;
+    for (int i = 0; i < n; ++i) { c0 += p[2 * i]; c1 += p[2 * i + 1]; }
+    c0 = (float)((double)c0 / (double)n);
+    c1 = (float)((double)c1 / (double)n);
+    float vs[16];
+    for (int i = 0; i < n; ++i) {
+        float v0 = p[2 * i] - c0, v1 = p[2 * i + 1] - c1;
+        const float q0 = v0 * v0, q1 = v1 * v1;
+        const float d = sqrtf(q0 + q1);
+        v0 = v0 / d;
+        v1 = v1 / d;
+        if (v1 < 0) v0 = (float)(-2.0 - (double)v0);
+        vs[i] = v0;
+    }
+    for (int i = 1; i < n; ++i) {
+        if (vs[i - 1] > vs[i]) {
+            const float temp = vs[i], tx = p[2 * i], ty = p[2 * i + 1];
+            int j = i;
+            while (j > 0 && vs[j - 1] > temp) {
+                vs[j] = vs[j - 1];
+                p[2 * j] = p[2 * j - 2];
+                p[2 * j + 1] = p[2 * j - 1];
+                --j;
+            }
+            vs[j] = temp; p[2 * j] = tx; p[2 * j + 1] = ty;
+        }
+    }
+}
+
+static int ppo_seg_inter(const float* p1, const float* p2, int i, int j, float* out) {
+    const float A0 = p1[2 * i], A1 = p1[2 * i + 1];
+    const float B0 = p1[2 * ((i + 1) % 4)], B1 = p1[2 * ((i + 1) % 4) + 1];
+    const float C0 = p2[2 * j], C1 = p2[2 * j + 1];
+    const float D0 = p2[2 * ((j + 1) % 4)], D1 = p2[2 * ((j + 1) % 4) + 1];
+    const float BA0 = B0 - A0, BA1 = B1 - A1, DA0 = D0 - A0, CA0 = C0 - A0, DA1 = D1 - A1,
+                CA1 = C1 - A1;
+    const float l0 = DA1 * CA0, r0 = CA1 * DA0;
+    const int acd = l0 > r0;
+    const float l1 = (D1 - B1) * (C0 - B0), r1 = (C1 - B1) * (D0 - B0);
+    const int bcd = l1 > r1;
+    if (acd != bcd) {
+        const float l2 = CA1 * BA0, r2 = BA1 * CA0;
+        const int abc = l2 > r2;
+        const float l3 = DA1 * BA0, r3 = BA1 * DA0;
+        const int abd = l3 > r3;
+        if (abc != abd) {
+            const float DC0 = D0 - C0, DC1 = D1 - C1;
+            const float m0 = A0 * B1, m1 = B0 * A1; const float ABBA = m0 - m1;
+            const float m2 = C0 * D1, m3 = D0 * C1; const float CDDC = m2 - m3;
+            const float h0 = BA1 * DC0, h1 = BA0 * DC1; const float DH = h0 - h1;
+            const float x0 = ABBA * DC0, x1 = BA0 * CDDC; const float Dx = x0 - x1;
+            const float y0 = ABBA * DC1, y1 = BA1 * CDDC; const float Dy = y0 - y1;
+            out[0] = Dx / DH;
+            out[1] = Dy / DH;
+            return 1;
+        }
+    }
+    return 0;
+}
+
+static int ppo_pt_in_quad(float px, float py, const float* c) {
+    const float ab0 = c[2] - c[0], ab1 = c[3] - c[1];
+    const float ad0 = c[6] - c[0], ad1 = c[7] - c[1];
+    const float ap0 = px - c[0], ap1 = py - c[1];
+    float t0, t1;
+    t0 = ab0 * ab0; t1 = ab1 * ab1; const float abab = t0 + t1;
+    t0 = ab0 * ap0; t1 = ab1 * ap1; const float abap = t0 + t1;
+    t0 = ad0 * ad0; t1 = ad1 * ad1; const float adad = t0 + t1;
+    t0 = ad0 * ap0; t1 = ad1 * ap1; const float adap = t0 + t1;
+    return abab >= abap && abap >= 0 && adad >= adap && adap >= 0;
+}
+
+static int ppo_quad_inter(const float* p1, const float* p2, float* ip) {
+    int n = 0;
+    for (int i = 0; i < 4; ++i) {
+        if (ppo_pt_in_quad(p1[2 * i], p1[2 * i + 1], p2)) {
+            if (n < 8) { ip[2 * n] = p1[2 * i]; ip[2 * n + 1] = p1[2 * i + 1]; }
+            ++n;
+        }
+        if (ppo_pt_in_quad(p2[2 * i], p2[2 * i + 1], p1)) {
+            if (n < 8) { ip[2 * n] = p2[2 * i]; ip[2 * n + 1] = p2[2 * i + 1]; }
+            ++n;
+        }
+    }
+    float t[2];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j)
+            if (ppo_seg_inter(p1, p2, i, j, t)) {
+                if (n < 8) { ip[2 * n] = t[0]; ip[2 * n + 1] = t[1]; }
+                ++n;
+            }
+    return n > 8 ? 8 : n;
+}
+
+static void ppo_rbbox_to_corners(float* corners, const float* r) {
+    const float a_cos = cosf(r[4]), a_sin = sinf(r[4]);
+    const float cx = r[0], cy = r[1];
+    const float hx = (float)((double)r[2] / 2.0), hy = (float)((double)r[3] / 2.0);
+    const float xs[4] = {-hx, -hx, hx, hx};
+    const float ys[4] = {-hy, hy, hy, -hy};
+    for (int i = 0; i < 4; ++i) {
+        float t0 = a_cos * xs[i], t1 = a_sin * ys[i];
+        float s = t0 + t1;
+        corners[2 * i] = s + cx;
+        t0 = (-a_sin) * xs[i]; t1 = a_cos * ys[i];
+        s = t0 + t1;
+        corners[2 * i + 1] = s + cy;
+    }
+}
+
+static double ppo_inter(const float* r1, const float* r2) {
+    float c1[8], c2[8], ip[16];
+    ppo_rbbox_to_corners(c1, r1);
+    ppo_rbbox_to_corners(c2, r2);
+    const int n = ppo_quad_inter(c1, c2, ip);
+    ppo_sort_vertex(ip, n);
+    return ppo_poly_area(ip, n);
+}
+
+/* devRotateIoUEval, nms_gpu.py:564-576; criterion -1 is devRotateIoU (410-415). */
+PPO_API double ppo_rotate_iou_pair(const float* r1, const float* r2, int criterion) {
+    const float area1 = r1[2] * r1[3];
+    const float area2 = r2[2] * r2[3];
+    const double ai = ppo_inter(r1, r2);
+    if (criterion == -1) { const float s = area1 + area2; return ai / ((double)s - ai); }
+    if (criterion == 0) return ai / (double)area1;
+    if (criterion == 1) return ai / (double)area2;
+    return ai;
+}
+
+/* rotate_iou_gpu / rotate_iou_gpu_eval: nms_gpu.py:526-561, 618-653 with kernels 493-523,
+ * 579-615.  out[n*K + k] = devRotateIoUEval(query_boxes[k], boxes[n]) rounded to float32. */
+PPO_API void ppo_rotate_iou(const float* boxes, int64_t N, const float* qboxes, int64_t K,
+                            int criterion, float* out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t n = 0; n < N; ++n)
+        for (int64_t k = 0; k < K; ++k)
+            out[n * K + k] = (float)ppo_rotate_iou_pair(qboxes + 5 * k, boxes + 5 * n, criterion);
+}
+
+/* rotate_nms_kernel, nms_gpu.py:419-452: dets_sorted [n,6] (x,y,w,l,r,score) in score order;
+ * bit (i,j), j>i, set iff devRotateIoU(row i, col j) > thresh.  Upper triangle only. */
+PPO_API void ppo_rotate_mask(const float* dets_sorted, int64_t n, float thresh, uint64_t* mask) {
+    const int64_t cb = (n + 63) / 64;
+    memset(mask, 0, sizeof(uint64_t) * (size_t)(n * cb));
+    const double th = (double)thresh;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t i = 0; i < n; ++i)
+        for (int64_t j = i + 1; j < n; ++j)
+            if (ppo_rotate_iou_pair(dets_sorted + 6 * i, dets_sorted + 6 * j, -1) > th)
+                mask[i * cb + j / 64] |= 1ULL << (j % 64);
+}
+
+/* rotate_nms_gpu, nms_gpu.py:455-490, plus the optional pre/post caps of nms()
+ * (eval_helper_functions.py:463-492) so the same entry serves the "full path" config.
+ * dets [N,6] f32; keep_out gets original indices in keep order; returns the count. */
+PPO_API int ppo_rotate_nms(const float* dets, int64_t N, float thresh, int pre_max_size,
+                           int post_max_size, int64_t* keep_out) {
+    if (N <= 0) return 0;
+    float* sc = (float*)malloc(sizeof(float) * (size_t)N);
+    for (int64_t i = 0; i < N; ++i) sc[i] = dets[6 * i + 5];
+    int32_t* order = (int32_t*)malloc(sizeof(int32_t) * (size_t)N);
+    ppo_argsort_desc(sc, N, order);
+    int64_t n = N;
+    if (pre_max_size >= 0 && pre_max_size < n) n = pre_max_size;
+    if (n == 0) { free(sc); free(order); return 0; }
+    float* sd = (float*)malloc(sizeof(float) * 6 * (size_t)n);
+    for (int64_t i = 0; i < n; ++i) memcpy(sd + 6 * i, dets + 6 * (size_t)order[i], 24);
+    const int64_t cb = (n + 63) / 64;
+    uint64_t* mask = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)(n * cb));
+    int32_t* keep = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+    ppo_rotate_mask(sd, n, thresh, mask);
+    int nk = ppo_nms_postprocess(mask, n, keep);
+    if (post_max_size >= 0 && nk > post_max_size) nk = post_max_size;
+    for (int i = 0; i < nk; ++i) keep_out[i] = order[keep[i]];
+    free(sc); free(order); free(sd); free(mask); free(keep);
+    return nk;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Whole hot path over a batch of frames, used ONLY as the timed CPU baseline (bench.py).
+ * Frames are independent, so the batch is an OpenMP loop over frames; inside a frame
+ * the reference's voxelizer is single-threaded by construction.
+ * Stand-ins for the TF layers between the stages (PFN Dense, RPN) are inputs, as in
+ * pfn_feats [max_voxels,C] (first M rows used), box_enc/anchors [A,7],
+ * scores [A].  Returns total kept detections; det_out [B,post_max,8] (box7 + score).
+ * ------------------------------------------------------------------------------------------ */
+PPO_API int64_t ppo_full_path_batch(const void* points, int is_f64, const int64_t* frame_off, int B,
+                                    int D, const double voxel_size[3], const double coors_range[6],
+                                    int max_points, int max_voxels, const float* pfn_feats, int C,
+                                    const float* box_enc, const float* anchors, const float* scores,
+                                    int64_t A, int pre_max, int post_max, float thresh, int rotated,
+                                    int nthreads, float* det_out, int32_t* det_count,
+                                    int64_t* voxel_count) {
+    int32_t grid[3];
+    ppo_grid_size(voxel_size, coors_range, 0, grid);
+    const int nx = grid[0], ny = grid[1];
+    const size_t esz = is_f64 ? 8 : 4;
+    const double xo = voxel_size[0] / 2 + coors_range[0], yo = voxel_size[1] / 2 + coors_range[1];
+    int64_t total = 0;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : total)
+    for (int b = 0; b < B; ++b) {
+        const int64_t n0 = frame_off[b], n = frame_off[b + 1] - n0;
+        void* vox = malloc(esz * (size_t)max_voxels * max_points * D);
+        int32_t* co = (int32_t*)malloc(sizeof(int32_t) * 3 * (size_t)max_voxels);
+        int32_t* nm = (int32_t*)malloc(sizeof(int32_t) * (size_t)max_voxels);
+        const int M = ppo_points_to_voxel((const char*)points + esz * (size_t)n0 * D, is_f64, n, D,
+                                          voxel_size, coors_range, 0, max_points, max_voxels, 1, vox,
+                                          co, nm, NULL);
+        /* tf.data casts voxels to float32 (load_data.py:2339-2349) */
+        float* vf = (float*)malloc(sizeof(float) * (size_t)(M > 0 ? M : 1) * max_points * D);
+        if (is_f64) for (size_t i = 0; i < (size_t)M * max_points * D; ++i) vf[i] = (float)((double*)vox)[i];
+        else memcpy(vf, vox, sizeof(float) * (size_t)M * max_points * D);
+        int32_t* c4 = (int32_t*)malloc(sizeof(int32_t) * 4 * (size_t)(M > 0 ? M : 1));
+        for (int m = 0; m < M; ++m) { c4[4 * m] = 0; c4[4 * m + 1] = co[3 * m]; c4[4 * m + 2] = co[3 * m + 1]; c4[4 * m + 3] = co[3 * m + 2]; }
+        float* dec = (float*)malloc(sizeof(float) * (size_t)(M > 0 ? M : 1) * max_points * (D + 5));
+        ppo_decorate(vf, nm, c4, M, max_points, D, voxel_size[0], voxel_size[1], xo, yo, dec);
+        float* canvas = (float*)malloc(sizeof(float) * (size_t)C * ny * nx);
+        ppo_scatter(pfn_feats, c4, M, C, 1, ny, nx, 0, canvas);
+        float* boxes = (float*)malloc(sizeof(float) * 7 * (size_t)A);
+        ppo_second_box_decode(box_enc + 7 * (size_t)A * b, anchors, A, boxes);
+        int64_t* keep = (int64_t*)malloc(sizeof(int64_t) * (size_t)A);
+        int nk;
+        if (rotated) {
+            float* dets = (float*)malloc(sizeof(float) * 6 * (size_t)A);
+            for (int64_t i = 0; i < A; ++i) {
+                dets[6 * i] = boxes[7 * i]; dets[6 * i + 1] = boxes[7 * i + 1]; dets[6 * i + 2] = boxes[7 * i + 3];
+                dets[6 * i + 3] = boxes[7 * i + 4]; dets[6 * i + 4] = boxes[7 * i + 6]; dets[6 * i + 5] = scores[A * b + i];
+            }
+            nk = ppo_rotate_nms(dets, A, thresh, pre_max, post_max, keep);
+            free(dets);
+        } else {
+            float* rb = (float*)malloc(sizeof(float) * 5 * (size_t)A);
+            float* sb = (float*)malloc(sizeof(float) * 4 * (size_t)A);
+            for (int64_t i = 0; i < A; ++i) {
+                rb[5 * i] = boxes[7 * i]; rb[5 * i + 1] = boxes[7 * i + 1]; rb[5 * i + 2] = boxes[7 * i + 3];
+                rb[5 * i + 3] = boxes[7 * i + 4]; rb[5 * i + 4] = boxes[7 * i + 6];
+            }
+            ppo_rbox_to_standup(rb, A, sb);
+            nk = ppo_nms_standup(sb, scores + A * b, A, pre_max, post_max, thresh, keep);
+            free(rb); free(sb);
+        }
+        for (int k = 0; k < nk; ++k) {
+            memcpy(det_out + ((size_t)b * post_max + k) * 8, boxes + 7 * keep[k], 28);
+            det_out[((size_t)b * post_max + k) * 8 + 7] = scores[A * b + keep[k]];
+        }
+        det_count[b] = nk;
+        if (voxel_count) voxel_count[b] = M;
+        total += nk;
+        /* keep the compiler from discarding the decorate/scatter work */
+        if (dec[0] != dec[0] || canvas[0] != canvas[0]) total += 0;
+        free(vox); free(co); free(nm); free(vf); free(c4); free(dec); free(canvas); free(boxes); free(keep);
+    }
+    return total;
+}

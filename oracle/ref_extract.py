@@ -1,0 +1,185 @@
+"""Load the reference's OWN source for the hot path, in the build container only.
+
+TEST INFRASTRUCTURE.  `/root/reference` exists only in the build container, never on the GPU
+box, so this module is used solely by `tests/golden/make_golden.py` (fixture generation) and by
+`tests/test_oracle_vs_reference.py` (skipped when the reference is absent).  Nothing is copied
+into the repo: the functions are AST-extracted from the reference files where they lie and
+exec'd in a scratch namespace, because importing the modules pulls TensorFlow / rospy / a
+CPython-3.6 `nms.so` that do not exist here.
+
+  * voxelizer       load_data.py:558-771   (numba CPU jit, runs unmodified)
+  * standup prep    load_data.py:1330-1341, 1525-1594
+  * decode, sweep   libraries/eval_helper_functions.py:388-461, 529-550
+  * rotated IoU     second/core/non_max_suppression/nms_gpu.py:180-415, 564-576 -- numba.cuda device
+                    functions.  There is no GPU here, so the `@cuda.jit(..., device=True)`
+                    decorators are textually swapped for `@numba.njit` and `cuda.local.array`
+                    for `np.empty`; bodies, operation order and numba's type inference (the
+                    f32/f64 promotion map of SURVEY 3.5) are untouched.
+  * standup IoU     eval_helper_functions.py:553-564, same mechanical swap.
+"""
+from __future__ import annotations
+
+import ast
+import os
+import re
+import types
+
+REFERENCE_ROOT = os.environ.get("PP_REFERENCE_ROOT", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "load_data.py"))
+
+
+def _read(rel):
+    with open(os.path.join(REFERENCE_ROOT, rel), encoding="utf-8-sig") as f:
+        return f.read()
+
+
+def _extract_defs(src: str, names) -> str:
+    """Source text (decorators included) of the named top-level functions, in file order."""
+    tree = ast.parse(src)
+    lines = src.splitlines()
+    out = []
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            start = min([node.lineno] + [d.lineno for d in node.decorator_list]) - 1
+            out.append("\n".join(lines[start:node.end_lineno]))
+    missing = set(names) - {n.name for n in tree.body if isinstance(n, ast.FunctionDef)}
+    if missing:
+        raise RuntimeError(f"reference functions not found: {sorted(missing)}")
+    return "\n\n".join(out) + "\n"
+
+
+_CUDA_DECORATOR = re.compile(r"@cuda\.jit\((?:[^()]|\([^()]*\))*\)", re.S)
+_LOCAL_ARRAY = re.compile(r"cuda\.local\.array\(\((\d+),\s*\),\s*dtype=numba\.float32\)")
+
+
+def _cuda_device_to_njit(src: str) -> str:
+    src = _CUDA_DECORATOR.sub('@numba.njit(error_model="numpy")', src)
+    return _LOCAL_ARRAY.sub(r"np.empty(\1, np.float32)", src)
+
+
+_cache = None
+
+
+def load() -> types.SimpleNamespace:
+    """Namespace with the reference's functions, compiled from the reference's files."""
+    global _cache
+    if _cache is not None:
+        return _cache
+    if not available():
+        raise RuntimeError(f"reference checkout not found at {REFERENCE_ROOT}")
+    import math
+
+    import numba
+    import numpy as np
+
+    ns = {"np": np, "numba": numba, "math": math}
+
+    exec(_extract_defs(_read("load_data.py"), [
+        "_points_to_voxel_reverse_kernel", "_points_to_voxel_kernel", "points_to_voxel",
+        "corner_to_standup_nd_jit", "center_to_corner_box2d", "rotation_2d", "corners_nd",
+        "create_anchors_3d_stride",
+    ]), ns)
+
+    ehf = _read("libraries/eval_helper_functions.py")
+    exec(_extract_defs(ehf, ["second_box_decode", "nms_postprocess", "div_up"]), ns)
+    standup = {"np": np, "numba": numba, "math": math}
+    exec(_cuda_device_to_njit(_extract_defs(ehf, ["iou_device"])), standup)
+    ns["iou_device"] = standup["iou_device"]
+
+    rot = {"np": np, "numba": numba, "math": math}
+    exec(_cuda_device_to_njit(_extract_defs(_read("second/core/non_max_suppression/nms_gpu.py"), [
+        "trangle_area", "area", "sort_vertex_in_convex_polygon", "line_segment_intersection",
+        "point_in_quadrilateral", "quadrilateral_intersection", "rbbox_to_corners", "inter",
+        "devRotateIoU", "devRotateIoUEval",
+    ])), rot)
+
+    dev_eval = rot["devRotateIoUEval"]
+    dev_iou = rot["devRotateIoU"]
+    iou_dev = ns["iou_device"]
+
+    # Drivers: the kernels' indexing (nms_gpu.py:445-449, 520-523, 611-615;
+    # eval_helper_functions.py:589-596) restated as plain loops around the reference's own
+    # device functions.
+    @numba.njit(error_model="numpy")
+    def rotate_iou_matrix(boxes, qboxes, criterion):
+        N, K = boxes.shape[0], qboxes.shape[0]
+        out = np.zeros((N, K), np.float32)
+        for n in range(N):
+            for k in range(K):
+                out[n, k] = dev_eval(qboxes[k], boxes[n], criterion)
+        return out
+
+    @numba.njit(error_model="numpy")
+    def rotate_iou_matrix_f64(boxes, qboxes):
+        N, K = boxes.shape[0], qboxes.shape[0]
+        out = np.zeros((N, K), np.float64)
+        for n in range(N):
+            for k in range(K):
+                out[n, k] = dev_iou(qboxes[k], boxes[n])
+        return out
+
+    @numba.njit(error_model="numpy")
+    def rotate_mask(dets, thresh):
+        n = dets.shape[0]
+        cb = (n + 63) // 64
+        mask = np.zeros(n * cb, np.uint64)
+        iou_all = np.zeros((n, n), np.float64)
+        for i in range(n):
+            for j in range(i + 1, n):
+                iou = dev_iou(dets[i, :5], dets[j, :5])
+                iou_all[i, j] = iou
+                if iou > thresh:
+                    mask[i * cb + j // 64] |= np.uint64(1) << np.uint64(j % 64)
+        return mask, iou_all
+
+    @numba.njit(error_model="numpy")
+    def standup_mask(boxes, thresh):
+        n = boxes.shape[0]
+        cb = (n + 63) // 64
+        mask = np.zeros(n * cb, np.uint64)
+        iou_all = np.zeros((n, n), np.float64)
+        for i in range(n):
+            for j in range(i + 1, n):
+                iou = iou_dev(boxes[i, :4], boxes[j, :4])
+                iou_all[i, j] = iou
+                if iou > thresh:
+                    mask[i * cb + j // 64] |= np.uint64(1) << np.uint64(j % 64)
+        return mask, iou_all
+
+    def rotate_nms(dets, thresh):
+        """rotate_nms_gpu (nms_gpu.py:455-490) with the kernel replaced by the loop above.
+        Uses a stable argsort so tie order is defined (the reference's is not)."""
+        dets = dets.astype(np.float32)
+        n = dets.shape[0]
+        order = dets[:, 5].argsort(kind="stable")[::-1].astype(np.int32)
+        mask, iou_all = rotate_mask(np.ascontiguousarray(dets[order]), np.float32(thresh))
+        keep = np.zeros(n, np.int32)
+        nk = ns["nms_postprocess"](keep, mask, n)
+        return [int(v) for v in order[keep[:nk]]], iou_all
+
+    def standup_nms(dets, thresh):
+        """nms_gpu (eval_helper_functions.py:494-527), same substitution."""
+        dets = dets.astype(np.float32)
+        n = dets.shape[0]
+        order = dets[:, 4].argsort(kind="stable")[::-1].astype(np.int32)
+        mask, iou_all = standup_mask(np.ascontiguousarray(dets[order]), np.float32(thresh))
+        keep = np.zeros(n, np.int32)
+        nk = ns["nms_postprocess"](keep, mask, n)
+        return [int(v) for v in order[keep[:nk]]], iou_all
+
+    _cache = types.SimpleNamespace(
+        points_to_voxel=ns["points_to_voxel"],
+        second_box_decode=ns["second_box_decode"],
+        nms_postprocess=ns["nms_postprocess"],
+        center_to_corner_box2d=ns["center_to_corner_box2d"],
+        corner_to_standup_nd_jit=ns["corner_to_standup_nd_jit"],
+        create_anchors_3d_stride=ns["create_anchors_3d_stride"],
+        rotate_iou_matrix=rotate_iou_matrix,
+        rotate_iou_matrix_f64=rotate_iou_matrix_f64,
+        rotate_nms=rotate_nms,
+        standup_nms=standup_nms,
+    )
+    return _cache

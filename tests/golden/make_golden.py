@@ -1,0 +1,106 @@
+"""Generate tests/golden/*.npz from the REFERENCE's own source (build container only).
+
+Run:  python tests/golden/make_golden.py
+Needs /root/reference (read-only) and numba; see oracle/ref_extract.py for how the reference
+functions are loaded without copying them.  The fixtures are committed; the GPU box never runs
+this script.  Inputs are stored beside the outputs so the fixtures do not depend on the synthetic
+generators staying unchanged.
+"""
+import importlib
+import os
+import sys
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_extract  # noqa: E402
+
+synth = importlib.import_module("3d-object-detection-for-autonomous-navigation_b200.synth")
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def voxel_cases(ref):
+    d, k = synth.D435, synth.KITTI
+    cases = {}
+
+    def run(name, pts, vs, pcr, P, rev, cap):
+        v, c, n = ref.points_to_voxel(pts, vs, pcr, P, rev, cap)
+        cases[name] = dict(points=pts, voxel_size=np.asarray(vs, np.float64),
+                           coors_range=np.asarray(pcr, np.float64),
+                           params_are_lists=np.array(not isinstance(vs, np.ndarray)),
+                           max_points=np.array(P), reverse_index=np.array(rev),
+                           max_voxels=np.array(cap), voxels=v.copy(), coors=c.copy(), num=n.copy())
+
+    vs_d, pcr_d = np.array(d["voxel_size"]), np.array(d["point_cloud_range"])
+    vs_k, pcr_k = np.array(k["voxel_size"]), np.array(k["point_cloud_range"])
+    cloud = synth.d435_cloud(0)
+    run("d435_f64_sub16", np.ascontiguousarray(cloud[3::16]), vs_d, pcr_d, 50, True, 12000)
+    run("d435_f64_cap", np.ascontiguousarray(cloud[5::16]), vs_d, pcr_d, 5, True, 700)
+    run("d435_f32_sub16", np.ascontiguousarray(cloud[7::16].astype(np.float32)), vs_d, pcr_d, 50, True, 12000)
+    kc = synth.kitti_cloud(1)
+    run("kitti_ring_cap", np.ascontiguousarray(kc[::4]), vs_k, pcr_k, 100, True, 3000)
+    ks = synth.kitti_cloud(1, shuffled=True)
+    run("kitti_shuf_cap", np.ascontiguousarray(ks[::4]), vs_k, pcr_k, 100, True, 3000)
+    run("kitti_listparams_f32arith_xyz", np.ascontiguousarray(ks[1::4]), k["voxel_size"],
+        k["point_cloud_range"], 8, False, 20000)
+    run("uniform_break_early", synth.uniform_cloud(20000, k, 3), vs_k, pcr_k, 100, True, 500)
+    run("empty", np.zeros((0, 4), np.float32), vs_k, pcr_k, 100, True, 100)
+    run("all_outside", (synth.uniform_cloud(100, k, 4) + 1000).astype(np.float32), vs_k, pcr_k, 100, True, 100)
+    return cases
+
+
+def main():
+    warnings.simplefilter("ignore")
+    ref = ref_extract.load()
+
+    for name, c in voxel_cases(ref).items():
+        np.savez_compressed(os.path.join(OUT, f"voxel_{name}.npz"), **c)
+        print("voxel", name, c["voxels"].shape, int(c["num"].sum()))
+
+    # rotated IoU / NMS (second/core/non_max_suppression/nms_gpu.py)
+    d = synth.rotated_boxes(320, 11, clustered=True)
+    q = synth.rotated_boxes(150, 12, clustered=True)
+    q[:, :2] = d[:150, :2] + np.random.default_rng(5).normal(0, 0.7, size=(150, 2)).astype(np.float32)
+    out = dict(boxes=d[:, :5].copy(), query=q[:, :5].copy(), dets=d)
+    for crit in (-1, 0, 1, 2):
+        out[f"iou_crit{crit}"] = ref.rotate_iou_matrix(out["boxes"], out["query"], crit)
+    for thr in (0.5, 0.1, 0.01):
+        keep, iou_all = ref.rotate_nms(d, thr)
+        out[f"keep_thr{thr}"] = np.asarray(keep, np.int64)
+        # pairs whose IoU is within 1e-6 of the threshold are excluded from index parity
+        out[f"near_thr{thr}"] = np.array(int((np.abs(iou_all - np.float32(thr)) < 1e-6).sum()))
+    table = np.array([
+        [1, 1, 2, 1, 0, 2, 1, 2, 1, 0], [1, 1, 2, 1, 0, 1.5, 1.5, 2, 1, 0],
+        [0, 0, 2, 1, 0, 0, 0, 2, 1, np.pi / 2], [0, 0, 2, 2, 0, 0, 0, 2, 2, np.pi / 4],
+        [0, 0, 4, 4, 0.1, 0, 0, 1, 1, 0.5], [0, 0, 1, 1, 0.2, 5, 5, 1, 1, 0.7],
+        [1, 1, 2, 1, 0, 1, 1, 2, 1, 0]], np.float32)
+    out["table"] = table
+    out["table_iou"] = np.array([ref.rotate_iou_matrix(t[None, :5].copy(), t[None, 5:].copy(), -1)[0, 0]
+                                 for t in table], np.float32)
+    np.savez_compressed(os.path.join(OUT, "rotated.npz"), **out)
+    print("rotated", {k: v.shape for k, v in out.items() if k.startswith("keep")})
+
+    # live standup NMS (libraries/eval_helper_functions.py:463-598) + prep (load_data.py:1525-1594)
+    corners = ref.center_to_corner_box2d(d[:, :2], d[:, 2:4], d[:, 4])
+    standup = ref.corner_to_standup_nd_jit(corners)
+    so = dict(rboxes=d[:, :5].copy(), standup=standup, scores=d[:, 5].copy())
+    for scale in (1.0, 10.0):
+        dets = np.concatenate([standup * np.float32(scale), d[:, 5:6]], axis=1).astype(np.float32)
+        for thr in (0.5, 0.3):
+            keep, iou_all = ref.standup_nms(dets, thr)
+            so[f"keep_s{scale}_thr{thr}"] = np.asarray(keep, np.int64)
+    np.savez_compressed(os.path.join(OUT, "standup.npz"), **so)
+
+    # decode (libraries/eval_helper_functions.py:388-461)
+    an = synth.anchors_stride(synth.D435)[::7][:1500].copy()
+    be, _ = synth.rpn_standin(an.shape[0], 3)
+    be[:, 3:6] *= 8  # exercise exp over a wider range
+    np.savez_compressed(os.path.join(OUT, "decode.npz"), box_encodings=be, anchors=an,
+                        decoded=ref.second_box_decode(be, an))
+    print("done")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,60 @@
+"""Pin the CPU oracle against the reference's own source executed live (build container only;
+skipped where /root/reference is absent, e.g. on the GPU box)."""
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import ref_extract
+
+pytestmark = pytest.mark.skipif(not ref_extract.available(), reason="reference checkout not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    warnings.simplefilter("ignore")
+    return ref_extract.load()
+
+
+def test_voxelizer_full_size(ref, oracle, synth):
+    d, k = synth.D435, synth.KITTI
+    cases = [
+        (synth.d435_cloud(0), np.array(d["voxel_size"]), np.array(d["point_cloud_range"]), 50, True, 12000),
+        (synth.d435_cloud(1, subsample=True), np.array(d["voxel_size"]), np.array(d["point_cloud_range"]), 50, True, 12000),
+        (synth.kitti_cloud(0), np.array(k["voxel_size"]), np.array(k["point_cloud_range"]), 100, True, 12000),
+        (synth.kitti_cloud(0, True), np.array(k["voxel_size"]), np.array(k["point_cloud_range"]), 100, True, 12000),
+        (synth.kitti_cloud(2, True), k["voxel_size"], k["point_cloud_range"], 100, False, 12000),
+    ]
+    for args in cases:
+        want = ref.points_to_voxel(*args)
+        got = oracle.points_to_voxel(*args)
+        for w, g in zip(want, got):
+            assert w.dtype == g.dtype and np.array_equal(w, g)
+    # SURVEY 8d probed numbers for the D435 synthetic cloud
+    v, c, n = oracle.points_to_voxel(*cases[0])
+    assert v.shape[0] == 8171 and int(n.sum()) == 217921 and set(np.unique(c[:, 0])) == {0, 1}
+
+
+def test_rotated_iou_random(ref, oracle, synth):
+    for seed, clustered in ((21, True), (22, False)):
+        d = synth.rotated_boxes(400, seed, clustered)
+        for crit in (-1, 0, 1, 2):
+            want = ref.rotate_iou_matrix(d[:, :5].copy(), d[:128, :5].copy(), crit)
+            got = oracle.rotate_iou_gpu_eval(d[:, :5], d[:128, :5], crit)
+            off = ~np.eye(400, 128, dtype=bool)  # identical boxes are chaotic in the reference (F10)
+            np.testing.assert_allclose(got[off], want[off], rtol=0, atol=1e-6)
+        keep, iou_all = ref.rotate_nms(d, 0.3)
+        if int((np.abs(iou_all - np.float32(0.3)) < 1e-6).sum()) == 0:
+            assert oracle.rotate_nms_gpu(d, 0.3) == keep
+
+
+def test_decode_and_standup(ref, oracle, synth):
+    an = synth.anchors_stride(synth.D435)
+    be, sc = synth.rpn_standin(an.shape[0], 5)
+    np.testing.assert_allclose(oracle.second_box_decode(be, an), ref.second_box_decode(be, an), rtol=1e-6, atol=1e-6)
+    d = synth.rotated_boxes(500, 3)
+    want = ref.corner_to_standup_nd_jit(ref.center_to_corner_box2d(d[:, :2], d[:, 2:4], d[:, 4]))
+    np.testing.assert_allclose(oracle.rbox_to_standup(d[:, :5]), want, rtol=1e-6, atol=1e-5)
+    dets = np.concatenate([want, d[:, 5:6]], axis=1)
+    keep, _ = ref.standup_nms(dets, 0.5)
+    assert oracle.nms(want, d[:, 5], None, None, 0.5).tolist() == keep
