@@ -1,0 +1,171 @@
+"""ctypes binding of libpp_b200.so (include/pp_b200.h).  No CPU fallback: if the library is not
+built, or no CUDA device is usable, every compute call raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+from . import build as _build
+
+PP_F32, PP_F64 = 0, 1
+PP_LAYOUT_NCHW, PP_LAYOUT_NHWC = 0, 1
+PP_NMS_STANDUP, PP_NMS_ROTATED = 0, 1
+
+
+class PPError(RuntimeError):
+    pass
+
+
+class VoxelCfg(C.Structure):
+    _fields_ = [("voxel_size", C.c_double * 3), ("coors_range", C.c_double * 6),
+                ("max_points", C.c_int32), ("max_voxels", C.c_int32),
+                ("reverse_index", C.c_int32), ("arith_f32", C.c_int32)]
+
+
+_vp, _i32, _i64, _f32, _f64, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_size_t
+_cfgp = C.POINTER(VoxelCfg)
+
+# name -> (restype, argtypes); must list every symbol include/pp_b200.h declares
+SIGNATURES = {
+    "pp_last_error_string": (C.c_char_p, []),
+    "pp_version": (C.c_int, []),
+    "pp_launch_count": (_i64, [C.c_int]),
+    "pp_grid_size": (C.c_int, [C.POINTER(_f64), C.POINTER(_f64), C.c_int, C.POINTER(_i32)]),
+    "pp_voxelize_workspace_bytes": (_sz, [_cfgp, _i64, C.c_int]),
+    "pp_voxelize_dev": (C.c_int, [_cfgp, _vp, C.c_int, C.c_int, _vp, C.c_int, _i64, _i64, C.c_int, _vp, _vp,
+                                  _vp, C.c_int, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pp_decorate_dev": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int, C.c_int, _f64, _f64, _f64, _f64, _vp, _vp]),
+    "pp_scatter_workspace_bytes": (_sz, [C.c_int, C.c_int, C.c_int, _i64]),
+    "pp_scatter_dev": (C.c_int, [_vp, _vp, _i64, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _sz, _vp]),
+    "pp_box_decode_dev": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    "pp_rbox_to_standup_dev": (C.c_int, [_vp, C.c_int, _i64, _vp, _vp]),
+    "pp_nms_workspace_bytes": (_sz, [C.c_int, C.c_int, _i64, C.c_int]),
+    "pp_nms_dev": (C.c_int, [C.c_int, _vp, C.c_int, _vp, _vp, C.c_int, _i64, C.c_int, C.c_int, _f32, _vp, _i64,
+                             _vp, _vp, _sz, _vp]),
+    "pp_rotate_iou_dev": (C.c_int, [_vp, _i64, _vp, _i64, C.c_int, _vp, _vp]),
+    "pp_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "pp_ctx_destroy": (None, [_vp]),
+    "pp_ctx_stream": (_vp, [_vp]),
+    "pp_ctx_device": (C.c_int, [_vp]),
+    "pp_ctx_sync": (C.c_int, [_vp]),
+    "pp_points_to_voxel_host": (C.c_int, [_vp, _cfgp, _vp, C.c_int, _i64, C.c_int, _vp, _vp, _vp, C.POINTER(_i32), _vp]),
+    "pp_decorate_host": (C.c_int, [_vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int, _f64, _f64, _f64, _f64, _vp]),
+    "pp_scatter_host": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    "pp_box_decode_host": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "pp_rbox_to_standup_host": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "pp_nms_host": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, C.c_int, C.c_int, _f32, _vp, C.POINTER(_i32)]),
+    "pp_rotate_iou_host": (C.c_int, [_vp, _vp, _i64, _vp, _i64, C.c_int, _vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib():
+    """The loaded shared library (built on first use when sources are newer)."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                path = _build.LIB
+                if _build.needs_build():
+                    try:
+                        _build.build()
+                    except Exception as e:  # noqa: BLE001
+                        if not os.path.exists(path):
+                            raise PPError(f"libpp_b200.so is not built and nvcc failed: {e}") from e
+                l = C.CDLL(path)
+                for name, (res, args) in SIGNATURES.items():
+                    fn = getattr(l, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = l
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = lib().pp_last_error_string().decode(errors="replace")
+        raise PPError(f"libpp_b200 error {rc}: {msg}")
+
+
+def launch_count(reset=False) -> int:
+    return int(lib().pp_launch_count(int(reset)))
+
+
+class Ctx:
+    """pp_ctx wrapper: stream + device arena for the host-buffer entry points."""
+
+    def __init__(self, device: int = 0):
+        h = _vp()
+        check(lib().pp_ctx_create(int(device), C.byref(h)))
+        self.handle = h
+        self.device = int(device)
+
+    @property
+    def stream(self) -> int:
+        return int(lib().pp_ctx_stream(self.handle) or 0)
+
+    def sync(self):
+        check(lib().pp_ctx_sync(self.handle))
+
+    def close(self):
+        if self.handle:
+            lib().pp_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+_tls = threading.local()
+_default_device = 0
+
+
+def set_device(device: int):
+    """Device used by the numpy drop-in functions on this thread (reference: device_id=0)."""
+    _tls.device = int(device)
+
+
+def ctx(device=None) -> Ctx:
+    """One context per (thread, device): the reference calls the voxelizer on the tf.data thread
+    and NMS on the main thread concurrently."""
+    if device is None:
+        device = getattr(_tls, "device", _default_device)
+    cache = getattr(_tls, "ctxs", None)
+    if cache is None:
+        cache = _tls.ctxs = {}
+    c = cache.get(device)
+    if c is None:
+        c = cache[device] = Ctx(device)
+    return c
+
+
+def make_cfg(voxel_size, coors_range, max_points, max_voxels, reverse_index, arith_f32) -> VoxelCfg:
+    cfg = VoxelCfg()
+    for i in range(3):
+        cfg.voxel_size[i] = float(voxel_size[i])
+    for i in range(6):
+        cfg.coors_range[i] = float(coors_range[i])
+    cfg.max_points = int(max_points)
+    cfg.max_voxels = int(max_voxels)
+    cfg.reverse_index = int(bool(reverse_index))
+    cfg.arith_f32 = int(bool(arith_f32))
+    return cfg
+
+
+def grid_size(voxel_size, coors_range, arith_f32=False):
+    g = (_i32 * 3)()
+    check(lib().pp_grid_size((_f64 * 3)(*map(float, voxel_size)), (_f64 * 6)(*map(float, coors_range)),
+                             int(arith_f32), g))
+    return [int(v) for v in g]
+
+
+def ptr(a: np.ndarray):
+    return a.ctypes.data_as(_vp)

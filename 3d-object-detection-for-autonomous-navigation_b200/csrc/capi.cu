@@ -1,0 +1,277 @@
+// C-ABI glue: thread-local error string, launch counter, pp_ctx (stream + device arena) and
+// the host-buffer entry points the reference's numpy call sites bind (include/pp_b200.h).
+#include <new>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "pp_common.cuh"
+
+namespace pp {
+
+static thread_local char g_err[512] = "";
+static thread_local int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches += n; }
+
+}  // namespace pp
+
+using namespace pp;
+
+extern "C" const char* pp_last_error_string(void) { return g_err; }
+extern "C" int pp_version(void) { return 100; }
+extern "C" int64_t pp_launch_count(int reset) {
+    const int64_t v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
+// ---- context ----------------------------------------------------------------------------------
+struct pp_ctx {
+    int device;
+    cudaStream_t stream;
+    struct Buf { void* p = nullptr; size_t cap = 0; };
+    Buf dev[12];
+    // grow-only device buffers, one per slot
+    int get(int slot, size_t bytes, void** out) {
+        Buf& b = dev[slot];
+        if (bytes < 256) bytes = 256;
+        if (b.cap < bytes) {
+            if (b.p) PP_CUDA(cudaFree(b.p));
+            b.p = nullptr; b.cap = 0;
+            const size_t want = bytes + bytes / 4;
+            PP_CUDA(cudaMalloc(&b.p, want));
+            b.cap = want;
+        }
+        *out = b.p;
+        return PP_OK;
+    }
+};
+
+extern "C" int pp_ctx_create(int device, pp_ctx** out) {
+    PP_CHECK_ARG(out, "pp_ctx_create: null out");
+    int ndev = 0;
+    PP_CUDA(cudaGetDeviceCount(&ndev));
+    PP_CHECK_ARG(device >= 0 && device < ndev, "pp_ctx_create: device %d of %d", device, ndev);
+    PP_CUDA(cudaSetDevice(device));
+    pp_ctx* c = new (std::nothrow) pp_ctx();
+    if (!c) { set_error("out of host memory"); return PP_E_NOMEM; }
+    c->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e));
+        delete c;
+        return PP_E_CUDA;
+    }
+    *out = c;
+    return PP_OK;
+}
+
+extern "C" void pp_ctx_destroy(pp_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& b : c->dev)
+        if (b.p) cudaFree(b.p);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+extern "C" void* pp_ctx_stream(pp_ctx* c) { return c ? static_cast<void*>(c->stream) : nullptr; }
+extern "C" int pp_ctx_device(pp_ctx* c) { return c ? c->device : -1; }
+extern "C" int pp_ctx_sync(pp_ctx* c) {
+    PP_CHECK_ARG(c, "null ctx");
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    return PP_OK;
+}
+
+#define PP_TRY(expr)          \
+    do {                      \
+        int rc__ = (expr);    \
+        if (rc__) return rc__; \
+    } while (0)
+
+#define PP_ENTER(c)                                   \
+    PP_CHECK_ARG(c, "null ctx");                      \
+    PP_CUDA(cudaSetDevice((c)->device));              \
+    cudaStream_t st = (c)->stream;                    \
+    (void)st
+
+// ---- host layer ---------------------------------------------------------------------------------
+extern "C" int pp_points_to_voxel_host(pp_ctx* c, const pp_voxel_cfg* cfg, const void* points,
+                                       int point_dtype, int64_t N, int D, void* voxels, int32_t* coors,
+                                       int32_t* num_points, int32_t* voxel_num_out, int32_t* point_slot) {
+    PP_ENTER(c);
+    PP_CHECK_ARG(cfg && voxels && coors && num_points && voxel_num_out && N >= 0, "pp_points_to_voxel_host: bad argument");
+    PP_CHECK_ARG(point_dtype == PP_F32 || point_dtype == PP_F64, "bad point_dtype");
+    const size_t esz = point_dtype == PP_F64 ? 8 : 4;
+    const int P = cfg->max_points, MV = cfg->max_voxels;
+    const size_t ws_bytes = pp_voxelize_workspace_bytes(cfg, N, 1);
+    PP_CHECK_ARG(ws_bytes > 0, "pp_points_to_voxel_host: bad config");
+    void *d_pts, *d_vox, *d_coors, *d_num, *d_misc, *d_ws, *d_slot = nullptr;
+    PP_TRY(c->get(0, (size_t)N * D * esz, &d_pts));
+    PP_TRY(c->get(1, (size_t)MV * P * D * esz, &d_vox));
+    PP_TRY(c->get(2, (size_t)MV * 3 * 4, &d_coors));
+    PP_TRY(c->get(3, (size_t)MV * 4, &d_num));
+    PP_TRY(c->get(4, 256, &d_misc));  // frame_offsets[2] (int64) | voxel_num | voxel_base[2]
+    PP_TRY(c->get(5, ws_bytes, &d_ws));
+    if (point_slot) PP_TRY(c->get(6, (size_t)N * 4, &d_slot));
+    int64_t* d_off = static_cast<int64_t*>(d_misc);
+    int32_t* d_vnum = reinterpret_cast<int32_t*>(d_off + 2);
+    int32_t* d_vbase = d_vnum + 1;
+    const int64_t off[2] = {0, N};
+    PP_CUDA(cudaMemcpyAsync(d_off, off, sizeof(off), cudaMemcpyHostToDevice, st));
+    if (N > 0) PP_CUDA(cudaMemcpyAsync(d_pts, points, (size_t)N * D * esz, cudaMemcpyHostToDevice, st));
+    PP_TRY(pp_voxelize_dev(cfg, d_pts, point_dtype, D, d_off, 1, N, N, point_dtype, d_vox, nullptr,
+                           static_cast<int32_t*>(d_coors), 3, static_cast<int32_t*>(d_num), MV, d_vnum,
+                           d_vbase, static_cast<int32_t*>(d_slot), nullptr, d_ws, ws_bytes, st));
+    int32_t m = 0;
+    PP_CUDA(cudaMemcpyAsync(&m, d_vnum, 4, cudaMemcpyDeviceToHost, st));
+    PP_CUDA(cudaStreamSynchronize(st));
+    *voxel_num_out = m;
+    if (m > 0) {
+        PP_CUDA(cudaMemcpyAsync(voxels, d_vox, (size_t)m * P * D * esz, cudaMemcpyDeviceToHost, st));
+        PP_CUDA(cudaMemcpyAsync(coors, d_coors, (size_t)m * 12, cudaMemcpyDeviceToHost, st));
+        PP_CUDA(cudaMemcpyAsync(num_points, d_num, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (point_slot && N > 0) PP_CUDA(cudaMemcpyAsync(point_slot, d_slot, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+    PP_CUDA(cudaStreamSynchronize(st));
+    return PP_OK;
+}
+
+extern "C" int pp_decorate_host(pp_ctx* c, const float* voxels, const int32_t* num_points, const int32_t* coors,
+                                int64_t M, int P, int D, double vx, double vy, double x_offset, double y_offset,
+                                float* out) {
+    PP_ENTER(c);
+    PP_CHECK_ARG(M >= 0 && P >= 1 && D >= 3, "pp_decorate_host: bad shape");
+    if (M == 0) return PP_OK;
+    void *d_v, *d_n, *d_c, *d_o;
+    PP_TRY(c->get(0, (size_t)M * P * D * 4, &d_v));
+    PP_TRY(c->get(1, (size_t)M * 4, &d_n));
+    PP_TRY(c->get(2, (size_t)M * 16, &d_c));
+    PP_TRY(c->get(3, (size_t)M * P * (D + 5) * 4, &d_o));
+    PP_CUDA(cudaMemcpyAsync(d_v, voxels, (size_t)M * P * D * 4, cudaMemcpyHostToDevice, st));
+    PP_CUDA(cudaMemcpyAsync(d_n, num_points, (size_t)M * 4, cudaMemcpyHostToDevice, st));
+    PP_CUDA(cudaMemcpyAsync(d_c, coors, (size_t)M * 16, cudaMemcpyHostToDevice, st));
+    PP_TRY(pp_decorate_dev(static_cast<float*>(d_v), static_cast<int32_t*>(d_n), static_cast<int32_t*>(d_c), M, P, D,
+                           vx, vy, x_offset, y_offset, static_cast<float*>(d_o), st));
+    PP_CUDA(cudaMemcpyAsync(out, d_o, (size_t)M * P * (D + 5) * 4, cudaMemcpyDeviceToHost, st));
+    PP_CUDA(cudaStreamSynchronize(st));
+    return PP_OK;
+}
+
+extern "C" int pp_scatter_host(pp_ctx* c, const float* feats, const int32_t* coords, int64_t M, int C, int B,
+                               int ny, int nx, int layout, float* out) {
+    PP_ENTER(c);
+    PP_CHECK_ARG(M >= 0 && C > 0 && B > 0 && ny > 0 && nx > 0 && out, "pp_scatter_host: bad argument");
+    const size_t ws_bytes = pp_scatter_workspace_bytes(B, ny, nx, M);
+    const size_t out_bytes = (size_t)B * C * ny * nx * 4;
+    void *d_f, *d_c, *d_o, *d_ws;
+    PP_TRY(c->get(0, (size_t)M * C * 4, &d_f));
+    PP_TRY(c->get(1, (size_t)M * 16, &d_c));
+    PP_TRY(c->get(2, out_bytes, &d_o));
+    PP_TRY(c->get(3, ws_bytes, &d_ws));
+    if (M > 0) {
+        PP_CUDA(cudaMemcpyAsync(d_f, feats, (size_t)M * C * 4, cudaMemcpyHostToDevice, st));
+        PP_CUDA(cudaMemcpyAsync(d_c, coords, (size_t)M * 16, cudaMemcpyHostToDevice, st));
+    }
+    PP_TRY(pp_scatter_dev(static_cast<float*>(d_f), static_cast<int32_t*>(d_c), M, nullptr, C, B, ny, nx, layout,
+                          static_cast<float*>(d_o), d_ws, ws_bytes, st));
+    PP_CUDA(cudaMemcpyAsync(out, d_o, out_bytes, cudaMemcpyDeviceToHost, st));
+    PP_CUDA(cudaStreamSynchronize(st));
+    return PP_OK;
+}
+
+extern "C" int pp_box_decode_host(pp_ctx* c, const float* box_encodings, const float* anchors, int64_t N, float* out) {
+    PP_ENTER(c);
+    PP_CHECK_ARG(N >= 0, "pp_box_decode_host: N < 0");
+    if (N == 0) return PP_OK;
+    void *d_e, *d_a, *d_o;
+    PP_TRY(c->get(0, (size_t)N * 28, &d_e));
+    PP_TRY(c->get(1, (size_t)N * 28, &d_a));
+    PP_TRY(c->get(2, (size_t)N * 28, &d_o));
+    PP_CUDA(cudaMemcpyAsync(d_e, box_encodings, (size_t)N * 28, cudaMemcpyHostToDevice, st));
+    PP_CUDA(cudaMemcpyAsync(d_a, anchors, (size_t)N * 28, cudaMemcpyHostToDevice, st));
+    PP_TRY(pp_box_decode_dev(static_cast<float*>(d_e), static_cast<float*>(d_a), N, 0, static_cast<float*>(d_o), st));
+    PP_CUDA(cudaMemcpyAsync(out, d_o, (size_t)N * 28, cudaMemcpyDeviceToHost, st));
+    PP_CUDA(cudaStreamSynchronize(st));
+    return PP_OK;
+}
+
+extern "C" int pp_rbox_to_standup_host(pp_ctx* c, const float* boxes, int64_t N, float* out) {
+    PP_ENTER(c);
+    PP_CHECK_ARG(N >= 0, "pp_rbox_to_standup_host: N < 0");
+    if (N == 0) return PP_OK;
+    void *d_b, *d_o;
+    PP_TRY(c->get(0, (size_t)N * 20, &d_b));
+    PP_TRY(c->get(1, (size_t)N * 16, &d_o));
+    PP_CUDA(cudaMemcpyAsync(d_b, boxes, (size_t)N * 20, cudaMemcpyHostToDevice, st));
+    PP_TRY(pp_rbox_to_standup_dev(static_cast<float*>(d_b), 5, N, static_cast<float*>(d_o), st));
+    PP_CUDA(cudaMemcpyAsync(out, d_o, (size_t)N * 16, cudaMemcpyDeviceToHost, st));
+    PP_CUDA(cudaStreamSynchronize(st));
+    return PP_OK;
+}
+
+extern "C" int pp_nms_host(pp_ctx* c, int kind, const float* boxes, const float* scores, int64_t N,
+                           int pre_max_size, int post_max_size, float thresh, int64_t* keep,
+                           int32_t* keep_count_out) {
+    PP_ENTER(c);
+    PP_CHECK_ARG(keep_count_out && N >= 0, "pp_nms_host: bad argument");
+    PP_CHECK_ARG(kind == PP_NMS_STANDUP || kind == PP_NMS_ROTATED, "pp_nms_host: bad kind");
+    *keep_count_out = 0;
+    if (N == 0) return PP_OK;
+    const int bs = kind == PP_NMS_ROTATED ? 5 : 4;
+    int64_t cap = N;
+    if (pre_max_size > 0 && pre_max_size < cap) cap = pre_max_size;
+    if (post_max_size > 0 && post_max_size < cap) cap = post_max_size;
+    const size_t ws_bytes = pp_nms_workspace_bytes(kind, 1, N, pre_max_size);
+    void *d_b, *d_s, *d_k, *d_ws;
+    PP_TRY(c->get(0, (size_t)N * bs * 4, &d_b));
+    PP_TRY(c->get(1, (size_t)N * 4, &d_s));
+    PP_TRY(c->get(2, (size_t)(cap + 1) * 4, &d_k));
+    PP_TRY(c->get(3, ws_bytes, &d_ws));
+    PP_CUDA(cudaMemcpyAsync(d_b, boxes, (size_t)N * bs * 4, cudaMemcpyHostToDevice, st));
+    PP_CUDA(cudaMemcpyAsync(d_s, scores, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+    int32_t* d_keep = static_cast<int32_t*>(d_k);
+    int32_t* d_cnt = d_keep + cap;
+    PP_TRY(pp_nms_dev(kind, static_cast<float*>(d_b), bs, static_cast<float*>(d_s), nullptr, 1, N, pre_max_size,
+                      post_max_size, thresh, d_keep, cap, d_cnt, d_ws, ws_bytes, st));
+    // keep indices + count in one copy
+    int32_t* h = static_cast<int32_t*>(malloc((size_t)(cap + 1) * 4));
+    if (!h) { set_error("out of host memory"); return PP_E_NOMEM; }
+    cudaError_t e = cudaMemcpyAsync(h, d_keep, (size_t)(cap + 1) * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        free(h);
+        set_error("pp_nms_host: %s", cudaGetErrorString(e));
+        return PP_E_CUDA;
+    }
+    const int32_t k = h[cap];
+    for (int32_t i = 0; i < k; ++i) keep[i] = h[i];
+    free(h);
+    *keep_count_out = k;
+    return PP_OK;
+}
+
+extern "C" int pp_rotate_iou_host(pp_ctx* c, const float* boxes, int64_t N, const float* query_boxes, int64_t K,
+                                  int criterion, float* out) {
+    PP_ENTER(c);
+    PP_CHECK_ARG(N >= 0 && K >= 0, "pp_rotate_iou_host: bad argument");
+    if (N == 0 || K == 0) return PP_OK;
+    void *d_b, *d_q, *d_o;
+    PP_TRY(c->get(0, (size_t)N * 20, &d_b));
+    PP_TRY(c->get(1, (size_t)K * 20, &d_q));
+    PP_TRY(c->get(2, (size_t)N * K * 4, &d_o));
+    PP_CUDA(cudaMemcpyAsync(d_b, boxes, (size_t)N * 20, cudaMemcpyHostToDevice, st));
+    PP_CUDA(cudaMemcpyAsync(d_q, query_boxes, (size_t)K * 20, cudaMemcpyHostToDevice, st));
+    PP_TRY(pp_rotate_iou_dev(static_cast<float*>(d_b), N, static_cast<float*>(d_q), K, criterion,
+                             static_cast<float*>(d_o), st));
+    PP_CUDA(cudaMemcpyAsync(out, d_o, (size_t)N * K * 4, cudaMemcpyDeviceToHost, st));
+    PP_CUDA(cudaStreamSynchronize(st));
+    return PP_OK;
+}

@@ -1,0 +1,529 @@
+// Batched NMS on sm_100a: score ordering, pairwise suppression bitmask, greedy sweep.
+//
+//   standup kind  nms / nms_gpu / nms_kernel / nms_postprocess,
+//                 libraries/eval_helper_functions.py:463-598 of the reference
+//   rotated kind  rotate_nms_gpu / rotate_nms_kernel, second/core/non_max_suppression/nms_gpu.py:419-490
+//   IoU matrix    rotate_iou_gpu(_eval), nms_gpu.py:493-653
+//
+// The reference sorts on the host, runs a 64-thread block per 64x64 tile (every tile, both
+// triangles, corners recomputed per pair), copies the N*N/64 mask to the host and sweeps there.
+// Here everything stays on the device, one frame per grid.z / per block:
+//   order   top-k radix select + bitonic sort (pre_max_size <= 1024), else a stable LSD radix sort;
+//           total order = descending score, ties by descending index.
+//   prep    per sorted box: corners, area, hull (rotated) once per box.
+//   mask    upper-triangle tiles only, 64 rows x 32 col-blocks per CTA, hull pre-reject, candidate
+//           bits first then polygon clips, rows of the tile stored as 256-byte runs.
+//   sweep   one CTA per frame, removed-bitmap in shared memory, early exit at post_max_size.
+#include <type_traits>
+
+#include "pp_common.cuh"
+#include "rotated_iou.cuh"
+
+namespace pp {
+
+constexpr int kSortThreads = 1024;
+constexpr int kSelectMaxK = 1024;
+
+__device__ __forceinline__ unsigned score_key(float s) {
+    if (s != s) return 0xFFFFFFFFu;  // numpy sorts NaN last, i.e. first after the [::-1]
+    const unsigned u = __float_as_uint(s);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Top-k (k <= 1024) per frame: radix select of the k-th largest key, compaction, bitonic sort.
+__global__ void __launch_bounds__(kSortThreads)
+nms_topk_kernel(const float* __restrict__ scores, const int* __restrict__ n_valid, int64_t N, int k,
+                int* __restrict__ order, int64_t order_stride, int* __restrict__ n_sorted) {
+    __shared__ unsigned hist[256];
+    __shared__ unsigned s_prefix, s_remaining, s_count;
+    __shared__ unsigned long long skey[kSelectMaxK];
+    const int b = blockIdx.x;
+    const float* sc = scores + (int64_t)b * N;
+    const int nv = n_valid ? max(0, min(n_valid[b], (int)N)) : (int)N;
+    const int kk = min(k, nv);
+    if (threadIdx.x == 0) n_sorted[b] = kk;
+    if (kk == 0) return;
+
+    unsigned T = 0, Tidx = 0;
+    if (kk < nv) {
+        // ---- k-th largest key
+        if (threadIdx.x == 0) { s_prefix = 0; s_remaining = (unsigned)kk; }
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+            __syncthreads();
+            const unsigned prefix = s_prefix;
+            for (int i = threadIdx.x; i < nv; i += kSortThreads) {
+                const unsigned key = score_key(sc[i]);
+                if (shift == 24 || ((key ^ prefix) >> (shift + 8)) == 0) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned acc = 0, rem = s_remaining;
+                int d = 255;
+                for (; d > 0; --d) {
+                    if (acc + hist[d] >= rem) break;
+                    acc += hist[d];
+                }
+                s_remaining = rem - acc;  // still needed among keys with this digit
+                s_prefix = prefix | ((unsigned)d << shift);
+                s_count = hist[d];
+            }
+            __syncthreads();
+        }
+        T = s_prefix;
+        const unsigned need_eq = s_remaining, have_eq = s_count;
+        __syncthreads();
+        if (have_eq > need_eq) {
+            // ---- among keys == T keep the need_eq largest indices (tie rule: descending index)
+            if (threadIdx.x == 0) { s_prefix = 0; s_remaining = need_eq; }
+            for (int shift = 24; shift >= 0; shift -= 8) {
+                if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+                __syncthreads();
+                const unsigned prefix = s_prefix;
+                for (int i = threadIdx.x; i < nv; i += kSortThreads) {
+                    if (score_key(sc[i]) != T) continue;
+                    const unsigned key = (unsigned)i;
+                    if (shift == 24 || ((key ^ prefix) >> (shift + 8)) == 0) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    unsigned acc = 0, rem = s_remaining;
+                    int d = 255;
+                    for (; d > 0; --d) {
+                        if (acc + hist[d] >= rem) break;
+                        acc += hist[d];
+                    }
+                    s_remaining = rem - acc;
+                    s_prefix = prefix | ((unsigned)d << shift);
+                }
+                __syncthreads();
+            }
+            Tidx = s_prefix;
+            __syncthreads();
+        }
+    }
+    // ---- compaction (arbitrary order) + bitonic sort, descending on (key, index)
+    if (threadIdx.x == 0) s_count = 0;
+    int np2 = 1;
+    while (np2 < kk) np2 <<= 1;
+    for (int i = threadIdx.x; i < np2; i += kSortThreads) skey[i] = 0ull;
+    __syncthreads();
+    for (int i = threadIdx.x; i < nv; i += kSortThreads) {
+        const unsigned key = score_key(sc[i]);
+        if (kk == nv || key > T || (key == T && (unsigned)i >= Tidx)) {
+            const unsigned pos = atomicAdd(&s_count, 1u);
+            if (pos < (unsigned)kSelectMaxK) skey[pos] = ((unsigned long long)key << 32) | (unsigned)i;
+        }
+    }
+    __syncthreads();
+    for (int size = 2; size <= np2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < (np2 >> 1); t += kSortThreads) {
+                const int lo = 2 * t - (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool desc = ((lo & size) == 0);
+                const unsigned long long a = skey[lo], c = skey[hi];
+                if ((a < c) == desc) { skey[lo] = c; skey[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < kk; i += kSortThreads)
+        order[(int64_t)b * order_stride + i] = (int)(skey[i] & 0xffffffffu);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Full stable LSD radix sort per frame (one CTA), ascending key / ascending index, read reversed.
+__global__ void __launch_bounds__(kSortThreads)
+nms_sort_kernel(const float* __restrict__ scores, const int* __restrict__ n_valid, int64_t N, int limit,
+                unsigned* __restrict__ kbuf /*[B][2][N]*/, int* __restrict__ ibuf /*[B][2][N]*/,
+                int* __restrict__ order, int64_t order_stride, int* __restrict__ n_sorted) {
+    __shared__ unsigned hist[256];
+    __shared__ unsigned base[256];
+    __shared__ unsigned short wcount[32][256];
+    __shared__ int sm[33];
+    const int b = blockIdx.x;
+    const float* sc = scores + (int64_t)b * N;
+    const int nv = n_valid ? max(0, min(n_valid[b], (int)N)) : (int)N;
+    const int n = limit > 0 ? min(limit, nv) : nv;
+    if (threadIdx.x == 0) n_sorted[b] = n;
+    if (n == 0) return;
+    unsigned* k0 = kbuf + (int64_t)b * 2 * N; unsigned* k1 = k0 + N;
+    int* i0 = ibuf + (int64_t)b * 2 * N; int* i1 = i0 + N;
+    const int lane = lane_id(), w = threadIdx.x >> 5;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 8 * pass;
+        const unsigned* kin = (pass & 1) ? k1 : k0; unsigned* kout = (pass & 1) ? k0 : k1;
+        const int* iin = (pass & 1) ? i1 : i0; int* iout = (pass & 1) ? i0 : i1;
+        if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < nv; i += kSortThreads) {
+            const unsigned key = pass == 0 ? score_key(sc[i]) : kin[i];
+            atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        {
+            int tot;
+            const int v = threadIdx.x < 256 ? (int)hist[threadIdx.x] : 0;
+            const int ex = block_excl_scan(v, &tot, sm);
+            if (threadIdx.x < 256) base[threadIdx.x] = (unsigned)ex;
+        }
+        __syncthreads();
+        for (int t0 = 0; t0 < nv; t0 += kSortThreads) {
+            for (int q = threadIdx.x; q < 32 * 256; q += kSortThreads) (&wcount[0][0])[q] = 0;
+            __syncthreads();
+            const int i = t0 + threadIdx.x;
+            const bool valid = i < nv;
+            unsigned key = 0; int idx = 0;
+            if (valid) { key = pass == 0 ? score_key(sc[i]) : kin[i]; idx = pass == 0 ? i : iin[i]; }
+            const int d = valid ? (int)((key >> shift) & 255u) : 256;
+            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            const int rank = __popc(peers & lanemask_lt());
+            if (valid && rank == 0) wcount[w][d] = (unsigned short)__popc(peers);
+            __syncthreads();
+            if (threadIdx.x < 256) {
+                unsigned run = 0;
+                for (int ww = 0; ww < 32; ++ww) {
+                    const unsigned c = wcount[ww][threadIdx.x];
+                    wcount[ww][threadIdx.x] = (unsigned short)run;
+                    run += c;
+                }
+                hist[threadIdx.x] = run;  // tile total for this digit
+            }
+            __syncthreads();
+            if (valid) {
+                const unsigned pos = base[d] + wcount[w][d] + rank;
+                kout[pos] = key;
+                iout[pos] = idx;
+            }
+            __syncthreads();
+            if (threadIdx.x < 256) base[threadIdx.x] += hist[threadIdx.x];
+            __syncthreads();
+        }
+        (void)lane;
+    }
+    // after 4 passes the result is back in buffer 0
+    for (int i = threadIdx.x; i < n; i += kSortThreads)
+        order[(int64_t)b * order_stride + i] = i0[nv - 1 - i];
+}
+
+// ---------------------------------------------------------------------------------------------
+struct __align__(16) RBoxG {  // 64 bytes in global / shared memory
+    float c[8];
+    float area, mnx, mny, mxx, mxy, pad0, pad1, pad2;
+};
+
+__device__ __forceinline__ void load_rbox(const RBoxG* g, RBox& r) {
+    const float4* p = reinterpret_cast<const float4*>(g);
+    const float4 a = p[0], b = p[1], c = p[2], d = p[3];
+    r.c[0] = a.x; r.c[1] = a.y; r.c[2] = a.z; r.c[3] = a.w;
+    r.c[4] = b.x; r.c[5] = b.y; r.c[6] = b.z; r.c[7] = b.w;
+    r.area = c.x; r.mnx = c.y; r.mny = c.z; r.mxx = c.w; r.mxy = d.x;
+}
+
+// gather boxes into score order; rotated: corners/area/hull once per box
+template <bool ROTATED>
+__global__ void __launch_bounds__(256)
+nms_prep_kernel(const float* __restrict__ boxes, int box_stride, int64_t N, const int* __restrict__ order,
+                int64_t order_stride, const int* __restrict__ n_sorted, void* __restrict__ sorted,
+                int64_t sorted_stride) {
+    const int b = blockIdx.y;
+    const int n = n_sorted[b];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const float* src = boxes + ((int64_t)b * N + order[(int64_t)b * order_stride + i]) * box_stride;
+    if (ROTATED) {
+        const float r[5] = {src[0], src[1], src[2], src[3], src[4]};
+        RBox rb;
+        rbox_prepare(r, rb);
+        float4* dst = reinterpret_cast<float4*>(static_cast<RBoxG*>(sorted) + (int64_t)b * sorted_stride + i);
+        dst[0] = make_float4(rb.c[0], rb.c[1], rb.c[2], rb.c[3]);
+        dst[1] = make_float4(rb.c[4], rb.c[5], rb.c[6], rb.c[7]);
+        dst[2] = make_float4(rb.area, rb.mnx, rb.mny, rb.mxx);
+        dst[3] = make_float4(rb.mxy, 0.f, 0.f, 0.f);
+    } else {
+        static_cast<float4*>(sorted)[(int64_t)b * sorted_stride + i] = make_float4(src[0], src[1], src[2], src[3]);
+    }
+}
+
+// iou_device, eval_helper_functions.py:553-564: float32 differences, then "+ 1" onwards in float64
+__device__ __forceinline__ double standup_iou(const float4& a, const float4& b) {
+    const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
+    const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
+    const double width = fmax((double)__fsub_rn(right, left) + 1.0, 0.0);
+    const double height = fmax((double)__fsub_rn(bottom, top) + 1.0, 0.0);
+    const double interS = width * height;
+    const double Sa = ((double)__fsub_rn(a.z, a.x) + 1.0) * ((double)__fsub_rn(a.w, a.y) + 1.0);
+    const double Sb = ((double)__fsub_rn(b.z, b.x) + 1.0) * ((double)__fsub_rn(b.w, b.y) + 1.0);
+    return interS / (Sa + Sb - interS);
+}
+
+constexpr int kMaskGroup = 32;  // col blocks per CTA
+constexpr int kMaskQ = 4;       // col blocks processed concurrently
+
+template <bool ROTATED>
+__global__ void __launch_bounds__(64 * kMaskQ)
+nms_mask_kernel(const void* __restrict__ sorted, int64_t sorted_stride, const int* __restrict__ n_sorted,
+                float thresh, unsigned long long* __restrict__ mask, int64_t mask_stride /*words per frame*/) {
+    using BoxG = typename std::conditional<ROTATED, RBoxG, float4>::type;
+    __shared__ BoxG s_col[kMaskQ * 64];
+    __shared__ unsigned long long s_tile[64][kMaskGroup + 1];
+    const int b = blockIdx.z, rb = blockIdx.y, grp = blockIdx.x;
+    const int n = n_sorted[b];
+    const int cb = (n + 63) >> 6;
+    if (rb >= cb) return;
+    const int cb0 = grp * kMaskGroup;
+    if (cb0 >= cb || cb0 + kMaskGroup - 1 < rb) return;  // nothing of the upper triangle here
+    const int r = threadIdx.x & 63, q = threadIdx.x >> 6;
+    const int row = rb * 64 + r;
+    const BoxG* sb = static_cast<const BoxG*>(sorted) + (int64_t)b * sorted_stride;
+    const double th = (double)thresh;
+
+    RBox rrow; float4 frow = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < n) {
+        if constexpr (ROTATED) load_rbox(reinterpret_cast<const RBoxG*>(sb) + row, rrow);
+        else frow = reinterpret_cast<const float4*>(sb)[row];
+    }
+    for (int s = 0; s < kMaskGroup / kMaskQ; ++s) {
+        const int cbase = cb0 + s * kMaskQ;  // first col block of this step
+        __syncthreads();
+        {
+            const int col = cbase * 64 + threadIdx.x;
+            if (col < n) s_col[threadIdx.x] = sb[col];
+        }
+        __syncthreads();
+        const int cbk = cbase + q;
+        unsigned long long word = 0ull;
+        if (row < n && cbk < cb && cbk >= rb) {
+            const int jn = min(64, n - cbk * 64);
+            const int j0 = (cbk == rb) ? r + 1 : 0;
+            if constexpr (ROTATED) {
+                unsigned long long cand = 0ull;
+                for (int j = j0; j < jn; ++j) {
+                    const RBoxG& c = s_col[q * 64 + j];
+                    const float scale = fmaxf(fmaxf(fabsf(rrow.mxx), fabsf(rrow.mnx)), fmaxf(fabsf(rrow.mxy), fabsf(rrow.mny)));
+                    const float eps = 1e-4f * fmaxf(1.f, scale);
+                    const bool dis = rrow.mnx > c.mxx + eps || c.mnx > rrow.mxx + eps ||
+                                     rrow.mny > c.mxy + eps || c.mny > rrow.mxy + eps;
+                    if (!dis) cand |= 1ull << j;
+                }
+                while (cand) {
+                    const int j = __ffsll((long long)cand) - 1;
+                    cand &= cand - 1;
+                    RBox cbx;
+                    load_rbox(&s_col[q * 64 + j], cbx);
+                    // devRotateIoU(row box, col box), nms_gpu.py:445-449
+                    const double ai = rbox_inter(rrow.c, cbx.c);
+                    const double iou = ai / ((double)__fadd_rn(rrow.area, cbx.area) - ai);
+                    if (iou > th) word |= 1ull << j;
+                }
+            } else {
+                for (int j = j0; j < jn; ++j)
+                    if (standup_iou(frow, reinterpret_cast<const float4*>(s_col)[q * 64 + j]) > th) word |= 1ull << j;
+            }
+        }
+        s_tile[r][s * kMaskQ + q] = word;
+    }
+    __syncthreads();
+    // rows of the tile as contiguous runs of up to 32 words
+    unsigned long long* mb = mask + (int64_t)b * mask_stride;
+    for (int k = threadIdx.x; k < 64 * kMaskGroup; k += 64 * kMaskQ) {
+        const int rr = k / kMaskGroup, cc = k - rr * kMaskGroup;
+        const int grow = rb * 64 + rr, gcb = cb0 + cc;
+        if (grow < n && gcb < cb && gcb >= rb) mb[(int64_t)grow * cb + gcb] = s_tile[rr][cc];
+    }
+}
+
+// Greedy sweep (nms_postprocess, eval_helper_functions.py:529-546): one CTA per frame.
+constexpr int kSweepThreads = 512;
+__global__ void __launch_bounds__(kSweepThreads)
+nms_sweep_kernel(const unsigned long long* __restrict__ mask, int64_t mask_stride,
+                 const int* __restrict__ n_sorted, const int* __restrict__ order, int64_t order_stride,
+                 int post_max, int* __restrict__ keep, int64_t keep_stride, int* __restrict__ keep_count) {
+    extern __shared__ unsigned long long remv[];
+    __shared__ unsigned long long s_diag[64];
+    __shared__ unsigned long long s_kept;
+    __shared__ int s_nkeep;
+    const int b = blockIdx.x;
+    const int n = n_sorted[b];
+    const int cb = (n + 63) >> 6;
+    const unsigned long long* mb = mask + (int64_t)b * mask_stride;
+    const int* ord = order + (int64_t)b * order_stride;
+    int* kp = keep + (int64_t)b * keep_stride;
+    int limit = (int)min((int64_t)(post_max > 0 ? post_max : n), keep_stride);
+    for (int j = threadIdx.x; j < cb; j += kSweepThreads) remv[j] = 0ull;
+    if (threadIdx.x == 0) s_nkeep = 0;
+    __syncthreads();
+    for (int k = 0; k < cb; ++k) {
+        const int base = k * 64;
+        const int cnt = min(64, n - base);
+        if (threadIdx.x < 64) s_diag[threadIdx.x] = threadIdx.x < cnt ? mb[(int64_t)(base + threadIdx.x) * cb + k] : 0ull;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long rm = remv[k], kept = 0ull;
+            int nk = s_nkeep;
+            for (int i = 0; i < cnt && nk < limit; ++i) {
+                if (!((rm >> i) & 1ull)) {
+                    kept |= 1ull << i;
+                    kp[nk++] = ord[base + i];
+                    rm |= s_diag[i];
+                }
+            }
+            s_kept = kept;
+            s_nkeep = nk;
+        }
+        __syncthreads();
+        const unsigned long long kept = s_kept;
+        if (s_nkeep >= limit) break;
+        if (kept) {
+            for (int j = k + 1 + threadIdx.x; j < cb; j += kSweepThreads) {
+                unsigned long long acc = 0ull, kk = kept;
+                while (kk) {
+                    const int i = __ffsll((long long)kk) - 1;
+                    kk &= kk - 1;
+                    acc |= mb[(int64_t)(base + i) * cb + j];
+                }
+                remv[j] |= acc;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) keep_count[b] = s_nkeep;
+}
+
+// rotate_iou_kernel(_eval), nms_gpu.py:493-523 / 579-615: out[n,k] = f(query k, box n)
+__global__ void __launch_bounds__(256)
+rotate_iou_matrix_kernel(const float* __restrict__ boxes, int64_t N, const float* __restrict__ qboxes,
+                         int64_t K, int criterion, float* __restrict__ out) {
+    __shared__ RBoxG s_q[64];
+    __shared__ RBoxG s_b[64];
+    const int64_t n0 = (int64_t)blockIdx.y * 64, k0 = (int64_t)blockIdx.x * 64;
+    if (threadIdx.x < 128) {
+        const bool isq = threadIdx.x < 64;
+        const int t = threadIdx.x & 63;
+        const int64_t g = (isq ? k0 : n0) + t;
+        if (g < (isq ? K : N)) {
+            const float* src = (isq ? qboxes : boxes) + g * 5;
+            const float r[5] = {src[0], src[1], src[2], src[3], src[4]};
+            RBox rb;
+            rbox_prepare(r, rb);
+            RBoxG& d = isq ? s_q[t] : s_b[t];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d.c[i] = rb.c[i];
+            d.area = rb.area; d.mnx = rb.mnx; d.mny = rb.mny; d.mxx = rb.mxx; d.mxy = rb.mxy;
+        }
+    }
+    __syncthreads();
+    // thread -> (box row, 16 consecutive queries): consecutive threads write consecutive k
+    for (int e = threadIdx.x; e < 64 * 64; e += 256) {
+        const int bn = e >> 6, qk = e & 63;
+        if (n0 + bn >= N || k0 + qk >= K) continue;
+        RBox q, bx;
+        load_rbox(&s_q[qk], q);
+        load_rbox(&s_b[bn], bx);
+        out[(n0 + bn) * K + k0 + qk] = (float)rbox_iou(q, bx, criterion);
+    }
+}
+
+}  // namespace pp
+
+using namespace pp;
+
+namespace {
+struct NmsWs {
+    int* order; int* n_sorted; void* sorted; unsigned long long* mask; unsigned* kbuf; int* ibuf;
+    int64_t n_cap, cb_cap; size_t total; bool full_sort;
+};
+NmsWs nms_carve(void* ws, int kind, int B, int64_t N, int pre_max) {
+    NmsWs w;
+    Carver c(ws);
+    w.n_cap = (pre_max > 0 && pre_max < N) ? pre_max : N;
+    w.cb_cap = (w.n_cap + 63) / 64;
+    w.full_sort = !(pre_max > 0 && pre_max <= kSelectMaxK) && !(N <= kSelectMaxK);
+    w.order = c.take<int>((size_t)B * w.n_cap + 1);
+    w.n_sorted = c.take<int>(B);
+    if (kind == PP_NMS_ROTATED) w.sorted = c.take<RBoxG>((size_t)B * w.n_cap + 1);
+    else w.sorted = c.take<float4>((size_t)B * w.n_cap + 1);
+    w.mask = c.take<unsigned long long>((size_t)B * w.n_cap * w.cb_cap + 1);
+    if (w.full_sort) {
+        w.kbuf = c.take<unsigned>((size_t)B * 2 * N);
+        w.ibuf = c.take<int>((size_t)B * 2 * N);
+    } else { w.kbuf = nullptr; w.ibuf = nullptr; }
+    w.total = c.used();
+    return w;
+}
+}  // namespace
+
+extern "C" size_t pp_nms_workspace_bytes(int kind, int B, int64_t N, int pre_max_size) {
+    if (B <= 0 || N < 0) return 0;
+    return nms_carve(nullptr, kind, B, N > 0 ? N : 1, pre_max_size).total + 256;
+}
+
+extern "C" int pp_nms_dev(int kind, const float* boxes, int box_stride, const float* scores,
+                          const int32_t* n_valid, int B, int64_t N, int pre_max_size, int post_max_size,
+                          float thresh, int32_t* keep, int64_t keep_stride, int32_t* keep_count,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+    PP_CHECK_ARG(kind == PP_NMS_STANDUP || kind == PP_NMS_ROTATED, "pp_nms_dev: bad kind");
+    PP_CHECK_ARG(B > 0 && B <= 65535 && N >= 0 && N < ((int64_t)1 << 31), "pp_nms_dev: bad B/N");
+    PP_CHECK_ARG(keep && keep_count && workspace && keep_stride > 0, "pp_nms_dev: null argument");
+    PP_CHECK_ARG(box_stride >= (kind == PP_NMS_ROTATED ? 5 : 4), "pp_nms_dev: box_stride too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (N == 0) {
+        PP_CUDA(cudaMemsetAsync(keep_count, 0, sizeof(int) * B, st));
+        return PP_OK;
+    }
+    PP_CHECK_ARG(boxes && scores, "pp_nms_dev: null boxes/scores");
+    const NmsWs w = nms_carve(workspace, kind, B, N, pre_max_size);
+    if (w.total > workspace_bytes) {
+        set_error("pp_nms_dev: workspace %zu < required %zu", workspace_bytes, w.total);
+        return PP_E_WORKSPACE;
+    }
+    PP_CHECK_ARG(w.cb_cap * 8 <= 200 * 1024, "pp_nms_dev: more than 1.6M boxes per frame after pre_max_size");
+    if (w.full_sort) {
+        nms_sort_kernel<<<B, kSortThreads, 0, st>>>(scores, n_valid, N, pre_max_size, w.kbuf, w.ibuf, w.order,
+                                                   w.n_cap, w.n_sorted);
+    } else {
+        const int k = (int)w.n_cap;
+        nms_topk_kernel<<<B, kSortThreads, 0, st>>>(scores, n_valid, N, k, w.order, w.n_cap, w.n_sorted);
+    }
+    PP_LAUNCHED();
+    {
+        const dim3 g((unsigned)ceil_div(w.n_cap, 256), B);
+        if (kind == PP_NMS_ROTATED)
+            nms_prep_kernel<true><<<g, 256, 0, st>>>(boxes, box_stride, N, w.order, w.n_cap, w.n_sorted, w.sorted, w.n_cap);
+        else
+            nms_prep_kernel<false><<<g, 256, 0, st>>>(boxes, box_stride, N, w.order, w.n_cap, w.n_sorted, w.sorted, w.n_cap);
+        PP_LAUNCHED();
+    }
+    {
+        const dim3 g((unsigned)ceil_div(w.cb_cap, kMaskGroup), (unsigned)w.cb_cap, B);
+        PP_CHECK_ARG(w.cb_cap <= 65535, "pp_nms_dev: too many boxes per frame");
+        if (kind == PP_NMS_ROTATED)
+            nms_mask_kernel<true><<<g, 64 * kMaskQ, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, thresh, w.mask, w.n_cap * w.cb_cap);
+        else
+            nms_mask_kernel<false><<<g, 64 * kMaskQ, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, thresh, w.mask, w.n_cap * w.cb_cap);
+        PP_LAUNCHED();
+    }
+    {
+        const size_t smem = (size_t)w.cb_cap * 8 + 8;
+        if (smem > 48 * 1024)
+            PP_CUDA(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nms_sweep_kernel<<<B, kSweepThreads, smem, st>>>(w.mask, w.n_cap * w.cb_cap, w.n_sorted, w.order, w.n_cap,
+                                                        post_max_size, keep, keep_stride, keep_count);
+        PP_LAUNCHED();
+    }
+    return PP_OK;
+}
+
+extern "C" int pp_rotate_iou_dev(const float* boxes, int64_t N, const float* query_boxes, int64_t K,
+                                 int criterion, float* out, void* stream) {
+    PP_CHECK_ARG(N >= 0 && K >= 0 && criterion >= -1 && criterion <= 2, "pp_rotate_iou_dev: bad arguments");
+    if (N == 0 || K == 0) return PP_OK;
+    PP_CHECK_ARG(boxes && query_boxes && out, "pp_rotate_iou_dev: null argument");
+    PP_CHECK_ARG(ceil_div(N, 64) <= 65535, "pp_rotate_iou_dev: N too large (chunk the boxes)");
+    const dim3 g((unsigned)ceil_div(K, 64), (unsigned)ceil_div(N, 64));
+    rotate_iou_matrix_kernel<<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(boxes, N, query_boxes, K, criterion, out);
+    PP_LAUNCHED();
+    return PP_OK;
+}

@@ -1,0 +1,102 @@
+// Shared host/device helpers for libpp_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "pp_b200.h"
+
+namespace pp {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define PP_CHECK_ARG(cond, ...)                \
+    do {                                       \
+        if (!(cond)) {                         \
+            pp::set_error(__VA_ARGS__);        \
+            return PP_E_INVALID;               \
+        }                                      \
+    } while (0)
+
+#define PP_CUDA(expr)                                                                      \
+    do {                                                                                   \
+        cudaError_t e__ = (expr);                                                          \
+        if (e__ != cudaSuccess) {                                                          \
+            pp::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                          __LINE__);                                                       \
+            return PP_E_CUDA;                                                              \
+        }                                                                                  \
+    } while (0)
+
+// after a kernel launch
+#define PP_LAUNCHED()                                                                        \
+    do {                                                                                     \
+        pp::count_launch();                                                                  \
+        cudaError_t e__ = cudaGetLastError();                                                \
+        if (e__ != cudaSuccess) {                                                            \
+            pp::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, \
+                          __LINE__);                                                         \
+            return PP_E_CUDA;                                                                \
+        }                                                                                    \
+    } while (0)
+
+constexpr int kNumSM = 148;  // B200
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Bump allocator over a caller-provided workspace.
+struct Carver {
+    char* base;
+    size_t off = 0;
+    explicit Carver(void* p) : base(static_cast<char*>(p)) {}
+    template <typename T>
+    T* take(size_t n) {
+        off = align_up(off, 256);
+        T* r = reinterpret_cast<T*>(base + off);
+        off += n * sizeof(T);
+        return r;
+    }
+    size_t used() const { return align_up(off, 256); }
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+// block-wide exclusive scan of one int per thread (blockDim.x multiple of 32, <= 1024)
+__device__ __forceinline__ int block_excl_scan(int v, int* total, int* sm /*[33]*/) {
+    const int lane = lane_id(), w = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    if (lane == 31) sm[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        const int nw = blockDim.x >> 5;
+        int x = lane < nw ? sm[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += u;
+        }
+        if (lane < nw) sm[lane] = x;  // inclusive over warps
+        if (lane == 31) sm[32] = x;
+    }
+    __syncthreads();
+    const int woff = w ? sm[w - 1] : 0;
+    *total = sm[32];
+    const int r = woff + inc - v;
+    __syncthreads();
+    return r;
+}
+#endif
+
+}  // namespace pp

@@ -1,0 +1,179 @@
+// PointPillarsScatter (model/pointpillars.py:285-341 of the reference) as a GATHER: the canvas is
+// written exactly once, with full-line stores, instead of memset + scattered atomics (+ the three
+// transposes and the python loop over the batch the reference does).
+//
+//   link   (pillars)  head[b,y,x] <- pillar row (atomicExch), next[row] <- previous head.
+//                     z is ignored; pillars that share (b,y,x) -- the two z slabs of the reference
+//                     grid, or any duplicate coords -- form a chain (lines 302, 317: scatter_nd adds).
+//   canvas (tiles)    one block per (b, y, 32 x): chains are sorted by row so the float32 sum has
+//                     a fixed order (ascending row, the order a sequential scatter-add uses), feature
+//                     rows are read with consecutive lanes on consecutive channels into a shared
+//                     [C][33] tile, and the tile is stored NCHW (drop-in) or NHWC (what the RPN
+//                     transposes to).  Empty tiles are pure zero stores.
+#include "pp_common.cuh"
+
+namespace pp {
+
+constexpr int kTileX = 32;
+constexpr int kScThreads = 256;
+constexpr int kChainMax = 4;
+
+__global__ void __launch_bounds__(256)
+scatter_link_kernel(const int* __restrict__ coords, int64_t M, const int* __restrict__ M_dev, int B,
+                    int ny, int nx, int* __restrict__ head, int* __restrict__ next) {
+    const int64_t Mv = M_dev ? min((int64_t)*M_dev, M) : M;
+    for (int64_t m = (int64_t)blockIdx.x * 256 + threadIdx.x; m < Mv; m += (int64_t)gridDim.x * 256) {
+        const int4 c = *reinterpret_cast<const int4*>(coords + 4 * m);  // (b, z, y, x)
+        if (c.x < 0 || c.x >= B || c.z < 0 || c.z >= ny || c.w < 0 || c.w >= nx) continue;
+        next[m] = atomicExch(&head[((int64_t)c.x * ny + c.z) * nx + c.w], (int)m);
+    }
+}
+
+template <bool NHWC>
+__global__ void __launch_bounds__(kScThreads)
+scatter_canvas_kernel(const float* __restrict__ feats, const int* __restrict__ head,
+                      const int* __restrict__ next, int C, int ny, int nx, float* __restrict__ out) {
+    extern __shared__ float tile[];  // [C][33]
+    __shared__ int s_chain[kTileX][kChainMax];
+    __shared__ int s_len[kTileX];
+    const int xt = blockIdx.x, y = blockIdx.y, b = blockIdx.z;
+    const int x0 = xt * kTileX;
+    const int wx = min(kTileX, nx - x0);
+    const int lane = lane_id(), w = threadIdx.x >> 5;
+    const int64_t cellbase = ((int64_t)b * ny + y) * nx + x0;
+
+    int any = 0;
+    if (threadIdx.x < kTileX) {
+        int len = 0;
+        if (threadIdx.x < wx) {
+            int m = head[cellbase + threadIdx.x];
+            // insertion sort of the chain by row index (ascending)
+            while (m >= 0) {
+                if (len < kChainMax) {
+                    int j = len;
+                    while (j > 0 && s_chain[threadIdx.x][j - 1] > m) {
+                        s_chain[threadIdx.x][j] = s_chain[threadIdx.x][j - 1];
+                        --j;
+                    }
+                    s_chain[threadIdx.x][j] = m;
+                }
+                ++len;
+                m = next[m];
+            }
+        }
+        s_len[threadIdx.x] = len;
+        any = len > 0;
+    }
+    any = __syncthreads_or(any);
+
+    if (any) {
+        for (int k = threadIdx.x; k < C * 33; k += kScThreads) tile[k] = 0.f;
+        __syncthreads();
+        for (int x = w; x < wx; x += kScThreads / 32) {
+            const int len = s_len[x];
+            if (len == 0) continue;
+            if (len <= kChainMax) {
+                for (int j = 0; j < len; ++j) {
+                    const float* row = feats + (int64_t)s_chain[x][j] * C;
+                    for (int c = lane; c < C; c += 32) tile[c * 33 + x] += row[c];
+                }
+            } else {
+                // long chain (many duplicate coords): walk it in ascending row order
+                int last = -1;
+                for (int j = 0; j < len; ++j) {
+                    int best = 0x7fffffff;
+                    for (int m = head[cellbase + x]; m >= 0; m = next[m])
+                        if (m > last && m < best) best = m;
+                    const float* row = feats + (int64_t)best * C;
+                    for (int c = lane; c < C; c += 32) tile[c * 33 + x] += row[c];
+                    last = best;
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    if (NHWC) {
+        // [b, y, x0..x0+wx, C] is one contiguous run of wx*C floats
+        float* dst = out + cellbase * C;
+        const int n = wx * C;
+        if (!any) {
+            if ((C & 3) == 0) {
+                float4* d4 = reinterpret_cast<float4*>(dst);
+                for (int k = threadIdx.x; k < n / 4; k += kScThreads) d4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                for (int k = threadIdx.x; k < n; k += kScThreads) dst[k] = 0.f;
+            }
+        } else {
+            for (int k = threadIdx.x; k < n; k += kScThreads) {
+                const int x = k / C, c = k - x * C;
+                dst[k] = tile[c * 33 + x];
+            }
+        }
+    } else {
+        // NCHW: channel c row segment at ((b*C + c)*ny + y)*nx + x0, wx floats
+        const bool vec = ((nx & 3) == 0) && ((wx & 3) == 0);
+        if (!any && vec) {
+            const int q = wx / 4;  // float4 per channel row
+            for (int k = threadIdx.x; k < C * q; k += kScThreads) {
+                const int c = k / q, i = k - c * q;
+                float4* d4 = reinterpret_cast<float4*>(out + (((int64_t)b * C + c) * ny + y) * nx + x0);
+                d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+            for (int c = w; c < C; c += kScThreads / 32) {
+                float* dst = out + (((int64_t)b * C + c) * ny + y) * nx + x0;
+                if (lane < wx) dst[lane] = any ? tile[c * 33 + lane] : 0.f;
+            }
+        }
+    }
+}
+
+}  // namespace pp
+
+using namespace pp;
+
+extern "C" size_t pp_scatter_workspace_bytes(int B, int ny, int nx, int64_t M) {
+    if (B <= 0 || ny <= 0 || nx <= 0 || M < 0) return 0;
+    return align_up((size_t)B * ny * nx * sizeof(int), 256) + align_up((size_t)(M + 1) * sizeof(int), 256) + 256;
+}
+
+extern "C" int pp_scatter_dev(const float* feats, const int32_t* coords, int64_t M, const int32_t* M_dev,
+                              int C, int B, int ny, int nx, int layout, float* out, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+    PP_CHECK_ARG(B > 0 && ny > 0 && nx > 0 && C > 0 && M >= 0, "pp_scatter_dev: bad shape");
+    PP_CHECK_ARG(B <= 65535 && ny <= 65535, "pp_scatter_dev: B and ny must be <= 65535");
+    PP_CHECK_ARG(layout == PP_LAYOUT_NCHW || layout == PP_LAYOUT_NHWC, "pp_scatter_dev: bad layout");
+    PP_CHECK_ARG(out && workspace && (M == 0 || (feats && coords)), "pp_scatter_dev: null argument");
+    PP_CHECK_ARG(M < ((int64_t)1 << 31), "pp_scatter_dev: M must be < 2^31");
+    const size_t smem = (size_t)C * 33 * sizeof(float);
+    PP_CHECK_ARG(smem <= 200 * 1024, "pp_scatter_dev: C=%d too large", C);
+    if (pp_scatter_workspace_bytes(B, ny, nx, M) > workspace_bytes) {
+        set_error("pp_scatter_dev: workspace %zu < required %zu", workspace_bytes,
+                  pp_scatter_workspace_bytes(B, ny, nx, M));
+        return PP_E_WORKSPACE;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Carver cv(workspace);
+    int* head = cv.take<int>((size_t)B * ny * nx);
+    int* next = cv.take<int>((size_t)M + 1);
+    PP_CUDA(cudaMemsetAsync(head, 0xff, (size_t)B * ny * nx * sizeof(int), st));
+    if (M > 0) {
+        int64_t blocks = ceil_div(M, 256);
+        if (blocks > (int64_t)kNumSM * 16) blocks = (int64_t)kNumSM * 16;
+        scatter_link_kernel<<<(unsigned)blocks, 256, 0, st>>>(coords, M, M_dev, B, ny, nx, head, next);
+        PP_LAUNCHED();
+    }
+    const dim3 g((unsigned)ceil_div(nx, kTileX), ny, B);
+    if (layout == PP_LAYOUT_NHWC) {
+        auto k = scatter_canvas_kernel<true>;
+        if (smem > 48 * 1024) PP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<g, kScThreads, smem, st>>>(feats, head, next, C, ny, nx, out);
+    } else {
+        auto k = scatter_canvas_kernel<false>;
+        if (smem > 48 * 1024) PP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<g, kScThreads, smem, st>>>(feats, head, next, C, ny, nx, out);
+    }
+    PP_LAUNCHED();
+    return PP_OK;
+}

@@ -1,0 +1,558 @@
+// Deterministic first-come pillarization on sm_100a.
+//
+// Replaces the sequential numba loop of the reference (load_data.py:593-692, wrapper 695-771)
+// with five data-parallel passes that reproduce its results bit for bit:
+//
+//   mark    (points)  cell id per point in the reference's float64/float32 arithmetic;
+//                     atomicMin(first_idx[cell], i); pos = atomicAdd(count[cell]) (warp-aggregated)
+//   cells   (cells)   occupied cells: set bit first_idx in a per-frame bitmap over point indices,
+//                     reserve count[cell] bucket entries, append to the occupied list
+//   rank    (frames)  popcount prefix over the bitmap: voxel id of a cell = number of set bits
+//                     below its first_idx == order of first touch.  The bit of rank max_voxels is
+//                     the reference's `break` position i*: every point >= i* is dropped
+//                     (load_data.py:630-634).  Last block scans voxel counts into packed row bases.
+//   bucket  (points)  bucket[offset[cell] + pos] = i      (unordered inside a cell)
+//   gather  (voxels)  one warp per kept voxel: select the max_points smallest indices < i*
+//                     (binary search on the index threshold), order them by counting, gather the
+//                     points, write the zero-padded voxel row (+ optional fused decoration).
+//
+// The only nondeterminism is the order inside a bucket, which the gather pass removes.
+#include <math.h>
+
+#include "pp_common.cuh"
+
+namespace pp {
+
+struct VoxParams {
+    double lo[3], vs[3];
+    float lo32[3], vs32[3];
+    int grid[3];  // nx, ny, nz
+    int ncell;
+    int max_points, max_voxels, reverse_index, arith_f32;
+    int D;
+    // decoration constants (model/pointpillars.py:121-124), float32 like TF constants
+    float vx, vy, x_off, y_off;
+};
+
+constexpr int kMarkThreads = 256;
+constexpr int kCellThreads = 256;
+constexpr int kRankThreads = 1024;
+constexpr int kGatherWarps = 8;
+
+__device__ __forceinline__ int64_t word_base(const int64_t* frame_off, int b) {
+    return (frame_off[b] >> 5) + b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// cell id in the reference's arithmetic (load_data.py:620-626).  -1: outside the grid or NaN.
+template <typename T, bool A32>
+__device__ __forceinline__ int cell_of(const T* q, const VoxParams& p) {
+    int c[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        if (A32) {
+            const float v = floorf(__fdiv_rn(__fsub_rn((float)q[j], p.lo32[j]), p.vs32[j]));
+            if (!(v >= 0.f) || !((double)v < (double)p.grid[j])) return -1;
+            c[j] = (int)v;
+        } else {
+            const double v = floor(__ddiv_rn(__dsub_rn((double)q[j], p.lo[j]), p.vs[j]));
+            if (!(v >= 0.0) || !(v < (double)p.grid[j])) return -1;
+            c[j] = (int)v;
+        }
+    }
+    return (c[2] * p.grid[1] + c[1]) * p.grid[0] + c[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pass 1: one point per thread.  The block's rows are staged through shared memory with 16-byte
+// loads (rows are 12/16/24/32 bytes, so per-thread row loads would be strided).
+template <typename T, bool A32>
+__global__ void __launch_bounds__(kMarkThreads)
+vox_mark_kernel(const T* __restrict__ points, const int64_t* __restrict__ frame_off, VoxParams p,
+                int64_t total_points, int aligned16, unsigned* __restrict__ first_idx,
+                int* __restrict__ cnt, int2* __restrict__ cellpos, int* __restrict__ point_slot) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int b = blockIdx.y;
+    const int64_t f0 = frame_off[b];
+    const int n = (int)(frame_off[b + 1] - f0);
+    const int base = blockIdx.x * kMarkThreads;
+    if (base >= n) return;
+    const int m = min(kMarkThreads, n - base);
+    const int row_bytes = p.D * (int)sizeof(T);
+    const int64_t start = (f0 + base) * (int64_t)row_bytes;  // byte offset into points
+    const int64_t end = start + (int64_t)m * row_bytes;
+    const int64_t total_bytes = total_points * (int64_t)row_bytes;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(points);
+    int shift;
+    if (aligned16) {
+        const int64_t a0 = start & ~(int64_t)15;
+        shift = (int)(start - a0);
+        const int nchunk = (int)((end - a0 + 15) >> 4);
+        for (int c = threadIdx.x; c < nchunk; c += kMarkThreads) {
+            const int64_t a = a0 + ((int64_t)c << 4);
+            if (a + 16 <= total_bytes) {
+                *reinterpret_cast<int4*>(smem + ((size_t)c << 4)) =
+                    __ldg(reinterpret_cast<const int4*>(src + a));
+            } else {
+                for (int k = 0; k < 16 && a + k < total_bytes; k += (int)sizeof(T))
+                    *reinterpret_cast<T*>(smem + ((size_t)c << 4) + k) =
+                        *reinterpret_cast<const T*>(src + a + k);
+            }
+        }
+    } else {
+        shift = 0;
+        const int nel = m * p.D;
+        for (int k = threadIdx.x; k < nel; k += kMarkThreads)
+            reinterpret_cast<T*>(smem)[k] = points[(f0 + base) * p.D + k];
+    }
+    __syncthreads();
+
+    const int t = threadIdx.x;
+    int cell = -1;
+    if (t < m) cell = cell_of<T, A32>(reinterpret_cast<const T*>(smem + shift + (size_t)t * row_bytes), p);
+    const unsigned peers = __match_any_sync(0xffffffffu, cell);
+    int pos = 0;
+    if (cell >= 0) {
+        const int leader = __ffs(peers) - 1;
+        const size_t gc = (size_t)b * p.ncell + cell;
+        int basepos = 0;
+        if ((int)lane_id() == leader) {
+            // lanes are in index order, so the leader carries the group's smallest index
+            atomicMin(&first_idx[gc], (unsigned)(base + t));
+            basepos = atomicAdd(&cnt[gc], __popc(peers));
+        }
+        basepos = __shfl_sync(peers, basepos, leader);
+        pos = basepos + __popc(peers & lanemask_lt());
+    }
+    if (t < m) {
+        cellpos[f0 + base + t] = make_int2(cell, pos);
+        if (point_slot) point_slot[f0 + base + t] = -1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pass 2: one cell per thread.
+__global__ void __launch_bounds__(kCellThreads)
+vox_cell_kernel(const unsigned* __restrict__ first_idx, const int* __restrict__ cnt,
+                const int64_t* __restrict__ frame_off, int ncell, unsigned* __restrict__ bitmap,
+                int* __restrict__ cell_off, int* __restrict__ frame_cursor,
+                int* __restrict__ occ_list, int* __restrict__ occ_count,
+                int* __restrict__ cell_voxel) {
+    __shared__ int sm[33];
+    __shared__ int s_base, s_obase;
+    const int b = blockIdx.y;
+    const int cell = blockIdx.x * kCellThreads + threadIdx.x;
+    const size_t gc = (size_t)b * ncell + cell;
+    const int c = cell < ncell ? cnt[gc] : 0;
+    int tot, otot;
+    const int ex = block_excl_scan(c, &tot, sm);
+    const int oex = block_excl_scan(c > 0, &otot, sm);
+    if (threadIdx.x == 0) {
+        s_base = tot ? atomicAdd(&frame_cursor[b], tot) : 0;
+        s_obase = otot ? atomicAdd(occ_count, otot) : 0;
+    }
+    __syncthreads();
+    if (cell < ncell && cell_voxel) cell_voxel[gc] = -1;
+    if (c > 0) {
+        const unsigned f = first_idx[gc];
+        atomicOr(&bitmap[word_base(frame_off, b) + (f >> 5)], 1u << (f & 31));
+        cell_off[gc] = s_base + ex;  // frame-local offset into the frame's bucket range
+        occ_list[s_obase + oex] = (int)gc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pass 3: one block per frame: exclusive popcount prefix over the frame's bitmap words, voxel
+// count, break position; the last block to finish scans the voxel counts of all frames.
+__global__ void __launch_bounds__(kRankThreads)
+vox_rank_kernel(const unsigned* __restrict__ bitmap, unsigned* __restrict__ word_prefix,
+                const int64_t* __restrict__ frame_off, int B, int max_voxels,
+                int* __restrict__ voxel_num, int* __restrict__ cutoff, int* __restrict__ voxel_base,
+                int* __restrict__ done_counter) {
+    __shared__ int sm[33];
+    __shared__ int s_cut, s_last;
+    const int b = blockIdx.x;
+    const int n = (int)(frame_off[b + 1] - frame_off[b]);
+    const int words = (n + 31) >> 5;
+    const int64_t wb = word_base(frame_off, b);
+    if (threadIdx.x == 0) s_cut = 0x7fffffff;
+    __syncthreads();
+    int running = 0;
+    for (int s = 0; s < words; s += kRankThreads) {
+        const int w = s + threadIdx.x;
+        const unsigned bits = w < words ? bitmap[wb + w] : 0u;
+        const int pc = __popc(bits);
+        int tot;
+        const int ex = running + block_excl_scan(pc, &tot, sm);
+        if (w < words) word_prefix[wb + w] = (unsigned)ex;
+        if (ex <= max_voxels && max_voxels < ex + pc)
+            s_cut = 32 * w + (int)__fns(bits, 0, max_voxels - ex + 1);
+        running += tot;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        voxel_num[b] = min(running, max_voxels);
+        cutoff[b] = s_cut;
+        __threadfence();
+        s_last = (atomicAdd(done_counter, 1) == B - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    running = 0;
+    for (int s = 0; s < B; s += kRankThreads) {
+        const int i = s + threadIdx.x;
+        const int v = i < B ? __ldcg(&voxel_num[i]) : 0;
+        int tot;
+        const int ex = running + block_excl_scan(v, &tot, sm);
+        if (i < B) voxel_base[i] = ex;
+        running += tot;
+    }
+    if (threadIdx.x == 0) {
+        voxel_base[B] = running;
+        *done_counter = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pass 4: bucket fill.
+__global__ void __launch_bounds__(256)
+vox_bucket_kernel(const int2* __restrict__ cellpos, const int64_t* __restrict__ frame_off, int ncell,
+                  const int* __restrict__ cell_off, int* __restrict__ bucket) {
+    const int b = blockIdx.y;
+    const int64_t f0 = frame_off[b];
+    const int n = (int)(frame_off[b + 1] - f0);
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int2 cp = cellpos[f0 + i];
+    if (cp.x >= 0) bucket[f0 + cell_off[(size_t)b * ncell + cp.x] + cp.y] = i;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pass 5: one warp per occupied cell.
+template <typename T, typename TO>
+__global__ void __launch_bounds__(kGatherWarps * 32)
+vox_gather_kernel(const T* __restrict__ points, const int64_t* __restrict__ frame_off, VoxParams p,
+                  const int* __restrict__ occ_list, const int* __restrict__ occ_count,
+                  const unsigned* __restrict__ first_idx, const int* __restrict__ cnt,
+                  const int* __restrict__ cell_off, const int* __restrict__ bucket,
+                  const unsigned* __restrict__ bitmap, const unsigned* __restrict__ word_prefix,
+                  const int* __restrict__ cutoff, const int* __restrict__ voxel_base,
+                  int64_t cap_rows, TO* __restrict__ voxels, float* __restrict__ decorated,
+                  int* __restrict__ coors, int coors_cols, int* __restrict__ num_points,
+                  int* __restrict__ point_slot, int* __restrict__ cell_voxel) {
+    extern __shared__ int gsm[];
+    const int P = p.max_points, D = p.D;
+    const int lane = lane_id(), w = threadIdx.x >> 5;
+    int* sel = gsm + (size_t)w * 2 * P;
+    int* ord = sel + P;
+    const int nocc = *occ_count;
+    const int nwarps = gridDim.x * kGatherWarps;
+    for (int e = blockIdx.x * kGatherWarps + w; e < nocc; e += nwarps) {
+        const int gc = occ_list[e];
+        const int b = gc / p.ncell, cell = gc - b * p.ncell;
+        const unsigned f = first_idx[gc];
+        const int64_t wb = word_base(frame_off, b);
+        const int rank = (int)word_prefix[wb + (f >> 5)] + __popc(bitmap[wb + (f >> 5)] & ((1u << (f & 31)) - 1u));
+        if (rank >= p.max_voxels) continue;
+        const int64_t row = (int64_t)voxel_base[b] + rank;
+        if (row >= cap_rows) continue;
+        const int64_t f0 = frame_off[b];
+        const int L = cnt[gc];
+        const int* seg = bucket + f0 + cell_off[gc];
+        const int cut = cutoff[b];
+
+        // how many of the cell's points precede the break position
+        int Lc = 0;
+        for (int k = lane; k < L; k += 32) Lc += seg[k] < cut;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) Lc += __shfl_xor_sync(0xffffffffu, Lc, o);
+        int thr = cut;  // keep indices < thr
+        if (Lc > P) {
+            // smallest thr with #{idx < thr} >= P (indices are distinct, so it is exactly P)
+            int lo = (int)f + 1, hi = cut;
+            while (lo < hi) {
+                const int mid = lo + ((hi - lo) >> 1);
+                int g = 0;
+                for (int k = lane; k < L; k += 32) g += seg[k] < mid;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+                if (g >= P) hi = mid; else lo = mid + 1;
+            }
+            thr = lo;
+        }
+        const int nsel = min(Lc, P);
+        // compact the selected indices
+        int nb = 0;
+        for (int k0 = 0; k0 < L; k0 += 32) {
+            const int k = k0 + lane;
+            const int v = k < L ? seg[k] : 0x7fffffff;
+            const bool pr = v < thr;
+            const unsigned bal = __ballot_sync(0xffffffffu, pr);
+            if (pr) sel[nb + __popc(bal & lanemask_lt())] = v;
+            nb += __popc(bal);
+        }
+        __syncwarp();
+        // arrival order = ascending point index: slot = number of smaller selected indices
+        for (int j = lane; j < nsel; j += 32) {
+            const int v = sel[j];
+            int r = 0;
+            for (int q = 0; q < nsel; ++q) r += sel[q] < v;
+            ord[r] = v;
+        }
+        __syncwarp();
+
+        if (lane == 0) {
+            num_points[row] = nsel;
+            const int x = cell % p.grid[0], y = (cell / p.grid[0]) % p.grid[1], z = cell / (p.grid[0] * p.grid[1]);
+            int* co = coors + row * coors_cols;
+            if (coors_cols == 4) *co++ = b;
+            if (p.reverse_index) { co[0] = z; co[1] = y; co[2] = x; }
+            else { co[0] = x; co[1] = y; co[2] = z; }
+            if (cell_voxel) cell_voxel[gc] = (int)row;
+        }
+        const T* fp = points + f0 * D;
+        if (voxels) {
+            TO* vrow = voxels + row * (int64_t)P * D;
+            const int nel = P * D;
+            for (int k = lane; k < nel; k += 32) {
+                const int s = k / D;
+                vrow[k] = s < nsel ? (TO)fp[(int64_t)ord[s] * D + (k - s * D)] : (TO)0;
+            }
+        }
+        if (point_slot)
+            for (int s = lane; s < nsel; s += 32) point_slot[f0 + ord[s]] = rank * P + s;
+        if (decorated) {
+            // model/pointpillars.py:143-203 on the float32 voxel row
+            float sx = 0.f, sy = 0.f, sz = 0.f;
+            for (int s = lane; s < nsel; s += 32) {
+                const T* q = fp + (int64_t)ord[s] * D;
+                sx += (float)q[0]; sy += (float)q[1]; sz += (float)q[2];
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                sx += __shfl_xor_sync(0xffffffffu, sx, o);
+                sy += __shfl_xor_sync(0xffffffffu, sy, o);
+                sz += __shfl_xor_sync(0xffffffffu, sz, o);
+            }
+            const float nf = (float)nsel;
+            const float mx = __fdiv_rn(sx, nf), my = __fdiv_rn(sy, nf), mz = __fdiv_rn(sz, nf);
+            const int cx = cell % p.grid[0], cy = (cell / p.grid[0]) % p.grid[1];
+            const float ex = __fadd_rn(__fmul_rn((float)cx, p.vx), p.x_off);
+            const float ey = __fadd_rn(__fmul_rn((float)cy, p.vy), p.y_off);
+            const int Do = D + 5;
+            float* drow = decorated + row * (int64_t)P * Do;
+            const int nel = P * Do;
+            for (int k = lane; k < nel; k += 32) {
+                const int s = k / Do, d = k - s * Do;
+                float v = 0.f;
+                if (s < nsel) {
+                    const T* q = fp + (int64_t)ord[s] * D;
+                    if (d < D) v = (float)q[d];
+                    else if (d == D) v = (float)q[0] - mx;
+                    else if (d == D + 1) v = (float)q[1] - my;
+                    else if (d == D + 2) v = (float)q[2] - mz;
+                    else if (d == D + 3) v = (float)q[0] - ex;
+                    else v = (float)q[1] - ey;
+                }
+                drow[k] = v;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct VoxWorkspace {
+    unsigned* first_idx;  // [B*ncell]  0xff init
+    int* cnt;             // [B*ncell]  zero init   -- zero region starts here
+    unsigned* bitmap;     // [nwords]
+    int* frame_cursor;    // [B]
+    int* occ_count;       // [1]
+    int* done_counter;    // [1]        -- zero region ends here
+    unsigned* word_prefix;  // [nwords]
+    int* cell_off;        // [B*ncell]
+    int* occ_list;        // [B*ncell] (worst case every cell occupied, bounded by total_points)
+    int* cutoff;          // [B]
+    int2* cellpos;        // [total_points]
+    int* bucket;          // [total_points]
+    size_t zero_begin, zero_end, total;
+};
+
+static VoxWorkspace carve(void* ws, int64_t ncell, int64_t total_points, int B) {
+    VoxWorkspace w;
+    Carver c(ws);
+    const size_t nc = (size_t)B * ncell;
+    const size_t nwords = (size_t)(total_points >> 5) + B + 2;
+    const size_t nocc = nc < (size_t)total_points ? nc : (size_t)total_points;
+    w.first_idx = c.take<unsigned>(nc);
+    w.zero_begin = c.used();
+    w.cnt = c.take<int>(nc);
+    w.bitmap = c.take<unsigned>(nwords);
+    w.frame_cursor = c.take<int>(B);
+    w.occ_count = c.take<int>(1);
+    w.done_counter = c.take<int>(1);
+    w.zero_end = c.used();
+    w.word_prefix = c.take<unsigned>(nwords);
+    w.cell_off = c.take<int>(nc);
+    w.occ_list = c.take<int>(nocc + 1);
+    w.cutoff = c.take<int>(B);
+    w.cellpos = c.take<int2>((size_t)total_points + 1);
+    w.bucket = c.take<int>((size_t)total_points + 1);
+    w.total = c.used();
+    return w;
+}
+
+static int64_t ncell_of(const pp_voxel_cfg* cfg, int32_t grid[3]) {
+    pp_grid_size(cfg->voxel_size, cfg->coors_range, cfg->arith_f32, grid);
+    return (int64_t)grid[0] * grid[1] * grid[2];
+}
+
+}  // namespace pp
+
+using namespace pp;
+
+extern "C" int pp_grid_size(const double voxel_size[3], const double coors_range[6], int arith_f32,
+                            int32_t grid_xyz[3]) {
+    for (int j = 0; j < 3; ++j) {
+        if (arith_f32) {
+            const float g = ((float)coors_range[3 + j] - (float)coors_range[j]) / (float)voxel_size[j];
+            grid_xyz[j] = (int32_t)nearbyintf(g);
+        } else {
+            const double g = (coors_range[3 + j] - coors_range[j]) / voxel_size[j];
+            grid_xyz[j] = (int32_t)nearbyint(g);
+        }
+    }
+    return PP_OK;
+}
+
+extern "C" size_t pp_voxelize_workspace_bytes(const pp_voxel_cfg* cfg, int64_t total_points,
+                                              int n_frames) {
+    if (!cfg || total_points < 0 || n_frames <= 0) return 0;
+    int32_t grid[3];
+    const int64_t ncell = ncell_of(cfg, grid);
+    if (ncell <= 0) return 0;
+    return carve(nullptr, ncell, total_points, n_frames).total + 256;
+}
+
+template <typename T, typename TO>
+static int launch_gather(const VoxParams& p, const VoxWorkspace& w, const void* points,
+                         const int64_t* frame_off, int64_t cap_rows, void* voxels, float* decorated,
+                         int32_t* coors, int coors_cols, int32_t* num_points,
+                         const int32_t* voxel_base, int32_t* point_slot, int32_t* cell_voxel,
+                         int64_t max_occ, cudaStream_t st) {
+    const size_t smem = (size_t)kGatherWarps * 2 * p.max_points * sizeof(int);
+    auto kern = vox_gather_kernel<T, TO>;
+    if (smem > 48 * 1024) PP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t blocks = ceil_div(max_occ, kGatherWarps);
+    const int64_t cap = (int64_t)kNumSM * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    kern<<<(unsigned)blocks, kGatherWarps * 32, smem, st>>>(
+        static_cast<const T*>(points), frame_off, p, w.occ_list, w.occ_count, w.first_idx, w.cnt,
+        w.cell_off, w.bucket, w.bitmap, w.word_prefix, w.cutoff, voxel_base, cap_rows,
+        static_cast<TO*>(voxels), decorated, coors, coors_cols, num_points, point_slot, cell_voxel);
+    PP_LAUNCHED();
+    return PP_OK;
+}
+
+extern "C" int pp_voxelize_dev(const pp_voxel_cfg* cfg, const void* points, int point_dtype, int D,
+                               const int64_t* frame_offsets, int n_frames, int64_t total_points,
+                               int64_t max_frame_points, int out_dtype, void* voxels,
+                               float* decorated, int32_t* coors, int coors_cols,
+                               int32_t* num_points, int64_t cap_rows, int32_t* voxel_num,
+                               int32_t* voxel_base, int32_t* point_slot, int32_t* cell_voxel,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+    PP_CHECK_ARG(cfg && frame_offsets && coors && num_points && voxel_num && voxel_base && workspace,
+                 "pp_voxelize_dev: null argument");
+    PP_CHECK_ARG(point_dtype == PP_F32 || point_dtype == PP_F64, "point_dtype must be PP_F32/PP_F64");
+    PP_CHECK_ARG(out_dtype == PP_F32 || (out_dtype == PP_F64 && point_dtype == PP_F64),
+                 "out_dtype must be PP_F32, or PP_F64 for float64 points");
+    PP_CHECK_ARG(D >= 3 && D <= 16, "D=%d outside [3,16]", D);
+    PP_CHECK_ARG(coors_cols == 3 || coors_cols == 4, "coors_cols must be 3 or 4");
+    PP_CHECK_ARG(n_frames > 0 && n_frames <= 65535, "n_frames=%d outside [1,65535]", n_frames);
+    PP_CHECK_ARG(total_points >= 0 && max_frame_points >= 0 && max_frame_points <= total_points,
+                 "bad point counts");
+    PP_CHECK_ARG(max_frame_points < (int64_t)1 << 31, "a frame may hold < 2^31 points");
+    PP_CHECK_ARG(cfg->max_points >= 1 && cfg->max_points <= 2048, "max_points=%d outside [1,2048]", cfg->max_points);
+    PP_CHECK_ARG(cfg->max_voxels >= 0, "max_voxels < 0");
+    PP_CHECK_ARG(!(cfg->arith_f32 && point_dtype == PP_F64), "arith_f32 needs float32 points");
+    PP_CHECK_ARG(total_points == 0 || points, "points is null");
+    int32_t grid[3];
+    const int64_t ncell = ncell_of(cfg, grid);
+    PP_CHECK_ARG(grid[0] > 0 && grid[1] > 0 && grid[2] > 0, "empty grid %d x %d x %d", grid[0], grid[1], grid[2]);
+    PP_CHECK_ARG(ncell * n_frames < ((int64_t)1 << 31), "n_frames * cells must be < 2^31");
+    const VoxWorkspace w = carve(workspace, ncell, total_points, n_frames);
+    if (w.total > workspace_bytes) {
+        set_error("pp_voxelize_dev: workspace %zu < required %zu", workspace_bytes, w.total);
+        return PP_E_WORKSPACE;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    VoxParams p;
+    for (int j = 0; j < 3; ++j) {
+        p.lo[j] = cfg->coors_range[j]; p.vs[j] = cfg->voxel_size[j];
+        p.lo32[j] = (float)cfg->coors_range[j]; p.vs32[j] = (float)cfg->voxel_size[j];
+        p.grid[j] = grid[j];
+    }
+    p.ncell = (int)ncell; p.max_points = cfg->max_points; p.max_voxels = cfg->max_voxels;
+    p.reverse_index = cfg->reverse_index; p.arith_f32 = cfg->arith_f32; p.D = D;
+    p.vx = (float)cfg->voxel_size[0]; p.vy = (float)cfg->voxel_size[1];
+    p.x_off = (float)(cfg->voxel_size[0] / 2 + cfg->coors_range[0]);
+    p.y_off = (float)(cfg->voxel_size[1] / 2 + cfg->coors_range[1]);
+
+    const size_t nc = (size_t)n_frames * ncell;
+    PP_CUDA(cudaMemsetAsync(w.first_idx, 0xff, nc * sizeof(unsigned), st));
+    PP_CUDA(cudaMemsetAsync(static_cast<char*>(workspace) + w.zero_begin, 0, w.zero_end - w.zero_begin, st));
+
+    if (max_frame_points > 0) {
+        const dim3 g((unsigned)ceil_div(max_frame_points, kMarkThreads), n_frames);
+        const int esz = point_dtype == PP_F64 ? 8 : 4;
+        const size_t smem = (size_t)kMarkThreads * D * esz + 32;
+        const int aligned16 = (reinterpret_cast<uintptr_t>(points) & 15) == 0;
+        if (point_dtype == PP_F64)
+            vox_mark_kernel<double, false><<<g, kMarkThreads, smem, st>>>(
+                static_cast<const double*>(points), frame_offsets, p, total_points, aligned16,
+                w.first_idx, w.cnt, w.cellpos, point_slot);
+        else if (cfg->arith_f32)
+            vox_mark_kernel<float, true><<<g, kMarkThreads, smem, st>>>(
+                static_cast<const float*>(points), frame_offsets, p, total_points, aligned16,
+                w.first_idx, w.cnt, w.cellpos, point_slot);
+        else
+            vox_mark_kernel<float, false><<<g, kMarkThreads, smem, st>>>(
+                static_cast<const float*>(points), frame_offsets, p, total_points, aligned16,
+                w.first_idx, w.cnt, w.cellpos, point_slot);
+        PP_LAUNCHED();
+    }
+    {
+        const dim3 g((unsigned)ceil_div(ncell, kCellThreads), n_frames);
+        vox_cell_kernel<<<g, kCellThreads, 0, st>>>(w.first_idx, w.cnt, frame_offsets, (int)ncell,
+                                                    w.bitmap, w.cell_off, w.frame_cursor, w.occ_list,
+                                                    w.occ_count, cell_voxel);
+        PP_LAUNCHED();
+    }
+    vox_rank_kernel<<<n_frames, kRankThreads, 0, st>>>(w.bitmap, w.word_prefix, frame_offsets, n_frames,
+                                                       cfg->max_voxels, voxel_num, w.cutoff, voxel_base,
+                                                       w.done_counter);
+    PP_LAUNCHED();
+    if (max_frame_points > 0) {
+        const dim3 g((unsigned)ceil_div(max_frame_points, 256), n_frames);
+        vox_bucket_kernel<<<g, 256, 0, st>>>(w.cellpos, frame_offsets, (int)ncell, w.cell_off, w.bucket);
+        PP_LAUNCHED();
+    }
+    const int64_t max_occ = (int64_t)nc < total_points ? (int64_t)nc : total_points;
+    if (max_occ > 0 && cap_rows > 0) {
+        int rc;
+        if (point_dtype == PP_F64 && out_dtype == PP_F64)
+            rc = launch_gather<double, double>(p, w, points, frame_offsets, cap_rows, voxels, decorated, coors,
+                                               coors_cols, num_points, voxel_base, point_slot, cell_voxel, max_occ, st);
+        else if (point_dtype == PP_F64)
+            rc = launch_gather<double, float>(p, w, points, frame_offsets, cap_rows, voxels, decorated, coors,
+                                              coors_cols, num_points, voxel_base, point_slot, cell_voxel, max_occ, st);
+        else
+            rc = launch_gather<float, float>(p, w, points, frame_offsets, cap_rows, voxels, decorated, coors,
+                                             coors_cols, num_points, voxel_base, point_slot, cell_voxel, max_occ, st);
+        if (rc) return rc;
+    }
+    return PP_OK;
+}

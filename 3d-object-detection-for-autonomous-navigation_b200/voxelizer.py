@@ -1,0 +1,55 @@
+"""Drop-in for the reference's `points_to_voxel` (load_data.py:695-771, call site 2966).
+
+Same signature, same numpy arrays out (voxels in the points' dtype, zero padded; coors int32
+(z,y,x) when reverse_index; num_points_per_voxel int32), bit-exact against the numba loop at
+load_data.py:593-692 -- computed by the sm_100a kernels in csrc/voxelize.cu.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def _arith_is_f32(points, voxel_size, coors_range) -> bool:
+    # numba promotion at load_data.py:622: float32 only if every operand is float32; python lists
+    # are cast to points.dtype first (load_data.py:726-729)
+    def dt(x):
+        return x.dtype if isinstance(x, np.ndarray) else points.dtype
+    return (points.dtype == np.float32 and dt(voxel_size) == np.float32 and dt(coors_range) == np.float32)
+
+
+def points_to_voxel(points, voxel_size, coors_range, max_points, reverse_index, max_voxels,
+                    return_point_slots=False, device=None):
+    """points [N,D] float32/float64 -> (voxels [M,max_points,D], coors [M,3], num_points [M]).
+
+    `return_point_slots` additionally returns the point-to-slot assignment [N] int32
+    (voxel*max_points+slot, -1 for dropped points); `device` picks the GPU (default: thread's)."""
+    points = np.asarray(points)
+    if points.dtype not in (np.float32, np.float64):
+        raise TypeError(f"points must be float32 or float64, got {points.dtype}")
+    if points.ndim != 2 or points.shape[1] < 3:
+        raise ValueError("points must be [N, >=3]")
+    points = np.ascontiguousarray(points)
+    f32 = _arith_is_f32(points, voxel_size, coors_range)
+    if not isinstance(voxel_size, np.ndarray):
+        voxel_size = np.array(voxel_size, dtype=points.dtype)
+    if not isinstance(coors_range, np.ndarray):
+        coors_range = np.array(coors_range, dtype=points.dtype)
+    cfg = _lib.make_cfg(voxel_size, coors_range, max_points, max_voxels, reverse_index, f32)
+    N, D = points.shape
+    voxels = np.empty((max_voxels, max_points, D), points.dtype)
+    coors = np.empty((max_voxels, 3), np.int32)
+    num = np.empty((max_voxels,), np.int32)
+    slots = np.empty((N,), np.int32) if return_point_slots else None
+    m = C.c_int32(0)
+    c = _lib.ctx(device)
+    _lib.check(_lib.lib().pp_points_to_voxel_host(
+        c.handle, C.byref(cfg), _lib.ptr(points), _lib.PP_F64 if points.dtype == np.float64 else _lib.PP_F32,
+        N, D, _lib.ptr(voxels), _lib.ptr(coors), _lib.ptr(num), C.byref(m),
+        _lib.ptr(slots) if return_point_slots else None))
+    M = m.value
+    out = (voxels[:M], coors[:M], num[:M])
+    return out + (slots,) if return_point_slots else out

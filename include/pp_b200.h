@@ -1,0 +1,201 @@
+/*
+ * pp_b200.h -- C ABI of the B200-native PointPillars pre/post-processing hot path.
+ *
+ * One shared library (libpp_b200.so, sm_100a) replaces the data-parallel stages of
+ * krullgit/3D-Object-Detection-for-autonomous-navigation.  Each entry point names the
+ * reference interface it stands in for (paths relative to the reference checkout).
+ *
+ * Two layers, both plain C (pointers + sizes, no framework types):
+ *
+ *   *_dev   device pointers in, device pointers out, asynchronous on the caller's stream,
+ *           caller-provided workspace.  This is what a DLPack / __cuda_array_interface__
+ *           consumer (TensorFlow via tf.experimental.dlpack, torch, cupy) binds.
+ *   *_host  host (numpy) buffers in and out through a pp_ctx that owns a stream, a device
+ *           arena and pinned staging.  Synchronous, like the reference's numpy functions.
+ *           This is what the reference's call sites bind through ctypes.
+ *
+ * Conventions
+ *   - Every function returns 0 on success, <0 on error (PP_E_*); pp_last_error_string() gives the
+ *     thread-local message.  Nothing throws or exits across this boundary.
+ *   - The library never frees or retains caller memory.  The only state is inside pp_ctx.
+ *   - A pp_ctx must not be used from two threads at once; create one per thread (the reference
+ *     calls the voxelizer on the tf.data thread and NMS on the main thread).
+ *   - `stream` is a cudaStream_t passed as void*.  The legacy default stream is never used
+ *     implicitly.
+ *   - There is no CPU fallback: without a CUDA device every compute entry returns PP_E_CUDA.
+ */
+#ifndef PP_B200_H
+#define PP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PP_API __attribute__((visibility("default")))
+
+#define PP_OK 0
+#define PP_E_INVALID (-1)   /* bad argument */
+#define PP_E_CUDA (-2)      /* CUDA runtime error (message has the cudaError string) */
+#define PP_E_WORKSPACE (-3) /* workspace / output capacity too small */
+#define PP_E_NOMEM (-4)
+
+#define PP_F32 0
+#define PP_F64 1
+
+#define PP_LAYOUT_NCHW 0 /* reference output of PointPillarsScatter.call */
+#define PP_LAYOUT_NHWC 1 /* what RPN.call transposes to (model/voxelnet.py:697) */
+
+PP_API const char* pp_last_error_string(void);
+PP_API int pp_version(void);
+/* Number of kernel launches issued by this thread through the library since the last reset
+ * (bench.py's gpu_launches). */
+PP_API int64_t pp_launch_count(int reset);
+
+/* ---- grid -------------------------------------------------------------------------------
+ * np.round((range[3:]-range[:3])/voxel_size).astype(int32), round-half-to-even:
+ * load_data.py:612-615 and 730-731.  arith_f32: the wrapper cast python lists to float32
+ * because points are float32 (load_data.py:726-729). */
+PP_API int pp_grid_size(const double voxel_size[3], const double coors_range[6], int arith_f32,
+                 int32_t grid_xyz[3]);
+
+/* ---- voxelizer --------------------------------------------------------------------------
+ * Replaces points_to_voxel / _points_to_voxel_reverse_kernel / _points_to_voxel_kernel,
+ * load_data.py:593-771 (call site load_data.py:2966), for a batch of independent frames.
+ * Bit-exact first-come semantics: voxel id = order of first touch, slot = order of arrival,
+ * max_points cap per voxel, and the scan BREAKS at the first point that would open voxel
+ * number max_voxels (load_data.py:630-634).  NaN coordinates drop the point (UB in the
+ * reference). */
+typedef struct pp_voxel_cfg {
+    double voxel_size[3];
+    double coors_range[6];
+    int32_t max_points;
+    int32_t max_voxels;
+    int32_t reverse_index; /* 1: coors are (z,y,x) (the reference's call), 0: (x,y,z) */
+    int32_t arith_f32;     /* 1 only when points AND voxel_size/coors_range were float32 */
+} pp_voxel_cfg;
+
+PP_API size_t pp_voxelize_workspace_bytes(const pp_voxel_cfg* cfg, int64_t total_points, int n_frames);
+
+/*  points         [total_points, D] point_dtype, frames concatenated
+ *  frame_offsets  device int64 [n_frames+1], frame b = rows [off[b], off[b+1])
+ *  max_frame_points  max over b of off[b+1]-off[b] (host knows it; sizes the grid)
+ *  voxels         [cap_rows, max_points, D] out_dtype (PP_F32, or PP_F64 when points are f64),
+ *                 frames packed back to back (merge_second_batch layout, load_data.py:2203-2214);
+ *                 every written row is zero-padded.  May be NULL when `decorated` is given.
+ *  decorated      optional [cap_rows, max_points, D+5] float32: PillarFeatureNet decoration
+ *                 (model/pointpillars.py:143-203) fused into the same pass
+ *  coors          [cap_rows, coors_cols] int32; coors_cols 3 = reference's per-frame coors,
+ *                 4 = (frame, c0, c1, c2) as merge_second_batch pads it
+ *  num_points     [cap_rows] int32
+ *  voxel_num      [n_frames] int32; voxel_base [n_frames+1] int32 exclusive scan (row of frame b's
+ *                 first voxel); cap_rows must be >= min(sum of per-frame voxel counts,
+ *                 n_frames*max_voxels) -- n_frames*max_voxels is always enough
+ *  point_slot     optional [total_points] int32: voxel_in_frame*max_points+slot, -1 if dropped
+ *  cell_voxel     optional [n_frames*nz*ny*nx] int32: packed row of the cell's voxel or -1
+ *                 (the reference's coor_to_voxelidx map) */
+PP_API int pp_voxelize_dev(const pp_voxel_cfg* cfg, const void* points, int point_dtype, int D,
+                    const int64_t* frame_offsets, int n_frames, int64_t total_points,
+                    int64_t max_frame_points, int out_dtype, void* voxels, float* decorated,
+                    int32_t* coors, int coors_cols, int32_t* num_points, int64_t cap_rows,
+                    int32_t* voxel_num, int32_t* voxel_base, int32_t* point_slot,
+                    int32_t* cell_voxel, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- pillar decoration ------------------------------------------------------------------
+ * Replaces lines 143-203 of PillarFeatureNet.call (model/pointpillars.py), constants 121-124,
+ * mask 23-49.  voxels [M,P,D] f32, num_points [M], coors [M,4] (batch,z,y,x) ->
+ * out [M,P,D+5] f32.  vx, vy, x_offset, y_offset as the reference computes them in python
+ * doubles (x_offset = vx/2 + range[0]); they are rounded to float32 like TF constants. */
+PP_API int pp_decorate_dev(const float* voxels, const int32_t* num_points, const int32_t* coors, int64_t M,
+                    int P, int D, double vx, double vy, double x_offset, double y_offset, float* out,
+                    void* stream);
+
+/* ---- scatter ----------------------------------------------------------------------------
+ * Replaces PointPillarsScatter.call, model/pointpillars.py:285-341: out[b,:,y,x] = SUM of the
+ * feature rows with coords (b,*,y,x) (z ignored, duplicates added, lines 302,317); everything
+ * else zero.  `out` is fully written (no memset needed).  Rows with b outside [0,B) or (y,x)
+ * outside the canvas are ignored.  M may be read from device (`M_dev`, e.g. voxel_base+n_frames)
+ * when the host does not know it; then M is the capacity. */
+PP_API size_t pp_scatter_workspace_bytes(int B, int ny, int nx, int64_t M);
+PP_API int pp_scatter_dev(const float* feats, const int32_t* coords, int64_t M, const int32_t* M_dev, int C,
+                   int B, int ny, int nx, int layout, float* out, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* ---- box decode -------------------------------------------------------------------------
+ * Replaces second_box_decode (default flags), libraries/eval_helper_functions.py:388-461
+ * (duplicate second/core/box_np_ops.py:69-104).  [N,7] f32 each, order x,y,z,w,l,h,r.
+ * `anchor_period` > 0: anchors holds anchor_period rows reused cyclically (one anchor set for a
+ * batch of frames); 0: one anchor row per encoding row. */
+PP_API int pp_box_decode_dev(const float* box_encodings, const float* anchors, int64_t N,
+                      int64_t anchor_period, float* out, void* stream);
+
+/* Rotated BEV box (x,y,w,l,r) [N,5] -> standup box (xmin,ymin,xmax,ymax) [N,4]:
+ * center_to_corner_box2d + corner_to_standup_nd_jit, load_data.py:1525-1594, 1330-1341, as
+ * called at model/voxelnet.py:1233-1249.  in_stride = floats per input row (5, or 7 to read
+ * x,y,w,l,r straight out of decoded [N,7] boxes at columns 0,1,3,4,6). */
+PP_API int pp_rbox_to_standup_dev(const float* boxes, int in_stride, int64_t N, float* out, void* stream);
+
+/* ---- NMS --------------------------------------------------------------------------------
+ * kind PP_NMS_STANDUP replaces nms / nms_gpu / nms_kernel / nms_postprocess,
+ *   libraries/eval_helper_functions.py:463-598 (axis-aligned IoU with the "+1" convention);
+ *   boxes [B,N,4] (xmin,ymin,xmax,ymax).
+ * kind PP_NMS_ROTATED replaces rotate_nms_gpu / rotate_nms_kernel / devRotateIoU,
+ *   second/core/non_max_suppression/nms_gpu.py:180-490; boxes [B,N,5] (x,y,w,l,angle).
+ * Both: scores [B,N]; order = descending score, ties by descending index; optional top
+ * pre_max_size (<=0: all), greedy suppression of IoU > thresh (strict, thresh rounded to
+ * float32), first post_max_size kept (<=0: all).
+ *   n_valid   optional device [B]: only the first n_valid[b] boxes of frame b are used
+ *   keep      [B, keep_stride] int32 indices into the frame's boxes, in keep order
+ *   keep_count[B] int32 (count is clipped to keep_stride) */
+#define PP_NMS_STANDUP 0
+#define PP_NMS_ROTATED 1
+PP_API size_t pp_nms_workspace_bytes(int kind, int B, int64_t N, int pre_max_size);
+PP_API int pp_nms_dev(int kind, const float* boxes, int box_stride, const float* scores,
+               const int32_t* n_valid, int B, int64_t N, int pre_max_size, int post_max_size,
+               float thresh, int32_t* keep, int64_t keep_stride, int32_t* keep_count,
+               void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- rotated IoU matrix -----------------------------------------------------------------
+ * Replaces rotate_iou_gpu and rotate_iou_gpu_eval, nms_gpu.py:526-561 and 618-653 (kernels
+ * 493-523, 579-615).  boxes [N,5], query_boxes [K,5] f32 -> out [N,K] f32,
+ * out[n,k] = devRotateIoUEval(query_boxes[k], boxes[n], criterion); criterion -1 IoU,
+ * 0 inter/area(query), 1 inter/area(box), 2 intersection area. */
+PP_API int pp_rotate_iou_dev(const float* boxes, int64_t N, const float* query_boxes, int64_t K,
+                      int criterion, float* out, void* stream);
+
+/* ---- context + host-buffer layer ----------------------------------------------------------- */
+typedef struct pp_ctx pp_ctx;
+PP_API int pp_ctx_create(int device, pp_ctx** out);
+PP_API void pp_ctx_destroy(pp_ctx* ctx);
+PP_API void* pp_ctx_stream(pp_ctx* ctx);
+PP_API int pp_ctx_device(pp_ctx* ctx);
+PP_API int pp_ctx_sync(pp_ctx* ctx);
+
+/* points_to_voxel(points, voxel_size, coors_range, max_points, reverse_index, max_voxels),
+ * load_data.py:695-771: host points [N,D] -> host voxels [max_voxels,max_points,D] in the
+ * points' dtype (only the first *voxel_num_out rows are written, zero padded), coors
+ * [max_voxels,3], num_points [max_voxels]; point_slot optional [N]. */
+PP_API int pp_points_to_voxel_host(pp_ctx* ctx, const pp_voxel_cfg* cfg, const void* points,
+                            int point_dtype, int64_t N, int D, void* voxels, int32_t* coors,
+                            int32_t* num_points, int32_t* voxel_num_out, int32_t* point_slot);
+PP_API int pp_decorate_host(pp_ctx* ctx, const float* voxels, const int32_t* num_points,
+                     const int32_t* coors, int64_t M, int P, int D, double vx, double vy,
+                     double x_offset, double y_offset, float* out);
+PP_API int pp_scatter_host(pp_ctx* ctx, const float* feats, const int32_t* coords, int64_t M, int C, int B,
+                    int ny, int nx, int layout, float* out);
+PP_API int pp_box_decode_host(pp_ctx* ctx, const float* box_encodings, const float* anchors, int64_t N,
+                       float* out);
+PP_API int pp_rbox_to_standup_host(pp_ctx* ctx, const float* boxes, int64_t N, float* out);
+/* keep: int64 [min(N, pre, post)]; *keep_count_out == 0 is the reference's `None`. */
+PP_API int pp_nms_host(pp_ctx* ctx, int kind, const float* boxes, const float* scores, int64_t N,
+                int pre_max_size, int post_max_size, float thresh, int64_t* keep,
+                int32_t* keep_count_out);
+PP_API int pp_rotate_iou_host(pp_ctx* ctx, const float* boxes, int64_t N, const float* query_boxes,
+                       int64_t K, int criterion, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PP_B200_H */
