@@ -77,7 +77,9 @@ rbox_to_standup_kernel(const float* __restrict__ boxes, int stride, int64_t N, f
     float cx, cy, w, l, r;
     if (stride == 7) { cx = b[0]; cy = b[1]; w = b[3]; l = b[4]; r = b[6]; }
     else { cx = b[0]; cy = b[1]; w = b[2]; l = b[3]; r = b[4]; }
-    const float s = sinf(r), c = cosf(r);
+    double ds, dc;
+    sincos((double)r, &ds, &dc);
+    const float s = (float)ds, c = (float)dc;
     const float hx[4] = {-0.5f, -0.5f, 0.5f, 0.5f};
     const float hy[4] = {-0.5f, 0.5f, 0.5f, -0.5f};
     float mnx = 0.f, mny = 0.f, mxx = 0.f, mxy = 0.f;

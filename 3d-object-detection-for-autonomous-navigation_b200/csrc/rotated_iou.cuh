@@ -21,7 +21,12 @@ struct RBox {      // 8 corner floats + area + hull
 
 // rbbox_to_corners, nms_gpu.py:367-390
 __device__ __forceinline__ void rbox_prepare(const float* r /*x,y,w,l,angle*/, RBox& o) {
-    const float a_cos = cosf(r[4]), a_sin = sinf(r[4]);
+    // float32 cos/sin as a correctly rounded libm returns them (the reference's numba path calls
+    // libm cosf/sinf; CUDA's cosf/sinf are 1-2 ulp off, which is enough to flip the inclusive
+    // corner tests).  Once per box, so the double-precision evaluation is off the pair loop.
+    double dsn, dcs;
+    sincos((double)r[4], &dsn, &dcs);
+    const float a_cos = (float)dcs, a_sin = (float)dsn;
     const float cx = r[0], cy = r[1];
     const float hx = (float)((double)r[2] / 2.0), hy = (float)((double)r[3] / 2.0);
     const float xs[4] = {-hx, -hx, hx, hx};
