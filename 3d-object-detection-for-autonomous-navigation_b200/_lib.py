@@ -33,6 +33,8 @@ SIGNATURES = {
     "pp_last_error_string": (C.c_char_p, []),
     "pp_version": (C.c_int, []),
     "pp_launch_count": (_i64, [C.c_int]),
+    "pp_profile_start": (C.c_int, []),
+    "pp_profile_stop": (C.c_int, [C.c_char_p, _sz, C.POINTER(_f32), C.c_int]),
     "pp_grid_size": (C.c_int, [C.POINTER(_f64), C.POINTER(_f64), C.c_int, C.POINTER(_i32)]),
     "pp_voxelize_workspace_bytes": (_sz, [_cfgp, _i64, C.c_int]),
     "pp_voxelize_dev": (C.c_int, [_cfgp, _vp, C.c_int, C.c_int, _vp, C.c_int, _i64, _i64, C.c_int, _vp, _vp,
@@ -45,6 +47,7 @@ SIGNATURES = {
     "pp_nms_workspace_bytes": (_sz, [C.c_int, C.c_int, _i64, C.c_int]),
     "pp_nms_dev": (C.c_int, [C.c_int, _vp, C.c_int, _vp, _vp, C.c_int, _i64, C.c_int, C.c_int, _f32, _vp, _i64,
                              _vp, _vp, _sz, _vp]),
+    "pp_gather_dets_dev": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _i64, _vp, _i64, _vp, C.c_int, _vp, _vp]),
     "pp_rotate_iou_dev": (C.c_int, [_vp, _i64, _vp, _i64, C.c_int, _vp, _vp]),
     "pp_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "pp_ctx_destroy": (None, [_vp]),
@@ -94,6 +97,19 @@ def check(rc: int):
 
 def launch_count(reset=False) -> int:
     return int(lib().pp_launch_count(int(reset)))
+
+
+def profile_start():
+    check(lib().pp_profile_start())
+
+
+def profile_stop(max_records=65536):
+    """-> list of (kernel name, device ms) in launch order since profile_start()."""
+    names = C.create_string_buffer(max_records * 24)
+    ms = (_f32 * max_records)()
+    n = lib().pp_profile_stop(names, len(names), ms, max_records)
+    labels = names.value.decode().split("\n")[:n]
+    return list(zip(labels, [float(ms[i]) for i in range(n)]))
 
 
 class Ctx:

@@ -103,6 +103,7 @@ extern "C" int pp_box_decode_dev(const float* box_encodings, const float* anchor
     PP_CHECK_ARG(N >= 0, "pp_box_decode_dev: N < 0");
     if (N == 0) return PP_OK;
     PP_CHECK_ARG(box_encodings && anchors && out, "pp_box_decode_dev: null argument");
+    PP_TIMED("box_decode", static_cast<cudaStream_t>(stream));
     box_decode_kernel<<<(unsigned)ceil_div(N, kBoxThreads), kBoxThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         box_encodings, anchors, N, anchor_period, out);
     PP_LAUNCHED();
@@ -114,6 +115,7 @@ extern "C" int pp_rbox_to_standup_dev(const float* boxes, int in_stride, int64_t
     if (N == 0) return PP_OK;
     PP_CHECK_ARG(boxes && out && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                  "pp_rbox_to_standup_dev: null or unaligned argument");
+    PP_TIMED("rbox_to_standup", static_cast<cudaStream_t>(stream));
     rbox_to_standup_kernel<<<(unsigned)ceil_div(N, kBoxThreads), kBoxThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         boxes, in_stride, N, out);
     PP_LAUNCHED();

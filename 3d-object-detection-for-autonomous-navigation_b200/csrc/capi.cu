@@ -1,6 +1,7 @@
 // C-ABI glue: thread-local error string, launch counter, pp_ctx (stream + device arena) and
 // the host-buffer entry points the reference's numpy call sites bind (include/pp_b200.h).
 #include <new>
+#include <vector>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -20,6 +21,22 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches += n; }
 
+struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+static thread_local bool g_prof_on = false;
+static thread_local std::vector<ProfRec>* g_prof = nullptr;
+
+LaunchTimer::LaunchTimer(const char* name, cudaStream_t st) : st_(st), slot_(-1) {
+    if (!g_prof_on) return;
+    ProfRec r{name, nullptr, nullptr};
+    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+    cudaEventRecord(r.e0, st);
+    g_prof->push_back(r);
+    slot_ = (int)g_prof->size() - 1;
+}
+LaunchTimer::~LaunchTimer() {
+    if (slot_ >= 0) cudaEventRecord((*g_prof)[slot_].e1, st_);
+}
+
 }  // namespace pp
 
 using namespace pp;
@@ -30,6 +47,42 @@ extern "C" int64_t pp_launch_count(int reset) {
     const int64_t v = g_launches;
     if (reset) g_launches = 0;
     return v;
+}
+
+extern "C" int pp_profile_start(void) {
+    if (!g_prof) g_prof = new std::vector<ProfRec>();
+    for (auto& r : *g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    g_prof->clear();
+    g_prof_on = true;
+    return PP_OK;
+}
+
+extern "C" int pp_profile_stop(char* names, size_t names_cap, float* ms, int max_records) {
+    g_prof_on = false;
+    if (!g_prof) return 0;
+    int n = 0;
+    size_t off = 0;
+    if (names && names_cap) names[0] = 0;
+    for (auto& r : *g_prof) {
+        if (cudaEventSynchronize(r.e1) == cudaSuccess && n < max_records) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) {
+                const size_t len = strlen(r.name);
+                if (names && off + len + 2 <= names_cap) {
+                    memcpy(names + off, r.name, len);
+                    names[off + len] = '\n';
+                    names[off + len + 1] = 0;
+                    off += len + 1;
+                    if (ms) ms[n] = t;
+                    ++n;
+                }
+            }
+        }
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    g_prof->clear();
+    return n;
 }
 
 // ---- context ----------------------------------------------------------------------------------

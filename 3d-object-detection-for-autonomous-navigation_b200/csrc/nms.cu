@@ -234,7 +234,9 @@ nms_prep_kernel(const float* __restrict__ boxes, int box_stride, int64_t N, cons
     if (i >= n) return;
     const float* src = boxes + ((int64_t)b * N + order[(int64_t)b * order_stride + i]) * box_stride;
     if (ROTATED) {
-        const float r[5] = {src[0], src[1], src[2], src[3], src[4]};
+        // box_stride 7: decoded boxes (x,y,z,w,l,h,r) -> BEV columns 0,1,3,4,6 (model/voxelnet.py:1233)
+        const bool dec7 = box_stride == 7;
+        const float r[5] = {src[0], src[1], dec7 ? src[3] : src[2], dec7 ? src[4] : src[3], dec7 ? src[6] : src[4]};
         RBox rb;
         rbox_prepare(r, rb);
         float4* dst = reinterpret_cast<float4*>(static_cast<RBoxG*>(sorted) + (int64_t)b * sorted_stride + i);
@@ -426,9 +428,40 @@ rotate_iou_matrix_kernel(const float* __restrict__ boxes, int64_t N, const float
     }
 }
 
+// final detections: out[b,k,:] = (boxes[b, keep[b,k], 0:box_dim], scores[b, keep[b,k]]), zero padded
+__global__ void __launch_bounds__(256)
+gather_dets_kernel(const float* __restrict__ boxes, int box_dim, const float* __restrict__ scores, int64_t N,
+                   const int* __restrict__ keep, int64_t keep_stride, const int* __restrict__ keep_count,
+                   int K, float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int od = box_dim + 1;
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= K * od) return;
+    const int k = e / od, d = e - k * od;
+    float v = 0.f;
+    if (k < min(keep_count[b], K)) {
+        const int64_t i = (int64_t)b * N + keep[(int64_t)b * keep_stride + k];
+        v = d < box_dim ? boxes[i * box_dim + d] : scores[i];
+    }
+    out[((int64_t)b * K + k) * od + d] = v;
+}
+
 }  // namespace pp
 
 using namespace pp;
+
+extern "C" int pp_gather_dets_dev(const float* boxes, int box_dim, const float* scores, int B, int64_t N,
+                                  const int32_t* keep, int64_t keep_stride, const int32_t* keep_count, int K,
+                                  float* out, void* stream) {
+    PP_CHECK_ARG(B > 0 && B <= 65535 && K > 0 && box_dim > 0 && N >= 0, "pp_gather_dets_dev: bad arguments");
+    PP_CHECK_ARG(boxes && scores && keep && keep_count && out, "pp_gather_dets_dev: null argument");
+    const dim3 g((unsigned)ceil_div((int64_t)K * (box_dim + 1), 256), B);
+    PP_TIMED("gather_dets", static_cast<cudaStream_t>(stream));
+    gather_dets_kernel<<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(boxes, box_dim, scores, N, keep, keep_stride,
+                                                                         keep_count, K, out);
+    PP_LAUNCHED();
+    return PP_OK;
+}
 
 namespace {
 struct NmsWs {
@@ -481,15 +514,18 @@ extern "C" int pp_nms_dev(int kind, const float* boxes, int box_stride, const fl
     }
     PP_CHECK_ARG(w.cb_cap * 8 <= 200 * 1024, "pp_nms_dev: more than 1.6M boxes per frame after pre_max_size");
     if (w.full_sort) {
+        PP_TIMED("nms_sort", st);
         nms_sort_kernel<<<B, kSortThreads, 0, st>>>(scores, n_valid, N, pre_max_size, w.kbuf, w.ibuf, w.order,
                                                    w.n_cap, w.n_sorted);
     } else {
         const int k = (int)w.n_cap;
+        PP_TIMED("nms_topk", st);
         nms_topk_kernel<<<B, kSortThreads, 0, st>>>(scores, n_valid, N, k, w.order, w.n_cap, w.n_sorted);
     }
     PP_LAUNCHED();
     {
         const dim3 g((unsigned)ceil_div(w.n_cap, 256), B);
+        PP_TIMED("nms_prep", st);
         if (kind == PP_NMS_ROTATED)
             nms_prep_kernel<true><<<g, 256, 0, st>>>(boxes, box_stride, N, w.order, w.n_cap, w.n_sorted, w.sorted, w.n_cap);
         else
@@ -499,6 +535,7 @@ extern "C" int pp_nms_dev(int kind, const float* boxes, int box_stride, const fl
     {
         const dim3 g((unsigned)ceil_div(w.cb_cap, kMaskGroup), (unsigned)w.cb_cap, B);
         PP_CHECK_ARG(w.cb_cap <= 65535, "pp_nms_dev: too many boxes per frame");
+        PP_TIMED("nms_mask", st);
         if (kind == PP_NMS_ROTATED)
             nms_mask_kernel<true><<<g, 64 * kMaskQ, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, thresh, w.mask, w.n_cap * w.cb_cap);
         else
@@ -509,6 +546,7 @@ extern "C" int pp_nms_dev(int kind, const float* boxes, int box_stride, const fl
         const size_t smem = (size_t)w.cb_cap * 8 + 8;
         if (smem > 48 * 1024)
             PP_CUDA(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PP_TIMED("nms_sweep", st);
         nms_sweep_kernel<<<B, kSweepThreads, smem, st>>>(w.mask, w.n_cap * w.cb_cap, w.n_sorted, w.order, w.n_cap,
                                                         post_max_size, keep, keep_stride, keep_count);
         PP_LAUNCHED();
@@ -523,6 +561,7 @@ extern "C" int pp_rotate_iou_dev(const float* boxes, int64_t N, const float* que
     PP_CHECK_ARG(boxes && query_boxes && out, "pp_rotate_iou_dev: null argument");
     PP_CHECK_ARG(ceil_div(N, 64) <= 65535, "pp_rotate_iou_dev: N too large (chunk the boxes)");
     const dim3 g((unsigned)ceil_div(K, 64), (unsigned)ceil_div(N, 64));
+    PP_TIMED("rotate_iou_matrix", static_cast<cudaStream_t>(stream));
     rotate_iou_matrix_kernel<<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(boxes, N, query_boxes, K, criterion, out);
     PP_LAUNCHED();
     return PP_OK;

@@ -11,6 +11,16 @@ namespace pp {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 
+// Per-launch CUDA-event timing (pp_profile_start/stop): when profiling is on, every kernel launch
+// is bracketed by two events on the launching stream.  Off by default: one thread-local branch.
+struct LaunchTimer {
+    LaunchTimer(const char* name, cudaStream_t st);
+    ~LaunchTimer();
+    cudaStream_t st_;
+    int slot_;
+};
+#define PP_TIMED(name, st) pp::LaunchTimer pp_timer__(name, st)
+
 #define PP_CHECK_ARG(cond, ...)                \
     do {                                       \
         if (!(cond)) {                         \

@@ -161,10 +161,12 @@ extern "C" int pp_scatter_dev(const float* feats, const int32_t* coords, int64_t
     if (M > 0) {
         int64_t blocks = ceil_div(M, 256);
         if (blocks > (int64_t)kNumSM * 16) blocks = (int64_t)kNumSM * 16;
+        PP_TIMED("scatter_link", st);
         scatter_link_kernel<<<(unsigned)blocks, 256, 0, st>>>(coords, M, M_dev, B, ny, nx, head, next);
         PP_LAUNCHED();
     }
     const dim3 g((unsigned)ceil_div(nx, kTileX), ny, B);
+    PP_TIMED("scatter_canvas", st);
     if (layout == PP_LAYOUT_NHWC) {
         auto k = scatter_canvas_kernel<true>;
         if (smem > 48 * 1024) PP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

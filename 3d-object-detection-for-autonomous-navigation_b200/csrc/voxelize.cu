@@ -448,6 +448,7 @@ static int launch_gather(const VoxParams& p, const VoxWorkspace& w, const void* 
     const int64_t cap = (int64_t)kNumSM * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
+    PP_TIMED("vox_gather", st);
     kern<<<(unsigned)blocks, kGatherWarps * 32, smem, st>>>(
         static_cast<const T*>(points), frame_off, p, w.occ_list, w.occ_count, w.first_idx, w.cnt,
         w.cell_off, w.bucket, w.bitmap, w.word_prefix, w.cutoff, voxel_base, cap_rows,
@@ -502,14 +503,18 @@ extern "C" int pp_voxelize_dev(const pp_voxel_cfg* cfg, const void* points, int 
     p.y_off = (float)(cfg->voxel_size[1] / 2 + cfg->coors_range[1]);
 
     const size_t nc = (size_t)n_frames * ncell;
-    PP_CUDA(cudaMemsetAsync(w.first_idx, 0xff, nc * sizeof(unsigned), st));
-    PP_CUDA(cudaMemsetAsync(static_cast<char*>(workspace) + w.zero_begin, 0, w.zero_end - w.zero_begin, st));
+    {
+        PP_TIMED("vox_memset", st);
+        PP_CUDA(cudaMemsetAsync(w.first_idx, 0xff, nc * sizeof(unsigned), st));
+        PP_CUDA(cudaMemsetAsync(static_cast<char*>(workspace) + w.zero_begin, 0, w.zero_end - w.zero_begin, st));
+    }
 
     if (max_frame_points > 0) {
         const dim3 g((unsigned)ceil_div(max_frame_points, kMarkThreads), n_frames);
         const int esz = point_dtype == PP_F64 ? 8 : 4;
         const size_t smem = (size_t)kMarkThreads * D * esz + 32;
         const int aligned16 = (reinterpret_cast<uintptr_t>(points) & 15) == 0;
+        PP_TIMED("vox_mark", st);
         if (point_dtype == PP_F64)
             vox_mark_kernel<double, false><<<g, kMarkThreads, smem, st>>>(
                 static_cast<const double*>(points), frame_offsets, p, total_points, aligned16,
@@ -526,17 +531,22 @@ extern "C" int pp_voxelize_dev(const pp_voxel_cfg* cfg, const void* points, int 
     }
     {
         const dim3 g((unsigned)ceil_div(ncell, kCellThreads), n_frames);
+        PP_TIMED("vox_cell", st);
         vox_cell_kernel<<<g, kCellThreads, 0, st>>>(w.first_idx, w.cnt, frame_offsets, (int)ncell,
                                                     w.bitmap, w.cell_off, w.frame_cursor, w.occ_list,
                                                     w.occ_count, cell_voxel);
         PP_LAUNCHED();
     }
-    vox_rank_kernel<<<n_frames, kRankThreads, 0, st>>>(w.bitmap, w.word_prefix, frame_offsets, n_frames,
-                                                       cfg->max_voxels, voxel_num, w.cutoff, voxel_base,
-                                                       w.done_counter);
-    PP_LAUNCHED();
+    {
+        PP_TIMED("vox_rank", st);
+        vox_rank_kernel<<<n_frames, kRankThreads, 0, st>>>(w.bitmap, w.word_prefix, frame_offsets, n_frames,
+                                                           cfg->max_voxels, voxel_num, w.cutoff, voxel_base,
+                                                           w.done_counter);
+        PP_LAUNCHED();
+    }
     if (max_frame_points > 0) {
         const dim3 g((unsigned)ceil_div(max_frame_points, 256), n_frames);
+        PP_TIMED("vox_bucket", st);
         vox_bucket_kernel<<<g, 256, 0, st>>>(w.cellpos, frame_offsets, (int)ncell, w.cell_off, w.bucket);
         PP_LAUNCHED();
     }

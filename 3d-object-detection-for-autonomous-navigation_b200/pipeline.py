@@ -1,0 +1,158 @@
+"""Device-resident, batched frame pipeline: voxelize(+decorate) -> scatter -> decode -> NMS.
+
+The numpy drop-ins (voxelizer.py, pillars.py, boxes.py, nms.py) move every tensor through the
+host, like the reference does.  This module chains the same `*_dev` C-ABI entry points on one
+stream with all intermediates left in HBM -- what a DLPack consumer (TensorFlow) would drive --
+and copies back only the final detections.  torch is used for device memory,
+streams and pinned host buffers only.
+
+Stand-ins: the PFN Dense/BN/ReLU/max (model/pointpillars.py:211-225) and the RPN
+(model/voxelnet.py:517-717) stay in the host framework; their outputs enter here as tensors
+(`pfn_feats`, `box_enc`, `scores`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import synth as _synth
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class FramePipeline:
+    """One GPU, up to `max_frames` frames of at most `max_total_points` points per run."""
+
+    def __init__(self, cfg, device=0, max_frames=64, max_total_points=None, rotated_nms=True,
+                 layout="NCHW", fused_decorate=True, keep_voxels=True, anchors=None):
+        self.cfg = cfg
+        self.dev = torch.device("cuda", device)
+        self.B = int(max_frames)
+        self.D = cfg["num_point_features"]
+        self.P = cfg["max_points"]
+        self.MV = cfg["max_voxels"]
+        self.C = cfg["num_filters"]
+        self.f64 = cfg["point_dtype"] == "float64"
+        self.nx, self.ny, self.nz = _synth.grid_size(cfg)
+        self.rotated = rotated_nms
+        self.layout = layout
+        self.fused = fused_decorate
+        self.keep_voxels = keep_voxels
+        self.vcfg = _lib.make_cfg(cfg["voxel_size"], cfg["point_cloud_range"], self.P, self.MV, True, False)
+        self.vx, self.vy = cfg["voxel_size"][:2]
+        self.xo = self.vx / 2 + cfg["point_cloud_range"][0]
+        self.yo = self.vy / 2 + cfg["point_cloud_range"][1]
+        self.pre = cfg["nms_pre_max_size"]
+        self.post = cfg["nms_post_max_size"]
+        self.thr = cfg["nms_iou_threshold"]
+        if max_total_points is None:
+            max_total_points = self.B * 410_000
+        self.max_pts = int(max_total_points)
+        L = _lib.lib()
+        with torch.cuda.device(self.dev):
+            an = _synth.anchors_stride(cfg) if anchors is None else np.asarray(anchors, np.float32)
+            self.anchors = torch.from_numpy(np.ascontiguousarray(an)).to(self.dev)
+            self.A = self.anchors.shape[0]
+            B, MV, P, D, Cc = self.B, self.MV, self.P, self.D, self.C
+            # The pillar cap: per frame at most min(max_voxels, cells) rows
+            self.cap_rows = B * min(MV, self.nx * self.ny * self.nz)
+            e = dict(device=self.dev)
+            self.voxels = torch.empty((self.cap_rows, P, D), dtype=torch.float32, **e) if keep_voxels else None
+            self.decorated = torch.empty((self.cap_rows, P, D + 5), dtype=torch.float32, **e)
+            self.coors = torch.empty((self.cap_rows, 4), dtype=torch.int32, **e)
+            self.num_points = torch.empty((self.cap_rows,), dtype=torch.int32, **e)
+            self.voxel_num = torch.zeros((B,), dtype=torch.int32, **e)
+            self.voxel_base = torch.zeros((B + 1,), dtype=torch.int32, **e)
+            self.canvas = torch.empty((B, Cc, self.ny, self.nx) if layout == "NCHW" else (B, self.ny, self.nx, Cc),
+                                      dtype=torch.float32, **e)
+            self.boxes = torch.empty((B, self.A, 7), dtype=torch.float32, **e)
+            self.standup = torch.empty((B, self.A, 4), dtype=torch.float32, **e)
+            self.keep = torch.empty((B, self.post), dtype=torch.int32, **e)
+            self.keep_count = torch.zeros((B,), dtype=torch.int32, **e)
+            self.dets = torch.empty((B, self.post, 8), dtype=torch.float32, **e)
+            self.ws_vox_bytes = int(L.pp_voxelize_workspace_bytes(C.byref(self.vcfg), self.max_pts, B))
+            self.ws_sc_bytes = int(L.pp_scatter_workspace_bytes(B, self.ny, self.nx, self.cap_rows))
+            kind = _lib.PP_NMS_ROTATED if rotated_nms else _lib.PP_NMS_STANDUP
+            self.nms_kind = kind
+            self.ws_nms_bytes = int(L.pp_nms_workspace_bytes(kind, B, self.A, self.pre))
+            self.ws_vox = torch.empty((self.ws_vox_bytes,), dtype=torch.uint8, **e)
+            self.ws_sc = torch.empty((self.ws_sc_bytes,), dtype=torch.uint8, **e)
+            self.ws_nms = torch.empty((self.ws_nms_bytes,), dtype=torch.uint8, **e)
+            self.dets_host = torch.empty((B, self.post, 8), dtype=torch.float32).pin_memory()
+            self.keep_count_host = torch.empty((B,), dtype=torch.int32).pin_memory()
+
+    # ---- stages (async on the current torch stream) ------------------------------------------
+    def voxelize(self, points, frame_off, n_frames, total_points, max_frame_points, stream):
+        L = _lib.lib()
+        _lib.check(L.pp_voxelize_dev(
+            C.byref(self.vcfg), _p(points), _lib.PP_F64 if points.dtype == torch.float64 else _lib.PP_F32, self.D,
+            _p(frame_off), n_frames, total_points, max_frame_points, _lib.PP_F32,
+            _p(self.voxels) if self.keep_voxels else None, _p(self.decorated) if self.fused else None,
+            _p(self.coors), 4, _p(self.num_points), self.cap_rows, _p(self.voxel_num), _p(self.voxel_base),
+            None, None, _p(self.ws_vox), self.ws_vox_bytes, stream))
+        if not self.fused:
+            # M is only known on the device: decorate the capacity (rows past M are scratch)
+            raise NotImplementedError("unfused decoration needs the host to know M; use fused_decorate=True")
+
+    def scatter(self, pfn_feats, n_frames, stream):
+        L = _lib.lib()
+        _lib.check(L.pp_scatter_dev(_p(pfn_feats), _p(self.coors), min(pfn_feats.shape[0], self.cap_rows),
+                                    C.c_void_p(self.voxel_base.data_ptr() + 4 * n_frames), self.C, n_frames, self.ny,
+                                    self.nx, _lib.PP_LAYOUT_NCHW if self.layout == "NCHW" else _lib.PP_LAYOUT_NHWC,
+                                    _p(self.canvas), _p(self.ws_sc), self.ws_sc_bytes, stream))
+
+    def postprocess(self, box_enc, scores, n_frames, stream):
+        L = _lib.lib()
+        A = self.A
+        _lib.check(L.pp_box_decode_dev(_p(box_enc), _p(self.anchors), n_frames * A, A, _p(self.boxes), stream))
+        if self.rotated:
+            _lib.check(L.pp_nms_dev(self.nms_kind, _p(self.boxes), 7, _p(scores), None, n_frames, A, self.pre,
+                                    self.post, self.thr, _p(self.keep), self.post, _p(self.keep_count),
+                                    _p(self.ws_nms), self.ws_nms_bytes, stream))
+        else:
+            _lib.check(L.pp_rbox_to_standup_dev(_p(self.boxes), 7, n_frames * A, _p(self.standup), stream))
+            _lib.check(L.pp_nms_dev(self.nms_kind, _p(self.standup), 4, _p(scores), None, n_frames, A, self.pre,
+                                    self.post, self.thr, _p(self.keep), self.post, _p(self.keep_count),
+                                    _p(self.ws_nms), self.ws_nms_bytes, stream))
+        _lib.check(L.pp_gather_dets_dev(_p(self.boxes), 7, _p(scores), n_frames, A, _p(self.keep), self.post,
+                                        _p(self.keep_count), self.post, _p(self.dets), stream))
+
+    # ---- whole path ---------------------------------------------------------------------------
+    def run(self, points, frame_off, n_frames, total_points, max_frame_points, pfn_feats, box_enc, scores):
+        """All arguments are device tensors (frame_off int64 [n_frames+1]); async."""
+        st = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        self.voxelize(points, frame_off, n_frames, total_points, max_frame_points, st)
+        self.scatter(pfn_feats, n_frames, st)
+        self.postprocess(box_enc, scores, n_frames, st)
+
+    def fetch(self, n_frames):
+        """Detections to pinned host memory (async on the current stream)."""
+        self.dets_host[:n_frames].copy_(self.dets[:n_frames], non_blocking=True)
+        self.keep_count_host[:n_frames].copy_(self.keep_count[:n_frames], non_blocking=True)
+        return self.dets_host, self.keep_count_host
+
+
+def shard_frames(n_frames, world_size, rank):
+    """Contiguous block sharding of independent frames across ranks: no collective
+    on the data path.  Returns (first, count)."""
+    base, rem = divmod(n_frames, world_size)
+    first = rank * base + min(rank, rem)
+    return first, base + (1 if rank < rem else 0)
+
+
+def gather_detections(local_dets, local_counts, world_size):
+    """Final detections are gathered on the host (rank 0) -- the only cross-rank step.
+    Uses torch.distributed (gloo/NCCL object gather) when initialised, else returns local."""
+    import torch.distributed as dist
+    if world_size == 1 or not dist.is_initialized():
+        return [local_dets], [local_counts]
+    dets_list = [None] * world_size if dist.get_rank() == 0 else None
+    cnts_list = [None] * world_size if dist.get_rank() == 0 else None
+    dist.gather_object(local_dets, dets_list, dst=0)
+    dist.gather_object(local_counts, cnts_list, dst=0)
+    return dets_list, cnts_list

@@ -54,6 +54,13 @@ PP_API int pp_version(void);
  * (bench.py's gpu_launches). */
 PP_API int64_t pp_launch_count(int reset);
 
+/* Per-launch device timing (the reference's measure_time_extended timers, model/voxelnet.py:
+ * 753-760, done with CUDA events on the launching stream).  pp_profile_start() arms this thread;
+ * pp_profile_stop() synchronises and returns the number of records: names as '\n'-separated
+ * text in launch order, ms[i] the device time of launch i. */
+PP_API int pp_profile_start(void);
+PP_API int pp_profile_stop(char* names, size_t names_cap, float* ms, int max_records);
+
 /* ---- grid -------------------------------------------------------------------------------
  * np.round((range[3:]-range[:3])/voxel_size).astype(int32), round-half-to-even:
  * load_data.py:612-615 and 730-731.  arith_f32: the wrapper cast python lists to float32
@@ -142,7 +149,8 @@ PP_API int pp_rbox_to_standup_dev(const float* boxes, int in_stride, int64_t N, 
  *   libraries/eval_helper_functions.py:463-598 (axis-aligned IoU with the "+1" convention);
  *   boxes [B,N,4] (xmin,ymin,xmax,ymax).
  * kind PP_NMS_ROTATED replaces rotate_nms_gpu / rotate_nms_kernel / devRotateIoU,
- *   second/core/non_max_suppression/nms_gpu.py:180-490; boxes [B,N,5] (x,y,w,l,angle).
+ *   second/core/non_max_suppression/nms_gpu.py:180-490; boxes [B,N,5] (x,y,w,l,angle), or
+ *   box_stride 7: decoded boxes (x,y,z,w,l,h,r), BEV columns 0,1,3,4,6 read in place.
  * Both: scores [B,N]; order = descending score, ties by descending index; optional top
  * pre_max_size (<=0: all), greedy suppression of IoU > thresh (strict, thresh rounded to
  * float32), first post_max_size kept (<=0: all).
@@ -156,6 +164,13 @@ PP_API int pp_nms_dev(int kind, const float* boxes, int box_stride, const float*
                const int32_t* n_valid, int B, int64_t N, int pre_max_size, int post_max_size,
                float thresh, int32_t* keep, int64_t keep_stride, int32_t* keep_count,
                void* workspace, size_t workspace_bytes, void* stream);
+
+/* Final detections of a batch (the only tensor the pipeline copies back to the host):
+ * out[b,k,:] = (boxes[b,keep[b,k],0:box_dim], scores[b,keep[b,k]]) for k < keep_count[b], zeros
+ * after.  Mirrors `box_preds[selected]`, `top_scores[selected]`, model/voxelnet.py:1281-1287. */
+PP_API int pp_gather_dets_dev(const float* boxes, int box_dim, const float* scores, int B, int64_t N,
+                       const int32_t* keep, int64_t keep_stride, const int32_t* keep_count, int K,
+                       float* out, void* stream);
 
 /* ---- rotated IoU matrix -----------------------------------------------------------------
  * Replaces rotate_iou_gpu and rotate_iou_gpu_eval, nms_gpu.py:526-561 and 618-653 (kernels
