@@ -24,8 +24,8 @@
 namespace pp {
 
 struct VoxParams {
-    double lo[3], vs[3];
-    float lo32[3], vs32[3];
+    double lo[3], vs[3], inv[3];
+    float lo32[3], vs32[3], inv32[3];
     int grid[3];  // nx, ny, nz
     int ncell;
     int max_points, max_voxels, reverse_index, arith_f32;
@@ -45,17 +45,29 @@ __device__ __forceinline__ int64_t word_base(const int64_t* frame_off, int b) {
 
 // ---------------------------------------------------------------------------------------------
 // cell id in the reference's arithmetic (load_data.py:620-626).  -1: outside the grid or NaN.
+// floor((p - lo) / vs) must equal the reference's correctly rounded IEEE division.
+// The quotient is first formed with a reciprocal multiply (relative error < 2^-51 in float64,
+// < 2^-22 in float32); only when it lands within a 2^-48 (2^-20) relative band of an integer --
+// where the two roundings could fall on different sides -- is the exact division evaluated.
 template <typename T, bool A32>
 __device__ __forceinline__ int cell_of(const T* q, const VoxParams& p) {
     int c[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         if (A32) {
-            const float v = floorf(__fdiv_rn(__fsub_rn((float)q[j], p.lo32[j]), p.vs32[j]));
+            const float d = __fsub_rn((float)q[j], p.lo32[j]);
+            const float qq = __fmul_rn(d, p.inv32[j]);
+            float v = floorf(qq);
+            const float frac = __fsub_rn(qq, v), tol = fabsf(qq) * 0x1p-20f + 1e-30f;
+            if (frac < tol || frac > 1.f - tol) v = floorf(__fdiv_rn(d, p.vs32[j]));
             if (!(v >= 0.f) || !((double)v < (double)p.grid[j])) return -1;
             c[j] = (int)v;
         } else {
-            const double v = floor(__ddiv_rn(__dsub_rn((double)q[j], p.lo[j]), p.vs[j]));
+            const double d = __dsub_rn((double)q[j], p.lo[j]);
+            const double qq = __dmul_rn(d, p.inv[j]);
+            double v = floor(qq);
+            const double frac = __dsub_rn(qq, v), tol = fabs(qq) * 0x1p-48 + 1e-300;
+            if (frac < tol || frac > 1.0 - tol) v = floor(__ddiv_rn(d, p.vs[j]));
             if (!(v >= 0.0) || !(v < (double)p.grid[j])) return -1;
             c[j] = (int)v;
         }
@@ -64,8 +76,13 @@ __device__ __forceinline__ int cell_of(const T* q, const VoxParams& p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Pass 1: one point per thread.  The block's rows are staged through shared memory with 16-byte
-// loads (rows are 12/16/24/32 bytes, so per-thread row loads would be strided).
+// Pass 1: kMarkPPT points per thread.  The block's rows are staged through shared memory with
+// 16-byte loads (rows are 12/16/24/32 bytes, so per-thread row loads would be strided); round r
+// of thread t handles point base + r*256 + t, so lanes of a warp always hold consecutive,
+// increasing point indices.  The rounds are independent: their atomics are in flight together.
+constexpr int kMarkPPT = 4;
+constexpr int kMarkTile = kMarkThreads * kMarkPPT;
+
 template <typename T, bool A32>
 __global__ void __launch_bounds__(kMarkThreads)
 vox_mark_kernel(const T* __restrict__ points, const int64_t* __restrict__ frame_off, VoxParams p,
@@ -75,9 +92,9 @@ vox_mark_kernel(const T* __restrict__ points, const int64_t* __restrict__ frame_
     const int b = blockIdx.y;
     const int64_t f0 = frame_off[b];
     const int n = (int)(frame_off[b + 1] - f0);
-    const int base = blockIdx.x * kMarkThreads;
+    const int base = blockIdx.x * kMarkTile;
     if (base >= n) return;
-    const int m = min(kMarkThreads, n - base);
+    const int m = min(kMarkTile, n - base);
     const int row_bytes = p.D * (int)sizeof(T);
     const int64_t start = (f0 + base) * (int64_t)row_bytes;  // byte offset into points
     const int64_t end = start + (int64_t)m * row_bytes;
@@ -107,26 +124,33 @@ vox_mark_kernel(const T* __restrict__ points, const int64_t* __restrict__ frame_
     }
     __syncthreads();
 
-    const int t = threadIdx.x;
-    int cell = -1;
-    if (t < m) cell = cell_of<T, A32>(reinterpret_cast<const T*>(smem + shift + (size_t)t * row_bytes), p);
-    const unsigned peers = __match_any_sync(0xffffffffu, cell);
-    int pos = 0;
-    if (cell >= 0) {
-        const int leader = __ffs(peers) - 1;
-        const size_t gc = (size_t)b * p.ncell + cell;
-        int basepos = 0;
-        if ((int)lane_id() == leader) {
-            // lanes are in index order, so the leader carries the group's smallest index
-            atomicMin(&first_idx[gc], (unsigned)(base + t));
-            basepos = atomicAdd(&cnt[gc], __popc(peers));
-        }
-        basepos = __shfl_sync(peers, basepos, leader);
-        pos = basepos + __popc(peers & lanemask_lt());
+    int cell[kMarkPPT];
+#pragma unroll
+    for (int r = 0; r < kMarkPPT; ++r) {
+        const int t = r * kMarkThreads + threadIdx.x;
+        cell[r] = t < m ? cell_of<T, A32>(reinterpret_cast<const T*>(smem + shift + (size_t)t * row_bytes), p) : -1;
     }
-    if (t < m) {
-        cellpos[f0 + base + t] = make_int2(cell, pos);
-        if (point_slot) point_slot[f0 + base + t] = -1;
+    unsigned peers[kMarkPPT];
+    int basepos[kMarkPPT];
+#pragma unroll
+    for (int r = 0; r < kMarkPPT; ++r) {
+        peers[r] = __match_any_sync(0xffffffffu, cell[r]);
+        basepos[r] = 0;
+        if (cell[r] >= 0 && (int)lane_id() == __ffs(peers[r]) - 1) {
+            // lanes are in index order, so the leader carries the group's smallest index
+            const size_t gc = (size_t)b * p.ncell + cell[r];
+            atomicMin(&first_idx[gc], (unsigned)(base + r * kMarkThreads + threadIdx.x));
+            basepos[r] = atomicAdd(&cnt[gc], __popc(peers[r]));
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kMarkPPT; ++r) {
+        const int t = r * kMarkThreads + threadIdx.x;
+        const int bp = __shfl_sync(0xffffffffu, basepos[r], __ffs(peers[r]) - 1);
+        if (t < m) {
+            cellpos[f0 + base + t] = make_int2(cell[r], bp + __popc(peers[r] & lanemask_lt()));
+            if (point_slot) point_slot[f0 + base + t] = -1;
+        }
     }
 }
 
@@ -215,22 +239,109 @@ vox_rank_kernel(const unsigned* __restrict__ bitmap, unsigned* __restrict__ word
 }
 
 // ---------------------------------------------------------------------------------------------
-// Pass 4: bucket fill.
+// Pass 4: bucket fill, 4 independent points per thread.
+constexpr int kBucketPPT = 4;
 __global__ void __launch_bounds__(256)
 vox_bucket_kernel(const int2* __restrict__ cellpos, const int64_t* __restrict__ frame_off, int ncell,
                   const int* __restrict__ cell_off, int* __restrict__ bucket) {
     const int b = blockIdx.y;
     const int64_t f0 = frame_off[b];
     const int n = (int)(frame_off[b + 1] - f0);
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
-    const int2 cp = cellpos[f0 + i];
-    if (cp.x >= 0) bucket[f0 + cell_off[(size_t)b * ncell + cp.x] + cp.y] = i;
+    const int base = blockIdx.x * 256 * kBucketPPT + threadIdx.x;
+    if (base - (int)threadIdx.x >= n) return;
+    int2 cp[kBucketPPT];
+    int off[kBucketPPT];
+#pragma unroll
+    for (int r = 0; r < kBucketPPT; ++r) {
+        const int i = base + r * 256;
+        cp[r] = i < n ? cellpos[f0 + i] : make_int2(-1, 0);
+    }
+#pragma unroll
+    for (int r = 0; r < kBucketPPT; ++r) off[r] = cp[r].x >= 0 ? cell_off[(size_t)b * ncell + cp[r].x] : 0;
+#pragma unroll
+    for (int r = 0; r < kBucketPPT; ++r)
+        if (cp[r].x >= 0) bucket[f0 + off[r] + cp[r].y] = base + r * 256;
 }
 
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
 // Pass 5: one warp per occupied cell.
-template <typename T, typename TO>
+//
+// A cell's bucket (unordered point indices) is loaded into registers, striped over the warp
+// (element r*32+lane), cut at the break position, and sorted ascending with a register bitonic
+// network: after the sort, slot s of the voxel is element s, so arrival order needs no shared
+// memory and no search.  Buckets longer than 256 indices (heavy skew) take a streaming path:
+// binary search on the index threshold, compaction, rank-by-counting.
+// The selected points are gathered from global memory exactly once (all loads of a round in
+// flight together) into a float32 row in shared memory; the voxel row and the fused
+// PillarFeatureNet decoration (model/pointpillars.py:143-203) are streamed from it with 16-byte
+// stores.  DS = compile-time point width (3, 4) or 0 for a runtime width.
+constexpr int kSegRegs = 8;  // register path handles buckets up to 32*kSegRegs indices
+constexpr int kIdxInf = 0x7fffffff;
+
+__device__ __forceinline__ void warp_store_row(float* __restrict__ dst, const float* __restrict__ src, int n, int lane) {
+    // dst: global, src: shared (16-byte aligned); n floats
+    const uintptr_t a = reinterpret_cast<uintptr_t>(dst);
+    if ((a & 15) == 0 && (n & 3) == 0) {
+        for (int k = lane; k < (n >> 2); k += 32)
+            reinterpret_cast<float4*>(dst)[k] = reinterpret_cast<const float4*>(src)[k];
+    } else if ((a & 7) == 0 && (n & 1) == 0) {
+        for (int k = lane; k < (n >> 1); k += 32)
+            reinterpret_cast<float2*>(dst)[k] = reinterpret_cast<const float2*>(src)[k];
+    } else {
+        for (int k = lane; k < n; k += 32) dst[k] = src[k];
+    }
+}
+
+// ascending bitonic sort of 32*R ints, element index i = r*32 + lane
+template <int R>
+__device__ __forceinline__ void warp_bitonic_sort(int (&v)[R], int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32 * R; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 32) {
+                const int rs = stride >> 5;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if ((r & rs) == 0) {
+                        const bool up = (((r * 32) & size) == 0);
+                        const int a = v[r], b = v[r | rs];
+                        const int lo = min(a, b), hi = max(a, b);
+                        v[r] = up ? lo : hi;
+                        v[r | rs] = up ? hi : lo;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int o = __shfl_xor_sync(0xffffffffu, v[r], stride);
+                    const bool up = (((r * 32 + lane) & size) == 0);
+                    const bool lower = ((lane & stride) == 0);
+                    v[r] = (up == lower) ? min(v[r], o) : max(v[r], o);
+                }
+            }
+        }
+    }
+}
+
+// load + cut + sort a bucket of up to 32*R indices; returns the number of valid entries
+template <int R>
+__device__ __forceinline__ int load_sort_bucket(const int* __restrict__ seg, int L, int cut, int lane, int (&v)[R]) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int k = lane + 32 * r;
+        const int x = k < L ? seg[k] : kIdxInf;
+        v[r] = x < cut ? x : kIdxInf;
+    }
+    warp_bitonic_sort<R>(v, lane);
+    int n = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) n += __popc(__ballot_sync(0xffffffffu, v[r] != kIdxInf));
+    return n;
+}
+
+template <typename T, typename TO, int DS>
 __global__ void __launch_bounds__(kGatherWarps * 32)
 vox_gather_kernel(const T* __restrict__ points, const int64_t* __restrict__ frame_off, VoxParams p,
                   const int* __restrict__ occ_list, const int* __restrict__ occ_count,
@@ -241,94 +352,133 @@ vox_gather_kernel(const T* __restrict__ points, const int64_t* __restrict__ fram
                   int64_t cap_rows, TO* __restrict__ voxels, float* __restrict__ decorated,
                   int* __restrict__ coors, int coors_cols, int* __restrict__ num_points,
                   int* __restrict__ point_slot, int* __restrict__ cell_voxel) {
-    extern __shared__ int gsm[];
-    const int P = p.max_points, D = p.D;
+    extern __shared__ __align__(16) unsigned char gsm_raw[];
+    const int P = p.max_points;
+    const int D = DS ? DS : p.D;
+    const int Do = D + 5;
     const int lane = lane_id(), w = threadIdx.x >> 5;
-    int* sel = gsm + (size_t)w * 2 * P;
-    int* ord = sel + P;
+    // per-warp carve: ord[P] (int) | vrow[P*D] (float); every region a multiple of 16 bytes
+    const int nord = (P + 3) & ~3, nvox = (P * D + 3) & ~3;
+    int* ord = reinterpret_cast<int*>(gsm_raw + (size_t)w * (nord + nvox) * 4);
+    float* vrow = reinterpret_cast<float*>(ord + nord);
+
     const int nocc = *occ_count;
     const int nwarps = gridDim.x * kGatherWarps;
     for (int e = blockIdx.x * kGatherWarps + w; e < nocc; e += nwarps) {
         const int gc = occ_list[e];
         const int b = gc / p.ncell, cell = gc - b * p.ncell;
         const unsigned f = first_idx[gc];
+        const int L = cnt[gc];
+        const int coff = cell_off[gc];
         const int64_t wb = word_base(frame_off, b);
         const int rank = (int)word_prefix[wb + (f >> 5)] + __popc(bitmap[wb + (f >> 5)] & ((1u << (f & 31)) - 1u));
         if (rank >= p.max_voxels) continue;
         const int64_t row = (int64_t)voxel_base[b] + rank;
         if (row >= cap_rows) continue;
         const int64_t f0 = frame_off[b];
-        const int L = cnt[gc];
-        const int* seg = bucket + f0 + cell_off[gc];
+        const int* seg = bucket + f0 + coff;
         const int cut = cutoff[b];
+        int nsel;
 
-        // how many of the cell's points precede the break position
-        int Lc = 0;
-        for (int k = lane; k < L; k += 32) Lc += seg[k] < cut;
+        // ---- ord[s] = point index of slot s
+        if (L <= 32) {
+            int v[1];
+            nsel = min(load_sort_bucket<1>(seg, L, cut, lane, v), P);
+            if (lane < nsel) ord[lane] = v[0];
+        } else if (L <= 64) {
+            int v[2];
+            nsel = min(load_sort_bucket<2>(seg, L, cut, lane, v), P);
 #pragma unroll
-        for (int o = 16; o; o >>= 1) Lc += __shfl_xor_sync(0xffffffffu, Lc, o);
-        int thr = cut;  // keep indices < thr
-        if (Lc > P) {
-            // smallest thr with #{idx < thr} >= P (indices are distinct, so it is exactly P)
-            int lo = (int)f + 1, hi = cut;
-            while (lo < hi) {
-                const int mid = lo + ((hi - lo) >> 1);
-                int g = 0;
-                for (int k = lane; k < L; k += 32) g += seg[k] < mid;
+            for (int r = 0; r < 2; ++r) if (r * 32 + lane < nsel) ord[r * 32 + lane] = v[r];
+        } else if (L <= 128) {
+            int v[4];
+            nsel = min(load_sort_bucket<4>(seg, L, cut, lane, v), P);
 #pragma unroll
-                for (int o = 16; o; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
-                if (g >= P) hi = mid; else lo = mid + 1;
+            for (int r = 0; r < 4; ++r) if (r * 32 + lane < nsel) ord[r * 32 + lane] = v[r];
+        } else if (L <= 32 * kSegRegs) {
+            int v[kSegRegs];
+            nsel = min(load_sort_bucket<kSegRegs>(seg, L, cut, lane, v), P);
+#pragma unroll
+            for (int r = 0; r < kSegRegs; ++r) if (r * 32 + lane < nsel) ord[r * 32 + lane] = v[r];
+        } else {
+            // ---- long bucket: threshold search streaming the bucket, then rank by counting.
+            // vrow doubles as the unordered selection buffer (P ints <= P*D floats).
+            int* sel = reinterpret_cast<int*>(vrow);
+            int Lc = 0;
+            for (int k = lane; k < L; k += 32) Lc += seg[k] < cut;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) Lc += __shfl_xor_sync(0xffffffffu, Lc, o);
+            int thr = cut;
+            if (Lc > P) {
+                // smallest thr with #{idx < thr} >= P (distinct indices => exactly P)
+                int lo = (int)f + 1, hi = cut;
+                while (lo < hi) {
+                    const int mid = lo + ((hi - lo) >> 1);
+                    int g = 0;
+                    for (int k = lane; k < L; k += 32) g += seg[k] < mid;
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+                    if (g >= P) hi = mid; else lo = mid + 1;
+                }
+                thr = lo;
             }
-            thr = lo;
-        }
-        const int nsel = min(Lc, P);
-        // compact the selected indices
-        int nb = 0;
-        for (int k0 = 0; k0 < L; k0 += 32) {
-            const int k = k0 + lane;
-            const int v = k < L ? seg[k] : 0x7fffffff;
-            const bool pr = v < thr;
-            const unsigned bal = __ballot_sync(0xffffffffu, pr);
-            if (pr) sel[nb + __popc(bal & lanemask_lt())] = v;
-            nb += __popc(bal);
-        }
-        __syncwarp();
-        // arrival order = ascending point index: slot = number of smaller selected indices
-        for (int j = lane; j < nsel; j += 32) {
-            const int v = sel[j];
-            int r = 0;
-            for (int q = 0; q < nsel; ++q) r += sel[q] < v;
-            ord[r] = v;
+            nsel = min(Lc, P);
+            int nb = 0;
+            for (int k0 = 0; k0 < L; k0 += 32) {
+                const int k = k0 + lane;
+                const int x = k < L ? seg[k] : kIdxInf;
+                const bool pr = x < thr;
+                const unsigned bal = __ballot_sync(0xffffffffu, pr);
+                if (pr) sel[nb + __popc(bal & lanemask_lt())] = x;
+                nb += __popc(bal);
+            }
+            __syncwarp();
+            for (int j = lane; j < nsel; j += 32) {
+                const int x = sel[j];
+                int r = 0;
+                for (int q = 0; q < nsel; ++q) r += sel[q] < x;
+                ord[r] = x;
+            }
         }
         __syncwarp();
 
+        const int cx = cell % p.grid[0], cy = (cell / p.grid[0]) % p.grid[1], cz = cell / (p.grid[0] * p.grid[1]);
         if (lane == 0) {
             num_points[row] = nsel;
-            const int x = cell % p.grid[0], y = (cell / p.grid[0]) % p.grid[1], z = cell / (p.grid[0] * p.grid[1]);
             int* co = coors + row * coors_cols;
             if (coors_cols == 4) *co++ = b;
-            if (p.reverse_index) { co[0] = z; co[1] = y; co[2] = x; }
-            else { co[0] = x; co[1] = y; co[2] = z; }
+            if (p.reverse_index) { co[0] = cz; co[1] = cy; co[2] = cx; }
+            else { co[0] = cx; co[1] = cy; co[2] = cz; }
             if (cell_voxel) cell_voxel[gc] = (int)row;
         }
         const T* fp = points + f0 * D;
-        if (voxels) {
-            TO* vrow = voxels + row * (int64_t)P * D;
-            const int nel = P * D;
-            for (int k = lane; k < nel; k += 32) {
-                const int s = k / D;
-                vrow[k] = s < nsel ? (TO)fp[(int64_t)ord[s] * D + (k - s * D)] : (TO)0;
+        // ---- gather each selected point once; zero the padding of the row
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        for (int s = lane; s < nsel; s += 32) {
+            const int pi = ord[s];
+            const T* q = fp + (int64_t)pi * D;
+            if (point_slot) point_slot[f0 + pi] = rank * P + s;
+            if (sizeof(TO) == 8) {
+                TO* vo = voxels + (row * (int64_t)P + s) * D;
+#pragma unroll
+                for (int d = 0; d < (DS ? DS : 16); ++d) if (d < D) vo[d] = (TO)q[d];
             }
+            float c[DS ? DS : 16];
+#pragma unroll
+            for (int d = 0; d < (DS ? DS : 16); ++d) if (d < D) c[d] = (float)q[d];
+#pragma unroll
+            for (int d = 0; d < (DS ? DS : 16); ++d) if (d < D) vrow[s * D + d] = c[d];
+            sx += c[0]; sy += c[1]; sz += c[2];
         }
-        if (point_slot)
-            for (int s = lane; s < nsel; s += 32) point_slot[f0 + ord[s]] = rank * P + s;
+        for (int k = nsel * D + lane; k < P * D; k += 32) vrow[k] = 0.f;
+        if (sizeof(TO) == 8) {
+            TO* vo = voxels + row * (int64_t)P * D;
+            for (int k = nsel * D + lane; k < P * D; k += 32) vo[k] = (TO)0;
+        }
+        __syncwarp();
+        if (voxels && sizeof(TO) == 4)
+            warp_store_row(reinterpret_cast<float*>(voxels) + row * (int64_t)P * D, vrow, P * D, lane);
         if (decorated) {
-            // model/pointpillars.py:143-203 on the float32 voxel row
-            float sx = 0.f, sy = 0.f, sz = 0.f;
-            for (int s = lane; s < nsel; s += 32) {
-                const T* q = fp + (int64_t)ord[s] * D;
-                sx += (float)q[0]; sy += (float)q[1]; sz += (float)q[2];
-            }
 #pragma unroll
             for (int o = 16; o; o >>= 1) {
                 sx += __shfl_xor_sync(0xffffffffu, sx, o);
@@ -337,25 +487,28 @@ vox_gather_kernel(const T* __restrict__ points, const int64_t* __restrict__ fram
             }
             const float nf = (float)nsel;
             const float mx = __fdiv_rn(sx, nf), my = __fdiv_rn(sy, nf), mz = __fdiv_rn(sz, nf);
-            const int cx = cell % p.grid[0], cy = (cell / p.grid[0]) % p.grid[1];
             const float ex = __fadd_rn(__fmul_rn((float)cx, p.vx), p.x_off);
             const float ey = __fadd_rn(__fmul_rn((float)cy, p.vy), p.y_off);
-            const int Do = D + 5;
             float* drow = decorated + row * (int64_t)P * Do;
             const int nel = P * Do;
-            for (int k = lane; k < nel; k += 32) {
+            auto value = [&](int k) -> float {
                 const int s = k / Do, d = k - s * Do;
-                float v = 0.f;
-                if (s < nsel) {
-                    const T* q = fp + (int64_t)ord[s] * D;
-                    if (d < D) v = (float)q[d];
-                    else if (d == D) v = (float)q[0] - mx;
-                    else if (d == D + 1) v = (float)q[1] - my;
-                    else if (d == D + 2) v = (float)q[2] - mz;
-                    else if (d == D + 3) v = (float)q[0] - ex;
-                    else v = (float)q[1] - ey;
+                if (s >= nsel) return 0.f;
+                const float* q = vrow + s * D;
+                if (d < D) return q[d];
+                if (d == D) return q[0] - mx;
+                if (d == D + 1) return q[1] - my;
+                if (d == D + 2) return q[2] - mz;
+                if (d == D + 3) return q[0] - ex;
+                return q[1] - ey;
+            };
+            if ((nel & 3) == 0 && (reinterpret_cast<uintptr_t>(drow) & 15) == 0) {
+                for (int k4 = lane; k4 < (nel >> 2); k4 += 32) {
+                    const int k = k4 << 2;
+                    reinterpret_cast<float4*>(drow)[k4] = make_float4(value(k), value(k + 1), value(k + 2), value(k + 3));
                 }
-                drow[k] = v;
+            } else {
+                for (int k = lane; k < nel; k += 32) drow[k] = value(k);
             }
         }
         __syncwarp();
@@ -435,17 +588,22 @@ extern "C" size_t pp_voxelize_workspace_bytes(const pp_voxel_cfg* cfg, int64_t t
     return carve(nullptr, ncell, total_points, n_frames).total + 256;
 }
 
-template <typename T, typename TO>
+template <typename T, typename TO, int DS>
 static int launch_gather(const VoxParams& p, const VoxWorkspace& w, const void* points,
                          const int64_t* frame_off, int64_t cap_rows, void* voxels, float* decorated,
                          int32_t* coors, int coors_cols, int32_t* num_points,
                          const int32_t* voxel_base, int32_t* point_slot, int32_t* cell_voxel,
                          int64_t max_occ, cudaStream_t st) {
-    const size_t smem = (size_t)kGatherWarps * 2 * p.max_points * sizeof(int);
-    auto kern = vox_gather_kernel<T, TO>;
+    const int P_ = p.max_points, D_ = p.D;
+    const size_t per_warp = (size_t)(((P_ + 3) & ~3) + ((P_ * D_ + 3) & ~3)) * 4;
+    const size_t smem = (size_t)kGatherWarps * per_warp;
+    PP_CHECK_ARG(smem <= 200 * 1024, "pp_voxelize_dev: max_points * D too large for the gather pass");
+    auto kern = vox_gather_kernel<T, TO, DS>;
     if (smem > 48 * 1024) PP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t blocks = ceil_div(max_occ, kGatherWarps);
-    const int64_t cap = (int64_t)kNumSM * 8;
+    int per_sm = 0;
+    PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kGatherWarps * 32, smem));
+    const int64_t cap = (int64_t)kNumSM * (per_sm > 0 ? per_sm : 1);  // persistent: one resident wave
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     PP_TIMED("vox_gather", st);
@@ -479,6 +637,8 @@ extern "C" int pp_voxelize_dev(const pp_voxel_cfg* cfg, const void* points, int 
     PP_CHECK_ARG(cfg->max_voxels >= 0, "max_voxels < 0");
     PP_CHECK_ARG(!(cfg->arith_f32 && point_dtype == PP_F64), "arith_f32 needs float32 points");
     PP_CHECK_ARG(total_points == 0 || points, "points is null");
+    PP_CHECK_ARG(voxels || decorated, "pp_voxelize_dev: voxels and decorated are both null");
+    PP_CHECK_ARG(!(out_dtype == PP_F64 && !voxels), "pp_voxelize_dev: float64 output needs voxels");
     int32_t grid[3];
     const int64_t ncell = ncell_of(cfg, grid);
     PP_CHECK_ARG(grid[0] > 0 && grid[1] > 0 && grid[2] > 0, "empty grid %d x %d x %d", grid[0], grid[1], grid[2]);
@@ -494,6 +654,7 @@ extern "C" int pp_voxelize_dev(const pp_voxel_cfg* cfg, const void* points, int 
     for (int j = 0; j < 3; ++j) {
         p.lo[j] = cfg->coors_range[j]; p.vs[j] = cfg->voxel_size[j];
         p.lo32[j] = (float)cfg->coors_range[j]; p.vs32[j] = (float)cfg->voxel_size[j];
+        p.inv[j] = 1.0 / p.vs[j]; p.inv32[j] = 1.0f / p.vs32[j];
         p.grid[j] = grid[j];
     }
     p.ncell = (int)ncell; p.max_points = cfg->max_points; p.max_voxels = cfg->max_voxels;
@@ -510,10 +671,16 @@ extern "C" int pp_voxelize_dev(const pp_voxel_cfg* cfg, const void* points, int 
     }
 
     if (max_frame_points > 0) {
-        const dim3 g((unsigned)ceil_div(max_frame_points, kMarkThreads), n_frames);
+        const dim3 g((unsigned)ceil_div(max_frame_points, kMarkTile), n_frames);
         const int esz = point_dtype == PP_F64 ? 8 : 4;
-        const size_t smem = (size_t)kMarkThreads * D * esz + 32;
+        const size_t smem = (size_t)kMarkTile * D * esz + 32;
         const int aligned16 = (reinterpret_cast<uintptr_t>(points) & 15) == 0;
+        PP_CHECK_ARG(smem <= 200 * 1024, "pp_voxelize_dev: D too large for the mark pass");
+        if (smem > 48 * 1024) {
+            PP_CUDA(cudaFuncSetAttribute(vox_mark_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PP_CUDA(cudaFuncSetAttribute(vox_mark_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PP_CUDA(cudaFuncSetAttribute(vox_mark_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
         PP_TIMED("vox_mark", st);
         if (point_dtype == PP_F64)
             vox_mark_kernel<double, false><<<g, kMarkThreads, smem, st>>>(
@@ -545,7 +712,7 @@ extern "C" int pp_voxelize_dev(const pp_voxel_cfg* cfg, const void* points, int 
         PP_LAUNCHED();
     }
     if (max_frame_points > 0) {
-        const dim3 g((unsigned)ceil_div(max_frame_points, 256), n_frames);
+        const dim3 g((unsigned)ceil_div(max_frame_points, 256 * kBucketPPT), n_frames);
         PP_TIMED("vox_bucket", st);
         vox_bucket_kernel<<<g, 256, 0, st>>>(w.cellpos, frame_offsets, (int)ncell, w.cell_off, w.bucket);
         PP_LAUNCHED();
@@ -553,15 +720,13 @@ extern "C" int pp_voxelize_dev(const pp_voxel_cfg* cfg, const void* points, int 
     const int64_t max_occ = (int64_t)nc < total_points ? (int64_t)nc : total_points;
     if (max_occ > 0 && cap_rows > 0) {
         int rc;
-        if (point_dtype == PP_F64 && out_dtype == PP_F64)
-            rc = launch_gather<double, double>(p, w, points, frame_offsets, cap_rows, voxels, decorated, coors,
-                                               coors_cols, num_points, voxel_base, point_slot, cell_voxel, max_occ, st);
-        else if (point_dtype == PP_F64)
-            rc = launch_gather<double, float>(p, w, points, frame_offsets, cap_rows, voxels, decorated, coors,
-                                              coors_cols, num_points, voxel_base, point_slot, cell_voxel, max_occ, st);
-        else
-            rc = launch_gather<float, float>(p, w, points, frame_offsets, cap_rows, voxels, decorated, coors,
-                                             coors_cols, num_points, voxel_base, point_slot, cell_voxel, max_occ, st);
+#define PP_GATHER(T, TO, DS)                                                                                   \
+    launch_gather<T, TO, DS>(p, w, points, frame_offsets, cap_rows, voxels, decorated, coors, coors_cols,     \
+                             num_points, voxel_base, point_slot, cell_voxel, max_occ, st)
+        if (point_dtype == PP_F64 && out_dtype == PP_F64) rc = PP_GATHER(double, double, 0);
+        else if (point_dtype == PP_F64) rc = D == 3 ? PP_GATHER(double, float, 3) : D == 4 ? PP_GATHER(double, float, 4) : PP_GATHER(double, float, 0);
+        else rc = D == 3 ? PP_GATHER(float, float, 3) : D == 4 ? PP_GATHER(float, float, 4) : PP_GATHER(float, float, 0);
+#undef PP_GATHER
         if (rc) return rc;
     }
     return PP_OK;
