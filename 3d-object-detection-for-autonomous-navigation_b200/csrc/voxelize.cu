@@ -18,16 +18,31 @@
 //
 // The only nondeterminism is the order inside a bucket, which the gather pass removes.
 #include <math.h>
+#include <stdlib.h>
 
 #include "pp_common.cuh"
 
 namespace pp {
+
+// n / d for 0 <= n < 2^31 with one 32x32->64 multiply (Granlund-Montgomery round-up magic)
+struct FastDiv {
+    unsigned d, m, s;
+    __host__ __device__ FastDiv() : d(1), m(0x80000000u), s(31) {}
+    __host__ explicit FastDiv(unsigned dd) : d(dd) {
+        unsigned l = 0;
+        while ((1ull << l) < dd) ++l;
+        s = 31 + l;
+        m = (unsigned)(((1ull << s) + dd - 1) / dd);
+    }
+    __device__ __forceinline__ int div(int n) const { return (int)(((unsigned long long)(unsigned)n * m) >> s); }
+};
 
 struct VoxParams {
     double lo[3], vs[3], inv[3];
     float lo32[3], vs32[3], inv32[3];
     int grid[3];  // nx, ny, nz
     int ncell;
+    FastDiv div_nx, div_nxny, div_ncell;
     int max_points, max_voxels, reverse_index, arith_f32;
     int D;
     // decoration constants (model/pointpillars.py:121-124), float32 like TF constants
@@ -86,10 +101,10 @@ constexpr int kMarkTile = kMarkThreads * kMarkPPT;
 template <typename T, bool A32>
 __global__ void __launch_bounds__(kMarkThreads)
 vox_mark_kernel(const T* __restrict__ points, const int64_t* __restrict__ frame_off, VoxParams p,
-                int64_t total_points, int aligned16, unsigned* __restrict__ first_idx,
+                int64_t total_points, int aligned16, int b0, unsigned* __restrict__ first_idx,
                 int* __restrict__ cnt, int2* __restrict__ cellpos, int* __restrict__ point_slot) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int b = blockIdx.y;
+    const int b = b0 + blockIdx.y;
     const int64_t f0 = frame_off[b];
     const int n = (int)(frame_off[b + 1] - f0);
     const int base = blockIdx.x * kMarkTile;
@@ -158,13 +173,13 @@ vox_mark_kernel(const T* __restrict__ points, const int64_t* __restrict__ frame_
 // Pass 2: one cell per thread.
 __global__ void __launch_bounds__(kCellThreads)
 vox_cell_kernel(const unsigned* __restrict__ first_idx, const int* __restrict__ cnt,
-                const int64_t* __restrict__ frame_off, int ncell, unsigned* __restrict__ bitmap,
+                const int64_t* __restrict__ frame_off, int ncell, int b0, unsigned* __restrict__ bitmap,
                 int* __restrict__ cell_off, int* __restrict__ frame_cursor,
                 int* __restrict__ occ_list, int* __restrict__ occ_count,
                 int* __restrict__ cell_voxel) {
     __shared__ int sm[33];
     __shared__ int s_base, s_obase;
-    const int b = blockIdx.y;
+    const int b = b0 + blockIdx.y;
     const int cell = blockIdx.x * kCellThreads + threadIdx.x;
     const size_t gc = (size_t)b * ncell + cell;
     const int c = cell < ncell ? cnt[gc] : 0;
@@ -190,12 +205,12 @@ vox_cell_kernel(const unsigned* __restrict__ first_idx, const int* __restrict__ 
 // count, break position; the last block to finish scans the voxel counts of all frames.
 __global__ void __launch_bounds__(kRankThreads)
 vox_rank_kernel(const unsigned* __restrict__ bitmap, unsigned* __restrict__ word_prefix,
-                const int64_t* __restrict__ frame_off, int B, int max_voxels,
+                const int64_t* __restrict__ frame_off, int b0, int B, int max_voxels,
                 int* __restrict__ voxel_num, int* __restrict__ cutoff, int* __restrict__ voxel_base,
                 int* __restrict__ done_counter) {
     __shared__ int sm[33];
     __shared__ int s_cut, s_last;
-    const int b = blockIdx.x;
+    const int b = b0 + blockIdx.x;
     const int n = (int)(frame_off[b + 1] - frame_off[b]);
     const int words = (n + 31) >> 5;
     const int64_t wb = word_base(frame_off, b);
@@ -223,17 +238,18 @@ vox_rank_kernel(const unsigned* __restrict__ bitmap, unsigned* __restrict__ word
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    running = 0;
+    // rows continue where the previous chunk of frames stopped (chunks run in stream order)
+    running = b0 ? __ldcg(&voxel_base[b0]) : 0;
     for (int s = 0; s < B; s += kRankThreads) {
         const int i = s + threadIdx.x;
-        const int v = i < B ? __ldcg(&voxel_num[i]) : 0;
+        const int v = i < B ? __ldcg(&voxel_num[b0 + i]) : 0;
         int tot;
         const int ex = running + block_excl_scan(v, &tot, sm);
-        if (i < B) voxel_base[i] = ex;
+        if (i < B) voxel_base[b0 + i] = ex;
         running += tot;
     }
     if (threadIdx.x == 0) {
-        voxel_base[B] = running;
+        voxel_base[b0 + B] = running;
         *done_counter = 0;
     }
 }
@@ -242,9 +258,9 @@ vox_rank_kernel(const unsigned* __restrict__ bitmap, unsigned* __restrict__ word
 // Pass 4: bucket fill, 4 independent points per thread.
 constexpr int kBucketPPT = 4;
 __global__ void __launch_bounds__(256)
-vox_bucket_kernel(const int2* __restrict__ cellpos, const int64_t* __restrict__ frame_off, int ncell,
+vox_bucket_kernel(const int2* __restrict__ cellpos, const int64_t* __restrict__ frame_off, int ncell, int b0,
                   const int* __restrict__ cell_off, int* __restrict__ bucket) {
-    const int b = blockIdx.y;
+    const int b = b0 + blockIdx.y;
     const int64_t f0 = frame_off[b];
     const int n = (int)(frame_off[b + 1] - f0);
     const int base = blockIdx.x * 256 * kBucketPPT + threadIdx.x;
@@ -357,19 +373,29 @@ vox_gather_kernel(const T* __restrict__ points, const int64_t* __restrict__ fram
     const int D = DS ? DS : p.D;
     const int Do = D + 5;
     const int lane = lane_id(), w = threadIdx.x >> 5;
-    // per-warp carve: ord[P] (int) | vrow[P*D] (float); every region a multiple of 16 bytes
-    const int nord = (P + 3) & ~3, nvox = (P * D + 3) & ~3;
-    int* ord = reinterpret_cast<int*>(gsm_raw + (size_t)w * (nord + nvox) * 4);
+    // per-warp carve: ord[P] (int) | vrow[P*D] | drow[P*Do] (float, only when DS != 3); every region
+    // a multiple of 16 bytes
+    const int nord = (P + 3) & ~3, nvox = (P * D + 3) & ~3, ndec = DS == 3 ? 0 : ((P * Do + 3) & ~3);
+    int* ord = reinterpret_cast<int*>(gsm_raw + (size_t)w * (nord + nvox + ndec) * 4);
     float* vrow = reinterpret_cast<float*>(ord + nord);
+    float* dsm = vrow + nvox;
 
     const int nocc = *occ_count;
     const int nwarps = gridDim.x * kGatherWarps;
-    for (int e = blockIdx.x * kGatherWarps + w; e < nocc; e += nwarps) {
-        const int gc = occ_list[e];
-        const int b = gc / p.ncell, cell = gc - b * p.ncell;
-        const unsigned f = first_idx[gc];
-        const int L = cnt[gc];
-        const int coff = cell_off[gc];
+    // one-deep software pipeline on the per-cell metadata: the next cell's first/count/offset
+    // loads are issued before this cell's bucket is processed
+    int e = blockIdx.x * kGatherWarps + w;
+    int gc_n = 0, L_n = 0, coff_n = 0;
+    unsigned f_n = 0;
+    if (e < nocc) { gc_n = occ_list[e]; f_n = first_idx[gc_n]; L_n = cnt[gc_n]; coff_n = cell_off[gc_n]; }
+    for (; e < nocc; e += nwarps) {
+        const int gc = gc_n, L = L_n, coff = coff_n;
+        const unsigned f = f_n;
+        if (e + nwarps < nocc) {
+            gc_n = occ_list[e + nwarps];
+            f_n = first_idx[gc_n]; L_n = cnt[gc_n]; coff_n = cell_off[gc_n];
+        }
+        const int b = p.div_ncell.div(gc), cell = gc - b * p.ncell;
         const int64_t wb = word_base(frame_off, b);
         const int rank = (int)word_prefix[wb + (f >> 5)] + __popc(bitmap[wb + (f >> 5)] & ((1u << (f & 31)) - 1u));
         if (rank >= p.max_voxels) continue;
@@ -442,7 +468,9 @@ vox_gather_kernel(const T* __restrict__ points, const int64_t* __restrict__ fram
         }
         __syncwarp();
 
-        const int cx = cell % p.grid[0], cy = (cell / p.grid[0]) % p.grid[1], cz = cell / (p.grid[0] * p.grid[1]);
+        const int cz = p.div_nxny.div(cell);
+        const int rem = cell - cz * p.grid[0] * p.grid[1];
+        const int cy = p.div_nx.div(rem), cx = rem - cy * p.grid[0];
         if (lane == 0) {
             num_points[row] = nsel;
             int* co = coors + row * coors_cols;
@@ -470,7 +498,12 @@ vox_gather_kernel(const T* __restrict__ points, const int64_t* __restrict__ fram
             for (int d = 0; d < (DS ? DS : 16); ++d) if (d < D) vrow[s * D + d] = c[d];
             sx += c[0]; sy += c[1]; sz += c[2];
         }
-        for (int k = nsel * D + lane; k < P * D; k += 32) vrow[k] = 0.f;
+        {   // zero the padding: scalar up to the next 16-byte boundary, then float4
+            const int z0 = nsel * D, z1 = min((z0 + 3) & ~3, P * D);
+            if (z0 + lane < z1) vrow[z0 + lane] = 0.f;
+            for (int k4 = ((z1 + 3) >> 2) + lane; k4 < (nvox >> 2); k4 += 32)
+                reinterpret_cast<float4*>(vrow)[k4] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         if (sizeof(TO) == 8) {
             TO* vo = voxels + row * (int64_t)P * D;
             for (int k = nsel * D + lane; k < P * D; k += 32) vo[k] = (TO)0;
@@ -490,25 +523,44 @@ vox_gather_kernel(const T* __restrict__ points, const int64_t* __restrict__ fram
             const float ex = __fadd_rn(__fmul_rn((float)cx, p.vx), p.x_off);
             const float ey = __fadd_rn(__fmul_rn((float)cy, p.vy), p.y_off);
             float* drow = decorated + row * (int64_t)P * Do;
-            const int nel = P * Do;
-            auto value = [&](int k) -> float {
-                const int s = k / Do, d = k - s * Do;
-                if (s >= nsel) return 0.f;
-                const float* q = vrow + s * D;
-                if (d < D) return q[d];
-                if (d == D) return q[0] - mx;
-                if (d == D + 1) return q[1] - my;
-                if (d == D + 2) return q[2] - mz;
-                if (d == D + 3) return q[0] - ex;
-                return q[1] - ey;
-            };
-            if ((nel & 3) == 0 && (reinterpret_cast<uintptr_t>(drow) & 15) == 0) {
-                for (int k4 = lane; k4 < (nel >> 2); k4 += 32) {
-                    const int k = k4 << 2;
-                    reinterpret_cast<float4*>(drow)[k4] = make_float4(value(k), value(k + 1), value(k + 2), value(k + 3));
+            if (DS == 3 && (reinterpret_cast<uintptr_t>(decorated) & 15) == 0) {
+                // 8 floats per point = two float4: (x,y,z,x-mx) and (y-my,z-mz,x-ex,y-ey)
+                float4* d4 = reinterpret_cast<float4*>(drow);
+                for (int c = lane; c < 2 * P; c += 32) {
+                    const int s = c >> 1;
+                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (s < nsel) {
+                        const float q0 = vrow[s * 3], q1 = vrow[s * 3 + 1], q2 = vrow[s * 3 + 2];
+                        o = (c & 1) ? make_float4(q1 - my, q2 - mz, q0 - ex, q1 - ey) : make_float4(q0, q1, q2, q0 - mx);
+                    }
+                    d4[c] = o;
+                }
+            } else if (DS == 3) {
+                for (int k = lane; k < P * 8; k += 32) {
+                    const int s = k >> 3, d = k & 7;
+                    float o = 0.f;
+                    if (s < nsel) {
+                        const float* q = vrow + s * 3;
+                        o = d < 3 ? q[d] : d == 3 ? q[0] - mx : d == 4 ? q[1] - my : d == 5 ? q[2] - mz : d == 6 ? q[0] - ex : q[1] - ey;
+                    }
+                    drow[k] = o;
                 }
             } else {
-                for (int k = lane; k < nel; k += 32) drow[k] = value(k);
+                // one point per lane into shared memory (stride Do words), then 16-byte row stores
+                for (int s = lane; s < P; s += 32) {
+                    float* o = dsm + s * Do;
+                    if (s < nsel) {
+                        const float* q = vrow + s * D;
+#pragma unroll
+                        for (int d = 0; d < (DS ? DS : 16); ++d) if (d < D) o[d] = q[d];
+                        o[D] = q[0] - mx; o[D + 1] = q[1] - my; o[D + 2] = q[2] - mz;
+                        o[D + 3] = q[0] - ex; o[D + 4] = q[1] - ey;
+                    } else {
+                        for (int d = 0; d < Do; ++d) o[d] = 0.f;
+                    }
+                }
+                __syncwarp();
+                warp_store_row(drow, dsm, P * Do, lane);
             }
         }
         __syncwarp();
@@ -521,8 +573,8 @@ struct VoxWorkspace {
     int* cnt;             // [B*ncell]  zero init   -- zero region starts here
     unsigned* bitmap;     // [nwords]
     int* frame_cursor;    // [B]
-    int* occ_count;       // [1]
-    int* done_counter;    // [1]        -- zero region ends here
+    int* occ_count;       // [B] (one per chunk of frames)
+    int* done_counter;    // [B]        -- zero region ends here
     unsigned* word_prefix;  // [nwords]
     int* cell_off;        // [B*ncell]
     int* occ_list;        // [B*ncell] (worst case every cell occupied, bounded by total_points)
@@ -543,12 +595,13 @@ static VoxWorkspace carve(void* ws, int64_t ncell, int64_t total_points, int B) 
     w.cnt = c.take<int>(nc);
     w.bitmap = c.take<unsigned>(nwords);
     w.frame_cursor = c.take<int>(B);
-    w.occ_count = c.take<int>(1);
-    w.done_counter = c.take<int>(1);
+    w.occ_count = c.take<int>(B);
+    w.done_counter = c.take<int>(B);
     w.zero_end = c.used();
     w.word_prefix = c.take<unsigned>(nwords);
     w.cell_off = c.take<int>(nc);
-    w.occ_list = c.take<int>(nocc + 1);
+    (void)nocc;
+    w.occ_list = c.take<int>(nc + 1);
     w.cutoff = c.take<int>(B);
     w.cellpos = c.take<int2>((size_t)total_points + 1);
     w.bucket = c.take<int>((size_t)total_points + 1);
@@ -593,9 +646,9 @@ static int launch_gather(const VoxParams& p, const VoxWorkspace& w, const void* 
                          const int64_t* frame_off, int64_t cap_rows, void* voxels, float* decorated,
                          int32_t* coors, int coors_cols, int32_t* num_points,
                          const int32_t* voxel_base, int32_t* point_slot, int32_t* cell_voxel,
-                         int64_t max_occ, cudaStream_t st) {
+                         const int* occ_list, const int* occ_count, int64_t max_occ, cudaStream_t st) {
     const int P_ = p.max_points, D_ = p.D;
-    const size_t per_warp = (size_t)(((P_ + 3) & ~3) + ((P_ * D_ + 3) & ~3)) * 4;
+    const size_t per_warp = (size_t)(((P_ + 3) & ~3) + ((P_ * D_ + 3) & ~3) + (DS == 3 ? 0 : ((P_ * (D_ + 5) + 3) & ~3))) * 4;
     const size_t smem = (size_t)kGatherWarps * per_warp;
     PP_CHECK_ARG(smem <= 200 * 1024, "pp_voxelize_dev: max_points * D too large for the gather pass");
     auto kern = vox_gather_kernel<T, TO, DS>;
@@ -608,7 +661,7 @@ static int launch_gather(const VoxParams& p, const VoxWorkspace& w, const void* 
     if (blocks < 1) blocks = 1;
     PP_TIMED("vox_gather", st);
     kern<<<(unsigned)blocks, kGatherWarps * 32, smem, st>>>(
-        static_cast<const T*>(points), frame_off, p, w.occ_list, w.occ_count, w.first_idx, w.cnt,
+        static_cast<const T*>(points), frame_off, p, occ_list, occ_count, w.first_idx, w.cnt,
         w.cell_off, w.bucket, w.bitmap, w.word_prefix, w.cutoff, voxel_base, cap_rows,
         static_cast<TO*>(voxels), decorated, coors, coors_cols, num_points, point_slot, cell_voxel);
     PP_LAUNCHED();
@@ -657,6 +710,8 @@ extern "C" int pp_voxelize_dev(const pp_voxel_cfg* cfg, const void* points, int 
         p.inv[j] = 1.0 / p.vs[j]; p.inv32[j] = 1.0f / p.vs32[j];
         p.grid[j] = grid[j];
     }
+    p.div_nx = FastDiv((unsigned)grid[0]); p.div_nxny = FastDiv((unsigned)(grid[0] * grid[1]));
+    p.div_ncell = FastDiv((unsigned)ncell);
     p.ncell = (int)ncell; p.max_points = cfg->max_points; p.max_voxels = cfg->max_voxels;
     p.reverse_index = cfg->reverse_index; p.arith_f32 = cfg->arith_f32; p.D = D;
     p.vx = (float)cfg->voxel_size[0]; p.vy = (float)cfg->voxel_size[1];
@@ -670,64 +725,85 @@ extern "C" int pp_voxelize_dev(const pp_voxel_cfg* cfg, const void* points, int 
         PP_CUDA(cudaMemsetAsync(static_cast<char*>(workspace) + w.zero_begin, 0, w.zero_end - w.zero_begin, st));
     }
 
-    if (max_frame_points > 0) {
-        const dim3 g((unsigned)ceil_div(max_frame_points, kMarkTile), n_frames);
-        const int esz = point_dtype == PP_F64 ? 8 : 4;
-        const size_t smem = (size_t)kMarkTile * D * esz + 32;
-        const int aligned16 = (reinterpret_cast<uintptr_t>(points) & 15) == 0;
-        PP_CHECK_ARG(smem <= 200 * 1024, "pp_voxelize_dev: D too large for the mark pass");
-        if (smem > 48 * 1024) {
-            PP_CUDA(cudaFuncSetAttribute(vox_mark_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            PP_CUDA(cudaFuncSetAttribute(vox_mark_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            PP_CUDA(cudaFuncSetAttribute(vox_mark_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // Frames are processed in chunks small enough that a chunk's points and its intermediates
+    // (cell/pos, buckets) stay resident in the 126 MB L2 between the five passes: the points are
+    // then read from HBM once, by the mark pass; the gather pass finds them in L2.
+    const int esz = point_dtype == PP_F64 ? 8 : 4;
+    int chunk_frames = n_frames;
+    {
+        const char* env = getenv("PP_VOX_CHUNK_MB");
+        const double chunk_mb = env ? atof(env) : 0.0;  // measured on B200: per-chunk launch tails cost more than the L2 hits save (profiles/r01_notes.md)
+        const double frame_mb = (double)max_frame_points * D * esz / 1e6;
+        if (chunk_mb > 0 && frame_mb > 0) {
+            chunk_frames = (int)(chunk_mb / frame_mb);
+            if (chunk_frames < 1) chunk_frames = 1;
+            if (chunk_frames > n_frames) chunk_frames = n_frames;
         }
-        PP_TIMED("vox_mark", st);
-        if (point_dtype == PP_F64)
-            vox_mark_kernel<double, false><<<g, kMarkThreads, smem, st>>>(
-                static_cast<const double*>(points), frame_offsets, p, total_points, aligned16,
-                w.first_idx, w.cnt, w.cellpos, point_slot);
-        else if (cfg->arith_f32)
-            vox_mark_kernel<float, true><<<g, kMarkThreads, smem, st>>>(
-                static_cast<const float*>(points), frame_offsets, p, total_points, aligned16,
-                w.first_idx, w.cnt, w.cellpos, point_slot);
-        else
-            vox_mark_kernel<float, false><<<g, kMarkThreads, smem, st>>>(
-                static_cast<const float*>(points), frame_offsets, p, total_points, aligned16,
-                w.first_idx, w.cnt, w.cellpos, point_slot);
-        PP_LAUNCHED();
     }
-    {
-        const dim3 g((unsigned)ceil_div(ncell, kCellThreads), n_frames);
-        PP_TIMED("vox_cell", st);
-        vox_cell_kernel<<<g, kCellThreads, 0, st>>>(w.first_idx, w.cnt, frame_offsets, (int)ncell,
-                                                    w.bitmap, w.cell_off, w.frame_cursor, w.occ_list,
-                                                    w.occ_count, cell_voxel);
-        PP_LAUNCHED();
+    const size_t mark_smem = (size_t)kMarkTile * D * esz + 32;
+    const int aligned16 = (reinterpret_cast<uintptr_t>(points) & 15) == 0;
+    PP_CHECK_ARG(mark_smem <= 200 * 1024, "pp_voxelize_dev: D too large for the mark pass");
+    if (mark_smem > 48 * 1024) {
+        PP_CUDA(cudaFuncSetAttribute(vox_mark_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mark_smem));
+        PP_CUDA(cudaFuncSetAttribute(vox_mark_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mark_smem));
+        PP_CUDA(cudaFuncSetAttribute(vox_mark_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mark_smem));
     }
-    {
-        PP_TIMED("vox_rank", st);
-        vox_rank_kernel<<<n_frames, kRankThreads, 0, st>>>(w.bitmap, w.word_prefix, frame_offsets, n_frames,
-                                                           cfg->max_voxels, voxel_num, w.cutoff, voxel_base,
-                                                           w.done_counter);
-        PP_LAUNCHED();
-    }
-    if (max_frame_points > 0) {
-        const dim3 g((unsigned)ceil_div(max_frame_points, 256 * kBucketPPT), n_frames);
-        PP_TIMED("vox_bucket", st);
-        vox_bucket_kernel<<<g, 256, 0, st>>>(w.cellpos, frame_offsets, (int)ncell, w.cell_off, w.bucket);
-        PP_LAUNCHED();
-    }
-    const int64_t max_occ = (int64_t)nc < total_points ? (int64_t)nc : total_points;
-    if (max_occ > 0 && cap_rows > 0) {
-        int rc;
+    int chunk_id = 0;
+    for (int b0 = 0; b0 < n_frames; b0 += chunk_frames, ++chunk_id) {
+        const int nb = n_frames - b0 < chunk_frames ? n_frames - b0 : chunk_frames;
+        int* occ_list = w.occ_list + (size_t)b0 * ncell;
+        int* occ_count = w.occ_count + chunk_id;
+        if (max_frame_points > 0) {
+            const dim3 g((unsigned)ceil_div(max_frame_points, kMarkTile), nb);
+            PP_TIMED("vox_mark", st);
+            if (point_dtype == PP_F64)
+                vox_mark_kernel<double, false><<<g, kMarkThreads, mark_smem, st>>>(
+                    static_cast<const double*>(points), frame_offsets, p, total_points, aligned16, b0,
+                    w.first_idx, w.cnt, w.cellpos, point_slot);
+            else if (cfg->arith_f32)
+                vox_mark_kernel<float, true><<<g, kMarkThreads, mark_smem, st>>>(
+                    static_cast<const float*>(points), frame_offsets, p, total_points, aligned16, b0,
+                    w.first_idx, w.cnt, w.cellpos, point_slot);
+            else
+                vox_mark_kernel<float, false><<<g, kMarkThreads, mark_smem, st>>>(
+                    static_cast<const float*>(points), frame_offsets, p, total_points, aligned16, b0,
+                    w.first_idx, w.cnt, w.cellpos, point_slot);
+            PP_LAUNCHED();
+        }
+        {
+            const dim3 g((unsigned)ceil_div(ncell, kCellThreads), nb);
+            PP_TIMED("vox_cell", st);
+            vox_cell_kernel<<<g, kCellThreads, 0, st>>>(w.first_idx, w.cnt, frame_offsets, (int)ncell, b0,
+                                                        w.bitmap, w.cell_off, w.frame_cursor, occ_list,
+                                                        occ_count, cell_voxel);
+            PP_LAUNCHED();
+        }
+        {
+            PP_TIMED("vox_rank", st);
+            vox_rank_kernel<<<nb, kRankThreads, 0, st>>>(w.bitmap, w.word_prefix, frame_offsets, b0, nb,
+                                                         cfg->max_voxels, voxel_num, w.cutoff, voxel_base,
+                                                         w.done_counter + chunk_id);
+            PP_LAUNCHED();
+        }
+        if (max_frame_points > 0) {
+            const dim3 g((unsigned)ceil_div(max_frame_points, 256 * kBucketPPT), nb);
+            PP_TIMED("vox_bucket", st);
+            vox_bucket_kernel<<<g, 256, 0, st>>>(w.cellpos, frame_offsets, (int)ncell, b0, w.cell_off, w.bucket);
+            PP_LAUNCHED();
+        }
+        const int64_t chunk_pts = (int64_t)nb * max_frame_points;
+        const int64_t max_occ = (int64_t)nb * ncell < chunk_pts ? (int64_t)nb * ncell : chunk_pts;
+        if (max_occ > 0 && cap_rows > 0) {
+            int rc;
 #define PP_GATHER(T, TO, DS)                                                                                   \
     launch_gather<T, TO, DS>(p, w, points, frame_offsets, cap_rows, voxels, decorated, coors, coors_cols,     \
-                             num_points, voxel_base, point_slot, cell_voxel, max_occ, st)
-        if (point_dtype == PP_F64 && out_dtype == PP_F64) rc = PP_GATHER(double, double, 0);
-        else if (point_dtype == PP_F64) rc = D == 3 ? PP_GATHER(double, float, 3) : D == 4 ? PP_GATHER(double, float, 4) : PP_GATHER(double, float, 0);
-        else rc = D == 3 ? PP_GATHER(float, float, 3) : D == 4 ? PP_GATHER(float, float, 4) : PP_GATHER(float, float, 0);
+                             num_points, voxel_base, point_slot, cell_voxel, occ_list, occ_count, max_occ, st)
+            if (point_dtype == PP_F64 && out_dtype == PP_F64) rc = PP_GATHER(double, double, 0);
+            else if (point_dtype == PP_F64) rc = D == 3 ? PP_GATHER(double, float, 3) : D == 4 ? PP_GATHER(double, float, 4) : PP_GATHER(double, float, 0);
+            else rc = D == 3 ? PP_GATHER(float, float, 3) : D == 4 ? PP_GATHER(float, float, 4) : PP_GATHER(float, float, 0);
 #undef PP_GATHER
-        if (rc) return rc;
+            if (rc) return rc;
+        }
     }
     return PP_OK;
 }
