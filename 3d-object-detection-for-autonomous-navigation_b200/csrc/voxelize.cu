@@ -117,20 +117,25 @@ vox_mark_kernel(const T* __restrict__ points, const int64_t* __restrict__ frame_
     const unsigned char* src = reinterpret_cast<const unsigned char*>(points);
     int shift;
     if (aligned16) {
+        // one TMA bulk copy brings the tile's byte range [a0, a1) into shared memory
+        __shared__ __align__(8) unsigned long long s_bar;
         const int64_t a0 = start & ~(int64_t)15;
         shift = (int)(start - a0);
-        const int nchunk = (int)((end - a0 + 15) >> 4);
-        for (int c = threadIdx.x; c < nchunk; c += kMarkThreads) {
-            const int64_t a = a0 + ((int64_t)c << 4);
-            if (a + 16 <= total_bytes) {
-                *reinterpret_cast<int4*>(smem + ((size_t)c << 4)) =
-                    __ldg(reinterpret_cast<const int4*>(src + a));
-            } else {
-                for (int k = 0; k < 16 && a + k < total_bytes; k += (int)sizeof(T))
-                    *reinterpret_cast<T*>(smem + ((size_t)c << 4) + k) =
-                        *reinterpret_cast<const T*>(src + a + k);
-            }
+        int64_t a1 = (end + 15) & ~(int64_t)15;
+        const int64_t tail0 = total_bytes & ~(int64_t)15;  // last full 16-byte chunk boundary of the buffer
+        if (a1 > tail0) a1 = tail0 > a0 ? tail0 : a0;
+        const unsigned bulk = (unsigned)(a1 - a0);
+        if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0 && bulk) {
+            mbar_arrive_expect_tx(&s_bar, bulk);
+            tma_bulk_g2s(smem, src + a0, bulk, &s_bar);
         }
+        // bytes of the tile past the buffer's last full chunk (at most one partial chunk)
+        for (int64_t a = a1 + (int64_t)threadIdx.x * (int)sizeof(T); a < end && a < total_bytes;
+             a += (int64_t)kMarkThreads * (int)sizeof(T))
+            *reinterpret_cast<T*>(smem + (a - a0)) = *reinterpret_cast<const T*>(src + a);
+        if (bulk) mbar_wait(&s_bar, 0);
     } else {
         shift = 0;
         const int nel = m * p.D;

@@ -1,0 +1,98 @@
+"""GPU: the batched, device-resident pipeline (packed pillars, fused decoration, scatter from device M,
+decode, NMS, detection gather) against the per-frame CPU oracle."""
+import importlib
+
+import numpy as np
+import pytest
+
+from conftest import PKG
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(synth, oracle, cfg, frames, rotated, layout):
+    import torch
+    pipeline = importlib.import_module(PKG + ".pipeline")
+    B = len(frames)
+    D = cfg["num_point_features"]
+    tdtype = torch.float64 if cfg["point_dtype"] == "float64" else torch.float32
+    pts = np.concatenate(frames)
+    off = np.cumsum([0] + [f.shape[0] for f in frames]).astype(np.int64)
+    pipe = pipeline.FramePipeline(cfg, device=0, max_frames=B, max_total_points=pts.shape[0], rotated_nms=rotated,
+                                  layout=layout)
+    A = pipe.A
+    box = np.stack([synth.rpn_standin(A, 50 + i)[0] for i in range(B)])
+    sco = np.stack([synth.rpn_standin(A, 50 + i)[1] for i in range(B)])
+    feats = synth.pfn_standin(pipe.cap_rows, cfg["num_filters"], 3)
+    dev = torch.device("cuda", 0)
+    d_pts = torch.from_numpy(pts).to(dev)
+    assert d_pts.dtype == tdtype
+    pipe.run(d_pts, torch.from_numpy(off).to(dev), B, pts.shape[0], max(f.shape[0] for f in frames),
+             torch.from_numpy(feats).to(dev), torch.from_numpy(box).to(dev), torch.from_numpy(sco).to(dev))
+    dets_h, cnt_h = pipe.fetch(B)
+    torch.cuda.synchronize()
+    vbase = pipe.voxel_base[:B + 1].cpu().numpy()
+    vnum = pipe.voxel_num[:B].cpu().numpy()
+    M = int(vbase[B])
+    vox = pipe.voxels[:M].cpu().numpy(); dec = pipe.decorated[:M].cpu().numpy()
+    coors = pipe.coors[:M].cpu().numpy(); num = pipe.num_points[:M].cpu().numpy()
+    canvas = pipe.canvas[:B].cpu().numpy()
+    vs, pcr = np.array(cfg["voxel_size"]), np.array(cfg["point_cloud_range"])
+    vx, vy = cfg["voxel_size"][:2]
+    xo, yo = vx / 2 + pcr[0], vy / 2 + pcr[1]
+    nx, ny, _ = synth.grid_size(cfg)
+    all_c4 = []
+    for b, f in enumerate(frames):
+        ov, oc, on = oracle.points_to_voxel(f, vs, pcr, cfg["max_points"], True, cfg["max_voxels"])
+        lo, hi = int(vbase[b]), int(vbase[b + 1])
+        assert hi - lo == ov.shape[0] == int(vnum[b])
+        assert np.array_equal(coors[lo:hi, 0], np.full(hi - lo, b)) and np.array_equal(coors[lo:hi, 1:], oc)
+        assert np.array_equal(num[lo:hi], on)
+        assert np.array_equal(vox[lo:hi], ov.astype(np.float32))
+        c4 = np.concatenate([np.full((oc.shape[0], 1), b, np.int32), oc], axis=1)
+        all_c4.append(c4)
+        want = oracle.decorate(ov.astype(np.float32), on, c4, vx, vy, xo, yo)
+        np.testing.assert_allclose(dec[lo:hi], want, rtol=1e-5, atol=1e-5 * (float(np.abs(ov).max()) + 1 if ov.size else 1.0))
+        # decode + NMS
+        boxes = oracle.second_box_decode(box[b], synth.anchors_stride(cfg))
+        if rotated:
+            dets = np.concatenate([boxes[:, [0, 1, 3, 4, 6]], sco[b][:, None]], axis=1)
+            keep = oracle.rotate_nms_gpu(dets, cfg["nms_iou_threshold"], cfg["nms_pre_max_size"], cfg["nms_post_max_size"])
+        else:
+            sb = oracle.rbox_to_standup(boxes[:, [0, 1, 3, 4, 6]])
+            k = oracle.nms(sb, sco[b], cfg["nms_pre_max_size"], cfg["nms_post_max_size"], cfg["nms_iou_threshold"])
+            keep = [] if k is None else k.tolist()
+        assert int(cnt_h[b]) == len(keep)
+        got = dets_h[b, :len(keep)].numpy()
+        np.testing.assert_allclose(got[:, :7], boxes[keep], rtol=1e-5, atol=1e-6)
+        assert np.array_equal(got[:, 7], sco[b][keep])
+        assert not dets_h[b, len(keep):].numpy().any()
+    want_canvas = oracle.scatter(feats[:M], np.concatenate(all_c4), B, ny, nx, layout)
+    assert np.array_equal(canvas, want_canvas)
+
+
+def test_pipeline_d435_batched_ragged(synth, oracle):
+    cfg = synth.D435
+    frames = [synth.d435_cloud(20), synth.d435_cloud(21, subsample=True), synth.d435_cloud(22)[:1000],
+              np.zeros((0, 3), np.float64), synth.d435_cloud(23)[::3]]
+    _run(synth, oracle, cfg, frames, rotated=True, layout="NCHW")
+    _run(synth, oracle, cfg, frames[:2], rotated=False, layout="NHWC")
+
+
+def test_pipeline_kitti_batched(synth, oracle):
+    cfg = dict(synth.KITTI)
+    frames = [synth.kitti_cloud(30), synth.kitti_cloud(31, shuffled=True), synth.uniform_cloud(50000, cfg, 32)]
+    _run(synth, oracle, cfg, frames, rotated=True, layout="NCHW")
+
+
+def test_profiler_and_launch_count(pp, synth):
+    _lib = importlib.import_module(PKG + "._lib")
+    pts = synth.d435_cloud(1, subsample=True)
+    pp.launch_count(reset=True)
+    _lib.profile_start()
+    pp.points_to_voxel(pts, np.array(synth.D435["voxel_size"]), np.array(synth.D435["point_cloud_range"]), 50, True, 12000)
+    rec = _lib.profile_stop()
+    names = [n for n, _ in rec]
+    assert names[:1] == ["vox_memset"] and {"vox_mark", "vox_cell", "vox_rank", "vox_bucket", "vox_gather"} <= set(names)
+    assert all(t >= 0 for _, t in rec)
+    assert pp.launch_count() == 5
