@@ -192,8 +192,11 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # Control plane only (barrier + max-over-ranks of the device time).  The data path has no
+        # collective (frames are independent), so no NCCL communicator is created; gloo on
+        # CPU scalars also keeps stdout to the single JSON line.
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("gloo")
 
     pp = importlib.import_module(PKG)
     pipeline = importlib.import_module(PKG + ".pipeline")
@@ -248,7 +251,7 @@ def main():
         barrier()
         ms = e0.elapsed_time(e1)
         if world > 1:
-            t = torch.tensor([ms], device=dev)
+            t = torch.tensor([ms], dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms
