@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libpp_b200.so")
+LIB = os.environ.get("PP_LIB") or os.path.join(HERE, "libpp_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -24,23 +24,44 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+def _deps():
+    return sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(ROOT, "include", "pp_b200.h")]
+
+
+def source_hash() -> str:
+    """Content hash of every input of the build (mtimes do not survive the snapshot to the GPU box)."""
+    import hashlib
+    h = hashlib.sha256()
+    h.update(" ".join(NVCC_FLAGS + os.environ.get("PP_NVCC_DEFS", "").split()).encode())
+    for d in _deps():
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
+    stamp = LIB + ".srchash"
+    if not os.path.exists(LIB) or not os.path.exists(stamp):
         return True
-    t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(ROOT, "include", "pp_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    if os.environ.get("PP_LIB"):
+        return False  # an explicitly selected prebuilt variant is used as is
+    with open(stamp) as f:
+        return f.read().strip() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB, *sources()]
+    extra = os.environ.get("PP_NVCC_DEFS", "").split()
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB, *sources()]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), file=sys.stderr)
     subprocess.run(cmd, check=True)
+    with open(LIB + ".srchash", "w") as f:
+        f.write(source_hash())
     return LIB
 
 

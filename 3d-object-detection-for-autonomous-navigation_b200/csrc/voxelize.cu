@@ -52,7 +52,13 @@ struct VoxParams {
 constexpr int kMarkThreads = 256;
 constexpr int kCellThreads = 256;
 constexpr int kRankThreads = 1024;
-constexpr int kGatherWarps = 8;
+#ifndef PP_GATHER_WARPS
+#define PP_GATHER_WARPS 8
+#endif
+#ifndef PP_GATHER_MINBLOCKS
+#define PP_GATHER_MINBLOCKS 5
+#endif
+constexpr int kGatherWarps = PP_GATHER_WARPS;
 
 __device__ __forceinline__ int64_t word_base(const int64_t* frame_off, int b) {
     return (frame_off[b] >> 5) + b;
@@ -95,82 +101,129 @@ __device__ __forceinline__ int cell_of(const T* q, const VoxParams& p) {
 // 16-byte loads (rows are 12/16/24/32 bytes, so per-thread row loads would be strided); round r
 // of thread t handles point base + r*256 + t, so lanes of a warp always hold consecutive,
 // increasing point indices.  The rounds are independent: their atomics are in flight together.
-constexpr int kMarkPPT = 4;
+#ifndef PP_MARK_PPT
+#define PP_MARK_PPT 4
+#endif
+constexpr int kMarkPPT = PP_MARK_PPT;
 constexpr int kMarkTile = kMarkThreads * kMarkPPT;
 
+// Persistent CTAs, two shared-memory stages: while a tile is being processed the TMA bulk copy
+// of the CTA's next tile is already in flight (the un-pipelined version spent a third of its
+// stall samples waiting on the tile load).  Tiles are numbered frame-major:
+// tile = frame_in_chunk * tiles_per_frame + tile_in_frame.
 template <typename T, bool A32>
 __global__ void __launch_bounds__(kMarkThreads)
 vox_mark_kernel(const T* __restrict__ points, const int64_t* __restrict__ frame_off, VoxParams p,
-                int64_t total_points, int aligned16, int b0, unsigned* __restrict__ first_idx,
-                int* __restrict__ cnt, int2* __restrict__ cellpos, int* __restrict__ point_slot) {
+                int64_t total_points, int aligned16, int b0, int n_frames, int tiles_per_frame,
+                unsigned* __restrict__ first_idx, int* __restrict__ cnt, int2* __restrict__ cellpos,
+                int* __restrict__ point_slot) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int b = b0 + blockIdx.y;
-    const int64_t f0 = frame_off[b];
-    const int n = (int)(frame_off[b + 1] - f0);
-    const int base = blockIdx.x * kMarkTile;
-    if (base >= n) return;
-    const int m = min(kMarkTile, n - base);
+    __shared__ __align__(8) unsigned long long s_bar[2];
     const int row_bytes = p.D * (int)sizeof(T);
-    const int64_t start = (f0 + base) * (int64_t)row_bytes;  // byte offset into points
-    const int64_t end = start + (int64_t)m * row_bytes;
+    const int stage_bytes = kMarkTile * row_bytes + 32;  // multiple of 16
     const int64_t total_bytes = total_points * (int64_t)row_bytes;
+    const int64_t tail0 = total_bytes & ~(int64_t)15;  // end of the buffer's last full 16-byte chunk
     const unsigned char* src = reinterpret_cast<const unsigned char*>(points);
-    int shift;
-    if (aligned16) {
-        // one TMA bulk copy brings the tile's byte range [a0, a1) into shared memory
-        __shared__ __align__(8) unsigned long long s_bar;
-        const int64_t a0 = start & ~(int64_t)15;
-        shift = (int)(start - a0);
-        int64_t a1 = (end + 15) & ~(int64_t)15;
-        const int64_t tail0 = total_bytes & ~(int64_t)15;  // last full 16-byte chunk boundary of the buffer
-        if (a1 > tail0) a1 = tail0 > a0 ? tail0 : a0;
-        const unsigned bulk = (unsigned)(a1 - a0);
-        if (threadIdx.x == 0) mbar_init(&s_bar, 1);
-        __syncthreads();
-        if (threadIdx.x == 0 && bulk) {
-            mbar_arrive_expect_tx(&s_bar, bulk);
-            tma_bulk_g2s(smem, src + a0, bulk, &s_bar);
-        }
-        // bytes of the tile past the buffer's last full chunk (at most one partial chunk)
-        for (int64_t a = a1 + (int64_t)threadIdx.x * (int)sizeof(T); a < end && a < total_bytes;
-             a += (int64_t)kMarkThreads * (int)sizeof(T))
-            *reinterpret_cast<T*>(smem + (a - a0)) = *reinterpret_cast<const T*>(src + a);
-        if (bulk) mbar_wait(&s_bar, 0);
-    } else {
-        shift = 0;
-        const int nel = m * p.D;
-        for (int k = threadIdx.x; k < nel; k += kMarkThreads)
-            reinterpret_cast<T*>(smem)[k] = points[(f0 + base) * p.D + k];
-    }
+    const int total_tiles = n_frames * tiles_per_frame;
+
+    if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
     __syncthreads();
 
-    int cell[kMarkPPT];
-#pragma unroll
-    for (int r = 0; r < kMarkPPT; ++r) {
-        const int t = r * kMarkThreads + threadIdx.x;
-        cell[r] = t < m ? cell_of<T, A32>(reinterpret_cast<const T*>(smem + shift + (size_t)t * row_bytes), p) : -1;
-    }
-    unsigned peers[kMarkPPT];
-    int basepos[kMarkPPT];
-#pragma unroll
-    for (int r = 0; r < kMarkPPT; ++r) {
-        peers[r] = __match_any_sync(0xffffffffu, cell[r]);
-        basepos[r] = 0;
-        if (cell[r] >= 0 && (int)lane_id() == __ffs(peers[r]) - 1) {
-            // lanes are in index order, so the leader carries the group's smallest index
-            const size_t gc = (size_t)b * p.ncell + cell[r];
-            atomicMin(&first_idx[gc], (unsigned)(base + r * kMarkThreads + threadIdx.x));
-            basepos[r] = atomicAdd(&cnt[gc], __popc(peers[r]));
+    // tile -> (frame, first point, count, byte range); all threads compute the same values
+    struct Tile { int b, base, m; int64_t f0, a0, a1; int shift; };
+    auto locate = [&](int tile, Tile& t) -> bool {
+        t.b = b0 + tile / tiles_per_frame;
+        t.f0 = frame_off[t.b];
+        const int n = (int)(frame_off[t.b + 1] - t.f0);
+        t.base = (tile % tiles_per_frame) * kMarkTile;
+        if (t.base >= n) return false;
+        t.m = min(kMarkTile, n - t.base);
+        const int64_t start = (t.f0 + t.base) * (int64_t)row_bytes;
+        const int64_t end = start + (int64_t)t.m * row_bytes;
+        t.a0 = start & ~(int64_t)15;
+        t.shift = (int)(start - t.a0);
+        t.a1 = (end + 15) & ~(int64_t)15;
+        if (t.a1 > tail0) t.a1 = tail0 > t.a0 ? tail0 : t.a0;
+        return true;
+    };
+    auto issue = [&](const Tile& t, int stage) {
+        const unsigned bulk = (unsigned)(t.a1 - t.a0);
+        if (aligned16 && bulk && threadIdx.x == 0) {
+            mbar_arrive_expect_tx(&s_bar[stage], bulk);
+            tma_bulk_g2s(smem + (size_t)stage * stage_bytes, src + t.a0, bulk, &s_bar[stage]);
         }
-    }
-#pragma unroll
-    for (int r = 0; r < kMarkPPT; ++r) {
-        const int t = r * kMarkThreads + threadIdx.x;
-        const int bp = __shfl_sync(0xffffffffu, basepos[r], __ffs(peers[r]) - 1);
-        if (t < m) {
-            cellpos[f0 + base + t] = make_int2(cell[r], bp + __popc(peers[r] & lanemask_lt()));
-            if (point_slot) point_slot[f0 + base + t] = -1;
+    };
+
+    unsigned phase0 = 0, phase1 = 0;
+    int tile = blockIdx.x;
+    Tile cur, nxt;
+    bool have_cur = false;
+    while (tile < total_tiles && !(have_cur = locate(tile, cur))) tile += gridDim.x;
+    if (have_cur) issue(cur, 0);
+    for (int it = 0; have_cur; ++it) {
+        const int stage = it & 1;
+        // look up and start loading the next non-empty tile of this CTA
+        int ntile = tile + gridDim.x;
+        bool have_nxt = false;
+        while (ntile < total_tiles && !(have_nxt = locate(ntile, nxt))) ntile += gridDim.x;
+        if (have_nxt) issue(nxt, stage ^ 1);
+
+        unsigned char* buf = smem + (size_t)stage * stage_bytes;
+        const int64_t end = (cur.f0 + cur.base + cur.m) * (int64_t)row_bytes;
+        if (aligned16) {
+            if (cur.a1 > cur.a0) {
+                mbar_wait(&s_bar[stage], stage ? phase1 : phase0);
+                if (stage) phase1 ^= 1; else phase0 ^= 1;
+            }
+            if (cur.a1 < end) {
+                // bytes past the buffer's last full chunk (only the very last tile of the buffer)
+                for (int64_t a = cur.a1 + (int64_t)threadIdx.x * (int)sizeof(T); a < end && a < total_bytes;
+                     a += (int64_t)kMarkThreads * (int)sizeof(T))
+                    *reinterpret_cast<T*>(buf + (a - cur.a0)) = *reinterpret_cast<const T*>(src + a);
+                __syncthreads();
+            }
+        } else {
+            const int nel = cur.m * p.D;
+            for (int k = threadIdx.x; k < nel; k += kMarkThreads)
+                reinterpret_cast<T*>(buf)[k] = points[(cur.f0 + cur.base) * p.D + k];
+            __syncthreads();
         }
+        const int shift = aligned16 ? cur.shift : 0;
+        const int b = cur.b, base = cur.base, m = cur.m;
+        const int64_t f0 = cur.f0;
+
+        int cell[kMarkPPT];
+#pragma unroll
+        for (int r = 0; r < kMarkPPT; ++r) {
+            const int t = r * kMarkThreads + threadIdx.x;
+            cell[r] = t < m ? cell_of<T, A32>(reinterpret_cast<const T*>(buf + shift + (size_t)t * row_bytes), p) : -1;
+        }
+        unsigned peers[kMarkPPT];
+        int basepos[kMarkPPT];
+#pragma unroll
+        for (int r = 0; r < kMarkPPT; ++r) {
+            peers[r] = __match_any_sync(0xffffffffu, cell[r]);
+            basepos[r] = 0;
+            if (cell[r] >= 0 && (int)lane_id() == __ffs(peers[r]) - 1) {
+                // lanes are in index order, so the leader carries the group's smallest index
+                const size_t gc = (size_t)b * p.ncell + cell[r];
+                atomicMin(&first_idx[gc], (unsigned)(base + r * kMarkThreads + threadIdx.x));
+                basepos[r] = atomicAdd(&cnt[gc], __popc(peers[r]));
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kMarkPPT; ++r) {
+            const int t = r * kMarkThreads + threadIdx.x;
+            const int bp = __shfl_sync(0xffffffffu, basepos[r], __ffs(peers[r]) - 1);
+            if (t < m) {
+                cellpos[f0 + base + t] = make_int2(cell[r], bp + __popc(peers[r] & lanemask_lt()));
+                if (point_slot) point_slot[f0 + base + t] = -1;
+            }
+        }
+        __syncthreads();  // every thread is done with this stage before it is refilled
+        cur = nxt;
+        tile = ntile;
+        have_cur = have_nxt;
     }
 }
 
@@ -180,7 +233,7 @@ __global__ void __launch_bounds__(kCellThreads)
 vox_cell_kernel(const unsigned* __restrict__ first_idx, const int* __restrict__ cnt,
                 const int64_t* __restrict__ frame_off, int ncell, int b0, unsigned* __restrict__ bitmap,
                 int* __restrict__ cell_off, int* __restrict__ frame_cursor,
-                int* __restrict__ occ_list, int* __restrict__ occ_count,
+                int* __restrict__ occ_list, int* __restrict__ frame_occ,
                 int* __restrict__ cell_voxel) {
     __shared__ int sm[33];
     __shared__ int s_base, s_obase;
@@ -193,7 +246,7 @@ vox_cell_kernel(const unsigned* __restrict__ first_idx, const int* __restrict__ 
     const int oex = block_excl_scan(c > 0, &otot, sm);
     if (threadIdx.x == 0) {
         s_base = tot ? atomicAdd(&frame_cursor[b], tot) : 0;
-        s_obase = otot ? atomicAdd(occ_count, otot) : 0;
+        s_obase = otot ? atomicAdd(&frame_occ[b], otot) : 0;
     }
     __syncthreads();
     if (cell < ncell && cell_voxel) cell_voxel[gc] = -1;
@@ -201,7 +254,7 @@ vox_cell_kernel(const unsigned* __restrict__ first_idx, const int* __restrict__ 
         const unsigned f = first_idx[gc];
         atomicOr(&bitmap[word_base(frame_off, b) + (f >> 5)], 1u << (f & 31));
         cell_off[gc] = s_base + ex;  // frame-local offset into the frame's bucket range
-        occ_list[s_obase + oex] = (int)gc;
+        occ_list[(size_t)b * ncell + s_obase + oex] = cell;  // frame-major: the gather pass walks frame by frame
     }
 }
 
@@ -212,7 +265,7 @@ __global__ void __launch_bounds__(kRankThreads)
 vox_rank_kernel(const unsigned* __restrict__ bitmap, unsigned* __restrict__ word_prefix,
                 const int64_t* __restrict__ frame_off, int b0, int B, int max_voxels,
                 int* __restrict__ voxel_num, int* __restrict__ cutoff, int* __restrict__ voxel_base,
-                int* __restrict__ done_counter) {
+                const int* __restrict__ frame_occ, int* __restrict__ occ_base, int* __restrict__ done_counter) {
     __shared__ int sm[33];
     __shared__ int s_cut, s_last;
     const int b = b0 + blockIdx.x;
@@ -253,8 +306,19 @@ vox_rank_kernel(const unsigned* __restrict__ bitmap, unsigned* __restrict__ word
         if (i < B) voxel_base[b0 + i] = ex;
         running += tot;
     }
+    if (threadIdx.x == 0) voxel_base[b0 + B] = running;
+    // occupied-cell list offsets of the chunk's frames (relative to the chunk)
+    running = 0;
+    for (int s = 0; s < B; s += kRankThreads) {
+        const int i = s + threadIdx.x;
+        const int v = i < B ? __ldcg(&frame_occ[b0 + i]) : 0;
+        int tot;
+        const int ex = running + block_excl_scan(v, &tot, sm);
+        if (i < B) occ_base[i] = ex;  // occ_base points at this chunk's [B+1] slice
+        running += tot;
+    }
     if (threadIdx.x == 0) {
-        voxel_base[b0 + B] = running;
+        occ_base[B] = running;
         *done_counter = 0;
     }
 }
@@ -314,6 +378,28 @@ __device__ __forceinline__ void warp_store_row(float* __restrict__ dst, const fl
     }
 }
 
+// same, but elements at or past `lim` are stored as zero (src need not be initialised there)
+__device__ __forceinline__ void warp_store_row_padded(float* __restrict__ dst, const float* __restrict__ src, int n, int lim, int lane) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(dst);
+    if ((a & 15) == 0 && (n & 3) == 0) {
+        for (int k = lane; k < (n >> 2); k += 32) {
+            float4 v = reinterpret_cast<const float4*>(src)[k];
+            const int e = k << 2;
+            v.x = e < lim ? v.x : 0.f; v.y = e + 1 < lim ? v.y : 0.f; v.z = e + 2 < lim ? v.z : 0.f; v.w = e + 3 < lim ? v.w : 0.f;
+            reinterpret_cast<float4*>(dst)[k] = v;
+        }
+    } else if ((a & 7) == 0 && (n & 1) == 0) {
+        for (int k = lane; k < (n >> 1); k += 32) {
+            float2 v = reinterpret_cast<const float2*>(src)[k];
+            const int e = k << 1;
+            v.x = e < lim ? v.x : 0.f; v.y = e + 1 < lim ? v.y : 0.f;
+            reinterpret_cast<float2*>(dst)[k] = v;
+        }
+    } else {
+        for (int k = lane; k < n; k += 32) dst[k] = k < lim ? src[k] : 0.f;
+    }
+}
+
 // ascending bitonic sort of 32*R ints, element index i = r*32 + lane
 template <int R>
 __device__ __forceinline__ void warp_bitonic_sort(int (&v)[R], int lane) {
@@ -363,9 +449,9 @@ __device__ __forceinline__ int load_sort_bucket(const int* __restrict__ seg, int
 }
 
 template <typename T, typename TO, int DS>
-__global__ void __launch_bounds__(kGatherWarps * 32)
-vox_gather_kernel(const T* __restrict__ points, const int64_t* __restrict__ frame_off, VoxParams p,
-                  const int* __restrict__ occ_list, const int* __restrict__ occ_count,
+__global__ void __launch_bounds__(kGatherWarps * 32, PP_GATHER_MINBLOCKS)
+vox_gather_kernel(const T* __restrict__ points, const int64_t* __restrict__ frame_off, VoxParams p, int b0, int nb,
+                  const int* __restrict__ occ_list, const int* __restrict__ occ_base,
                   const unsigned* __restrict__ first_idx, const int* __restrict__ cnt,
                   const int* __restrict__ cell_off, const int* __restrict__ bucket,
                   const unsigned* __restrict__ bitmap, const unsigned* __restrict__ word_prefix,
@@ -385,22 +471,30 @@ vox_gather_kernel(const T* __restrict__ points, const int64_t* __restrict__ fram
     float* vrow = reinterpret_cast<float*>(ord + nord);
     float* dsm = vrow + nvox;
 
-    const int nocc = *occ_count;
+    // occupied cells are listed per frame (occ_list[b*ncell + k], k < occ_base[bl+1]-occ_base[bl]); the
+    // grid walks them frame by frame so that one or two frames' points are live in L2 at a time
+    const int nocc = occ_base[nb];
     const int nwarps = gridDim.x * kGatherWarps;
     // one-deep software pipeline on the per-cell metadata: the next cell's first/count/offset
     // loads are issued before this cell's bucket is processed
     int e = blockIdx.x * kGatherWarps + w;
-    int gc_n = 0, L_n = 0, coff_n = 0;
+    int bl_n = 0, gc_n = 0, L_n = 0, coff_n = 0;
     unsigned f_n = 0;
-    if (e < nocc) { gc_n = occ_list[e]; f_n = first_idx[gc_n]; L_n = cnt[gc_n]; coff_n = cell_off[gc_n]; }
+    if (e < nocc) {
+        while (e >= occ_base[bl_n + 1]) ++bl_n;
+        gc_n = (b0 + bl_n) * p.ncell + occ_list[(size_t)(b0 + bl_n) * p.ncell + (e - occ_base[bl_n])];
+        f_n = first_idx[gc_n]; L_n = cnt[gc_n]; coff_n = cell_off[gc_n];
+    }
     for (; e < nocc; e += nwarps) {
-        const int gc = gc_n, L = L_n, coff = coff_n;
+        const int gc = gc_n, L = L_n, coff = coff_n, b = b0 + bl_n;
         const unsigned f = f_n;
+        const int cell = gc - b * p.ncell;
         if (e + nwarps < nocc) {
-            gc_n = occ_list[e + nwarps];
+            const int en = e + nwarps;
+            while (en >= occ_base[bl_n + 1]) ++bl_n;
+            gc_n = (b0 + bl_n) * p.ncell + occ_list[(size_t)(b0 + bl_n) * p.ncell + (en - occ_base[bl_n])];
             f_n = first_idx[gc_n]; L_n = cnt[gc_n]; coff_n = cell_off[gc_n];
         }
-        const int b = p.div_ncell.div(gc), cell = gc - b * p.ncell;
         const int64_t wb = word_base(frame_off, b);
         const int rank = (int)word_prefix[wb + (f >> 5)] + __popc(bitmap[wb + (f >> 5)] & ((1u << (f & 31)) - 1u));
         if (rank >= p.max_voxels) continue;
@@ -503,19 +597,13 @@ vox_gather_kernel(const T* __restrict__ points, const int64_t* __restrict__ fram
             for (int d = 0; d < (DS ? DS : 16); ++d) if (d < D) vrow[s * D + d] = c[d];
             sx += c[0]; sy += c[1]; sz += c[2];
         }
-        {   // zero the padding: scalar up to the next 16-byte boundary, then float4
-            const int z0 = nsel * D, z1 = min((z0 + 3) & ~3, P * D);
-            if (z0 + lane < z1) vrow[z0 + lane] = 0.f;
-            for (int k4 = ((z1 + 3) >> 2) + lane; k4 < (nvox >> 2); k4 += 32)
-                reinterpret_cast<float4*>(vrow)[k4] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
         if (sizeof(TO) == 8) {
             TO* vo = voxels + row * (int64_t)P * D;
             for (int k = nsel * D + lane; k < P * D; k += 32) vo[k] = (TO)0;
         }
         __syncwarp();
-        if (voxels && sizeof(TO) == 4)
-            warp_store_row(reinterpret_cast<float*>(voxels) + row * (int64_t)P * D, vrow, P * D, lane);
+        if (voxels && sizeof(TO) == 4)  // padding (k >= nsel*D) is written as zeros without touching smem
+            warp_store_row_padded(reinterpret_cast<float*>(voxels) + row * (int64_t)P * D, vrow, P * D, nsel * D, lane);
         if (decorated) {
 #pragma unroll
             for (int o = 16; o; o >>= 1) {
@@ -531,14 +619,15 @@ vox_gather_kernel(const T* __restrict__ points, const int64_t* __restrict__ fram
             if (DS == 3 && (reinterpret_cast<uintptr_t>(decorated) & 15) == 0) {
                 // 8 floats per point = two float4: (x,y,z,x-mx) and (y-my,z-mz,x-ex,y-ey)
                 float4* d4 = reinterpret_cast<float4*>(drow);
-                for (int c = lane; c < 2 * P; c += 32) {
-                    const int s = c >> 1;
-                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int s = lane; s < P; s += 32) {
+                    float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
                     if (s < nsel) {
                         const float q0 = vrow[s * 3], q1 = vrow[s * 3 + 1], q2 = vrow[s * 3 + 2];
-                        o = (c & 1) ? make_float4(q1 - my, q2 - mz, q0 - ex, q1 - ey) : make_float4(q0, q1, q2, q0 - mx);
+                        o0 = make_float4(q0, q1, q2, q0 - mx);
+                        o1 = make_float4(q1 - my, q2 - mz, q0 - ex, q1 - ey);
                     }
-                    d4[c] = o;
+                    d4[2 * s] = o0;
+                    d4[2 * s + 1] = o1;
                 }
             } else if (DS == 3) {
                 for (int k = lane; k < P * 8; k += 32) {
@@ -578,12 +667,13 @@ struct VoxWorkspace {
     int* cnt;             // [B*ncell]  zero init   -- zero region starts here
     unsigned* bitmap;     // [nwords]
     int* frame_cursor;    // [B]
-    int* occ_count;       // [B] (one per chunk of frames)
+    int* frame_occ;       // [B] occupied cells per frame
     int* done_counter;    // [B]        -- zero region ends here
     unsigned* word_prefix;  // [nwords]
     int* cell_off;        // [B*ncell]
     int* occ_list;        // [B*ncell] (worst case every cell occupied, bounded by total_points)
     int* cutoff;          // [B]
+    int* occ_base;        // [2B+1] per-chunk exclusive scans of frame_occ
     int2* cellpos;        // [total_points]
     int* bucket;          // [total_points]
     size_t zero_begin, zero_end, total;
@@ -600,7 +690,7 @@ static VoxWorkspace carve(void* ws, int64_t ncell, int64_t total_points, int B) 
     w.cnt = c.take<int>(nc);
     w.bitmap = c.take<unsigned>(nwords);
     w.frame_cursor = c.take<int>(B);
-    w.occ_count = c.take<int>(B);
+    w.frame_occ = c.take<int>(B);
     w.done_counter = c.take<int>(B);
     w.zero_end = c.used();
     w.word_prefix = c.take<unsigned>(nwords);
@@ -608,6 +698,7 @@ static VoxWorkspace carve(void* ws, int64_t ncell, int64_t total_points, int B) 
     (void)nocc;
     w.occ_list = c.take<int>(nc + 1);
     w.cutoff = c.take<int>(B);
+    w.occ_base = c.take<int>(2 * (size_t)B + 2);
     w.cellpos = c.take<int2>((size_t)total_points + 1);
     w.bucket = c.take<int>((size_t)total_points + 1);
     w.total = c.used();
@@ -651,7 +742,7 @@ static int launch_gather(const VoxParams& p, const VoxWorkspace& w, const void* 
                          const int64_t* frame_off, int64_t cap_rows, void* voxels, float* decorated,
                          int32_t* coors, int coors_cols, int32_t* num_points,
                          const int32_t* voxel_base, int32_t* point_slot, int32_t* cell_voxel,
-                         const int* occ_list, const int* occ_count, int64_t max_occ, cudaStream_t st) {
+                         int b0, int nb, const int* occ_base, int64_t max_occ, cudaStream_t st) {
     const int P_ = p.max_points, D_ = p.D;
     const size_t per_warp = (size_t)(((P_ + 3) & ~3) + ((P_ * D_ + 3) & ~3) + (DS == 3 ? 0 : ((P_ * (D_ + 5) + 3) & ~3))) * 4;
     const size_t smem = (size_t)kGatherWarps * per_warp;
@@ -666,7 +757,7 @@ static int launch_gather(const VoxParams& p, const VoxWorkspace& w, const void* 
     if (blocks < 1) blocks = 1;
     PP_TIMED("vox_gather", st);
     kern<<<(unsigned)blocks, kGatherWarps * 32, smem, st>>>(
-        static_cast<const T*>(points), frame_off, p, occ_list, occ_count, w.first_idx, w.cnt,
+        static_cast<const T*>(points), frame_off, p, b0, nb, w.occ_list, occ_base, w.first_idx, w.cnt,
         w.cell_off, w.bucket, w.bitmap, w.word_prefix, w.cutoff, voxel_base, cap_rows,
         static_cast<TO*>(voxels), decorated, coors, coors_cols, num_points, point_slot, cell_voxel);
     PP_LAUNCHED();
@@ -745,7 +836,10 @@ extern "C" int pp_voxelize_dev(const pp_voxel_cfg* cfg, const void* points, int 
             if (chunk_frames > n_frames) chunk_frames = n_frames;
         }
     }
-    const size_t mark_smem = (size_t)kMarkTile * D * esz + 32;
+    const size_t mark_smem = 2 * ((size_t)kMarkTile * D * esz + 32);  // two pipeline stages
+    int mark_ctas_per_sm = (int)((size_t)(220 * 1024) / (mark_smem + 1024));
+    if (mark_ctas_per_sm > 8) mark_ctas_per_sm = 8;
+    if (mark_ctas_per_sm < 1) mark_ctas_per_sm = 1;
     const int aligned16 = (reinterpret_cast<uintptr_t>(points) & 15) == 0;
     PP_CHECK_ARG(mark_smem <= 200 * 1024, "pp_voxelize_dev: D too large for the mark pass");
     if (mark_smem > 48 * 1024) {
@@ -756,22 +850,24 @@ extern "C" int pp_voxelize_dev(const pp_voxel_cfg* cfg, const void* points, int 
     int chunk_id = 0;
     for (int b0 = 0; b0 < n_frames; b0 += chunk_frames, ++chunk_id) {
         const int nb = n_frames - b0 < chunk_frames ? n_frames - b0 : chunk_frames;
-        int* occ_list = w.occ_list + (size_t)b0 * ncell;
-        int* occ_count = w.occ_count + chunk_id;
+        int* occ_base = w.occ_base + b0 + chunk_id;  // this chunk's [nb+1] slice
         if (max_frame_points > 0) {
-            const dim3 g((unsigned)ceil_div(max_frame_points, kMarkTile), nb);
+            const int tpf = (int)ceil_div(max_frame_points, kMarkTile);
+            const int64_t tiles = (int64_t)tpf * nb;
+            int64_t g = (int64_t)kNumSM * mark_ctas_per_sm;
+            if (g > tiles) g = tiles;
             PP_TIMED("vox_mark", st);
             if (point_dtype == PP_F64)
-                vox_mark_kernel<double, false><<<g, kMarkThreads, mark_smem, st>>>(
-                    static_cast<const double*>(points), frame_offsets, p, total_points, aligned16, b0,
+                vox_mark_kernel<double, false><<<(unsigned)g, kMarkThreads, mark_smem, st>>>(
+                    static_cast<const double*>(points), frame_offsets, p, total_points, aligned16, b0, nb, tpf,
                     w.first_idx, w.cnt, w.cellpos, point_slot);
             else if (cfg->arith_f32)
-                vox_mark_kernel<float, true><<<g, kMarkThreads, mark_smem, st>>>(
-                    static_cast<const float*>(points), frame_offsets, p, total_points, aligned16, b0,
+                vox_mark_kernel<float, true><<<(unsigned)g, kMarkThreads, mark_smem, st>>>(
+                    static_cast<const float*>(points), frame_offsets, p, total_points, aligned16, b0, nb, tpf,
                     w.first_idx, w.cnt, w.cellpos, point_slot);
             else
-                vox_mark_kernel<float, false><<<g, kMarkThreads, mark_smem, st>>>(
-                    static_cast<const float*>(points), frame_offsets, p, total_points, aligned16, b0,
+                vox_mark_kernel<float, false><<<(unsigned)g, kMarkThreads, mark_smem, st>>>(
+                    static_cast<const float*>(points), frame_offsets, p, total_points, aligned16, b0, nb, tpf,
                     w.first_idx, w.cnt, w.cellpos, point_slot);
             PP_LAUNCHED();
         }
@@ -779,15 +875,15 @@ extern "C" int pp_voxelize_dev(const pp_voxel_cfg* cfg, const void* points, int 
             const dim3 g((unsigned)ceil_div(ncell, kCellThreads), nb);
             PP_TIMED("vox_cell", st);
             vox_cell_kernel<<<g, kCellThreads, 0, st>>>(w.first_idx, w.cnt, frame_offsets, (int)ncell, b0,
-                                                        w.bitmap, w.cell_off, w.frame_cursor, occ_list,
-                                                        occ_count, cell_voxel);
+                                                        w.bitmap, w.cell_off, w.frame_cursor, w.occ_list,
+                                                        w.frame_occ, cell_voxel);
             PP_LAUNCHED();
         }
         {
             PP_TIMED("vox_rank", st);
             vox_rank_kernel<<<nb, kRankThreads, 0, st>>>(w.bitmap, w.word_prefix, frame_offsets, b0, nb,
                                                          cfg->max_voxels, voxel_num, w.cutoff, voxel_base,
-                                                         w.done_counter + chunk_id);
+                                                         w.frame_occ, occ_base, w.done_counter + chunk_id);
             PP_LAUNCHED();
         }
         if (max_frame_points > 0) {
@@ -802,7 +898,7 @@ extern "C" int pp_voxelize_dev(const pp_voxel_cfg* cfg, const void* points, int 
             int rc;
 #define PP_GATHER(T, TO, DS)                                                                                   \
     launch_gather<T, TO, DS>(p, w, points, frame_offsets, cap_rows, voxels, decorated, coors, coors_cols,     \
-                             num_points, voxel_base, point_slot, cell_voxel, occ_list, occ_count, max_occ, st)
+                             num_points, voxel_base, point_slot, cell_voxel, b0, nb, occ_base, max_occ, st)
             if (point_dtype == PP_F64 && out_dtype == PP_F64) rc = PP_GATHER(double, double, 0);
             else if (point_dtype == PP_F64) rc = D == 3 ? PP_GATHER(double, float, 3) : D == 4 ? PP_GATHER(double, float, 4) : PP_GATHER(double, float, 0);
             else rc = D == 3 ? PP_GATHER(float, float, 3) : D == 4 ? PP_GATHER(float, float, 4) : PP_GATHER(float, float, 0);
