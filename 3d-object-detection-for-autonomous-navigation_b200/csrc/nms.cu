@@ -32,18 +32,48 @@ __device__ __forceinline__ unsigned score_key(float s) {
 
 // ---------------------------------------------------------------------------------------------
 // Top-k (k <= 1024) per frame: radix select of the k-th largest key, compaction, bitonic sort.
-__global__ void __launch_bounds__(kSortThreads)
-nms_topk_kernel(const float* __restrict__ scores, const int* __restrict__ n_valid, int64_t N, int k,
-                int* __restrict__ order, int64_t order_stride, int* __restrict__ n_sorted) {
+// Warp 0: find the digit d (255..0) where the count of keys with a larger digit is < rem <= that
+// count + hist[d]; returns d and the number still needed inside digit d.  8 bins per lane.
+__device__ __forceinline__ void select_digit(const unsigned* hist, unsigned rem, unsigned prefix, int shift,
+                                             unsigned* prefix_out, unsigned* rem_out, unsigned* cnt_out) {
+    const int lane = lane_id();
+    // lane l owns bins 255-8l .. 248-8l (descending)
+    unsigned h[8], tot = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { h[q] = hist[255 - 8 * lane - q]; tot += h[q]; }
+    unsigned inc = tot;  // inclusive prefix over lanes (descending bins)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    const unsigned before = inc - tot;  // keys in bins above this lane's range
+    const bool mine = before < rem && rem <= inc;
+    const unsigned bal = __ballot_sync(0xffffffffu, mine);
+    if (bal == 0) {  // fewer than rem keys in total: take digit 0
+        const unsigned total = __shfl_sync(0xffffffffu, inc, 31);
+        if (lane == 0) { *prefix_out = prefix; *rem_out = rem - total + hist[0]; *cnt_out = hist[0]; }
+        return;
+    }
+    if (mine) {
+        unsigned acc = before;
+        int q = 0;
+        for (; q < 7; ++q) {
+            if (acc + h[q] >= rem) break;
+            acc += h[q];
+        }
+        *prefix_out = prefix | ((unsigned)(255 - 8 * lane - q) << shift);
+        *rem_out = rem - acc;
+        *cnt_out = h[q];
+    }
+}
+
+// Block-wide: the kk (<= kSelectMaxK) best of sc[0..nv) by (score desc, index desc), sorted, as
+// (key<<32 | index) in skey[0..kk).  All kSortThreads threads of the block must call it.
+__device__ __forceinline__ void block_topk(const float* __restrict__ sc, int nv, int kk,
+                                           unsigned long long* skey /*[kSelectMaxK]*/) {
     __shared__ unsigned hist[256];
-    __shared__ unsigned s_prefix, s_remaining, s_count;
-    __shared__ unsigned long long skey[kSelectMaxK];
-    const int b = blockIdx.x;
-    const float* sc = scores + (int64_t)b * N;
-    const int nv = n_valid ? max(0, min(n_valid[b], (int)N)) : (int)N;
-    const int kk = min(k, nv);
-    if (threadIdx.x == 0) n_sorted[b] = kk;
-    if (kk == 0) return;
+    __shared__ unsigned s_prefix, s_remaining, s_count, s_scratch;
 
     unsigned T = 0, Tidx = 0;
     if (kk < nv) {
@@ -53,21 +83,23 @@ nms_topk_kernel(const float* __restrict__ scores, const int* __restrict__ n_vali
             if (threadIdx.x < 256) hist[threadIdx.x] = 0;
             __syncthreads();
             const unsigned prefix = s_prefix;
-            for (int i = threadIdx.x; i < nv; i += kSortThreads) {
-                const unsigned key = score_key(sc[i]);
-                if (shift == 24 || ((key ^ prefix) >> (shift + 8)) == 0) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+            // warp-aggregated histogram: scores cluster in a few top-byte bins, a plain atomicAdd
+            // would serialise the whole block on one shared-memory word
+            for (int i0 = 0; i0 < nv; i0 += kSortThreads) {
+                const int i = i0 + threadIdx.x;
+                int d = -1;
+                if (i < nv) {
+                    const unsigned key = score_key(sc[i]);
+                    if (shift == 24 || ((key ^ prefix) >> (shift + 8)) == 0) d = (int)((key >> shift) & 255u);
+                }
+                const unsigned peers = __match_any_sync(0xffffffffu, d);
+                if (d >= 0 && (int)lane_id() == __ffs(peers) - 1) atomicAdd(&hist[d], (unsigned)__popc(peers));
             }
             __syncthreads();
-            if (threadIdx.x == 0) {
-                unsigned acc = 0, rem = s_remaining;
-                int d = 255;
-                for (; d > 0; --d) {
-                    if (acc + hist[d] >= rem) break;
-                    acc += hist[d];
-                }
-                s_remaining = rem - acc;  // still needed among keys with this digit
-                s_prefix = prefix | ((unsigned)d << shift);
-                s_count = hist[d];
+            if (threadIdx.x < 32) {
+                const unsigned rem = s_remaining;
+                __syncwarp();
+                select_digit(hist, rem, prefix, shift, &s_prefix, &s_remaining, &s_count);
             }
             __syncthreads();
         }
@@ -87,15 +119,10 @@ nms_topk_kernel(const float* __restrict__ scores, const int* __restrict__ n_vali
                     if (shift == 24 || ((key ^ prefix) >> (shift + 8)) == 0) atomicAdd(&hist[(key >> shift) & 255u], 1u);
                 }
                 __syncthreads();
-                if (threadIdx.x == 0) {
-                    unsigned acc = 0, rem = s_remaining;
-                    int d = 255;
-                    for (; d > 0; --d) {
-                        if (acc + hist[d] >= rem) break;
-                        acc += hist[d];
-                    }
-                    s_remaining = rem - acc;
-                    s_prefix = prefix | ((unsigned)d << shift);
+                if (threadIdx.x < 32) {
+                    const unsigned rem = s_remaining;
+                    __syncwarp();
+                    select_digit(hist, rem, prefix, shift, &s_prefix, &s_remaining, &s_scratch);
                 }
                 __syncthreads();
             }
@@ -129,6 +156,19 @@ nms_topk_kernel(const float* __restrict__ scores, const int* __restrict__ n_vali
             __syncthreads();
         }
     }
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+nms_topk_kernel(const float* __restrict__ scores, const int* __restrict__ n_valid, int64_t N, int k,
+                int* __restrict__ order, int64_t order_stride, int* __restrict__ n_sorted) {
+    __shared__ unsigned long long skey[kSelectMaxK];
+    const int b = blockIdx.x;
+    const float* sc = scores + (int64_t)b * N;
+    const int nv = n_valid ? max(0, min(n_valid[b], (int)N)) : (int)N;
+    const int kk = min(k, nv);
+    if (threadIdx.x == 0) n_sorted[b] = kk;
+    if (kk == 0) return;
+    block_topk(sc, nv, kk, skey);
     for (int i = threadIdx.x; i < kk; i += kSortThreads)
         order[(int64_t)b * order_stride + i] = (int)(skey[i] & 0xffffffffu);
 }
@@ -428,6 +468,81 @@ rotate_iou_matrix_kernel(const float* __restrict__ boxes, int64_t N, const float
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Whole NMS of one frame in one CTA when at most kSmallN boxes survive pre_max_size (the live
+// path: pre_max_size = 100, configs/train.yaml:176): top-k, per-box prep, all pairs spread over
+// the block with the mask in shared memory, sweep by one thread.  One launch instead of four and
+// no global intermediates.
+constexpr int kSmallN = 128;
+template <bool ROTATED>
+__global__ void __launch_bounds__(kSortThreads)
+nms_small_kernel(const float* __restrict__ boxes, int box_stride, const float* __restrict__ scores,
+                 const int* __restrict__ n_valid, int64_t N, int k, int post_max, float thresh,
+                 int* __restrict__ keep, int64_t keep_stride, int* __restrict__ keep_count) {
+    using BoxG = typename std::conditional<ROTATED, RBoxG, float4>::type;
+    __shared__ unsigned long long skey[kSelectMaxK];
+    __shared__ BoxG s_box[kSmallN];
+    __shared__ unsigned long long s_mask[kSmallN][2];
+    const int b = blockIdx.x;
+    const float* sc = scores + (int64_t)b * N;
+    const int nv = n_valid ? max(0, min(n_valid[b], (int)N)) : (int)N;
+    const int n = min(min(k, kSmallN), nv);
+    if (n == 0) {
+        if (threadIdx.x == 0) keep_count[b] = 0;
+        return;
+    }
+    block_topk(sc, nv, n, skey);
+    if (threadIdx.x < n) {
+        const float* src = boxes + ((int64_t)b * N + (int)(skey[threadIdx.x] & 0xffffffffu)) * box_stride;
+        if constexpr (ROTATED) {
+            const bool dec7 = box_stride == 7;
+            const float r[5] = {src[0], src[1], dec7 ? src[3] : src[2], dec7 ? src[4] : src[3], dec7 ? src[6] : src[4]};
+            RBox rb;
+            rbox_prepare(r, rb);
+            RBoxG& d = s_box[threadIdx.x];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d.c[i] = rb.c[i];
+            d.area = rb.area; d.mnx = rb.mnx; d.mny = rb.mny; d.mxx = rb.mxx; d.mxy = rb.mxy;
+        } else {
+            s_box[threadIdx.x] = make_float4(src[0], src[1], src[2], src[3]);
+        }
+        s_mask[threadIdx.x][0] = 0ull;
+        s_mask[threadIdx.x][1] = 0ull;
+    }
+    __syncthreads();
+    const double th = (double)thresh;
+    for (int idx = threadIdx.x; idx < n * n; idx += kSortThreads) {
+        const int i = idx / n, j = idx - i * n;
+        if (j <= i) continue;
+        bool sup;
+        if constexpr (ROTATED) {
+            RBox a, c;
+            load_rbox(&s_box[i], a);
+            load_rbox(&s_box[j], c);
+            sup = rbox_iou(a, c, -1) > th;  // devRotateIoU(row, col), nms_gpu.py:445-449
+        } else {
+            sup = standup_iou(s_box[i], s_box[j]) > th;
+        }
+        if (sup) atomicOr(&s_mask[i][j >> 6], 1ull << (j & 63));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long rm0 = 0ull, rm1 = 0ull;
+        const int limit = (int)min((int64_t)(post_max > 0 ? post_max : n), keep_stride);
+        int nk = 0;
+        int* kp = keep + (int64_t)b * keep_stride;
+        for (int i = 0; i < n && nk < limit; ++i) {
+            const unsigned long long rm = i < 64 ? rm0 : rm1;
+            if (!((rm >> (i & 63)) & 1ull)) {
+                kp[nk++] = (int)(skey[i] & 0xffffffffu);
+                rm0 |= s_mask[i][0];
+                rm1 |= s_mask[i][1];
+            }
+        }
+        keep_count[b] = nk;
+    }
+}
+
 // final detections: out[b,k,:] = (boxes[b, keep[b,k], 0:box_dim], scores[b, keep[b,k]]), zero padded
 __global__ void __launch_bounds__(256)
 gather_dets_kernel(const float* __restrict__ boxes, int box_dim, const float* __restrict__ scores, int64_t N,
@@ -513,6 +628,17 @@ extern "C" int pp_nms_dev(int kind, const float* boxes, int box_stride, const fl
         return PP_E_WORKSPACE;
     }
     PP_CHECK_ARG(w.cb_cap * 8 <= 200 * 1024, "pp_nms_dev: more than 1.6M boxes per frame after pre_max_size");
+    if (w.n_cap <= kSmallN) {
+        PP_TIMED("nms_small", st);
+        if (kind == PP_NMS_ROTATED)
+            nms_small_kernel<true><<<B, kSortThreads, 0, st>>>(boxes, box_stride, scores, n_valid, N, (int)w.n_cap,
+                                                              post_max_size, thresh, keep, keep_stride, keep_count);
+        else
+            nms_small_kernel<false><<<B, kSortThreads, 0, st>>>(boxes, box_stride, scores, n_valid, N, (int)w.n_cap,
+                                                               post_max_size, thresh, keep, keep_stride, keep_count);
+        PP_LAUNCHED();
+        return PP_OK;
+    }
     if (w.full_sort) {
         PP_TIMED("nms_sort", st);
         nms_sort_kernel<<<B, kSortThreads, 0, st>>>(scores, n_valid, N, pre_max_size, w.kbuf, w.ibuf, w.order,

@@ -67,26 +67,49 @@ scatter_canvas_kernel(const float* __restrict__ feats, const int* __restrict__ h
     any = __syncthreads_or(any);
 
     if (any) {
-        for (int k = threadIdx.x; k < C * 33; k += kScThreads) tile[k] = 0.f;
-        __syncthreads();
+        // Each warp owns whole x columns of the tile and writes every channel of them (zeros for an
+        // empty cell), so the tile needs no clearing.  Sums run in registers in ascending row order.
+        const bool vec = ((C & 3) == 0) && ((reinterpret_cast<uintptr_t>(feats) & 15) == 0);
         for (int x = w; x < wx; x += kScThreads / 32) {
             const int len = s_len[x];
-            if (len == 0) continue;
-            if (len <= kChainMax) {
-                for (int j = 0; j < len; ++j) {
-                    const float* row = feats + (int64_t)s_chain[x][j] * C;
-                    for (int c = lane; c < C; c += 32) tile[c * 33 + x] += row[c];
+            if (vec) {
+                for (int c4 = lane; c4 < (C >> 2); c4 += 32) {
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (len <= kChainMax) {
+                        for (int j = 0; j < len; ++j) {
+                            const float4 v = __ldg(reinterpret_cast<const float4*>(feats + (int64_t)s_chain[x][j] * C) + c4);
+                            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                        }
+                    } else {
+                        int last = -1;
+                        for (int j = 0; j < len; ++j) {
+                            int best = 0x7fffffff;
+                            for (int m = head[cellbase + x]; m >= 0; m = next[m])
+                                if (m > last && m < best) best = m;
+                            const float4 v = __ldg(reinterpret_cast<const float4*>(feats + (int64_t)best * C) + c4);
+                            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                            last = best;
+                        }
+                    }
+                    float* t = tile + (c4 << 2) * 33 + x;
+                    t[0] = acc.x; t[33] = acc.y; t[66] = acc.z; t[99] = acc.w;
                 }
             } else {
-                // long chain (many duplicate coords): walk it in ascending row order
-                int last = -1;
-                for (int j = 0; j < len; ++j) {
-                    int best = 0x7fffffff;
-                    for (int m = head[cellbase + x]; m >= 0; m = next[m])
-                        if (m > last && m < best) best = m;
-                    const float* row = feats + (int64_t)best * C;
-                    for (int c = lane; c < C; c += 32) tile[c * 33 + x] += row[c];
-                    last = best;
+                for (int c = lane; c < C; c += 32) {
+                    float acc = 0.f;
+                    if (len <= kChainMax) {
+                        for (int j = 0; j < len; ++j) acc += feats[(int64_t)s_chain[x][j] * C + c];
+                    } else {
+                        int last = -1;
+                        for (int j = 0; j < len; ++j) {
+                            int best = 0x7fffffff;
+                            for (int m = head[cellbase + x]; m >= 0; m = next[m])
+                                if (m > last && m < best) best = m;
+                            acc += feats[(int64_t)best * C + c];
+                            last = best;
+                        }
+                    }
+                    tile[c * 33 + x] = acc;
                 }
             }
         }
@@ -112,13 +135,17 @@ scatter_canvas_kernel(const float* __restrict__ feats, const int* __restrict__ h
         }
     } else {
         // NCHW: channel c row segment at ((b*C + c)*ny + y)*nx + x0, wx floats
-        const bool vec = ((nx & 3) == 0) && ((wx & 3) == 0);
-        if (!any && vec) {
-            const int q = wx / 4;  // float4 per channel row
+        const bool vec = ((nx & 3) == 0) && ((wx & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+        if (vec) {
+            const int q = wx >> 2;  // float4 per channel row
             for (int k = threadIdx.x; k < C * q; k += kScThreads) {
                 const int c = k / q, i = k - c * q;
-                float4* d4 = reinterpret_cast<float4*>(out + (((int64_t)b * C + c) * ny + y) * nx + x0);
-                d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (any) {
+                    const float* t = tile + c * 33 + (i << 2);
+                    v = make_float4(t[0], t[1], t[2], t[3]);
+                }
+                reinterpret_cast<float4*>(out + (((int64_t)b * C + c) * ny + y) * nx + x0)[i] = v;
             }
         } else {
             for (int c = w; c < C; c += kScThreads / 32) {

@@ -29,7 +29,7 @@ class FramePipeline:
     """One GPU, up to `max_frames` frames of at most `max_total_points` points per run."""
 
     def __init__(self, cfg, device=0, max_frames=64, max_total_points=None, rotated_nms=True,
-                 layout="NCHW", fused_decorate=True, keep_voxels=True, anchors=None):
+                 layout="NCHW", fused_decorate=True, keep_voxels=True, anchors=None, overlap_post=True):
         self.cfg = cfg
         self.dev = torch.device("cuda", device)
         self.B = int(max_frames)
@@ -83,6 +83,8 @@ class FramePipeline:
             self.ws_vox = torch.empty((self.ws_vox_bytes,), dtype=torch.uint8, **e)
             self.ws_sc = torch.empty((self.ws_sc_bytes,), dtype=torch.uint8, **e)
             self.ws_nms = torch.empty((self.ws_nms_bytes,), dtype=torch.uint8, **e)
+            self.post_stream = torch.cuda.Stream(device=self.dev) if overlap_post else None
+            self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
             self.dets_host = torch.empty((B, self.post, 8), dtype=torch.float32).pin_memory()
             self.keep_count_host = torch.empty((B,), dtype=torch.int32).pin_memory()
 
@@ -124,11 +126,25 @@ class FramePipeline:
 
     # ---- whole path ---------------------------------------------------------------------------
     def run(self, points, frame_off, n_frames, total_points, max_frame_points, pfn_feats, box_enc, scores):
-        """All arguments are device tensors (frame_off int64 [n_frames+1]); async."""
-        st = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        """All arguments are device tensors (frame_off int64 [n_frames+1]); async on the current stream.
+
+        Pre-processing (voxelize, scatter) and post-processing (decode, NMS) touch disjoint tensors --
+        in serving, the post stage of one batch runs while the next batch is being voxelized -- so the
+        post stage is issued on a side stream that forks from and joins back into the current stream."""
+        main = torch.cuda.current_stream(self.dev)
+        st = C.c_void_p(main.cuda_stream)
+        if self.post_stream is None:
+            self.voxelize(points, frame_off, n_frames, total_points, max_frame_points, st)
+            self.scatter(pfn_feats, n_frames, st)
+            self.postprocess(box_enc, scores, n_frames, st)
+            return
+        self._ev_fork.record(main)
+        self.post_stream.wait_event(self._ev_fork)
+        self.postprocess(box_enc, scores, n_frames, C.c_void_p(self.post_stream.cuda_stream))
+        self._ev_join.record(self.post_stream)
         self.voxelize(points, frame_off, n_frames, total_points, max_frame_points, st)
         self.scatter(pfn_feats, n_frames, st)
-        self.postprocess(box_enc, scores, n_frames, st)
+        main.wait_event(self._ev_join)
 
     def fetch(self, n_frames):
         """Detections to pinned host memory (async on the current stream)."""
