@@ -347,8 +347,14 @@ def main():
         dom = max(cand, key=cand.get)
         bytes_launch = ab[dom] * F
         achieved = bytes_launch / (cand[dom] * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("frames") == F and dom in tj.get("kernels", {}):
+                traffic = tj["kernels"][dom]  # dram bytes per launch from the committed ncu --set full capture
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_launch, "launch_ms": cand[dom],
                 "kernel_share_of_step": cand[dom] / step_kernel_ms if step_kernel_ms else None}
     path_gbs = ab["total"] * F * args.steps / (ms * 1e-3) / 1e9 / world * world  # per GPU == aggregate/world
