@@ -64,7 +64,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception as e:  # noqa: BLE001
@@ -169,7 +169,7 @@ def workload_config(cfg, frames, n_pts, gpus):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=64, help="frames per GPU per step")
@@ -285,7 +285,6 @@ def main():
     pp.launch_count(reset=True)
     ms = timed(step_resident, args.steps)
     launches = pp.launch_count(reset=True)
-    clocks = sampler.stop() if rank == 0 else None
     fps = world * F * args.steps / (ms / 1e3)
 
     # ---- e2e: pinned host points in, detections out, every step ---------------------------------
@@ -311,6 +310,7 @@ def main():
             ms_ = float(t.item())
         return ms_
     ms_e2e = timed_e2e(args.steps)
+    clocks = sampler.stop() if rank == 0 else None  # sampled over both timed regions (value + e2e)
     fps_e2e = world * F * args.steps / (ms_e2e / 1e3)
     h2d = total * 3 * 8
     d2h = F * pipe.post * 8 * 4 + F * 4
