@@ -9,10 +9,12 @@ Drop-in Python surface (same names, argument meaning and return types as the ref
     rbox_to_standup        load_data.py:1525-1594 + 1330-1341 (as used at model/voxelnet.py:1233-1249)
     nms, nms_gpu           libraries/eval_helper_functions.py:463-527
     rotate_nms_gpu, rotate_iou_gpu, rotate_iou_gpu_eval   second/core/non_max_suppression/nms_gpu.py
+    anchors_mask           load_data.py:3043-3072 ("next" row N1)
 
 The compute lives in libpp_b200.so (csrc/*.cu, include/pp_b200.h).  There is no CPU fallback.
 """
 from ._lib import PPError, Ctx, ctx, grid_size, launch_count, lib, set_device  # noqa: F401
+from .anchors import anchors_mask  # noqa: F401
 from .boxes import rbox_to_standup, second_box_decode  # noqa: F401
 from .nms import nms, nms_gpu, rotate_iou_gpu, rotate_iou_gpu_eval, rotate_nms_gpu  # noqa: F401
 from .pillars import PillarFeatureNet, PointPillarsScatter, pillar_decorate, scatter  # noqa: F401

@@ -311,6 +311,34 @@ extern "C" int pp_nms_host(pp_ctx* c, int kind, const float* boxes, const float*
     return PP_OK;
 }
 
+extern "C" int pp_anchors_mask_host(pp_ctx* c, const int32_t* coors, int64_t M, const float* anchors, int64_t A,
+                                    const double voxel_size[3], const double coors_range[6], float threshold,
+                                    float* area_out, uint8_t* mask_out) {
+    PP_ENTER(c);
+    PP_CHECK_ARG(M >= 0 && A >= 0 && voxel_size && coors_range, "pp_anchors_mask_host: bad argument");
+    if (A == 0) return PP_OK;
+    int32_t grid[3];
+    pp_grid_size(voxel_size, coors_range, 0, grid);
+    const size_t ws_bytes = pp_anchor_mask_workspace_bytes(1, grid[1], grid[0]);
+    void *d_co, *d_an, *d_cells, *d_area, *d_mask, *d_ws;
+    PP_TRY(c->get(0, (size_t)M * 12, &d_co));
+    PP_TRY(c->get(1, (size_t)A * 28, &d_an));
+    PP_TRY(c->get(2, (size_t)A * 16, &d_cells));
+    PP_TRY(c->get(3, (size_t)A * 4, &d_area));
+    PP_TRY(c->get(4, (size_t)A, &d_mask));
+    PP_TRY(c->get(5, ws_bytes, &d_ws));
+    if (M > 0) PP_CUDA(cudaMemcpyAsync(d_co, coors, (size_t)M * 12, cudaMemcpyHostToDevice, st));
+    PP_CUDA(cudaMemcpyAsync(d_an, anchors, (size_t)A * 28, cudaMemcpyHostToDevice, st));
+    PP_TRY(pp_anchor_cells_dev(static_cast<float*>(d_an), A, voxel_size, coors_range, static_cast<int32_t*>(d_cells), st));
+    PP_TRY(pp_anchor_mask_dev(static_cast<int32_t*>(d_co), 3, M, nullptr, 1, grid[1], grid[0], static_cast<int32_t*>(d_cells),
+                              A, threshold, nullptr, static_cast<float*>(d_area), static_cast<uint8_t*>(d_mask), nullptr,
+                              d_ws, ws_bytes, st));
+    if (area_out) PP_CUDA(cudaMemcpyAsync(area_out, d_area, (size_t)A * 4, cudaMemcpyDeviceToHost, st));
+    if (mask_out) PP_CUDA(cudaMemcpyAsync(mask_out, d_mask, (size_t)A, cudaMemcpyDeviceToHost, st));
+    PP_CUDA(cudaStreamSynchronize(st));
+    return PP_OK;
+}
+
 extern "C" int pp_rotate_iou_host(pp_ctx* c, const float* boxes, int64_t N, const float* query_boxes, int64_t K,
                                   int criterion, float* out) {
     PP_ENTER(c);

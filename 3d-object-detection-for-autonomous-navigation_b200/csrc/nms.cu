@@ -32,6 +32,18 @@ __device__ __forceinline__ unsigned score_key(float s) {
 
 // ---------------------------------------------------------------------------------------------
 // Top-k (k <= 1024) per frame: radix select of the k-th largest key, compaction, bitonic sort.
+// Boxes whose score is -inf are absent (pp_anchor_mask_dev writes -inf for masked-out anchors: the
+// reference gathers `box_preds[a_mask]` before scoring, model/voxelnet.py:1119-1137).  Block-wide count
+// of present scores; all threads of the block must call it.
+__device__ __forceinline__ int block_count_present(const float* __restrict__ sc, int nv) {
+    int total = 0;
+    for (int i0 = 0; i0 < nv; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        total += __syncthreads_count(i < nv && sc[i] != -INFINITY);
+    }
+    return total;
+}
+
 // Warp 0: find the digit d (255..0) where the count of keys with a larger digit is < rem <= that
 // count + hist[d]; returns d and the number still needed inside digit d.  8 bins per lane.
 __device__ __forceinline__ void select_digit(const unsigned* hist, unsigned rem, unsigned prefix, int shift,
@@ -165,7 +177,7 @@ nms_topk_kernel(const float* __restrict__ scores, const int* __restrict__ n_vali
     const int b = blockIdx.x;
     const float* sc = scores + (int64_t)b * N;
     const int nv = n_valid ? max(0, min(n_valid[b], (int)N)) : (int)N;
-    const int kk = min(k, nv);
+    const int kk = min(k, block_count_present(sc, nv));
     if (threadIdx.x == 0) n_sorted[b] = kk;
     if (kk == 0) return;
     block_topk(sc, nv, kk, skey);
@@ -186,7 +198,8 @@ nms_sort_kernel(const float* __restrict__ scores, const int* __restrict__ n_vali
     const int b = blockIdx.x;
     const float* sc = scores + (int64_t)b * N;
     const int nv = n_valid ? max(0, min(n_valid[b], (int)N)) : (int)N;
-    const int n = limit > 0 ? min(limit, nv) : nv;
+    const int present = block_count_present(sc, nv);
+    const int n = limit > 0 ? min(limit, present) : present;
     if (threadIdx.x == 0) n_sorted[b] = n;
     if (n == 0) return;
     unsigned* k0 = kbuf + (int64_t)b * 2 * N; unsigned* k1 = k0 + N;
@@ -486,7 +499,7 @@ nms_small_kernel(const float* __restrict__ boxes, int box_stride, const float* _
     const int b = blockIdx.x;
     const float* sc = scores + (int64_t)b * N;
     const int nv = n_valid ? max(0, min(n_valid[b], (int)N)) : (int)N;
-    const int n = min(min(k, kSmallN), nv);
+    const int n = min(min(k, kSmallN), block_count_present(sc, nv));
     if (n == 0) {
         if (threadIdx.x == 0) keep_count[b] = 0;
         return;

@@ -29,7 +29,8 @@ class FramePipeline:
     """One GPU, up to `max_frames` frames of at most `max_total_points` points per run."""
 
     def __init__(self, cfg, device=0, max_frames=64, max_total_points=None, rotated_nms=True,
-                 layout="NCHW", fused_decorate=True, keep_voxels=True, anchors=None, overlap_post=True):
+                 layout="NCHW", fused_decorate=True, keep_voxels=True, anchors=None, overlap_post=True,
+                 anchor_area_threshold=None):
         self.cfg = cfg
         self.dev = torch.device("cuda", device)
         self.B = int(max_frames)
@@ -83,6 +84,20 @@ class FramePipeline:
             self.ws_vox = torch.empty((self.ws_vox_bytes,), dtype=torch.uint8, **e)
             self.ws_sc = torch.empty((self.ws_sc_bytes,), dtype=torch.uint8, **e)
             self.ws_nms = torch.empty((self.ws_nms_bytes,), dtype=torch.uint8, **e)
+            # "next" row N1: anchor mask from the voxelizer's coors (load_data.py:3043-3072); the masked
+            # scores then feed NMS, which is the device form of `box_preds[a_mask]` (model/voxelnet.py:1119)
+            self.area_thr = anchor_area_threshold
+            if anchor_area_threshold is not None:
+                self.anchor_cells = torch.empty((self.A, 4), dtype=torch.int32, **e)
+                self.anchor_mask = torch.empty((B, self.A), dtype=torch.uint8, **e)
+                self.masked_scores = torch.empty((B, self.A), dtype=torch.float32, **e)
+                self.ws_am_bytes = int(L.pp_anchor_mask_workspace_bytes(B, self.ny, self.nx))
+                self.ws_am = torch.empty((self.ws_am_bytes,), dtype=torch.uint8, **e)
+                vs3 = (C.c_double * 3)(*map(float, cfg["voxel_size"]))
+                pcr6 = (C.c_double * 6)(*map(float, cfg["point_cloud_range"]))
+                _lib.check(L.pp_anchor_cells_dev(_p(self.anchors), self.A, vs3, pcr6, _p(self.anchor_cells),
+                                                 C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)))
+                overlap_post = False  # the post stage now depends on the voxelizer's coors
             self.post_stream = torch.cuda.Stream(device=self.dev) if overlap_post else None
             self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
             self.dets_host = torch.empty((B, self.post, 8), dtype=torch.float32).pin_memory()
@@ -136,6 +151,12 @@ class FramePipeline:
         if self.post_stream is None:
             self.voxelize(points, frame_off, n_frames, total_points, max_frame_points, st)
             self.scatter(pfn_feats, n_frames, st)
+            if self.area_thr is not None:
+                _lib.check(_lib.lib().pp_anchor_mask_dev(
+                    _p(self.coors), 4, self.cap_rows, C.c_void_p(self.voxel_base.data_ptr() + 4 * n_frames), n_frames,
+                    self.ny, self.nx, _p(self.anchor_cells), self.A, float(self.area_thr), _p(scores), None,
+                    _p(self.anchor_mask), _p(self.masked_scores), _p(self.ws_am), self.ws_am_bytes, st))
+                scores = self.masked_scores
             self.postprocess(box_enc, scores, n_frames, st)
             return
         self._ev_fork.record(main)

@@ -153,7 +153,8 @@ PP_API int pp_rbox_to_standup_dev(const float* boxes, int in_stride, int64_t N, 
  *   box_stride 7: decoded boxes (x,y,z,w,l,h,r), BEV columns 0,1,3,4,6 read in place.
  * Both: scores [B,N]; order = descending score, ties by descending index; optional top
  * pre_max_size (<=0: all), greedy suppression of IoU > thresh (strict, thresh rounded to
- * float32), first post_max_size kept (<=0: all).
+ * float32), first post_max_size kept (<=0: all).  Boxes whose score is -inf are treated as absent
+ * (see pp_anchor_mask_dev).
  *   n_valid   optional device [B]: only the first n_valid[b] boxes of frame b are used
  *   keep      [B, keep_stride] int32 indices into the frame's boxes, in keep order
  *   keep_count[B] int32 (count is clipped to keep_stride) */
@@ -179,6 +180,23 @@ PP_API int pp_gather_dets_dev(const float* boxes, int box_dim, const float* scor
  * 0 inter/area(query), 1 inter/area(box), 2 intersection area. */
 PP_API int pp_rotate_iou_dev(const float* boxes, int64_t N, const float* query_boxes, int64_t K,
                       int criterion, float* out, void* stream);
+
+/* ---- anchor mask ("next" row N1) ---------------------------------------------------------------
+ * Replaces the per-sample anchor mask of the data loader, load_data.py:3043-3072:
+ * sparse_sum_for_anchors_mask (586-591) + cumsum(0).cumsum(1) + fused_get_anchors_area (558-584) on
+ * rbbox2d_to_near_bbox(anchors[:, [0,1,3,4,6]]) (534-548), mask = area > anchor_area_threshold.
+ *   pp_anchor_cells_dev   anchors [A,7] f32 -> cells [A,4] int32 (x0,y0,x1,y1), once per anchor set
+ *   pp_anchor_mask_dev    coors [M,coors_cols] (3: one frame (z,y,x); 4: (frame,z,y,x)), M or *M_dev rows ->
+ *                         area [B,A] f32 (optional), mask [B,A] uint8 (optional),
+ *                         masked_scores [B,A] = mask ? scores : -inf (optional; pp_nms_dev ignores -inf
+ *                         scores, which is how the reference's `box_preds[a_mask]` gather is expressed) */
+PP_API int pp_anchor_cells_dev(const float* anchors, int64_t A, const double voxel_size[3],
+                        const double coors_range[6], int32_t* cells, void* stream);
+PP_API size_t pp_anchor_mask_workspace_bytes(int B, int ny, int nx);
+PP_API int pp_anchor_mask_dev(const int32_t* coors, int coors_cols, int64_t M, const int32_t* M_dev, int B, int ny,
+                       int nx, const int32_t* cells, int64_t A, float threshold, const float* scores,
+                       float* area, uint8_t* mask, float* masked_scores, void* workspace,
+                       size_t workspace_bytes, void* stream);
 
 /* ---- context + host-buffer layer ----------------------------------------------------------- */
 typedef struct pp_ctx pp_ctx;
@@ -207,6 +225,10 @@ PP_API int pp_rbox_to_standup_host(pp_ctx* ctx, const float* boxes, int64_t N, f
 PP_API int pp_nms_host(pp_ctx* ctx, int kind, const float* boxes, const float* scores, int64_t N,
                 int pre_max_size, int post_max_size, float thresh, int64_t* keep,
                 int32_t* keep_count_out);
+/* anchors_area / anchors_mask of one frame, load_data.py:3043-3072: coors [M,3] (z,y,x), anchors [A,7]. */
+PP_API int pp_anchors_mask_host(pp_ctx* ctx, const int32_t* coors, int64_t M, const float* anchors, int64_t A,
+                         const double voxel_size[3], const double coors_range[6], float threshold,
+                         float* area_out, uint8_t* mask_out);
 PP_API int pp_rotate_iou_host(pp_ctx* ctx, const float* boxes, int64_t N, const float* query_boxes,
                        int64_t K, int criterion, float* out);
 

@@ -196,6 +196,35 @@ def rotate_iou_pair(r1, r2, criterion=-1) -> float:
     return float(lib().ppo_rotate_iou_pair(_p(a), _p(b), int(criterion)))
 
 
+def rbbox2d_to_near_bbox(rbboxes):
+    """load_data.py:534-548."""
+    r = np.ascontiguousarray(rbboxes, np.float32)
+    out = np.empty((r.shape[0], 4), np.float32)
+    lib().ppo_rbbox2d_to_near_bbox(_p(r), C.c_int64(r.shape[0]), _p(out))
+    return out
+
+
+def anchor_cells(anchors, voxel_size, coors_range):
+    a = np.ascontiguousarray(anchors, np.float32).reshape(-1, 7)
+    g = (C.c_int32 * 3)(*grid_size(voxel_size, coors_range))
+    out = np.empty((a.shape[0], 4), np.int32)
+    lib().ppo_anchor_cells(_p(a), C.c_int64(a.shape[0]), _d3(voxel_size), _d3(coors_range), g, _p(out))
+    return out
+
+
+def anchors_mask(coors, anchors, voxel_size, coors_range, threshold=1):
+    """load_data.py:3043-3072 for one frame: coors [M,3] (z,y,x) -> (anchors_area f32 [A], mask bool [A])."""
+    co = np.ascontiguousarray(coors, np.int32)
+    cells = anchor_cells(anchors, voxel_size, coors_range)
+    nx, ny, _ = grid_size(voxel_size, coors_range)
+    A = cells.shape[0]
+    area = np.empty((A,), np.float32)
+    mask = np.empty((A,), np.uint8)
+    lib().ppo_anchors_mask(_p(co), C.c_int64(co.shape[0]), ny, nx, _p(cells), C.c_int64(A), C.c_float(threshold),
+                           _p(area), _p(mask))
+    return area, mask.astype(bool)
+
+
 def full_path_batch(points, frame_off, voxel_size, coors_range, max_points, max_voxels, pfn_feats,
                     box_enc, anchors, scores, pre_max, post_max, thresh, rotated=True, nthreads=0):
     """CPU baseline of the whole path over a batch (bench.py only)."""

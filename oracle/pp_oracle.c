@@ -17,6 +17,7 @@
  * Build: plain C99, `gcc -O2 -ffp-contract=off -fno-fast-math` (no FMA contraction: the numba
  * CPU oracle derived from the reference source does not contract either).
  */
+#define _GNU_SOURCE
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -574,6 +575,72 @@ PPO_API int ppo_rotate_nms(const float* dets, int64_t N, float thresh, int pre_m
     for (int i = 0; i < nk; ++i) keep_out[i] = order[keep[i]];
     free(sc); free(order); free(sd); free(mask); free(keep);
     return nk;
+}
+
+
+/* ------------------------------------------------------------------------------------------
+ * "Next" row N1 -- anchor mask (load_data.py:3043-3072).
+ *   rbbox2d_to_near_bbox   load_data.py:534-548 (limit_period 805-806, center_to_minmax_2d_0_5 550-551):
+ *       float32 numpy arithmetic on anchors[:, [0,1,3,4,6]]
+ *   fused_get_anchors_area load_data.py:558-584: cell = floor((bv - offset) / stride) in float64
+ *       (float32 bv, float64 offset/stride), stored to int32, clipped to the grid
+ *   sparse_sum_for_anchors_mask 586-591 + cumsum(0).cumsum(1): pillar counts per (y,x), integral image
+ *   mask = area > anchor_area_threshold
+ * ------------------------------------------------------------------------------------------ */
+PPO_API void ppo_rbbox2d_to_near_bbox(const float* rb, int64_t N, float* out) {
+    const float pi = (float)M_PI;
+    for (int64_t i = 0; i < N; ++i) {
+        const float* r = rb + 5 * i;
+        float t = r[4] / pi;
+        t = t + 0.5f;
+        t = floorf(t) * pi;
+        const float lim = fabsf(r[4] - t);
+        const int cond = lim > (float)(M_PI / 4);
+        const float dx = cond ? r[3] : r[2], dy = cond ? r[2] : r[3];
+        out[4 * i + 0] = r[0] - dx / 2.f;
+        out[4 * i + 1] = r[1] - dy / 2.f;
+        out[4 * i + 2] = r[0] + dx / 2.f;
+        out[4 * i + 3] = r[1] + dy / 2.f;
+    }
+}
+
+/* cell rectangle of every anchor: (x0,y0,x1,y1) as fused_get_anchors_area computes them */
+PPO_API void ppo_anchor_cells(const float* anchors /*[A,7]*/, int64_t A, const double voxel_size[3],
+                              const double coors_range[6], const int32_t grid_xyz[3], int32_t* cells /*[A,4]*/) {
+    for (int64_t i = 0; i < A; ++i) {
+        const float* a = anchors + 7 * i;
+        const float rb[5] = {a[0], a[1], a[3], a[4], a[6]};
+        float bv[4];
+        ppo_rbbox2d_to_near_bbox(rb, 1, bv);
+        int32_t c0 = (int32_t)floor(((double)bv[0] - coors_range[0]) / voxel_size[0]);
+        int32_t c1 = (int32_t)floor(((double)bv[1] - coors_range[1]) / voxel_size[1]);
+        int32_t c2 = (int32_t)floor(((double)bv[2] - coors_range[0]) / voxel_size[0]);
+        int32_t c3 = (int32_t)floor(((double)bv[3] - coors_range[1]) / voxel_size[1]);
+        cells[4 * i + 0] = c0 > 0 ? c0 : 0;
+        cells[4 * i + 1] = c1 > 0 ? c1 : 0;
+        cells[4 * i + 2] = c2 < grid_xyz[0] - 1 ? c2 : grid_xyz[0] - 1;
+        cells[4 * i + 3] = c3 < grid_xyz[1] - 1 ? c3 : grid_xyz[1] - 1;
+    }
+}
+
+/* coors [M,3] (z,y,x) of ONE frame -> area [A] float32, mask [A] uint8 */
+PPO_API void ppo_anchors_mask(const int32_t* coors, int64_t M, int ny, int nx, const int32_t* cells, int64_t A,
+                              float threshold, float* area, uint8_t* mask) {
+    float* map = (float*)calloc((size_t)ny * nx, sizeof(float));
+    for (int64_t m = 0; m < M; ++m) map[(size_t)coors[3 * m + 1] * nx + coors[3 * m + 2]] += 1.f;
+    for (int y = 1; y < ny; ++y)
+        for (int x = 0; x < nx; ++x) map[(size_t)y * nx + x] += map[(size_t)(y - 1) * nx + x];
+    for (int y = 0; y < ny; ++y)
+        for (int x = 1; x < nx; ++x) map[(size_t)y * nx + x] += map[(size_t)y * nx + x - 1];
+    for (int64_t i = 0; i < A; ++i) {
+        const int32_t* c = cells + 4 * i;
+        const float ID = map[(size_t)c[3] * nx + c[2]], IA = map[(size_t)c[1] * nx + c[0]];
+        const float IB = map[(size_t)c[3] * nx + c[0]], IC = map[(size_t)c[1] * nx + c[2]];
+        const float v = ID - IB - IC + IA;
+        area[i] = v;
+        mask[i] = v > threshold;
+    }
+    free(map);
 }
 
 /* ------------------------------------------------------------------------------------------

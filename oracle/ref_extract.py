@@ -80,8 +80,31 @@ def load() -> types.SimpleNamespace:
     exec(_extract_defs(_read("load_data.py"), [
         "_points_to_voxel_reverse_kernel", "_points_to_voxel_kernel", "points_to_voxel",
         "corner_to_standup_nd_jit", "center_to_corner_box2d", "rotation_2d", "corners_nd",
-        "create_anchors_3d_stride",
+        "create_anchors_3d_stride", "sparse_sum_for_anchors_mask", "fused_get_anchors_area",
+        "rbbox2d_to_near_bbox", "limit_period", "center_to_minmax_2d", "center_to_minmax_2d_0_5",
     ]), ns)
+
+    def anchors_mask(coors, anchors, voxel_size, point_cloud_range, threshold):
+        """load_data.py:3043-3072 verbatim call sequence for one frame."""
+        voxel_size = np.asarray(voxel_size, np.float64)
+        pcr = np.asarray(point_cloud_range, np.float64)
+        grid_size = np.round((pcr[3:] - pcr[:3]) / voxel_size).astype(np.int64)
+        anchors_bv = ns["rbbox2d_to_near_bbox"](anchors[:, [0, 1, 3, 4, 6]])
+        dense = ns["sparse_sum_for_anchors_mask"](coors, tuple(grid_size[::-1][1:]))
+        dense = dense.cumsum(0)
+        dense = dense.cumsum(1)
+        area = ns["fused_get_anchors_area"](dense, anchors_bv, voxel_size, pcr, grid_size)
+        return area, area > threshold
+
+    def create_anchors(feature_size, sizes, strides, offsets, rotations):
+        """create_anchors_3d_stride under numpy>=2 (np.meshgrid returns a tuple there; the reference
+        assigns into it, so hand it a list-returning meshgrid for the duration of the call)."""
+        real = np.meshgrid
+        try:
+            np.meshgrid = lambda *a, **k: list(real(*a, **k))
+            return ns["create_anchors_3d_stride"](feature_size, sizes, strides, offsets, rotations)
+        finally:
+            np.meshgrid = real
 
     ehf = _read("libraries/eval_helper_functions.py")
     exec(_extract_defs(ehf, ["second_box_decode", "nms_postprocess", "div_up"]), ns)
@@ -176,7 +199,9 @@ def load() -> types.SimpleNamespace:
         nms_postprocess=ns["nms_postprocess"],
         center_to_corner_box2d=ns["center_to_corner_box2d"],
         corner_to_standup_nd_jit=ns["corner_to_standup_nd_jit"],
-        create_anchors_3d_stride=ns["create_anchors_3d_stride"],
+        create_anchors_3d_stride=create_anchors,
+        anchors_mask=anchors_mask,
+        rbbox2d_to_near_bbox=ns["rbbox2d_to_near_bbox"],
         rotate_iou_matrix=rotate_iou_matrix,
         rotate_iou_matrix_f64=rotate_iou_matrix_f64,
         rotate_nms=rotate_nms,

@@ -99,6 +99,20 @@ def main():
     be[:, 3:6] *= 8  # exercise exp over a wider range
     np.savez_compressed(os.path.join(OUT, "decode.npz"), box_encodings=be, anchors=an,
                         decoded=ref.second_box_decode(be, an))
+    # anchor mask, "next" row N1 (load_data.py:3043-3072)
+    am = {}
+    for cfg, fs, pts, stride in ((synth.D435, [1, 64, 80], synth.d435_cloud(3, True)[:30000], 1),
+                                 (synth.KITTI, [1, 248, 216], synth.kitti_cloud(3), 16)):
+        vs, pcr = np.array(cfg["voxel_size"]), np.array(cfg["point_cloud_range"])
+        anchors = ref.create_anchors_3d_stride(fs, cfg["anchor_sizes"], cfg["anchor_strides"], cfg["anchor_offsets"],
+                                               cfg["anchor_rotations"]).reshape(-1, 7)[::stride].copy()
+        _, coors, _ = ref.points_to_voxel(pts, vs, pcr, cfg["max_points"], True, cfg["max_voxels"])
+        area, mask = ref.anchors_mask(coors, anchors, vs, pcr, 1)
+        n = cfg["name"]
+        am.update({f"{n}_anchors": anchors, f"{n}_coors": coors.copy(), f"{n}_voxel_size": vs, f"{n}_range": pcr,
+                   f"{n}_area": area, f"{n}_mask": mask})
+        print("anchor mask", n, anchors.shape, float(mask.mean()))
+    np.savez_compressed(os.path.join(OUT, "anchor_mask.npz"), **am)
     print("done")
 
 

@@ -237,3 +237,37 @@ def test_rotated_nms_vs_oracle(pp, oracle, synth, n, clustered):
         iou = oracle.rotate_iou_gpu_eval(ds[:, :5], ds[:, :5], -1)
         assert (np.abs(iou - 0.5) < IOU_ATOL).any(), "keep lists differ without a near-threshold pair"
     assert pp.rotate_nms_gpu(d, 0.5, pre_max_size=100, post_max_size=50) == oracle.rotate_nms_gpu(d, 0.5, 100, 50)
+
+
+def test_anchor_mask(pp, oracle, synth):
+    """N1: anchors_area / anchors_mask, integer-exact against the reference fixture and the oracle."""
+    g = golden("anchor_mask.npz")
+    for n in ("d435i", "kitti"):
+        area, mask = pp.anchors_mask(g[f"{n}_coors"], g[f"{n}_anchors"], g[f"{n}_voxel_size"], g[f"{n}_range"], 1)
+        assert area.dtype == np.float32 and mask.dtype == bool
+        assert np.array_equal(area, g[f"{n}_area"]) and np.array_equal(mask, g[f"{n}_mask"])
+    for cfg, pts in ((synth.D435, synth.d435_cloud(12)), (synth.KITTI, synth.kitti_cloud(12, True))):
+        vs, pcr = np.array(cfg["voxel_size"]), np.array(cfg["point_cloud_range"])
+        _, c, _ = oracle.points_to_voxel(pts, vs, pcr, cfg["max_points"], True, cfg["max_voxels"])
+        an = synth.anchors_stride(cfg)
+        for thr in (1, 0, 3):
+            got = pp.anchors_mask(c, an, vs, pcr, thr)
+            want = oracle.anchors_mask(c, an, vs, pcr, thr)
+            assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    a, m = pp.anchors_mask(np.zeros((0, 3), np.int32), synth.anchors_stride(synth.D435), synth.D435["voxel_size"],
+                           synth.D435["point_cloud_range"])
+    assert not a.any() and not m.any()
+
+
+def test_nms_ignores_minus_inf_scores(pp, oracle, synth):
+    """Masked-out anchors carry score -inf and must behave as if gathered away (model/voxelnet.py:1119-1137)."""
+    d = synth.rotated_boxes(3000, 31, clustered=True)
+    rng = np.random.default_rng(1)
+    on = rng.random(3000) < 0.3
+    idx = np.nonzero(on)[0]
+    masked = d.copy(); masked[~on, 5] = -np.inf
+    for pre, post in ((100, 50), (None, None), (2000, None)):
+        want = [int(idx[k]) for k in oracle.rotate_nms_gpu(d[on], 0.5, pre, post)]
+        assert pp.rotate_nms_gpu(masked, 0.5, pre_max_size=pre, post_max_size=post) == want
+    none = d.copy(); none[:, 5] = -np.inf
+    assert pp.rotate_nms_gpu(none, 0.5, pre_max_size=100, post_max_size=50) == []

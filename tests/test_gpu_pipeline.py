@@ -85,6 +85,43 @@ def test_pipeline_kitti_batched(synth, oracle):
     _run(synth, oracle, cfg, frames, rotated=True, layout="NCHW")
 
 
+def test_pipeline_with_anchor_mask(synth, oracle):
+    """N1 wired into the batch pipeline: masked-out anchors never reach NMS (model/voxelnet.py:1119-1137)."""
+    import torch
+    pipeline = importlib.import_module(PKG + ".pipeline")
+    cfg = synth.D435
+    frames = [synth.d435_cloud(40)[:60000], synth.d435_cloud(41, subsample=True), synth.d435_cloud(42)[200000:230000]]
+    B = len(frames)
+    pts = np.concatenate(frames)
+    off = np.cumsum([0] + [f.shape[0] for f in frames]).astype(np.int64)
+    pipe = pipeline.FramePipeline(cfg, device=0, max_frames=B, max_total_points=pts.shape[0], anchor_area_threshold=1)
+    A = pipe.A
+    an = synth.anchors_stride(cfg)
+    box = np.stack([synth.rpn_standin(A, 70 + i)[0] for i in range(B)])
+    sco = np.stack([synth.rpn_standin(A, 70 + i)[1] for i in range(B)])
+    feats = synth.pfn_standin(pipe.cap_rows, cfg["num_filters"], 3)
+    dev = torch.device("cuda", 0)
+    pipe.run(torch.from_numpy(pts).to(dev), torch.from_numpy(off).to(dev), B, pts.shape[0], max(f.shape[0] for f in frames),
+             torch.from_numpy(feats).to(dev), torch.from_numpy(box).to(dev), torch.from_numpy(sco).to(dev))
+    dets_h, cnt_h = pipe.fetch(B)
+    torch.cuda.synchronize()
+    vs, pcr = np.array(cfg["voxel_size"]), np.array(cfg["point_cloud_range"])
+    gm = pipe.anchor_mask.cpu().numpy().astype(bool)
+    for b, f in enumerate(frames):
+        _, oc, _ = oracle.points_to_voxel(f, vs, pcr, cfg["max_points"], True, cfg["max_voxels"])
+        _, mask = oracle.anchors_mask(oc, an, vs, pcr, 1)
+        assert np.array_equal(gm[b], mask) and 0 < mask.sum() < A
+        idx = np.nonzero(mask)[0]
+        boxes = oracle.second_box_decode(box[b], an)
+        dets = np.concatenate([boxes[:, [0, 1, 3, 4, 6]], sco[b][:, None]], axis=1)[idx]
+        keep = [int(idx[k]) for k in oracle.rotate_nms_gpu(dets, cfg["nms_iou_threshold"], cfg["nms_pre_max_size"],
+                                                           cfg["nms_post_max_size"])]
+        assert int(cnt_h[b]) == len(keep)
+        got = dets_h[b, :len(keep)].numpy()
+        np.testing.assert_allclose(got[:, :7], boxes[keep], rtol=1e-5, atol=1e-6)
+        assert np.array_equal(got[:, 7], sco[b][keep])
+
+
 def test_profiler_and_launch_count(pp, synth):
     _lib = importlib.import_module(PKG + "._lib")
     pts = synth.d435_cloud(1, subsample=True)

@@ -130,3 +130,11 @@ def test_decorate_scatter_numpy_restating(oracle, synth):
     want = want.transpose(0, 2, 1).reshape(2, 16, 64, 80)
     np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6)
     np.testing.assert_array_equal(oracle.scatter(feats, c4b, 2, 64, 80, "NHWC"), got.transpose(0, 2, 3, 1))
+
+
+def test_anchor_mask_golden(oracle):
+    g = golden("anchor_mask.npz")
+    for n in ("d435i", "kitti"):
+        area, mask = oracle.anchors_mask(g[f"{n}_coors"], g[f"{n}_anchors"], g[f"{n}_voxel_size"], g[f"{n}_range"], 1)
+        assert area.dtype == np.float32 and np.array_equal(area, g[f"{n}_area"])
+        assert np.array_equal(mask, g[f"{n}_mask"])

@@ -58,3 +58,19 @@ def test_decode_and_standup(ref, oracle, synth):
     dets = np.concatenate([want, d[:, 5:6]], axis=1)
     keep, _ = ref.standup_nms(dets, 0.5)
     assert oracle.nms(want, d[:, 5], None, None, 0.5).tolist() == keep
+
+
+def test_anchors_and_mask(ref, oracle, synth):
+    for cfg, fs in ((synth.D435, [1, 64, 80]), (synth.KITTI, [1, 248, 216])):
+        ra = ref.create_anchors_3d_stride(fs, cfg["anchor_sizes"], cfg["anchor_strides"], cfg["anchor_offsets"],
+                                          cfg["anchor_rotations"]).reshape(-1, 7)
+        an = synth.anchors_stride(cfg)
+        assert ra.dtype == an.dtype and np.array_equal(ra, an)
+        vs, pcr = np.array(cfg["voxel_size"]), np.array(cfg["point_cloud_range"])
+        pts = synth.d435_cloud(9, True) if cfg["name"] == "d435i" else synth.kitti_cloud(9, True)
+        _, c, _ = oracle.points_to_voxel(pts, vs, pcr, cfg["max_points"], True, cfg["max_voxels"])
+        assert np.array_equal(ref.rbbox2d_to_near_bbox(ra[:, [0, 1, 3, 4, 6]]), oracle.rbbox2d_to_near_bbox(an[:, [0, 1, 3, 4, 6]]))
+        for thr in (1, 0, 4):
+            wa, wm = ref.anchors_mask(c, ra, vs, pcr, thr)
+            ga, gm = oracle.anchors_mask(c, an, vs, pcr, thr)
+            assert np.array_equal(wa, ga) and np.array_equal(wm, gm)
