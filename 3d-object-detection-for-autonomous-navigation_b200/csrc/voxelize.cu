@@ -228,7 +228,9 @@ vox_mark_kernel(const T* __restrict__ points, const int64_t* __restrict__ frame_
 }
 
 // ---------------------------------------------------------------------------------------------
-// Pass 2: one cell per thread.
+// Pass 2: four consecutive cells per thread.  Blocks that see no occupied cell (most of a KITTI
+// grid) leave after one barrier.
+constexpr int kCellPerThread = 4;
 __global__ void __launch_bounds__(kCellThreads)
 vox_cell_kernel(const unsigned* __restrict__ first_idx, const int* __restrict__ cnt,
                 const int64_t* __restrict__ frame_off, int ncell, int b0, unsigned* __restrict__ bitmap,
@@ -238,23 +240,45 @@ vox_cell_kernel(const unsigned* __restrict__ first_idx, const int* __restrict__ 
     __shared__ int sm[33];
     __shared__ int s_base, s_obase;
     const int b = b0 + blockIdx.y;
-    const int cell = blockIdx.x * kCellThreads + threadIdx.x;
-    const size_t gc = (size_t)b * ncell + cell;
-    const int c = cell < ncell ? cnt[gc] : 0;
+    const int cell0 = (blockIdx.x * kCellThreads + threadIdx.x) * kCellPerThread;
+    const size_t gc0 = (size_t)b * ncell + cell0;
+    int c[kCellPerThread];
+    if (cell0 + kCellPerThread <= ncell && ((gc0 & 3) == 0)) {
+        const int4 v = *reinterpret_cast<const int4*>(cnt + gc0);
+        c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < kCellPerThread; ++j) c[j] = cell0 + j < ncell ? cnt[gc0 + j] : 0;
+    }
+    if (cell_voxel) {
+#pragma unroll
+        for (int j = 0; j < kCellPerThread; ++j) if (cell0 + j < ncell) cell_voxel[gc0 + j] = -1;
+    }
+    int tcnt = 0, tocc = 0;
+#pragma unroll
+    for (int j = 0; j < kCellPerThread; ++j) { tcnt += c[j]; tocc += c[j] > 0; }
+    if (!__syncthreads_or(tocc)) return;
     int tot, otot;
-    const int ex = block_excl_scan(c, &tot, sm);
-    const int oex = block_excl_scan(c > 0, &otot, sm);
+    int ex = block_excl_scan(tcnt, &tot, sm);
+    int oex = block_excl_scan(tocc, &otot, sm);
     if (threadIdx.x == 0) {
-        s_base = tot ? atomicAdd(&frame_cursor[b], tot) : 0;
-        s_obase = otot ? atomicAdd(&frame_occ[b], otot) : 0;
+        s_base = atomicAdd(&frame_cursor[b], tot);
+        s_obase = atomicAdd(&frame_occ[b], otot);
     }
     __syncthreads();
-    if (cell < ncell && cell_voxel) cell_voxel[gc] = -1;
-    if (c > 0) {
-        const unsigned f = first_idx[gc];
-        atomicOr(&bitmap[word_base(frame_off, b) + (f >> 5)], 1u << (f & 31));
-        cell_off[gc] = s_base + ex;  // frame-local offset into the frame's bucket range
-        occ_list[(size_t)b * ncell + s_obase + oex] = cell;  // frame-major: the gather pass walks frame by frame
+    ex += s_base;
+    oex += s_obase;
+    const int64_t wb = word_base(frame_off, b);
+#pragma unroll
+    for (int j = 0; j < kCellPerThread; ++j) {
+        if (c[j] > 0) {
+            const unsigned f = first_idx[gc0 + j];
+            atomicOr(&bitmap[wb + (f >> 5)], 1u << (f & 31));
+            cell_off[gc0 + j] = ex;  // frame-local offset into the frame's bucket range
+            occ_list[(size_t)b * ncell + oex] = cell0 + j;  // frame-major: the gather pass walks frame by frame
+            ex += c[j];
+            ++oex;
+        }
     }
 }
 
@@ -872,7 +896,7 @@ extern "C" int pp_voxelize_dev(const pp_voxel_cfg* cfg, const void* points, int 
             PP_LAUNCHED();
         }
         {
-            const dim3 g((unsigned)ceil_div(ncell, kCellThreads), nb);
+            const dim3 g((unsigned)ceil_div(ncell, kCellThreads * kCellPerThread), nb);
             PP_TIMED("vox_cell", st);
             vox_cell_kernel<<<g, kCellThreads, 0, st>>>(w.first_idx, w.cnt, frame_offsets, (int)ncell, b0,
                                                         w.bitmap, w.cell_off, w.frame_cursor, w.occ_list,
