@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(kCellThreads)
 vox_cell_kernel(const unsigned* __restrict__ first_idx, const int* __restrict__ cnt,
                 const int64_t* __restrict__ frame_off, int ncell, int b0, unsigned* __restrict__ bitmap,
                 int* __restrict__ cell_off, int* __restrict__ frame_cursor,
-                int* __restrict__ occ_list, int* __restrict__ frame_occ,
+                int4* __restrict__ occ_desc, int* __restrict__ frame_occ,
                 int* __restrict__ cell_voxel) {
     __shared__ int sm[33];
     __shared__ int s_base, s_obase;
@@ -268,14 +268,17 @@ vox_cell_kernel(const unsigned* __restrict__ first_idx, const int* __restrict__ 
     __syncthreads();
     ex += s_base;
     oex += s_obase;
-    const int64_t wb = word_base(frame_off, b);
+    const int64_t f0 = frame_off[b];
+    const int64_t wb = (f0 >> 5) + b;
 #pragma unroll
     for (int j = 0; j < kCellPerThread; ++j) {
         if (c[j] > 0) {
             const unsigned f = first_idx[gc0 + j];
             atomicOr(&bitmap[wb + (f >> 5)], 1u << (f & 31));
             cell_off[gc0 + j] = ex;  // frame-local offset into the frame's bucket range
-            occ_list[(size_t)b * ncell + oex] = cell0 + j;  // frame-major: the gather pass walks frame by frame
+            // one 16-byte descriptor per occupied cell, listed frame by frame: everything the later
+            // passes need comes from a single coalesced load {cell, first index, count, bucket offset}
+            occ_desc[(size_t)b * ncell + oex] = make_int4(cell0 + j, (int)f, c[j], (int)(f0 + ex));
             ex += c[j];
             ++oex;
         }
@@ -345,6 +348,38 @@ vox_rank_kernel(const unsigned* __restrict__ bitmap, unsigned* __restrict__ word
         occ_base[B] = running;
         *done_counter = 0;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pass 3b: one thread per occupied cell: voxel id (rank of its first index) -> packed output row,
+// coordinates of the row, optional cell->row map.  The descriptor's `first` field becomes the row
+// (-1 for cells past the max_voxels cap).
+__global__ void __launch_bounds__(256)
+vox_rowmap_kernel(int4* __restrict__ occ_desc, const int* __restrict__ occ_base, const int64_t* __restrict__ frame_off,
+                  VoxParams p, int b0, const unsigned* __restrict__ bitmap, const unsigned* __restrict__ word_prefix,
+                  const int* __restrict__ voxel_base, int64_t cap_rows, int* __restrict__ coors, int coors_cols,
+                  int* __restrict__ cell_voxel) {
+    const int bl = blockIdx.y, b = b0 + bl;
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= occ_base[bl + 1] - occ_base[bl]) return;
+    int4 d = occ_desc[(size_t)b * p.ncell + k];
+    const unsigned f = (unsigned)d.y;
+    const int64_t wb = word_base(frame_off, b);
+    const int rank = (int)word_prefix[wb + (f >> 5)] + __popc(bitmap[wb + (f >> 5)] & ((1u << (f & 31)) - 1u));
+    int64_t row = rank < p.max_voxels ? (int64_t)voxel_base[b] + rank : -1;
+    if (row >= cap_rows) row = -1;
+    d.y = (int)row;
+    occ_desc[(size_t)b * p.ncell + k] = d;
+    if (row < 0) return;
+    const int cell = d.x;
+    const int cz = p.div_nxny.div(cell);
+    const int rem = cell - cz * p.grid[0] * p.grid[1];
+    const int cy = p.div_nx.div(rem), cx = rem - cy * p.grid[0];
+    int* co = coors + row * coors_cols;
+    if (coors_cols == 4) *co++ = b;
+    if (p.reverse_index) { co[0] = cz; co[1] = cy; co[2] = cx; }
+    else { co[0] = cx; co[1] = cy; co[2] = cz; }
+    if (cell_voxel) cell_voxel[(size_t)b * p.ncell + cell] = (int)row;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -471,18 +506,25 @@ __device__ __forceinline__ int load_sort_bucket(const int* __restrict__ seg, int
     for (int r = 0; r < R; ++r) n += __popc(__ballot_sync(0xffffffffu, v[r] != kIdxInf));
     return n;
 }
+// same for values already in registers
+template <int R>
+__device__ __forceinline__ int sort_bucket_regs(int cut, int lane, int (&v)[R]) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = v[r] < cut ? v[r] : kIdxInf;
+    warp_bitonic_sort<R>(v, lane);
+    int n = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) n += __popc(__ballot_sync(0xffffffffu, v[r] != kIdxInf));
+    return n;
+}
 
 template <typename T, typename TO, int DS>
 __global__ void __launch_bounds__(kGatherWarps * 32, PP_GATHER_MINBLOCKS)
 vox_gather_kernel(const T* __restrict__ points, const int64_t* __restrict__ frame_off, VoxParams p, int b0, int nb,
-                  const int* __restrict__ occ_list, const int* __restrict__ occ_base,
-                  const unsigned* __restrict__ first_idx, const int* __restrict__ cnt,
-                  const int* __restrict__ cell_off, const int* __restrict__ bucket,
-                  const unsigned* __restrict__ bitmap, const unsigned* __restrict__ word_prefix,
-                  const int* __restrict__ cutoff, const int* __restrict__ voxel_base,
-                  int64_t cap_rows, TO* __restrict__ voxels, float* __restrict__ decorated,
-                  int* __restrict__ coors, int coors_cols, int* __restrict__ num_points,
-                  int* __restrict__ point_slot, int* __restrict__ cell_voxel) {
+                  const int4* __restrict__ occ_desc, const int* __restrict__ occ_base,
+                  const int* __restrict__ bucket, const int* __restrict__ cutoff,
+                  const int* __restrict__ voxel_base, TO* __restrict__ voxels, float* __restrict__ decorated,
+                  int* __restrict__ num_points, int* __restrict__ point_slot) {
     extern __shared__ __align__(16) unsigned char gsm_raw[];
     const int P = p.max_points;
     const int D = DS ? DS : p.D;
@@ -495,48 +537,57 @@ vox_gather_kernel(const T* __restrict__ points, const int64_t* __restrict__ fram
     float* vrow = reinterpret_cast<float*>(ord + nord);
     float* dsm = vrow + nvox;
 
-    // occupied cells are listed per frame (occ_list[b*ncell + k], k < occ_base[bl+1]-occ_base[bl]); the
-    // grid walks them frame by frame so that one or two frames' points are live in L2 at a time
+    // Occupied cells are listed frame by frame as 16-byte descriptors {cell, row, count, bucket offset}.
+    // Two-deep software pipeline per warp: while cell e is processed, the descriptor of cell e+2*stride
+    // and the first 64 bucket entries (+ frame constants) of cell e+stride are already in flight, so a
+    // cell costs one exposed memory round trip (the point gather) instead of three.
     const int nocc = occ_base[nb];
     const int nwarps = gridDim.x * kGatherWarps;
-    // one-deep software pipeline on the per-cell metadata: the next cell's first/count/offset
-    // loads are issued before this cell's bucket is processed
+    auto load_desc = [&](int ee, int& bl) -> int4 {
+        while (ee >= occ_base[bl + 1]) ++bl;
+        return occ_desc[(size_t)(b0 + bl) * p.ncell + (ee - occ_base[bl])];
+    };
+    auto load_head = [&](const int4& d, int bl, int& v0, int& v1, int& cut, int64_t& f0) {
+        const int* seg = bucket + d.w;
+        v0 = (d.y >= 0 && lane < d.z) ? seg[lane] : kIdxInf;
+        v1 = (d.y >= 0 && lane + 32 < d.z) ? seg[lane + 32] : kIdxInf;
+        cut = cutoff[b0 + bl];
+        f0 = frame_off[b0 + bl];
+    };
     int e = blockIdx.x * kGatherWarps + w;
-    int bl_n = 0, gc_n = 0, L_n = 0, coff_n = 0;
-    unsigned f_n = 0;
-    if (e < nocc) {
-        while (e >= occ_base[bl_n + 1]) ++bl_n;
-        gc_n = (b0 + bl_n) * p.ncell + occ_list[(size_t)(b0 + bl_n) * p.ncell + (e - occ_base[bl_n])];
-        f_n = first_idx[gc_n]; L_n = cnt[gc_n]; coff_n = cell_off[gc_n];
-    }
+    int4 d0 = make_int4(0, -1, 0, 0), d1 = d0;
+    int bl0 = 0, bl1 = 0, bl2 = 0;
+    int hv0 = kIdxInf, hv1 = kIdxInf, hcut = 0;
+    int64_t hf0 = 0;
+    if (e < nocc) d0 = load_desc(e, bl0);
+    bl1 = bl0;
+    if (e + nwarps < nocc) d1 = load_desc(e + nwarps, bl1);
+    bl2 = bl1;
+    if (e < nocc) load_head(d0, bl0, hv0, hv1, hcut, hf0);
+
     for (; e < nocc; e += nwarps) {
-        const int gc = gc_n, L = L_n, coff = coff_n, b = b0 + bl_n;
-        const unsigned f = f_n;
-        const int cell = gc - b * p.ncell;
-        if (e + nwarps < nocc) {
-            const int en = e + nwarps;
-            while (en >= occ_base[bl_n + 1]) ++bl_n;
-            gc_n = (b0 + bl_n) * p.ncell + occ_list[(size_t)(b0 + bl_n) * p.ncell + (en - occ_base[bl_n])];
-            f_n = first_idx[gc_n]; L_n = cnt[gc_n]; coff_n = cell_off[gc_n];
-        }
-        const int64_t wb = word_base(frame_off, b);
-        const int rank = (int)word_prefix[wb + (f >> 5)] + __popc(bitmap[wb + (f >> 5)] & ((1u << (f & 31)) - 1u));
-        if (rank >= p.max_voxels) continue;
-        const int64_t row = (int64_t)voxel_base[b] + rank;
-        if (row >= cap_rows) continue;
-        const int64_t f0 = frame_off[b];
-        const int* seg = bucket + f0 + coff;
-        const int cut = cutoff[b];
+        int4 d2 = d1;
+        if (e + 2 * nwarps < nocc) d2 = load_desc(e + 2 * nwarps, bl2);
+        int nv0 = kIdxInf, nv1 = kIdxInf, ncut = 0;
+        int64_t nf0 = 0;
+        if (e + nwarps < nocc) load_head(d1, bl1, nv0, nv1, ncut, nf0);
+
+      if (d0.y >= 0) {
+        const int cell = d0.x, L = d0.z, b = b0 + bl0;
+        const int64_t row = d0.y;
+        const int64_t f0 = hf0;
+        const int* seg = bucket + d0.w;
+        const int cut = hcut;
         int nsel;
 
         // ---- ord[s] = point index of slot s
         if (L <= 32) {
-            int v[1];
-            nsel = min(load_sort_bucket<1>(seg, L, cut, lane, v), P);
+            int v[1] = {hv0};
+            nsel = min(sort_bucket_regs<1>(cut, lane, v), P);
             if (lane < nsel) ord[lane] = v[0];
         } else if (L <= 64) {
-            int v[2];
-            nsel = min(load_sort_bucket<2>(seg, L, cut, lane, v), P);
+            int v[2] = {hv0, hv1};
+            nsel = min(sort_bucket_regs<2>(cut, lane, v), P);
 #pragma unroll
             for (int r = 0; r < 2; ++r) if (r * 32 + lane < nsel) ord[r * 32 + lane] = v[r];
         } else if (L <= 128) {
@@ -560,7 +611,7 @@ vox_gather_kernel(const T* __restrict__ points, const int64_t* __restrict__ fram
             int thr = cut;
             if (Lc > P) {
                 // smallest thr with #{idx < thr} >= P (distinct indices => exactly P)
-                int lo = (int)f + 1, hi = cut;
+                int lo = 0, hi = cut;
                 while (lo < hi) {
                     const int mid = lo + ((hi - lo) >> 1);
                     int g = 0;
@@ -572,14 +623,14 @@ vox_gather_kernel(const T* __restrict__ points, const int64_t* __restrict__ fram
                 thr = lo;
             }
             nsel = min(Lc, P);
-            int nb = 0;
+            int nb_ = 0;
             for (int k0 = 0; k0 < L; k0 += 32) {
                 const int k = k0 + lane;
                 const int x = k < L ? seg[k] : kIdxInf;
                 const bool pr = x < thr;
                 const unsigned bal = __ballot_sync(0xffffffffu, pr);
-                if (pr) sel[nb + __popc(bal & lanemask_lt())] = x;
-                nb += __popc(bal);
+                if (pr) sel[nb_ + __popc(bal & lanemask_lt())] = x;
+                nb_ += __popc(bal);
             }
             __syncwarp();
             for (int j = lane; j < nsel; j += 32) {
@@ -591,17 +642,10 @@ vox_gather_kernel(const T* __restrict__ points, const int64_t* __restrict__ fram
         }
         __syncwarp();
 
-        const int cz = p.div_nxny.div(cell);
-        const int rem = cell - cz * p.grid[0] * p.grid[1];
+        const int rem = cell - p.div_nxny.div(cell) * p.grid[0] * p.grid[1];
         const int cy = p.div_nx.div(rem), cx = rem - cy * p.grid[0];
-        if (lane == 0) {
-            num_points[row] = nsel;
-            int* co = coors + row * coors_cols;
-            if (coors_cols == 4) *co++ = b;
-            if (p.reverse_index) { co[0] = cz; co[1] = cy; co[2] = cx; }
-            else { co[0] = cx; co[1] = cy; co[2] = cz; }
-            if (cell_voxel) cell_voxel[gc] = (int)row;
-        }
+        if (lane == 0) num_points[row] = nsel;
+        const int rank = point_slot ? (int)(row - voxel_base[b]) : 0;
         const T* fp = points + f0 * D;
         // ---- gather each selected point once; zero the padding of the row
         float sx = 0.f, sy = 0.f, sz = 0.f;
@@ -682,6 +726,11 @@ vox_gather_kernel(const T* __restrict__ points, const int64_t* __restrict__ fram
             }
         }
         __syncwarp();
+      }
+        // rotate the pipeline
+        d0 = d1; d1 = d2;
+        bl0 = bl1; bl1 = bl2;
+        hv0 = nv0; hv1 = nv1; hcut = ncut; hf0 = nf0;
     }
 }
 
@@ -695,7 +744,7 @@ struct VoxWorkspace {
     int* done_counter;    // [B]        -- zero region ends here
     unsigned* word_prefix;  // [nwords]
     int* cell_off;        // [B*ncell]
-    int* occ_list;        // [B*ncell] (worst case every cell occupied, bounded by total_points)
+    int4* occ_desc;       // [B*ncell] descriptors of occupied cells, frame-major
     int* cutoff;          // [B]
     int* occ_base;        // [2B+1] per-chunk exclusive scans of frame_occ
     int2* cellpos;        // [total_points]
@@ -720,7 +769,7 @@ static VoxWorkspace carve(void* ws, int64_t ncell, int64_t total_points, int B) 
     w.word_prefix = c.take<unsigned>(nwords);
     w.cell_off = c.take<int>(nc);
     (void)nocc;
-    w.occ_list = c.take<int>(nc + 1);
+    w.occ_desc = c.take<int4>(nc + 1);
     w.cutoff = c.take<int>(B);
     w.occ_base = c.take<int>(2 * (size_t)B + 2);
     w.cellpos = c.take<int2>((size_t)total_points + 1);
@@ -763,10 +812,9 @@ extern "C" size_t pp_voxelize_workspace_bytes(const pp_voxel_cfg* cfg, int64_t t
 
 template <typename T, typename TO, int DS>
 static int launch_gather(const VoxParams& p, const VoxWorkspace& w, const void* points,
-                         const int64_t* frame_off, int64_t cap_rows, void* voxels, float* decorated,
-                         int32_t* coors, int coors_cols, int32_t* num_points,
-                         const int32_t* voxel_base, int32_t* point_slot, int32_t* cell_voxel,
-                         int b0, int nb, const int* occ_base, int64_t max_occ, cudaStream_t st) {
+                         const int64_t* frame_off, void* voxels, float* decorated, int32_t* num_points,
+                         const int32_t* voxel_base, int32_t* point_slot, int b0, int nb, const int* occ_base,
+                         int64_t max_occ, cudaStream_t st) {
     const int P_ = p.max_points, D_ = p.D;
     const size_t per_warp = (size_t)(((P_ + 3) & ~3) + ((P_ * D_ + 3) & ~3) + (DS == 3 ? 0 : ((P_ * (D_ + 5) + 3) & ~3))) * 4;
     const size_t smem = (size_t)kGatherWarps * per_warp;
@@ -781,9 +829,8 @@ static int launch_gather(const VoxParams& p, const VoxWorkspace& w, const void* 
     if (blocks < 1) blocks = 1;
     PP_TIMED("vox_gather", st);
     kern<<<(unsigned)blocks, kGatherWarps * 32, smem, st>>>(
-        static_cast<const T*>(points), frame_off, p, b0, nb, w.occ_list, occ_base, w.first_idx, w.cnt,
-        w.cell_off, w.bucket, w.bitmap, w.word_prefix, w.cutoff, voxel_base, cap_rows,
-        static_cast<TO*>(voxels), decorated, coors, coors_cols, num_points, point_slot, cell_voxel);
+        static_cast<const T*>(points), frame_off, p, b0, nb, w.occ_desc, occ_base, w.bucket, w.cutoff, voxel_base,
+        static_cast<TO*>(voxels), decorated, num_points, point_slot);
     PP_LAUNCHED();
     return PP_OK;
 }
@@ -816,6 +863,7 @@ extern "C" int pp_voxelize_dev(const pp_voxel_cfg* cfg, const void* points, int 
     const int64_t ncell = ncell_of(cfg, grid);
     PP_CHECK_ARG(grid[0] > 0 && grid[1] > 0 && grid[2] > 0, "empty grid %d x %d x %d", grid[0], grid[1], grid[2]);
     PP_CHECK_ARG(ncell * n_frames < ((int64_t)1 << 31), "n_frames * cells must be < 2^31");
+    PP_CHECK_ARG(total_points < ((int64_t)1 << 31), "a batch may hold < 2^31 points (bucket offsets are int32)");
     const VoxWorkspace w = carve(workspace, ncell, total_points, n_frames);
     if (w.total > workspace_bytes) {
         set_error("pp_voxelize_dev: workspace %zu < required %zu", workspace_bytes, w.total);
@@ -899,7 +947,7 @@ extern "C" int pp_voxelize_dev(const pp_voxel_cfg* cfg, const void* points, int 
             const dim3 g((unsigned)ceil_div(ncell, kCellThreads * kCellPerThread), nb);
             PP_TIMED("vox_cell", st);
             vox_cell_kernel<<<g, kCellThreads, 0, st>>>(w.first_idx, w.cnt, frame_offsets, (int)ncell, b0,
-                                                        w.bitmap, w.cell_off, w.frame_cursor, w.occ_list,
+                                                        w.bitmap, w.cell_off, w.frame_cursor, w.occ_desc,
                                                         w.frame_occ, cell_voxel);
             PP_LAUNCHED();
         }
@@ -910,19 +958,27 @@ extern "C" int pp_voxelize_dev(const pp_voxel_cfg* cfg, const void* points, int 
                                                          w.frame_occ, occ_base, w.done_counter + chunk_id);
             PP_LAUNCHED();
         }
+        const int64_t chunk_pts = (int64_t)nb * max_frame_points;
+        const int64_t frame_occ_max = ncell < max_frame_points ? ncell : max_frame_points;
+        if (frame_occ_max > 0) {
+            const dim3 g((unsigned)ceil_div(frame_occ_max, 256), nb);
+            PP_TIMED("vox_rowmap", st);
+            vox_rowmap_kernel<<<g, 256, 0, st>>>(w.occ_desc, occ_base, frame_offsets, p, b0, w.bitmap, w.word_prefix,
+                                                 voxel_base, cap_rows, coors, coors_cols, cell_voxel);
+            PP_LAUNCHED();
+        }
         if (max_frame_points > 0) {
             const dim3 g((unsigned)ceil_div(max_frame_points, 256 * kBucketPPT), nb);
             PP_TIMED("vox_bucket", st);
             vox_bucket_kernel<<<g, 256, 0, st>>>(w.cellpos, frame_offsets, (int)ncell, b0, w.cell_off, w.bucket);
             PP_LAUNCHED();
         }
-        const int64_t chunk_pts = (int64_t)nb * max_frame_points;
         const int64_t max_occ = (int64_t)nb * ncell < chunk_pts ? (int64_t)nb * ncell : chunk_pts;
         if (max_occ > 0 && cap_rows > 0) {
             int rc;
 #define PP_GATHER(T, TO, DS)                                                                                   \
-    launch_gather<T, TO, DS>(p, w, points, frame_offsets, cap_rows, voxels, decorated, coors, coors_cols,     \
-                             num_points, voxel_base, point_slot, cell_voxel, b0, nb, occ_base, max_occ, st)
+    launch_gather<T, TO, DS>(p, w, points, frame_offsets, voxels, decorated, num_points, voxel_base,          \
+                             point_slot, b0, nb, occ_base, max_occ, st)
             if (point_dtype == PP_F64 && out_dtype == PP_F64) rc = PP_GATHER(double, double, 0);
             else if (point_dtype == PP_F64) rc = D == 3 ? PP_GATHER(double, float, 3) : D == 4 ? PP_GATHER(double, float, 4) : PP_GATHER(double, float, 0);
             else rc = D == 3 ? PP_GATHER(float, float, 3) : D == 4 ? PP_GATHER(float, float, 4) : PP_GATHER(float, float, 0);
