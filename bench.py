@@ -46,7 +46,7 @@ def algorithmic_bytes(cfg, n_points, m_pillars, n_anchors, pre_max, grid, s_in):
                 total=vox + dec + sca + dcd + nms,
                 # per-kernel split used for the dominant-kernel roofline
                 vox_mark=n_points * D * s_in,
-                vox_gather=m_pillars * P * D * 4 + m_pillars * 16 + dec,
+                vox_gather=m_pillars * P * D * 4 + m_pillars * 4 + dec,  # voxel rows + num_points + decorated rows
                 scatter_canvas=sca)
 
 
@@ -359,7 +359,7 @@ def main():
                 "kernel_share_of_step": cand[dom] / step_kernel_ms if step_kernel_ms else None}
     path_gbs = ab["total"] * F * args.steps / (ms * 1e-3) / 1e9 / world * world  # per GPU == aggregate/world
     vs_gbs = (ab["voxelize"] + ab["decorate"] + ab["scatter"]) * F / max(1e-9, sum(
-        kern_ms.get(k, 0.0) for k in ("vox_memset", "vox_mark", "vox_cell", "vox_rank", "vox_bucket", "vox_gather",
+        kern_ms.get(k, 0.0) for k in ("vox_memset", "vox_mark", "vox_cell", "vox_rank", "vox_rowmap", "vox_bucket", "vox_gather",
                                       "scatter_link", "scatter_canvas")) * 1e-3) / 1e9
 
     # ---- CPU baseline (oracle port, bounded sample) ----------------------------------------------
