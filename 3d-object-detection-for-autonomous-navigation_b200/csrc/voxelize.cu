@@ -649,6 +649,37 @@ vox_gather_kernel(const T* __restrict__ points, const int64_t* __restrict__ fram
         const T* fp = points + f0 * D;
         // ---- gather each selected point once; zero the padding of the row
         float sx = 0.f, sy = 0.f, sz = 0.f;
+        if (P <= 64 && DS != 0) {
+            // both rounds of point loads are issued before either is consumed (one exposed round trip)
+            T raw[2][DS ? DS : 1];
+            int pi[2];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int s = r * 32 + lane;
+                pi[r] = s < nsel ? ord[s] : 0;
+                const T* q = fp + (int64_t)pi[r] * D;
+#pragma unroll
+                for (int d = 0; d < (DS ? DS : 1); ++d) raw[r][d] = s < nsel ? q[d] : (T)0;
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int s = r * 32 + lane;
+                if (s < nsel) {
+                    if (point_slot) point_slot[f0 + pi[r]] = rank * P + s;
+                    if (sizeof(TO) == 8) {
+                        TO* vo = voxels + (row * (int64_t)P + s) * D;
+#pragma unroll
+                        for (int d = 0; d < (DS ? DS : 1); ++d) vo[d] = (TO)raw[r][d];
+                    }
+                    float c[DS ? DS : 1];
+#pragma unroll
+                    for (int d = 0; d < (DS ? DS : 1); ++d) c[d] = (float)raw[r][d];
+#pragma unroll
+                    for (int d = 0; d < (DS ? DS : 1); ++d) vrow[s * D + d] = c[d];
+                    sx += c[0]; sy += c[1 % (DS ? DS : 1)]; sz += c[2 % (DS ? DS : 1)];
+                }
+            }
+        } else
         for (int s = lane; s < nsel; s += 32) {
             const int pi = ord[s];
             const T* q = fp + (int64_t)pi * D;
@@ -732,6 +763,274 @@ vox_gather_kernel(const T* __restrict__ points, const int64_t* __restrict__ fram
         bl0 = bl1; bl1 = bl2;
         hv0 = nv0; hv1 = nv1; hcut = ncut; hf0 = nf0;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pass 5, asynchronous variant (float32 output rows, max_points <= 64, point width 3 or 4).
+// Same algorithm as vox_gather_kernel, restructured as a three-stage cp.async pipeline per warp so
+// that no global-memory round trip is exposed:
+//     iteration i:  H  cp.async the bucket head (first 64 indices) of pillar i+2       -> hd[(i+2)%3]
+//                   S  pillar i+1: head from shared memory -> register bitonic sort -> slot order;
+//                      cp.async the selected point rows                                 -> raw[(i+1)%2]
+//                   F  pillar i: point rows from shared memory -> float32 row, mean, decoration,
+//                      16-byte streaming stores
+// Descriptors are read 32 pillars at a time (lane k keeps the descriptor of pillar i+k) and handed
+// around with shuffles.  Buckets longer than 64 indices fetch their tail synchronously in stage S.
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src, int bytes) {
+    const unsigned d = smem_u32(smem_dst);
+    if (bytes == 16) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+    else if (bytes == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename T, int DS>
+__global__ void __launch_bounds__(kGatherWarps * 32, PP_GATHER_MINBLOCKS)
+vox_gather_async_kernel(const T* __restrict__ points, const int64_t* __restrict__ frame_off, VoxParams p, int b0, int nb,
+                        const int4* __restrict__ occ_desc, const int* __restrict__ occ_base,
+                        const int* __restrict__ bucket, const int* __restrict__ cutoff,
+                        const int* __restrict__ voxel_base, float* __restrict__ voxels, float* __restrict__ decorated,
+                        int* __restrict__ num_points, int* __restrict__ point_slot) {
+    extern __shared__ __align__(16) unsigned char gsm_raw[];
+    constexpr int D = DS, Do = DS + 5;
+    constexpr int kRowBytes = DS * (int)sizeof(T);
+    constexpr int kCopy = (kRowBytes % 16 == 0) ? 16 : (kRowBytes % 8 == 0) ? 8 : 4;
+    const int P = p.max_points;  // <= 64
+    const int lane = lane_id(), w = threadIdx.x >> 5;
+    // per-warp carve (bytes): hd[3][64] int | so[2][64] int | raw[2][64*kRowBytes] | vrow[64*D] float
+    constexpr int kWarpBytes = 3 * 64 * 4 + 2 * 64 * 4 + 2 * 64 * kRowBytes + 64 * D * 4;
+    unsigned char* base = gsm_raw + (size_t)w * kWarpBytes;
+    int* hd = reinterpret_cast<int*>(base);
+    int* so = hd + 3 * 64;
+    unsigned char* raw = reinterpret_cast<unsigned char*>(so + 2 * 64);
+    float* vrow = reinterpret_cast<float*>(raw + 2 * 64 * kRowBytes);
+
+    const int nocc = occ_base[nb];
+    const int nwarps = gridDim.x * kGatherWarps;
+    const int e0 = blockIdx.x * kGatherWarps + w;
+    if (e0 >= nocc) return;
+    const int niter = (nocc - e0 + nwarps - 1) / nwarps;
+
+    // descriptor window: lane k holds pillar (win + k); refilled every 32 iterations
+    int4 dwin = make_int4(0, -1, 0, 0);
+    int dwin_bl = 0, bl_fill = 0;  // frame of the lane's descriptor; monotone frame pointer for the fills
+    auto fill = [&](int it0) {
+        // lanes look up consecutive pillars of this warp: it0 + lane
+        const int it = it0 + lane;
+        dwin = make_int4(0, -1, 0, 0);
+        int bl = bl_fill;
+        if (it < niter) {
+            const int ee = e0 + it * nwarps;
+            while (ee >= occ_base[bl + 1]) ++bl;
+            dwin = occ_desc[(size_t)(b0 + bl) * p.ncell + (ee - occ_base[bl])];
+        }
+        dwin_bl = bl;
+        bl_fill = __shfl_sync(0xffffffffu, bl, 0);  // later fills (same or later window) start from lane 0's frame
+    };
+    auto desc_of = [&](int it, int4& d, int& bl) {
+        const int k = it & 31;
+        d.x = __shfl_sync(0xffffffffu, dwin.x, k); d.y = __shfl_sync(0xffffffffu, dwin.y, k);
+        d.z = __shfl_sync(0xffffffffu, dwin.z, k); d.w = __shfl_sync(0xffffffffu, dwin.w, k);
+        bl = __shfl_sync(0xffffffffu, dwin_bl, k);
+    };
+    // stage H: bucket head of pillar `it` -> hd[it % 3]
+    auto stage_head = [&](int it, const int4& d) {
+        if (it < niter && d.y >= 0) {
+            const int* seg = bucket + d.w;
+            int* dst = hd + (it % 3) * 64;
+            if (lane < d.z) cp_async(dst + lane, seg + lane, 4);
+            if (lane + 32 < d.z) cp_async(dst + lane + 32, seg + lane + 32, 4);
+        }
+        cp_async_commit();
+    };
+
+    // per-stage state carried from S(i+1) to F(i+1)
+    int s_nsel = 0, s_row = -1, s_cell = 0, s_b = 0;
+    int64_t s_f0 = 0;
+    // stage S for pillar `it` (descriptor d, frame bl): slot order -> so[it&1], point rows -> raw[it&1]
+    auto stage_sort = [&](int it, const int4& d, int bl) {
+        s_row = -1;
+        if (it < niter && d.y >= 0) {
+            const int L = d.z, b = b0 + bl;
+            const int* seg = bucket + d.w;
+            const int cut = cutoff[b];
+            const int64_t f0 = frame_off[b];
+            const int* h = hd + (it % 3) * 64;
+            int* o = so + (it & 1) * 64;
+            int nsel;
+            if (L <= 32) {
+                int v[1] = {lane < L ? h[lane] : kIdxInf};
+                nsel = sort_bucket_regs<1>(cut, lane, v);
+                o[lane] = v[0];
+            } else if (L <= 64) {
+                int v[2] = {h[lane], lane + 32 < L ? h[lane + 32] : kIdxInf};
+                nsel = sort_bucket_regs<2>(cut, lane, v);
+                o[lane] = v[0]; o[lane + 32] = v[1];
+            } else if (L <= 128) {
+                int v[4];
+                nsel = load_sort_bucket<4>(seg, L, cut, lane, v);
+                o[lane] = v[0]; o[lane + 32] = v[1];
+            } else if (L <= 32 * kSegRegs) {
+                int v[kSegRegs];
+                nsel = load_sort_bucket<kSegRegs>(seg, L, cut, lane, v);
+                o[lane] = v[0]; o[lane + 32] = v[1];
+            } else {
+                // long bucket (heavy skew): threshold search streaming the bucket, then rank by counting;
+                // vrow is free here (stage F of the previous pillar has finished with it)
+                int* sel = reinterpret_cast<int*>(vrow);
+                int Lc = 0;
+                for (int k = lane; k < L; k += 32) Lc += seg[k] < cut;
+#pragma unroll
+                for (int q = 16; q; q >>= 1) Lc += __shfl_xor_sync(0xffffffffu, Lc, q);
+                int thr = cut;
+                if (Lc > P) {
+                    int lo = 0, hi = cut;
+                    while (lo < hi) {
+                        const int mid = lo + ((hi - lo) >> 1);
+                        int g = 0;
+                        for (int k = lane; k < L; k += 32) g += seg[k] < mid;
+#pragma unroll
+                        for (int q = 16; q; q >>= 1) g += __shfl_xor_sync(0xffffffffu, g, q);
+                        if (g >= P) hi = mid; else lo = mid + 1;
+                    }
+                    thr = lo;
+                }
+                nsel = min(Lc, P);
+                int nb_ = 0;
+                for (int k0 = 0; k0 < L; k0 += 32) {
+                    const int k = k0 + lane;
+                    const int x = k < L ? seg[k] : kIdxInf;
+                    const bool pr = x < thr;
+                    const unsigned bal = __ballot_sync(0xffffffffu, pr);
+                    if (pr) sel[nb_ + __popc(bal & lanemask_lt())] = x;
+                    nb_ += __popc(bal);
+                }
+                __syncwarp();
+                for (int j = lane; j < nsel; j += 32) {
+                    const int x = sel[j];
+                    int r = 0;
+                    for (int q = 0; q < nsel; ++q) r += sel[q] < x;
+                    o[r] = x;
+                }
+            }
+            nsel = min(nsel, P);
+            __syncwarp();
+            // point rows of the selected slots, asynchronously
+            unsigned char* rdst = raw + (size_t)(it & 1) * 64 * kRowBytes;
+            const unsigned char* psrc = reinterpret_cast<const unsigned char*>(points) + f0 * kRowBytes;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int sidx = r * 32 + lane;
+                if (sidx < nsel) {
+                    const int pi = o[sidx];
+                    const unsigned char* src = psrc + (int64_t)pi * kRowBytes;
+#pragma unroll
+                    for (int c = 0; c < kRowBytes / kCopy; ++c) cp_async(rdst + sidx * kRowBytes + c * kCopy, src + c * kCopy, kCopy);
+                }
+            }
+            s_nsel = nsel; s_row = d.y; s_cell = d.x; s_b = b; s_f0 = f0;
+        }
+        cp_async_commit();
+    };
+
+    // ---- prologue: descriptors, heads of pillars 0 and 1, sort of pillar 0
+    fill(0);
+    {
+        int4 d; int bl;
+        desc_of(0, d, bl); stage_head(0, d);
+        if (niter > 1) { desc_of(1, d, bl); stage_head(1, d); } else cp_async_commit();
+        cp_async_wait<1>();  // head 0 landed
+        __syncwarp();
+        desc_of(0, d, bl);
+        stage_sort(0, d, bl);
+    }
+    for (int it = 0; it < niter; ++it) {
+        // state of pillar `it` (produced by its stage S)
+        const int nsel = s_nsel, cell = s_cell, b = s_b;
+        const int64_t row = s_row, f0 = s_f0;
+        // window refill happens when pillar it+2 moves into a new 32-block; pillars it+1 / it+2 may
+        // straddle the refill, so fetch their descriptors before refilling
+        int4 d1, d2; int bl1, bl2;
+        if (((it + 1) & 31) == 0) { fill(it + 1); }
+        desc_of(it + 1, d1, bl1);
+        if (((it + 2) & 31) == 0 && ((it + 1) & 31) != 0) {
+            // pillar it+2 is the first of the next window: it needs the refill, but it+1 (already fetched) does not
+            fill(it + 2);
+        }
+        desc_of(it + 2, d2, bl2);
+        stage_head(it + 2, d2);          // group H(it+2)
+        cp_async_wait<1>();              // everything except H(it+2): H(it+1) and P(it) are complete
+        __syncwarp();
+        stage_sort(it + 1, d1, bl1);     // group P(it+1); overwrites the carried state for the next iteration
+
+        if (row >= 0) {
+            // ---- stage F: raw point rows -> float32 row (+ sums)
+            const unsigned char* rsrc = raw + (size_t)(it & 1) * 64 * kRowBytes;
+            const int* o = so + (it & 1) * 64;
+            float sx = 0.f, sy = 0.f, sz = 0.f;
+            const int rank = point_slot ? (int)(row - voxel_base[b]) : 0;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int sidx = r * 32 + lane;
+                if (sidx < nsel) {
+                    const T* q = reinterpret_cast<const T*>(rsrc + sidx * kRowBytes);
+                    float c[DS];
+#pragma unroll
+                    for (int dd = 0; dd < DS; ++dd) c[dd] = (float)q[dd];
+#pragma unroll
+                    for (int dd = 0; dd < DS; ++dd) vrow[sidx * DS + dd] = c[dd];
+                    sx += c[0]; sy += c[1]; sz += c[2];
+                    if (point_slot) point_slot[f0 + o[sidx]] = rank * P + sidx;
+                }
+            }
+            if (lane == 0) num_points[row] = nsel;
+            __syncwarp();
+            if (voxels) warp_store_row_padded(voxels + row * (int64_t)P * D, vrow, P * D, nsel * D, lane);
+            if (decorated) {
+#pragma unroll
+                for (int q = 16; q; q >>= 1) {
+                    sx += __shfl_xor_sync(0xffffffffu, sx, q);
+                    sy += __shfl_xor_sync(0xffffffffu, sy, q);
+                    sz += __shfl_xor_sync(0xffffffffu, sz, q);
+                }
+                const float nf = (float)nsel;
+                const float mx = __fdiv_rn(sx, nf), my = __fdiv_rn(sy, nf), mz = __fdiv_rn(sz, nf);
+                const int rem = cell - p.div_nxny.div(cell) * p.grid[0] * p.grid[1];
+                const int cy = p.div_nx.div(rem), cx = rem - cy * p.grid[0];
+                const float ex = __fadd_rn(__fmul_rn((float)cx, p.vx), p.x_off);
+                const float ey = __fadd_rn(__fmul_rn((float)cy, p.vy), p.y_off);
+                float* drow = decorated + row * (int64_t)P * Do;
+                if (DS == 3 && (reinterpret_cast<uintptr_t>(decorated) & 15) == 0) {
+                    float4* d4 = reinterpret_cast<float4*>(drow);
+                    for (int s2 = lane; s2 < P; s2 += 32) {
+                        float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+                        if (s2 < nsel) {
+                            const float q0 = vrow[s2 * 3], q1 = vrow[s2 * 3 + 1], q2 = vrow[s2 * 3 + 2];
+                            o0 = make_float4(q0, q1, q2, q0 - mx);
+                            o1 = make_float4(q1 - my, q2 - mz, q0 - ex, q1 - ey);
+                        }
+                        d4[2 * s2] = o0;
+                        d4[2 * s2 + 1] = o1;
+                    }
+                } else {
+                    for (int k = lane; k < P * Do; k += 32) {
+                        const int s2 = k / Do, dd = k - s2 * Do;
+                        float ov = 0.f;
+                        if (s2 < nsel) {
+                            const float* q = vrow + s2 * D;
+                            ov = dd < D ? q[dd] : dd == D ? q[0] - mx : dd == D + 1 ? q[1] - my : dd == D + 2 ? q[2] - mz
+                                 : dd == D + 3 ? q[0] - ex : q[1] - ey;
+                        }
+                        drow[k] = ov;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -831,6 +1130,30 @@ static int launch_gather(const VoxParams& p, const VoxWorkspace& w, const void* 
     kern<<<(unsigned)blocks, kGatherWarps * 32, smem, st>>>(
         static_cast<const T*>(points), frame_off, p, b0, nb, w.occ_desc, occ_base, w.bucket, w.cutoff, voxel_base,
         static_cast<TO*>(voxels), decorated, num_points, point_slot);
+    PP_LAUNCHED();
+    return PP_OK;
+}
+
+template <typename T, int DS>
+static int launch_gather_async(const VoxParams& p, const VoxWorkspace& w, const void* points,
+                               const int64_t* frame_off, float* voxels, float* decorated, int32_t* num_points,
+                               const int32_t* voxel_base, int32_t* point_slot, int b0, int nb, const int* occ_base,
+                               int64_t max_occ, cudaStream_t st) {
+    constexpr int kRowBytes = DS * (int)sizeof(T);
+    constexpr size_t kWarpBytes = 3 * 64 * 4 + 2 * 64 * 4 + 2 * 64 * kRowBytes + 64 * DS * 4;
+    const size_t smem = (size_t)kGatherWarps * kWarpBytes;
+    auto kern = vox_gather_async_kernel<T, DS>;
+    if (smem > 48 * 1024) PP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t blocks = ceil_div(max_occ, kGatherWarps);
+    int per_sm = 0;
+    PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kGatherWarps * 32, smem));
+    const int64_t cap = (int64_t)kNumSM * (per_sm > 0 ? per_sm : 1);
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    PP_TIMED("vox_gather", st);
+    kern<<<(unsigned)blocks, kGatherWarps * 32, smem, st>>>(
+        static_cast<const T*>(points), frame_off, p, b0, nb, w.occ_desc, occ_base, w.bucket, w.cutoff, voxel_base,
+        voxels, decorated, num_points, point_slot);
     PP_LAUNCHED();
     return PP_OK;
 }
@@ -976,6 +1299,23 @@ extern "C" int pp_voxelize_dev(const pp_voxel_cfg* cfg, const void* points, int 
         const int64_t max_occ = (int64_t)nb * ncell < chunk_pts ? (int64_t)nb * ncell : chunk_pts;
         if (max_occ > 0 && cap_rows > 0) {
             int rc;
+            // cp.async pipeline variant: float32 rows, at most two slots per lane, 3- or 4-wide points
+            const int row_bytes = D * esz;
+            const int copy = row_bytes % 16 == 0 ? 16 : row_bytes % 8 == 0 ? 8 : 4;
+            const bool use_async = out_dtype == PP_F32 && cfg->max_points <= 64 && (D == 3 || D == 4) &&
+                                   (reinterpret_cast<uintptr_t>(points) % copy) == 0 && getenv("PP_VOX_ASYNC_GATHER");
+            // (measured on B200: the cp.async variant is correct but slower, 0.74 vs 0.47 ms -- it trades the exposed
+            //  point-gather latency for shared-memory/shuffle (MIO) pressure; kept behind PP_VOX_ASYNC_GATHER=1)
+#define PP_GATHER_A(T, DS)                                                                                     \
+    launch_gather_async<T, DS>(p, w, points, frame_offsets, static_cast<float*>(voxels), decorated, num_points, \
+                               voxel_base, point_slot, b0, nb, occ_base, max_occ, st)
+            if (use_async) {
+                if (point_dtype == PP_F64) rc = D == 3 ? PP_GATHER_A(double, 3) : PP_GATHER_A(double, 4);
+                else rc = D == 3 ? PP_GATHER_A(float, 3) : PP_GATHER_A(float, 4);
+                if (rc) return rc;
+                continue;
+            }
+#undef PP_GATHER_A
 #define PP_GATHER(T, TO, DS)                                                                                   \
     launch_gather<T, TO, DS>(p, w, points, frame_offsets, voxels, decorated, num_points, voxel_base,          \
                              point_slot, b0, nb, occ_base, max_occ, st)
