@@ -53,3 +53,27 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f
                 assert "libpp_oracle" not in text and "pp_oracle" not in text, f
+
+
+def test_argument_validation_needs_no_gpu(pp):
+    """Bad arguments are rejected with an error code + message before any CUDA call."""
+    import ctypes as C
+    _lib = importlib.import_module(PKG + "._lib")
+    L = _lib.lib()
+    cfg = _lib.make_cfg([0.16, 0.16, 4.0], [0, -39.68, -3, 69.12, 39.68, 1], 100, 12000, True, False)
+    one = C.c_void_p(16)
+    args = [C.byref(cfg), one, 0, 4, one, 1, 10, 10, 0, one, None, one, 4, one, 100, one, one, None, None, one, 1 << 30, None]
+    bad = list(args); bad[3] = 2          # D < 3
+    assert L.pp_voxelize_dev(*bad) == -1 and b"D=2" in L.pp_last_error_string()
+    bad = list(args); bad[12] = 5         # coors_cols
+    assert L.pp_voxelize_dev(*bad) == -1
+    bad = list(args); bad[8] = 1          # float64 output for float32 points
+    assert L.pp_voxelize_dev(*bad) == -1
+    bad = list(args); bad[20] = 16        # workspace too small
+    assert L.pp_voxelize_dev(*bad) == -3 and b"workspace" in L.pp_last_error_string()
+    assert L.pp_scatter_dev(one, one, 10, None, 64, 0, 4, 4, 0, one, one, 1 << 20, None) == -1
+    assert L.pp_nms_dev(7, one, 5, one, None, 1, 10, -1, -1, 0.5, one, 10, one, one, 1 << 20, None) == -1
+    assert L.pp_rotate_iou_dev(one, 4, one, 4, 9, one, None) == -1
+    with pytest.raises(pp.PPError):
+        _lib.check(-1)
+    assert L.pp_voxelize_workspace_bytes(C.byref(cfg), 120000, 64) > 64 * 214272 * 16
