@@ -77,7 +77,18 @@ amask_scan_y_kernel(int* __restrict__ map, int B, int ny, int nx) {
     const int b = (int)(t / nx), x = (int)(t - (int64_t)b * nx);
     int* col = map + (int64_t)b * ny * nx + x;
     int acc = 0;
-    for (int y = 0; y < ny; ++y) {
+    int y = 0;
+    for (; y + 8 <= ny; y += 8) {  // eight independent loads in flight, the running sum is the only chain
+        int v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = col[(int64_t)(y + k) * nx];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            acc += v[k];
+            col[(int64_t)(y + k) * nx] = acc;
+        }
+    }
+    for (; y < ny; ++y) {
         acc += col[(int64_t)y * nx];
         col[(int64_t)y * nx] = acc;
     }
