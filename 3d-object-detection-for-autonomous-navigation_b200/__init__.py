@@ -16,7 +16,8 @@ The compute lives in libpp_b200.so (csrc/*.cu, include/pp_b200.h).  There is no 
 from ._lib import PPError, Ctx, ctx, grid_size, launch_count, lib, set_device  # noqa: F401
 from .anchors import anchors_mask  # noqa: F401
 from .boxes import rbox_to_standup, second_box_decode  # noqa: F401
-from .nms import nms, nms_gpu, rotate_iou_gpu, rotate_iou_gpu_eval, rotate_nms_gpu  # noqa: F401
+from .nms import (bev_box_overlap, d3_box_overlap, nms, nms_gpu, rotate_iou_gpu, rotate_iou_gpu_eval,  # noqa: F401
+                  rotate_nms_gpu)
 from .pillars import PillarFeatureNet, PointPillarsScatter, pillar_decorate, scatter  # noqa: F401
 from .voxelizer import points_to_voxel  # noqa: F401
 from . import synth  # noqa: F401

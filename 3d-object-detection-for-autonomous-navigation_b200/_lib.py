@@ -49,6 +49,7 @@ SIGNATURES = {
                              _vp, _vp, _sz, _vp]),
     "pp_gather_dets_dev": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _i64, _vp, _i64, _vp, C.c_int, _vp, _vp]),
     "pp_rotate_iou_dev": (C.c_int, [_vp, _i64, _vp, _i64, C.c_int, _vp, _vp]),
+    "pp_d3_box_overlap_dev": (C.c_int, [_vp, _i64, _vp, _i64, C.c_int, _vp, _vp]),
     "pp_anchor_cells_dev": (C.c_int, [_vp, _i64, C.POINTER(_f64), C.POINTER(_f64), _vp, _vp]),
     "pp_anchor_mask_workspace_bytes": (_sz, [C.c_int, C.c_int, C.c_int]),
     "pp_anchor_mask_dev": (C.c_int, [_vp, C.c_int, _i64, _vp, C.c_int, C.c_int, C.c_int, _vp, _i64, _f32, _vp, _vp, _vp,
@@ -65,6 +66,7 @@ SIGNATURES = {
     "pp_rbox_to_standup_host": (C.c_int, [_vp, _vp, _i64, _vp]),
     "pp_nms_host": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, C.c_int, C.c_int, _f32, _vp, C.POINTER(_i32)]),
     "pp_anchors_mask_host": (C.c_int, [_vp, _vp, _i64, _vp, _i64, C.POINTER(_f64), C.POINTER(_f64), _f32, _vp, _vp]),
+    "pp_d3_box_overlap_host": (C.c_int, [_vp, _vp, _i64, _vp, _i64, C.c_int, _vp]),
     "pp_rotate_iou_host": (C.c_int, [_vp, _vp, _i64, _vp, _i64, C.c_int, _vp]),
 }
 

@@ -339,6 +339,24 @@ extern "C" int pp_anchors_mask_host(pp_ctx* c, const int32_t* coors, int64_t M, 
     return PP_OK;
 }
 
+extern "C" int pp_d3_box_overlap_host(pp_ctx* c, const double* boxes, int64_t N, const double* query_boxes, int64_t K,
+                                      int criterion, float* out) {
+    PP_ENTER(c);
+    PP_CHECK_ARG(N >= 0 && K >= 0, "pp_d3_box_overlap_host: bad argument");
+    if (N == 0 || K == 0) return PP_OK;
+    void *d_b, *d_q, *d_o;
+    PP_TRY(c->get(0, (size_t)N * 56, &d_b));
+    PP_TRY(c->get(1, (size_t)K * 56, &d_q));
+    PP_TRY(c->get(2, (size_t)N * K * 4, &d_o));
+    PP_CUDA(cudaMemcpyAsync(d_b, boxes, (size_t)N * 56, cudaMemcpyHostToDevice, st));
+    PP_CUDA(cudaMemcpyAsync(d_q, query_boxes, (size_t)K * 56, cudaMemcpyHostToDevice, st));
+    PP_TRY(pp_d3_box_overlap_dev(static_cast<double*>(d_b), N, static_cast<double*>(d_q), K, criterion,
+                                 static_cast<float*>(d_o), st));
+    PP_CUDA(cudaMemcpyAsync(out, d_o, (size_t)N * K * 4, cudaMemcpyDeviceToHost, st));
+    PP_CUDA(cudaStreamSynchronize(st));
+    return PP_OK;
+}
+
 extern "C" int pp_rotate_iou_host(pp_ctx* c, const float* boxes, int64_t N, const float* query_boxes, int64_t K,
                                   int criterion, float* out) {
     PP_ENTER(c);

@@ -574,9 +574,72 @@ gather_dets_kernel(const float* __restrict__ boxes, int box_dim, const float* __
     out[((int64_t)b * K + k) * od + d] = v;
 }
 
+// d3_box_overlap (second/utils/eval.py:131-163): BEV intersection of camera boxes (columns 0,2,3,5,6, float32,
+// criterion 2) x height overlap and the chosen ratio in float64, stored as float32.  "Next" row N4.
+__global__ void __launch_bounds__(256)
+d3_overlap_kernel(const double* __restrict__ boxes, int64_t N, const double* __restrict__ qboxes, int64_t K,
+                  int criterion, float* __restrict__ out) {
+    __shared__ RBoxG s_q[64];
+    __shared__ RBoxG s_b[64];
+    __shared__ double s_qh[64][3], s_bh[64][3];  // y, height, volume
+    const int64_t n0 = (int64_t)blockIdx.y * 64, k0 = (int64_t)blockIdx.x * 64;
+    if (threadIdx.x < 128) {
+        const bool isq = threadIdx.x < 64;
+        const int t = threadIdx.x & 63;
+        const int64_t g = (isq ? k0 : n0) + t;
+        if (g < (isq ? K : N)) {
+            const double* src = (isq ? qboxes : boxes) + g * 7;
+            const float r[5] = {(float)src[0], (float)src[2], (float)src[3], (float)src[5], (float)src[6]};
+            RBox rb;
+            rbox_prepare(r, rb);
+            RBoxG& d = isq ? s_q[t] : s_b[t];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d.c[i] = rb.c[i];
+            d.area = rb.area; d.mnx = rb.mnx; d.mny = rb.mny; d.mxx = rb.mxx; d.mxy = rb.mxy;
+            double* h = isq ? s_qh[t] : s_bh[t];
+            h[0] = src[1]; h[1] = src[4]; h[2] = __dmul_rn(__dmul_rn(src[3], src[4]), src[5]);
+        }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 64 * 64; e += 256) {
+        const int bn = e >> 6, qk = e & 63;
+        if (n0 + bn >= N || k0 + qk >= K) continue;
+        RBox q, bx;
+        load_rbox(&s_q[qk], q);
+        load_rbox(&s_b[bn], bx);
+        float rinc = (float)rbox_iou(q, bx, 2);
+        if (rinc > 0.f) {
+            const double by = s_bh[bn][0], qy = s_qh[qk][0];
+            const double iw = __dsub_rn(fmin(by, qy), fmax(__dsub_rn(by, s_bh[bn][1]), __dsub_rn(qy, s_qh[qk][1])));
+            if (iw > 0.0) {
+                const double inc = __dmul_rn(iw, (double)rinc);
+                const double a1 = s_bh[bn][2], a2 = s_qh[qk][2];
+                const double ua = criterion == -1 ? __dsub_rn(__dadd_rn(a1, a2), inc) : criterion == 0 ? a1 : criterion == 1 ? a2 : 1.0;
+                rinc = (float)__ddiv_rn(inc, ua);
+            } else {
+                rinc = 0.f;
+            }
+        }
+        out[(n0 + bn) * K + k0 + qk] = rinc;
+    }
+}
+
 }  // namespace pp
 
 using namespace pp;
+
+extern "C" int pp_d3_box_overlap_dev(const double* boxes, int64_t N, const double* query_boxes, int64_t K,
+                                     int criterion, float* out, void* stream) {
+    PP_CHECK_ARG(N >= 0 && K >= 0 && criterion >= -1 && criterion <= 2, "pp_d3_box_overlap_dev: bad arguments");
+    if (N == 0 || K == 0) return PP_OK;
+    PP_CHECK_ARG(boxes && query_boxes && out, "pp_d3_box_overlap_dev: null argument");
+    PP_CHECK_ARG(ceil_div(N, 64) <= 65535, "pp_d3_box_overlap_dev: N too large (chunk the boxes)");
+    const dim3 g((unsigned)ceil_div(K, 64), (unsigned)ceil_div(N, 64));
+    PP_TIMED("d3_overlap", static_cast<cudaStream_t>(stream));
+    d3_overlap_kernel<<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(boxes, N, query_boxes, K, criterion, out);
+    PP_LAUNCHED();
+    return PP_OK;
+}
 
 extern "C" int pp_gather_dets_dev(const float* boxes, int box_dim, const float* scores, int B, int64_t N,
                                   const int32_t* keep, int64_t keep_stride, const int32_t* keep_count, int K,

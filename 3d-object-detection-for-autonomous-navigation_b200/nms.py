@@ -72,3 +72,23 @@ def rotate_iou_gpu_eval(boxes, query_boxes, criterion=-1, device_id=0):
 
 def rotate_iou_gpu(boxes, query_boxes, device_id=0):
     return rotate_iou_gpu_eval(boxes, query_boxes, -1, device_id)
+
+
+def bev_box_overlap(boxes, qboxes, criterion=-1):
+    """second/utils/eval.py:126-128."""
+    return rotate_iou_gpu_eval(boxes, qboxes, criterion)
+
+
+def d3_box_overlap(boxes, qboxes, criterion=-1, device_id=0):
+    """second/utils/eval.py:159-163: camera boxes [N,7], [K,7] (x,y,z,l,h,w,ry) -> [N,K] float32 3-D overlap.
+    The height/ratio arithmetic is float64 (what numba does for float64 annotations; float32 inputs are
+    widened exactly)."""
+    b = np.ascontiguousarray(np.asarray(boxes), np.float64)
+    q = np.ascontiguousarray(np.asarray(qboxes), np.float64)
+    out = np.zeros((b.shape[0], q.shape[0]), np.float32)
+    if b.shape[0] == 0 or q.shape[0] == 0:
+        return out
+    c = _lib.ctx(device_id)
+    _lib.check(_lib.lib().pp_d3_box_overlap_host(c.handle, _lib.ptr(b), b.shape[0], _lib.ptr(q), q.shape[0], int(criterion),
+                                                 _lib.ptr(out)))
+    return out

@@ -160,3 +160,15 @@ def rotated_boxes(n, seed=0, clustered=False, cfg=KITTI):
     a = rng.uniform(-np.pi, np.pi, size=n)
     s = rng.permutation(np.linspace(0.0, 1.0, n))
     return np.stack([x, y, w, l, a, s], axis=1).astype(np.float32)
+
+
+def camera_boxes(n, seed=0):
+    """KITTI-eval style camera boxes [n,7] float64 (x,y,z,l,h,w,ry) in loose clusters (so pairs overlap)."""
+    r = np.random.default_rng(seed)
+    k = max(1, n // 25)
+    c = r.integers(0, k, n)
+    cx = r.uniform(-10, 10, k)[c] + r.normal(0, 1.2, n)
+    cz = r.uniform(5, 40, k)[c] + r.normal(0, 1.2, n)
+    y = r.uniform(1.0, 2.0, n)
+    return np.stack([cx, y, cz, r.uniform(3.2, 4.8, n), r.uniform(1.3, 1.9, n), r.uniform(1.4, 1.9, n),
+                     r.uniform(-np.pi, np.pi, n)], axis=1)

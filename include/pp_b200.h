@@ -181,6 +181,11 @@ PP_API int pp_gather_dets_dev(const float* boxes, int box_dim, const float* scor
 PP_API int pp_rotate_iou_dev(const float* boxes, int64_t N, const float* query_boxes, int64_t K,
                       int criterion, float* out, void* stream);
 
+/* "Next" row N4: d3_box_overlap, second/utils/eval.py:131-163 (bev_box_overlap, 126-128, is pp_rotate_iou_dev).
+ * boxes [N,7], query_boxes [K,7] float64 camera boxes (x,y,z,l,h,w,ry) -> out [N,K] float32. */
+PP_API int pp_d3_box_overlap_dev(const double* boxes, int64_t N, const double* query_boxes, int64_t K,
+                          int criterion, float* out, void* stream);
+
 /* ---- anchor mask ("next" row N1) ---------------------------------------------------------------
  * Replaces the per-sample anchor mask of the data loader, load_data.py:3043-3072:
  * sparse_sum_for_anchors_mask (586-591) + cumsum(0).cumsum(1) + fused_get_anchors_area (558-584) on
@@ -229,6 +234,8 @@ PP_API int pp_nms_host(pp_ctx* ctx, int kind, const float* boxes, const float* s
 PP_API int pp_anchors_mask_host(pp_ctx* ctx, const int32_t* coors, int64_t M, const float* anchors, int64_t A,
                          const double voxel_size[3], const double coors_range[6], float threshold,
                          float* area_out, uint8_t* mask_out);
+PP_API int pp_d3_box_overlap_host(pp_ctx* ctx, const double* boxes, int64_t N, const double* query_boxes, int64_t K,
+                           int criterion, float* out);
 PP_API int pp_rotate_iou_host(pp_ctx* ctx, const float* boxes, int64_t N, const float* query_boxes,
                        int64_t K, int criterion, float* out);
 

@@ -225,6 +225,16 @@ def anchors_mask(coors, anchors, voxel_size, coors_range, threshold=1):
     return area, mask.astype(bool)
 
 
+def d3_box_overlap(boxes, qboxes, criterion=-1):
+    """second/utils/eval.py:159-163 (float64 camera boxes [N,7], [K,7]) -> [N,K] float32."""
+    b = np.ascontiguousarray(boxes, np.float64)
+    q = np.ascontiguousarray(qboxes, np.float64)
+    out = np.zeros((b.shape[0], q.shape[0]), np.float32)
+    if b.shape[0] and q.shape[0]:
+        lib().ppo_d3_box_overlap(_p(b), C.c_int64(b.shape[0]), _p(q), C.c_int64(q.shape[0]), int(criterion), _p(out))
+    return out
+
+
 def full_path_batch(points, frame_off, voxel_size, coors_range, max_points, max_voxels, pfn_feats,
                     box_enc, anchors, scores, pre_max, post_max, thresh, rotated=True, nthreads=0):
     """CPU baseline of the whole path over a batch (bench.py only)."""

@@ -643,6 +643,46 @@ PPO_API void ppo_anchors_mask(const int32_t* coors, int64_t M, int ny, int nx, c
     free(map);
 }
 
+
+/* ------------------------------------------------------------------------------------------
+ * "Next" row N4 -- KITTI-eval 3-D overlap: d3_box_overlap / d3_box_overlap_kernel,
+ * second/utils/eval.py:131-163 (bev_box_overlap, 126-128, is rotate_iou_gpu_eval itself).
+ * boxes [N,7], qboxes [K,7] float64 camera boxes (x,y,z,l,h,w,ry); BEV columns [0,2,3,5,6] go through
+ * the float32 rotated intersection (criterion 2), the height overlap and the ratio are float64
+ * (numba promotes float64 boxes x float32 rinc), the result is stored back into the float32 matrix.
+ * ------------------------------------------------------------------------------------------ */
+PPO_API void ppo_d3_box_overlap(const double* boxes, int64_t N, const double* qboxes, int64_t K, int criterion,
+                                float* out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < N; ++i) {
+        const double* b = boxes + 7 * i;
+        const float rb[5] = {(float)b[0], (float)b[2], (float)b[3], (float)b[5], (float)b[6]};
+        for (int64_t j = 0; j < K; ++j) {
+            const double* q = qboxes + 7 * j;
+            const float rq[5] = {(float)q[0], (float)q[2], (float)q[3], (float)q[5], (float)q[6]};
+            float rinc = (float)ppo_rotate_iou_pair(rq, rb, 2);
+            if (rinc > 0) {
+                const double top = b[1] < q[1] ? b[1] : q[1];
+                const double b0 = b[1] - b[4], q0 = q[1] - q[4];
+                const double iw = top - (b0 > q0 ? b0 : q0);
+                if (iw > 0) {
+                    const double area1 = b[3] * b[4] * b[5], area2 = q[3] * q[4] * q[5];
+                    const double inc = iw * (double)rinc;
+                    double ua;
+                    if (criterion == -1) ua = area1 + area2 - inc;
+                    else if (criterion == 0) ua = area1;
+                    else if (criterion == 1) ua = area2;
+                    else ua = 1.0;
+                    rinc = (float)(inc / ua);
+                } else {
+                    rinc = 0.f;
+                }
+            }
+            out[i * K + j] = rinc;
+        }
+    }
+}
+
 /* ------------------------------------------------------------------------------------------
  * Whole hot path over a batch of frames, used ONLY as the timed CPU baseline (bench.py).
  * Frames are independent, so the batch is an OpenMP loop over frames; inside a frame

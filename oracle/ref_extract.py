@@ -193,6 +193,16 @@ def load() -> types.SimpleNamespace:
         nk = ns["nms_postprocess"](keep, mask, n)
         return [int(v) for v in order[keep[:nk]]], iou_all
 
+    ev = {"np": np, "numba": numba, "math": math}
+    exec(_extract_defs(_read("second/utils/eval.py"), ["d3_box_overlap_kernel"]), ev)
+
+    def d3_box_overlap(boxes, qboxes, criterion=-1):
+        """second/utils/eval.py:159-163 with rotate_iou_gpu_eval replaced by the CPU run of its device code."""
+        rinc = rotate_iou_matrix(np.ascontiguousarray(boxes[:, [0, 2, 3, 5, 6]].astype(np.float32)),
+                                 np.ascontiguousarray(qboxes[:, [0, 2, 3, 5, 6]].astype(np.float32)), 2)
+        ev["d3_box_overlap_kernel"](boxes, qboxes, rinc, criterion)
+        return rinc
+
     _cache = types.SimpleNamespace(
         points_to_voxel=ns["points_to_voxel"],
         second_box_decode=ns["second_box_decode"],
@@ -201,6 +211,7 @@ def load() -> types.SimpleNamespace:
         corner_to_standup_nd_jit=ns["corner_to_standup_nd_jit"],
         create_anchors_3d_stride=create_anchors,
         anchors_mask=anchors_mask,
+        d3_box_overlap=d3_box_overlap,
         rbbox2d_to_near_bbox=ns["rbbox2d_to_near_bbox"],
         rotate_iou_matrix=rotate_iou_matrix,
         rotate_iou_matrix_f64=rotate_iou_matrix_f64,

@@ -113,6 +113,12 @@ def main():
                    f"{n}_area": area, f"{n}_mask": mask})
         print("anchor mask", n, anchors.shape, float(mask.mean()))
     np.savez_compressed(os.path.join(OUT, "anchor_mask.npz"), **am)
+    # 3-D overlap of the KITTI eval, "next" row N4 (second/utils/eval.py:131-163)
+    b, q = synth.camera_boxes(260, 1), synth.camera_boxes(140, 2)
+    d3 = dict(boxes=b, query=q)
+    for crit in (-1, 0, 1, 2):
+        d3[f"d3_crit{crit}"] = ref.d3_box_overlap(b, q, crit)
+    np.savez_compressed(os.path.join(OUT, "d3_overlap.npz"), **d3)
     print("done")
 
 

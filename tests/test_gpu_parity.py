@@ -271,3 +271,19 @@ def test_nms_ignores_minus_inf_scores(pp, oracle, synth):
         assert pp.rotate_nms_gpu(masked, 0.5, pre_max_size=pre, post_max_size=post) == want
     none = d.copy(); none[:, 5] = -np.inf
     assert pp.rotate_nms_gpu(none, 0.5, pre_max_size=100, post_max_size=50) == []
+
+
+def test_d3_and_bev_overlap(pp, oracle, synth):
+    """N4: KITTI-eval overlaps (second/utils/eval.py:126-163)."""
+    g = golden("d3_overlap.npz")
+    for crit in (-1, 0, 1, 2):
+        got = pp.d3_box_overlap(g["boxes"], g["query"], crit)
+        assert got.dtype == np.float32 and got.shape == (260, 140)
+        # volumes are ~12 m^3 and BEV areas ~8 m^2: same one-corner-ulp sensitivity as the rotated IoU
+        np.testing.assert_allclose(got, g[f"d3_crit{crit}"], rtol=0, atol=2e-4 if crit == 2 else IOU_ATOL)
+        assert np.array_equal(got > 0, g[f"d3_crit{crit}"] > 0)
+    b, q = synth.camera_boxes(1000, 3), synth.camera_boxes(700, 4)
+    np.testing.assert_allclose(pp.d3_box_overlap(b, q, -1), oracle.d3_box_overlap(b, q, -1), rtol=0, atol=IOU_ATOL)
+    bev_b, bev_q = b[:, [0, 2, 3, 5, 6]], q[:, [0, 2, 3, 5, 6]]
+    np.testing.assert_allclose(pp.bev_box_overlap(bev_b, bev_q, -1), oracle.rotate_iou_gpu_eval(bev_b, bev_q, -1), rtol=0, atol=IOU_ATOL)
+    assert pp.d3_box_overlap(b[:0], q, -1).shape == (0, 700)

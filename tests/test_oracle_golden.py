@@ -138,3 +138,11 @@ def test_anchor_mask_golden(oracle):
         area, mask = oracle.anchors_mask(g[f"{n}_coors"], g[f"{n}_anchors"], g[f"{n}_voxel_size"], g[f"{n}_range"], 1)
         assert area.dtype == np.float32 and np.array_equal(area, g[f"{n}_area"])
         assert np.array_equal(mask, g[f"{n}_mask"])
+
+
+def test_d3_overlap_golden(oracle):
+    g = golden("d3_overlap.npz")
+    for crit in (-1, 0, 1, 2):
+        got = oracle.d3_box_overlap(g["boxes"], g["query"], crit)
+        assert got.dtype == np.float32
+        np.testing.assert_allclose(got, g[f"d3_crit{crit}"], rtol=0, atol=1e-6)

@@ -74,3 +74,9 @@ def test_anchors_and_mask(ref, oracle, synth):
             wa, wm = ref.anchors_mask(c, ra, vs, pcr, thr)
             ga, gm = oracle.anchors_mask(c, an, vs, pcr, thr)
             assert np.array_equal(wa, ga) and np.array_equal(wm, gm)
+
+
+def test_d3_box_overlap(ref, oracle, synth):
+    b, q = synth.camera_boxes(300, 7), synth.camera_boxes(180, 8)
+    for crit in (-1, 0, 1, 2):
+        np.testing.assert_allclose(oracle.d3_box_overlap(b, q, crit), ref.d3_box_overlap(b, q, crit), rtol=0, atol=1e-6)
