@@ -1,22 +1,24 @@
 // Deterministic first-come pillarization on sm_100a.
 //
 // Replaces the sequential numba loop of the reference (load_data.py:593-692, wrapper 695-771)
-// with five data-parallel passes that reproduce its results bit for bit:
+// with six data-parallel passes, batched over frames, that reproduce its results bit for bit:
 //
-//   mark    (points)  cell id per point in the reference's float64/float32 arithmetic;
+//   mark    (points)  persistent CTAs, 1024-point tiles staged by TMA bulk copies (two stages);
+//                     cell id per point in the reference's float64/float32 arithmetic;
 //                     atomicMin(first_idx[cell], i); pos = atomicAdd(count[cell]) (warp-aggregated)
-//   cells   (cells)   occupied cells: set bit first_idx in a per-frame bitmap over point indices,
-//                     reserve count[cell] bucket entries, append to the occupied list
+//   cell    (cells)   occupied cells: set bit first_idx in a per-frame bitmap over point indices,
+//                     reserve count[cell] bucket entries, emit a 16-byte descriptor per occupied cell
 //   rank    (frames)  popcount prefix over the bitmap: voxel id of a cell = number of set bits
 //                     below its first_idx == order of first touch.  The bit of rank max_voxels is
 //                     the reference's `break` position i*: every point >= i* is dropped
 //                     (load_data.py:630-634).  Last block scans voxel counts into packed row bases.
+//   rowmap  (cells)   rank -> packed output row (or -1 past the cap); coors; optional cell->row map
 //   bucket  (points)  bucket[offset[cell] + pos] = i      (unordered inside a cell)
-//   gather  (voxels)  one warp per kept voxel: select the max_points smallest indices < i*
-//                     (binary search on the index threshold), order them by counting, gather the
-//                     points, write the zero-padded voxel row (+ optional fused decoration).
+//   gather  (voxels)  one warp per kept voxel, two-deep software pipeline: bucket into registers, cut
+//                     at i*, register bitonic sort => slot order (the max_points smallest indices),
+//                     gather the points once, write the zero-padded voxel row + fused decoration.
 //
-// The only nondeterminism is the order inside a bucket, which the gather pass removes.
+// The only nondeterminism is the order inside a bucket, which the sort in the gather pass removes.
 #include <math.h>
 #include <stdlib.h>
 
@@ -42,7 +44,7 @@ struct VoxParams {
     float lo32[3], vs32[3], inv32[3];
     int grid[3];  // nx, ny, nz
     int ncell;
-    FastDiv div_nx, div_nxny, div_ncell;
+    FastDiv div_nx, div_nxny;
     int max_points, max_voxels, reverse_index, arith_f32;
     int D;
     // decoration constants (model/pointpillars.py:121-124), float32 like TF constants
@@ -1205,7 +1207,6 @@ extern "C" int pp_voxelize_dev(const pp_voxel_cfg* cfg, const void* points, int 
         p.grid[j] = grid[j];
     }
     p.div_nx = FastDiv((unsigned)grid[0]); p.div_nxny = FastDiv((unsigned)(grid[0] * grid[1]));
-    p.div_ncell = FastDiv((unsigned)ncell);
     p.ncell = (int)ncell; p.max_points = cfg->max_points; p.max_voxels = cfg->max_voxels;
     p.reverse_index = cfg->reverse_index; p.arith_f32 = cfg->arith_f32; p.D = D;
     p.vx = (float)cfg->voxel_size[0]; p.vy = (float)cfg->voxel_size[1];
