@@ -1,0 +1,45 @@
+"""BASELINE.json configs[1]: the full pre/post path on ONE d435i-shaped frame through the numpy drop-in
+functions (host buffers in and out, synchronous), next to the CPU oracle on the same inputs.
+Latency-bound: reports microseconds per call and kernel launches per call."""
+import importlib, json, os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import oracle
+pp = importlib.import_module("3d-object-detection-for-autonomous-navigation_b200")
+synth = pp.synth; cfg = synth.D435
+vs, pcr = np.array(cfg["voxel_size"]), np.array(cfg["point_cloud_range"])
+vx, vy = cfg["voxel_size"][:2]; xo, yo = vx / 2 + pcr[0], vy / 2 + pcr[1]
+nx, ny, _ = synth.grid_size(cfg)
+full, sub = synth.d435_cloud(0), synth.d435_cloud(0, subsample=True)
+an = synth.anchors_stride(cfg); be, sc = synth.rpn_standin(an.shape[0], 0)
+
+def bench(fn, reps=30):
+    fn(); fn()
+    pp.launch_count(reset=True)
+    t = []
+    for _ in range(reps):
+        t0 = time.perf_counter(); r = fn(); t.append(time.perf_counter() - t0)
+    return float(np.median(t)) * 1e6, pp.launch_count(reset=True) / reps, r
+
+out = {}
+for name, pts in (("full_407040", full), ("subsampled_101760", sub)):
+    g_us, g_l, (v, c, n) = bench(lambda: pp.points_to_voxel(pts, vs, pcr, 50, True, 12000))
+    c_us, _, _ = bench(lambda: oracle.points_to_voxel(pts, vs, pcr, 50, True, 12000), 5)
+    out[f"points_to_voxel_{name}"] = {"gpu_us": g_us, "cpu_us": c_us, "launches": g_l}
+v32 = v.astype(np.float32); c4 = np.concatenate([np.zeros((c.shape[0], 1), np.int32), c], 1)
+feats = synth.pfn_standin(c4.shape[0], 128, 0)
+boxes = oracle.second_box_decode(be, an); top = np.argsort(sc)[-100:]
+sb = oracle.rbox_to_standup(boxes[top][:, [0, 1, 3, 4, 6]]); dets = np.concatenate([boxes[:, [0, 1, 3, 4, 6]], sc[:, None]], 1)
+cases = {
+    "pillar_decorate": (lambda: pp.pillar_decorate(v32, n, c4, vx, vy, xo, yo), lambda: oracle.decorate(v32, n, c4, vx, vy, xo, yo)),
+    "scatter": (lambda: pp.scatter(feats, c4, 1, ny, nx), lambda: oracle.scatter(feats, c4, 1, ny, nx)),
+    "second_box_decode_10240": (lambda: pp.second_box_decode(be, an), lambda: oracle.second_box_decode(be, an)),
+    "second_box_decode_100": (lambda: pp.second_box_decode(be[top], an[top]), lambda: oracle.second_box_decode(be[top], an[top])),
+    "live_nms_100_boxes": (lambda: pp.nms(sb, sc[top], 100, 50, 0.5), lambda: oracle.nms(sb, sc[top], 100, 50, 0.5)),
+    "rotate_nms_10240_pre100": (lambda: pp.rotate_nms_gpu(dets, 0.5, pre_max_size=100, post_max_size=50), lambda: oracle.rotate_nms_gpu(dets, 0.5, 100, 50)),
+    "anchors_mask_10240": (lambda: pp.anchors_mask(c, an, vs, pcr, 1), lambda: oracle.anchors_mask(c, an, vs, pcr, 1)),
+}
+for k, (g, cfn) in cases.items():
+    g_us, g_l, _ = bench(g); c_us, _, _ = bench(cfn, 5)
+    out[k] = {"gpu_us": g_us, "cpu_us": c_us, "launches": g_l}
+print(json.dumps(out))
