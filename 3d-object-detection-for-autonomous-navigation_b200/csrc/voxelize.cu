@@ -88,11 +88,21 @@ __device__ __forceinline__ int cell_of(const T* q, const VoxParams& p) {
         } else {
             const double d = __dsub_rn((double)q[j], p.lo[j]);
             const double qq = __dmul_rn(d, p.inv[j]);
-            double v = floor(qq);
-            const double frac = __dsub_rn(qq, v), tol = fabs(qq) * 0x1p-48 + 1e-300;
-            if (frac < tol || frac > 1.0 - tol) v = floor(__ddiv_rn(d, p.vs[j]));
-            if (!(v >= 0.0) || !(v < (double)p.grid[j])) return -1;
-            c[j] = (int)v;
+            if (!(fabs(qq) < 2.0e9)) return -1;  // far outside any grid, inf or NaN
+            // floor without the conversion (XU) pipe: qq + 1.5*2^52 rounded down leaves floor(qq) in the
+            // low mantissa bits (two's complement), and subtracting the constant gives it back as a double
+            const double kMagic = 6755399441055744.0;
+            const double t = __dadd_rd(qq, kMagic);
+            int ci = __double2loint(t);
+            const double fl = __dsub_rn(t, kMagic);
+            const double frac = __dsub_rn(qq, fl), tol = fabs(qq) * 0x1p-48 + 1e-300;
+            if (frac < tol || frac > 1.0 - tol) {
+                const double v = floor(__ddiv_rn(d, p.vs[j]));  // the reference's exact quotient (rare path)
+                if (!(v >= 0.0) || !(v < (double)p.grid[j])) return -1;
+                ci = (int)v;
+            }
+            if (ci < 0 || ci >= p.grid[j]) return -1;
+            c[j] = ci;
         }
     }
     return (c[2] * p.grid[1] + c[1]) * p.grid[0] + c[0];
