@@ -315,6 +315,22 @@ def main():
     h2d = total * 3 * 8
     d2h = F * pipe.post * 8 * 4 + F * 4
 
+    # ---- BASELINE configs[1] literally: ONE frame per step (latency-bound; reported beside the batched number) ----
+    pipe1 = pipeline.FramePipeline(cfg, device=local_rank, max_frames=1, max_total_points=n_pts, rotated_nms=True,
+                                   layout="NCHW", fused_decorate=True, keep_voxels=True)
+    d_off1 = d_off[:2].contiguous()
+
+    def step_single():
+        pipe1.run(d_pts[:n_pts], d_off1, 1, n_pts, n_pts, d_feats, d_box[:1], d_sco[:1])
+    for _ in range(5):
+        step_single()
+    pp.launch_count(reset=True)
+    n_single = max(20, args.steps)
+    ms_single = timed(step_single, n_single)
+    single = {"us_per_frame": ms_single / n_single * 1e3, "frames_per_s": world * n_single / (ms_single / 1e3),
+              "launches_per_frame": pp.launch_count(reset=True) / n_single,
+              "note": "one d435i frame per step, device-resident, same kernels; latency-bound (SURVEY 8d config 2)"}
+
     # ---- per-kernel device times (CUDA events on the launching stream, outside the timed region) ----
     per_kernel = {}
     if args.profile_steps > 0:
@@ -405,6 +421,7 @@ def main():
         "clocks": clocks,
         "roofline": roof,
         "cpu_baseline": cpu,
+        "single_frame": single,
         "path": {"pillars_per_frame": m_pillars, "detections_per_step": n_dets,
                  "algorithmic_bytes_per_frame": ab["total"],
                  "path_gbs_per_gpu": ab["total"] * F / (ms / args.steps * 1e-3) / 1e9,
