@@ -482,6 +482,212 @@ rotate_iou_matrix_kernel(const float* __restrict__ boxes, int64_t N, const float
 }
 
 // ---------------------------------------------------------------------------------------------
+// Stripe-sequential NMS for large box counts (> kStripeMin after pre_max_size).
+//
+// Greedy NMS keeps box j iff no KEPT box of higher score overlaps it.  The all-pairs bitmask of the
+// reference (N^2/128 bytes: 1.25 GB at 100 k boxes) spends most of its work on rows of boxes that
+// end up suppressed.  Here the score-ordered boxes are processed in stripes of kStripe:
+//   cross   every box of the stripe against the boxes kept so far (compact array), early exit on the
+//           first suppressor -- no mask, only a dead flag per box
+//   mask    the usual upper-triangle bitmask, but only inside the stripe and only for live rows
+//   sweep   greedy sweep of the stripe seeded with the dead flags; kept boxes are appended to the
+//           compact kept array (and to the output) for the following stripes
+// The result is identical to the all-pairs algorithm (same IoU function, same argument order
+// (higher score first), same strict > test).
+constexpr int kStripe = 2048;           // boxes per stripe = kMaskGroup * 64
+constexpr int kStripeMin = 16384;       // use the stripe path above this many boxes per frame
+constexpr int kCrossThreads = 128;
+constexpr int kCrossSplit = 8;          // kept-list splits scanned by different CTAs
+
+template <bool ROTATED>
+__global__ void __launch_bounds__(kCrossThreads)
+nms_cross_kernel(const void* __restrict__ sorted, int64_t sorted_stride, const int* __restrict__ n_sorted, int base,
+                 const void* __restrict__ kept_box, const int* __restrict__ kept_cnt, int limit, float thresh,
+                 unsigned char* __restrict__ dead /*[B][kStripe]*/) {
+    using BoxG = typename std::conditional<ROTATED, RBoxG, float4>::type;
+    __shared__ BoxG s_k[64];
+    const int b = blockIdx.y, split = blockIdx.z;
+    const int n = n_sorted[b];
+    const int nk = kept_cnt[b];
+    if (nk >= limit) return;  // post_max_size reached: nothing more will be kept
+    const int j = blockIdx.x * kCrossThreads + threadIdx.x;  // box inside the stripe
+    const bool valid = base + j < n;
+    if (!__syncthreads_or(valid)) return;
+    const BoxG* sb = static_cast<const BoxG*>(sorted) + (int64_t)b * sorted_stride;
+    const BoxG* kb = static_cast<const BoxG*>(kept_box) + (int64_t)b * sorted_stride;
+    volatile unsigned char* dflag = dead + (int64_t)b * kStripe;
+    RBox me; float4 mef = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+        if constexpr (ROTATED) load_rbox(reinterpret_cast<const RBoxG*>(sb) + base + j, me);
+        else mef = reinterpret_cast<const float4*>(sb)[base + j];
+    }
+    const double th = (double)thresh;
+    bool alive = valid;
+    const int ntile = (nk + 63) >> 6;
+    for (int t = split; t < ntile; t += kCrossSplit) {
+        if (alive && dflag[j]) alive = false;  // another split already found a suppressor
+        if (!__syncthreads_or(alive)) break;
+        const int k0 = t << 6, kn = min(64, nk - k0);
+        if ((int)threadIdx.x < kn) s_k[threadIdx.x] = kb[k0 + threadIdx.x];
+        __syncthreads();
+        if (alive) {
+            for (int i = 0; i < kn; ++i) {
+                bool sup;
+                if constexpr (ROTATED) {
+                    const RBoxG& c = s_k[i];
+                    const float scale = fmaxf(fmaxf(fabsf(c.mxx), fabsf(c.mnx)), fmaxf(fabsf(c.mxy), fabsf(c.mny)));
+                    const float eps = 1e-4f * fmaxf(1.f, scale);
+                    if (c.mnx > me.mxx + eps || me.mnx > c.mxx + eps || c.mny > me.mxy + eps || me.mny > c.mxy + eps) continue;
+                    RBox kbx;
+                    load_rbox(&s_k[i], kbx);
+                    const double ai = rbox_inter(kbx.c, me.c);  // devRotateIoU(higher score, lower score)
+                    sup = ai / ((double)__fadd_rn(kbx.area, me.area) - ai) > th;
+                } else {
+                    sup = standup_iou(reinterpret_cast<const float4*>(s_k)[i], mef) > th;
+                }
+                if (sup) { alive = false; dflag[j] = 1; break; }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// upper-triangle mask inside one stripe, live rows only (layout [kStripe][kMaskGroup] words per frame)
+template <bool ROTATED>
+__global__ void __launch_bounds__(64 * kMaskQ)
+nms_stripe_mask_kernel(const void* __restrict__ sorted, int64_t sorted_stride, const int* __restrict__ n_sorted, int base,
+                       const int* __restrict__ kept_cnt, int limit, const unsigned char* __restrict__ dead, float thresh,
+                       unsigned long long* __restrict__ mask) {
+    using BoxG = typename std::conditional<ROTATED, RBoxG, float4>::type;
+    __shared__ BoxG s_col[kMaskQ * 64];
+    const int b = blockIdx.y, rb = blockIdx.x;
+    if (kept_cnt[b] >= limit) return;
+    const int n = min(kStripe, n_sorted[b] - base);
+    const int cb = (n + 63) >> 6;
+    if (n <= 0 || rb >= cb) return;
+    const int r = threadIdx.x & 63, q = threadIdx.x >> 6;
+    const int row = rb * 64 + r;
+    const BoxG* sb = static_cast<const BoxG*>(sorted) + (int64_t)b * sorted_stride + base;
+    const unsigned char* df = dead + (int64_t)b * kStripe;
+    unsigned long long* mb = mask + (int64_t)b * kStripe * kMaskGroup;
+    const double th = (double)thresh;
+    const bool live = row < n && !df[row];
+    RBox rrow; float4 frow = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+        if constexpr (ROTATED) load_rbox(reinterpret_cast<const RBoxG*>(sb) + row, rrow);
+        else frow = reinterpret_cast<const float4*>(sb)[row];
+    }
+    for (int cbase = rb & ~(kMaskQ - 1); cbase < cb; cbase += kMaskQ) {
+        __syncthreads();
+        {
+            const int col = cbase * 64 + threadIdx.x;
+            if (col < n) s_col[threadIdx.x] = sb[col];
+        }
+        __syncthreads();
+        const int cbk = cbase + q;
+        if (live && cbk < cb && cbk >= rb) {
+            unsigned long long word = 0ull;
+            const int jn = min(64, n - cbk * 64);
+            const int j0 = (cbk == rb) ? r + 1 : 0;
+            for (int jj = j0; jj < jn; ++jj) {
+                if (df[cbk * 64 + jj]) continue;  // a dead column can never be kept: its bit is irrelevant
+                bool sup;
+                if constexpr (ROTATED) {
+                    const RBoxG& c = s_col[q * 64 + jj];
+                    const float scale = fmaxf(fmaxf(fabsf(rrow.mxx), fabsf(rrow.mnx)), fmaxf(fabsf(rrow.mxy), fabsf(rrow.mny)));
+                    const float eps = 1e-4f * fmaxf(1.f, scale);
+                    if (rrow.mnx > c.mxx + eps || c.mnx > rrow.mxx + eps || rrow.mny > c.mxy + eps || c.mny > rrow.mxy + eps) continue;
+                    RBox cbx;
+                    load_rbox(&s_col[q * 64 + jj], cbx);
+                    const double ai = rbox_inter(rrow.c, cbx.c);
+                    sup = ai / ((double)__fadd_rn(rrow.area, cbx.area) - ai) > th;
+                } else {
+                    sup = standup_iou(frow, reinterpret_cast<const float4*>(s_col)[q * 64 + jj]) > th;
+                }
+                if (sup) word |= 1ull << jj;
+            }
+            mb[(int64_t)row * kMaskGroup + cbk] = word;
+        }
+    }
+}
+
+// sweep of one stripe seeded with the dead flags; appends the kept boxes
+template <bool ROTATED>
+__global__ void __launch_bounds__(256)
+nms_stripe_sweep_kernel(const void* __restrict__ sorted, int64_t sorted_stride, const int* __restrict__ n_sorted, int base,
+                        const unsigned long long* __restrict__ mask, unsigned char* __restrict__ dead,
+                        const int* __restrict__ order, int limit, void* __restrict__ kept_box, int* __restrict__ kept_cnt,
+                        int* __restrict__ keep, int64_t keep_stride) {
+    using BoxG = typename std::conditional<ROTATED, RBoxG, float4>::type;
+    __shared__ unsigned long long remv[kMaskGroup];
+    __shared__ int s_list[kStripe];
+    __shared__ int s_nk;
+    const int b = blockIdx.x;
+    const int n = min(kStripe, n_sorted[b] - base);
+    unsigned char* df = dead + (int64_t)b * kStripe;
+    const int nk0 = kept_cnt[b];
+    if (n <= 0 || nk0 >= limit) {
+        for (int k = threadIdx.x; k < kStripe; k += 256) df[k] = 0;
+        return;
+    }
+    const int cb = (n + 63) >> 6;
+    const unsigned long long* mb = mask + (int64_t)b * kStripe * kMaskGroup;
+    // seed the removed-set with the dead flags (and clear them for the next stripe)
+    if (threadIdx.x < kMaskGroup) remv[threadIdx.x] = 0ull;
+    __syncthreads();
+    for (int k = threadIdx.x; k < kStripe; k += 256) {
+        if (df[k]) atomicOr(&remv[k >> 6], 1ull << (k & 63));
+        df[k] = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        // one warp: lane w owns removed-word w; the kept test is broadcast from the owning lane
+        const int lane = threadIdx.x;
+        unsigned long long rm = lane < kMaskGroup ? remv[lane] : 0ull;
+        int nk = 0;
+        // rows are fetched eight at a time ahead of the (serial) keep test, so the L2 latency of a kept
+        // row's mask is not on the dependency chain; rows of dead boxes hold stale words and are never used
+        for (int i0 = 0; i0 < n && nk0 + nk < limit; i0 += 8) {
+            unsigned long long rows[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                rows[u] = (i0 + u < n && lane < cb) ? mb[(int64_t)(i0 + u) * kMaskGroup + lane] : 0ull;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u;
+                if (i < n && nk0 + nk < limit) {
+                    const unsigned long long wv = __shfl_sync(0xffffffffu, rm, i >> 6);
+                    if (!((wv >> (i & 63)) & 1ull)) {
+                        if (lane == 0) s_list[nk] = i;
+                        ++nk;
+                        if (lane >= (i >> 6)) rm |= rows[u];
+                    }
+                }
+            }
+        }
+        if (lane == 0) s_nk = nk;
+    }
+    __syncthreads();
+    const int nk = s_nk;
+    const BoxG* sb = static_cast<const BoxG*>(sorted) + (int64_t)b * sorted_stride + base;
+    BoxG* kb = static_cast<BoxG*>(kept_box) + (int64_t)b * sorted_stride + nk0;
+    const int* ord = order + (int64_t)b * sorted_stride + base;
+    int* kp = keep + (int64_t)b * keep_stride;
+    for (int k = threadIdx.x; k < nk; k += 256) {
+        const int i = s_list[k];
+        kb[k] = sb[i];
+        if (nk0 + k < keep_stride) kp[nk0 + k] = ord[i];
+    }
+    if (threadIdx.x == 0) kept_cnt[b] = nk0 + nk;
+}
+
+__global__ void nms_stripe_finish_kernel(const int* __restrict__ kept_cnt, int limit, int64_t keep_stride, int B,
+                                         int* __restrict__ keep_count) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) keep_count[b] = (int)min((int64_t)min(kept_cnt[b], limit), keep_stride);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Whole NMS of one frame in one CTA when at most kSmallN boxes survive pre_max_size (the live
 // path: pre_max_size = 100, configs/train.yaml:176): top-k, per-box prep, all pairs spread over
 // the block with the mask in shared memory, sweep by one thread.  One launch instead of four and
@@ -657,7 +863,8 @@ extern "C" int pp_gather_dets_dev(const float* boxes, int box_dim, const float* 
 namespace {
 struct NmsWs {
     int* order; int* n_sorted; void* sorted; unsigned long long* mask; unsigned* kbuf; int* ibuf;
-    int64_t n_cap, cb_cap; size_t total; bool full_sort;
+    void* kept_box; int* kept_cnt; unsigned char* dead;
+    int64_t n_cap, cb_cap; size_t total; bool full_sort, stripes;
 };
 NmsWs nms_carve(void* ws, int kind, int B, int64_t N, int pre_max) {
     NmsWs w;
@@ -669,7 +876,17 @@ NmsWs nms_carve(void* ws, int kind, int B, int64_t N, int pre_max) {
     w.n_sorted = c.take<int>(B);
     if (kind == PP_NMS_ROTATED) w.sorted = c.take<RBoxG>((size_t)B * w.n_cap + 1);
     else w.sorted = c.take<float4>((size_t)B * w.n_cap + 1);
-    w.mask = c.take<unsigned long long>((size_t)B * w.n_cap * w.cb_cap + 1);
+    w.stripes = w.n_cap > kStripeMin;
+    w.kept_box = nullptr; w.kept_cnt = nullptr; w.dead = nullptr;
+    if (w.stripes) {
+        w.mask = c.take<unsigned long long>((size_t)B * kStripe * kMaskGroup + 1);
+        if (kind == PP_NMS_ROTATED) w.kept_box = c.take<RBoxG>((size_t)B * w.n_cap + 1);
+        else w.kept_box = c.take<float4>((size_t)B * w.n_cap + 1);
+        w.kept_cnt = c.take<int>(B);
+        w.dead = c.take<unsigned char>((size_t)B * kStripe);
+    } else {
+        w.mask = c.take<unsigned long long>((size_t)B * w.n_cap * w.cb_cap + 1);
+    }
     if (w.full_sort) {
         w.kbuf = c.take<unsigned>((size_t)B * 2 * N);
         w.ibuf = c.take<int>((size_t)B * 2 * N);
@@ -733,6 +950,37 @@ extern "C" int pp_nms_dev(int kind, const float* boxes, int box_stride, const fl
         else
             nms_prep_kernel<false><<<g, 256, 0, st>>>(boxes, box_stride, N, w.order, w.n_cap, w.n_sorted, w.sorted, w.n_cap);
         PP_LAUNCHED();
+    }
+    if (w.stripes) {
+        const int limit = post_max_size > 0 ? post_max_size : 0x7fffffff;
+        PP_CUDA(cudaMemsetAsync(w.kept_cnt, 0, sizeof(int) * B, st));
+        PP_CUDA(cudaMemsetAsync(w.dead, 0, (size_t)B * kStripe, st));
+        const bool rot = kind == PP_NMS_ROTATED;
+        for (int64_t base = 0; base < w.n_cap; base += kStripe) {
+            if (base > 0) {
+                const dim3 g(kStripe / kCrossThreads, B, kCrossSplit);
+                PP_TIMED("nms_cross", st);
+                if (rot) nms_cross_kernel<true><<<g, kCrossThreads, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, (int)base, w.kept_box, w.kept_cnt, limit, thresh, w.dead);
+                else nms_cross_kernel<false><<<g, kCrossThreads, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, (int)base, w.kept_box, w.kept_cnt, limit, thresh, w.dead);
+                PP_LAUNCHED();
+            }
+            {
+                const dim3 g(kMaskGroup, B);
+                PP_TIMED("nms_stripe_mask", st);
+                if (rot) nms_stripe_mask_kernel<true><<<g, 64 * kMaskQ, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, (int)base, w.kept_cnt, limit, w.dead, thresh, w.mask);
+                else nms_stripe_mask_kernel<false><<<g, 64 * kMaskQ, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, (int)base, w.kept_cnt, limit, w.dead, thresh, w.mask);
+                PP_LAUNCHED();
+            }
+            {
+                PP_TIMED("nms_stripe_sweep", st);
+                if (rot) nms_stripe_sweep_kernel<true><<<B, 256, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, (int)base, w.mask, w.dead, w.order, limit, w.kept_box, w.kept_cnt, keep, keep_stride);
+                else nms_stripe_sweep_kernel<false><<<B, 256, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, (int)base, w.mask, w.dead, w.order, limit, w.kept_box, w.kept_cnt, keep, keep_stride);
+                PP_LAUNCHED();
+            }
+        }
+        nms_stripe_finish_kernel<<<(unsigned)ceil_div(B, 128), 128, 0, st>>>(w.kept_cnt, limit, keep_stride, B, keep_count);
+        PP_LAUNCHED();
+        return PP_OK;
     }
     {
         const dim3 g((unsigned)ceil_div(w.cb_cap, kMaskGroup), (unsigned)w.cb_cap, B);

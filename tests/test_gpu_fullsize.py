@@ -120,3 +120,27 @@ def test_rotated_nms_100k(pp, oracle, synth, clustered):
     want = [int(top[i]) for i in oracle.rotate_nms_gpu(d[top], 0.5)]
     got = [int(k) for k in keep if d[k, 5] >= d[top[-1], 5]]
     assert got == want
+
+
+def test_stripe_nms_equals_all_pairs_nms(pp, oracle, synth):
+    """Above 16 384 boxes pp_nms_dev switches to the stripe-sequential algorithm; it must return exactly
+    what the all-pairs bitmask algorithm returns (here: 20 000 boxes vs the same boxes split so that the
+    all-pairs path handles them, and vs the CPU oracle on a prefix-closed subset)."""
+    n = 20_000
+    for clustered in (False, True):
+        d = synth.rotated_boxes(n, 91, clustered=clustered)
+        got = pp.rotate_nms_gpu(d, 0.5)                                  # stripes
+        top = oracle.argsort_desc(d[:, 5])
+        want_all = pp.rotate_nms_gpu(d[top[:16000]], 0.5)                # all-pairs path on the 16 000 best
+        prefix = [int(top[i]) for i in want_all]
+        assert got[:len(prefix)] == prefix
+        want = [int(top[i]) for i in oracle.rotate_nms_gpu(d[top[:4000]], 0.5)]
+        assert got[:len(want)] == want
+        # caps: pre_max keeps the stripe path (17 000 > 16 384), post_max stops early
+        g2 = pp.rotate_nms_gpu(d, 0.5, pre_max_size=17000, post_max_size=123)
+        assert g2 == got[:123]
+        # standup kind through the same path
+        sb = oracle.rbox_to_standup(d[:, :5]) * np.float32(10)
+        k_all = pp.nms(sb[top[:16000]], d[top[:16000], 5], None, None, 0.5)
+        k_str = pp.nms(sb, d[:, 5], None, None, 0.5)
+        assert k_str[:len(k_all)].tolist() == [int(top[i]) for i in k_all]
