@@ -487,7 +487,8 @@ rotate_iou_matrix_kernel(const float* __restrict__ boxes, int64_t N, const float
 // Greedy NMS keeps box j iff no KEPT box of higher score overlaps it.  The all-pairs bitmask of the
 // reference (N^2/128 bytes: 1.25 GB at 100 k boxes) spends most of its work on rows of boxes that
 // end up suppressed.  Here the score-ordered boxes are processed in stripes of kStripe:
-//   cross   every box of the stripe against the boxes kept so far (compact array), early exit on the
+//   cross   every box of the stripe against the boxes kept so far -- only those in the 3x3 neighbourhood of
+//           its bin in a uniform grid over box centres (bin edge >= the largest hull), early exit on the
 //           first suppressor -- no mask, only a dead flag per box
 //   mask    the usual upper-triangle bitmask, but only inside the stripe and only for live rows
 //   sweep   greedy sweep of the stripe seeded with the dead flags; kept boxes are appended to the
@@ -497,58 +498,130 @@ rotate_iou_matrix_kernel(const float* __restrict__ boxes, int64_t N, const float
 constexpr int kStripe = 2048;           // boxes per stripe = kMaskGroup * 64
 constexpr int kStripeMin = 16384;       // use the stripe path above this many boxes per frame
 constexpr int kCrossThreads = 128;
-constexpr int kCrossSplit = 8;          // kept-list splits scanned by different CTAs
 
+// Uniform grid over the box centres of one frame.  Bin edge >= the largest hull extent (+ margin), so two
+// boxes whose hulls touch have centres in the same or in adjacent bins: the cross stage only has to look
+// at the kept boxes of a 3x3 neighbourhood instead of the whole kept list.
+struct StripeGrid { float ox, oy, inv_s; int gx, gy; };
+constexpr int kGridMax = 512;
+
+template <bool ROTATED>
+__device__ __forceinline__ void box_centre_extent(const void* sorted, int64_t i, float& cx, float& cy, float& ext) {
+    if constexpr (ROTATED) {
+        const RBoxG* g = static_cast<const RBoxG*>(sorted) + i;
+        cx = 0.5f * (g->mnx + g->mxx); cy = 0.5f * (g->mny + g->mxy);
+        ext = fmaxf(g->mxx - g->mnx, g->mxy - g->mny);
+    } else {
+        const float4 v = static_cast<const float4*>(sorted)[i];
+        cx = 0.5f * (v.x + v.z); cy = 0.5f * (v.y + v.w);
+        ext = fmaxf(v.z - v.x, v.w - v.y) + 1.f;  // the "+1" convention makes boxes within one unit overlap
+    }
+}
+
+template <bool ROTATED>
+__global__ void __launch_bounds__(1024)
+nms_grid_setup_kernel(const void* __restrict__ sorted, int64_t sorted_stride, const int* __restrict__ n_sorted,
+                      StripeGrid* __restrict__ grid) {
+    __shared__ float s_red[5][32];
+    const int b = blockIdx.x;
+    const int n = n_sorted[b];
+    using BoxG = typename std::conditional<ROTATED, RBoxG, float4>::type;
+    const BoxG* sb = static_cast<const BoxG*>(sorted) + (int64_t)b * sorted_stride;
+    float mnx = 3.0e38f, mny = 3.0e38f, mxx = -3.0e38f, mxy = -3.0e38f, ext = 0.f;
+    for (int i = threadIdx.x; i < n; i += 1024) {
+        float cx, cy, e;
+        box_centre_extent<ROTATED>(sb, i, cx, cy, e);
+        if (cx == cx && cy == cy && e == e) {  // NaN boxes never overlap anything: leave them out of the bounds
+            mnx = fminf(mnx, cx); mxx = fmaxf(mxx, cx); mny = fminf(mny, cy); mxy = fmaxf(mxy, cy); ext = fmaxf(ext, e);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+        mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o)); mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+        ext = fmaxf(ext, __shfl_xor_sync(0xffffffffu, ext, o));
+    }
+    const int lane = lane_id(), w = threadIdx.x >> 5;
+    if (lane == 0) { s_red[0][w] = mnx; s_red[1][w] = mny; s_red[2][w] = mxx; s_red[3][w] = mxy; s_red[4][w] = ext; }
+    __syncthreads();
+    if (w == 0) {
+        mnx = s_red[0][lane]; mny = s_red[1][lane]; mxx = s_red[2][lane]; mxy = s_red[3][lane]; ext = s_red[4][lane];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+            mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o)); mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+            ext = fmaxf(ext, __shfl_xor_sync(0xffffffffu, ext, o));
+        }
+        if (lane == 0) {
+            StripeGrid g;
+            if (!(mxx >= mnx)) { mnx = mny = 0.f; mxx = mxy = 0.f; }
+            const float scale = fmaxf(fmaxf(fabsf(mnx), fabsf(mxx)), fmaxf(fabsf(mny), fabsf(mxy))) + ext;
+            // edge: largest extent + the hull test's guard band (1e-4 relative) with a wide margin
+            float edge = ext * 1.01f + 1e-3f * fmaxf(1.f, scale);
+            edge = fmaxf(edge, fmaxf(mxx - mnx, mxy - mny) / (float)(kGridMax - 2));
+            g.ox = mnx; g.oy = mny; g.inv_s = 1.f / edge;
+            g.gx = min(kGridMax, (int)((mxx - mnx) * g.inv_s) + 2);
+            g.gy = min(kGridMax, (int)((mxy - mny) * g.inv_s) + 2);
+            grid[b] = g;
+        }
+    }
+}
+
+__device__ __forceinline__ void grid_bin(const StripeGrid& g, float cx, float cy, int& bx, int& by) {
+    // NaN / out-of-bounds centres clamp into the grid (NaN boxes can neither suppress nor be suppressed)
+    const float fx = (cx - g.ox) * g.inv_s, fy = (cy - g.oy) * g.inv_s;
+    bx = fx >= 0.f ? min((int)fx, g.gx - 1) : 0;
+    by = fy >= 0.f ? min((int)fy, g.gy - 1) : 0;
+}
+
+// cross stage: one thread per box of the stripe; walks the kept boxes of the 3x3 bin neighbourhood
 template <bool ROTATED>
 __global__ void __launch_bounds__(kCrossThreads)
 nms_cross_kernel(const void* __restrict__ sorted, int64_t sorted_stride, const int* __restrict__ n_sorted, int base,
                  const void* __restrict__ kept_box, const int* __restrict__ kept_cnt, int limit, float thresh,
+                 const StripeGrid* __restrict__ grid, const int* __restrict__ bin_head, const int* __restrict__ bin_next,
                  unsigned char* __restrict__ dead /*[B][kStripe]*/) {
     using BoxG = typename std::conditional<ROTATED, RBoxG, float4>::type;
-    __shared__ BoxG s_k[64];
-    const int b = blockIdx.y, split = blockIdx.z;
+    const int b = blockIdx.y;
     const int n = n_sorted[b];
-    const int nk = kept_cnt[b];
-    if (nk >= limit) return;  // post_max_size reached: nothing more will be kept
+    if (kept_cnt[b] >= limit) return;  // post_max_size reached: nothing more will be kept
     const int j = blockIdx.x * kCrossThreads + threadIdx.x;  // box inside the stripe
-    const bool valid = base + j < n;
-    if (!__syncthreads_or(valid)) return;
+    if (base + j >= n) return;
     const BoxG* sb = static_cast<const BoxG*>(sorted) + (int64_t)b * sorted_stride;
     const BoxG* kb = static_cast<const BoxG*>(kept_box) + (int64_t)b * sorted_stride;
-    volatile unsigned char* dflag = dead + (int64_t)b * kStripe;
+    const int* head = bin_head + (int64_t)b * kGridMax * kGridMax;
+    const int* next = bin_next + (int64_t)b * sorted_stride;
+    const StripeGrid g = grid[b];
     RBox me; float4 mef = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) {
-        if constexpr (ROTATED) load_rbox(reinterpret_cast<const RBoxG*>(sb) + base + j, me);
-        else mef = reinterpret_cast<const float4*>(sb)[base + j];
-    }
+    float cx, cy, e;
+    box_centre_extent<ROTATED>(sb, base + j, cx, cy, e);
+    if constexpr (ROTATED) load_rbox(reinterpret_cast<const RBoxG*>(sb) + base + j, me);
+    else mef = reinterpret_cast<const float4*>(sb)[base + j];
+    int bx, by;
+    grid_bin(g, cx, cy, bx, by);
     const double th = (double)thresh;
-    bool alive = valid;
-    const int ntile = (nk + 63) >> 6;
-    for (int t = split; t < ntile; t += kCrossSplit) {
-        if (alive && dflag[j]) alive = false;  // another split already found a suppressor
-        if (!__syncthreads_or(alive)) break;
-        const int k0 = t << 6, kn = min(64, nk - k0);
-        if ((int)threadIdx.x < kn) s_k[threadIdx.x] = kb[k0 + threadIdx.x];
-        __syncthreads();
-        if (alive) {
-            for (int i = 0; i < kn; ++i) {
+    for (int dy = -1; dy <= 1; ++dy) {
+        const int yy = by + dy;
+        if (yy < 0 || yy >= g.gy) continue;
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int xx = bx + dx;
+            if (xx < 0 || xx >= g.gx) continue;
+            for (int k = head[yy * kGridMax + xx]; k >= 0; k = next[k]) {
                 bool sup;
                 if constexpr (ROTATED) {
-                    const RBoxG& c = s_k[i];
-                    const float scale = fmaxf(fmaxf(fabsf(c.mxx), fabsf(c.mnx)), fmaxf(fabsf(c.mxy), fabsf(c.mny)));
-                    const float eps = 1e-4f * fmaxf(1.f, scale);
-                    if (c.mnx > me.mxx + eps || me.mnx > c.mxx + eps || c.mny > me.mxy + eps || me.mny > c.mxy + eps) continue;
                     RBox kbx;
-                    load_rbox(&s_k[i], kbx);
+                    load_rbox(reinterpret_cast<const RBoxG*>(kb) + k, kbx);
+                    const float scale = fmaxf(fmaxf(fabsf(kbx.mxx), fabsf(kbx.mnx)), fmaxf(fabsf(kbx.mxy), fabsf(kbx.mny)));
+                    const float eps = 1e-4f * fmaxf(1.f, scale);
+                    if (kbx.mnx > me.mxx + eps || me.mnx > kbx.mxx + eps || kbx.mny > me.mxy + eps || me.mny > kbx.mxy + eps) continue;
                     const double ai = rbox_inter(kbx.c, me.c);  // devRotateIoU(higher score, lower score)
                     sup = ai / ((double)__fadd_rn(kbx.area, me.area) - ai) > th;
                 } else {
-                    sup = standup_iou(reinterpret_cast<const float4*>(s_k)[i], mef) > th;
+                    sup = standup_iou(reinterpret_cast<const float4*>(kb)[k], mef) > th;
                 }
-                if (sup) { alive = false; dflag[j] = 1; break; }
+                if (sup) { dead[(int64_t)b * kStripe + j] = 1; return; }
             }
         }
-        __syncthreads();
     }
 }
 
@@ -617,6 +690,7 @@ __global__ void __launch_bounds__(256)
 nms_stripe_sweep_kernel(const void* __restrict__ sorted, int64_t sorted_stride, const int* __restrict__ n_sorted, int base,
                         const unsigned long long* __restrict__ mask, unsigned char* __restrict__ dead,
                         const int* __restrict__ order, int limit, void* __restrict__ kept_box, int* __restrict__ kept_cnt,
+                        const StripeGrid* __restrict__ grid, int* __restrict__ bin_head, int* __restrict__ bin_next,
                         int* __restrict__ keep, int64_t keep_stride) {
     using BoxG = typename std::conditional<ROTATED, RBoxG, float4>::type;
     __shared__ unsigned long long remv[kMaskGroup];
@@ -673,10 +747,19 @@ nms_stripe_sweep_kernel(const void* __restrict__ sorted, int64_t sorted_stride, 
     BoxG* kb = static_cast<BoxG*>(kept_box) + (int64_t)b * sorted_stride + nk0;
     const int* ord = order + (int64_t)b * sorted_stride + base;
     int* kp = keep + (int64_t)b * keep_stride;
+    const StripeGrid g = grid[b];
+    int* head = bin_head + (int64_t)b * kGridMax * kGridMax;
+    int* next = bin_next + (int64_t)b * sorted_stride;
     for (int k = threadIdx.x; k < nk; k += 256) {
         const int i = s_list[k];
         kb[k] = sb[i];
         if (nk0 + k < keep_stride) kp[nk0 + k] = ord[i];
+        // publish the kept box in its grid bin for the cross stage of the following stripes
+        float cx, cy, e;
+        box_centre_extent<ROTATED>(sb, i, cx, cy, e);
+        int bx, by;
+        grid_bin(g, cx, cy, bx, by);
+        next[nk0 + k] = atomicExch(&head[by * kGridMax + bx], nk0 + k);
     }
     if (threadIdx.x == 0) kept_cnt[b] = nk0 + nk;
 }
@@ -863,7 +946,7 @@ extern "C" int pp_gather_dets_dev(const float* boxes, int box_dim, const float* 
 namespace {
 struct NmsWs {
     int* order; int* n_sorted; void* sorted; unsigned long long* mask; unsigned* kbuf; int* ibuf;
-    void* kept_box; int* kept_cnt; unsigned char* dead;
+    void* kept_box; int* kept_cnt; unsigned char* dead; void* grid; int* bin_head; int* bin_next;
     int64_t n_cap, cb_cap; size_t total; bool full_sort, stripes;
 };
 NmsWs nms_carve(void* ws, int kind, int B, int64_t N, int pre_max) {
@@ -877,13 +960,16 @@ NmsWs nms_carve(void* ws, int kind, int B, int64_t N, int pre_max) {
     if (kind == PP_NMS_ROTATED) w.sorted = c.take<RBoxG>((size_t)B * w.n_cap + 1);
     else w.sorted = c.take<float4>((size_t)B * w.n_cap + 1);
     w.stripes = w.n_cap > kStripeMin;
-    w.kept_box = nullptr; w.kept_cnt = nullptr; w.dead = nullptr;
+    w.kept_box = nullptr; w.kept_cnt = nullptr; w.dead = nullptr; w.grid = nullptr; w.bin_head = nullptr; w.bin_next = nullptr;
     if (w.stripes) {
         w.mask = c.take<unsigned long long>((size_t)B * kStripe * kMaskGroup + 1);
         if (kind == PP_NMS_ROTATED) w.kept_box = c.take<RBoxG>((size_t)B * w.n_cap + 1);
         else w.kept_box = c.take<float4>((size_t)B * w.n_cap + 1);
         w.kept_cnt = c.take<int>(B);
         w.dead = c.take<unsigned char>((size_t)B * kStripe);
+        w.grid = c.take<StripeGrid>(B);
+        w.bin_head = c.take<int>((size_t)B * kGridMax * kGridMax);
+        w.bin_next = c.take<int>((size_t)B * w.n_cap + 1);
     } else {
         w.mask = c.take<unsigned long long>((size_t)B * w.n_cap * w.cb_cap + 1);
     }
@@ -909,6 +995,7 @@ extern "C" int pp_nms_dev(int kind, const float* boxes, int box_stride, const fl
     PP_CHECK_ARG(B > 0 && B <= 65535 && N >= 0 && N < ((int64_t)1 << 31), "pp_nms_dev: bad B/N");
     PP_CHECK_ARG(keep && keep_count && workspace && keep_stride > 0, "pp_nms_dev: null argument");
     PP_CHECK_ARG(box_stride >= (kind == PP_NMS_ROTATED ? 5 : 4), "pp_nms_dev: box_stride too small");
+    PP_CHECK_ARG(thresh >= 0.f, "pp_nms_dev: the IoU threshold must be >= 0 (disjoint boxes are never tested)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (N == 0) {
         PP_CUDA(cudaMemsetAsync(keep_count, 0, sizeof(int) * B, st));
@@ -955,13 +1042,21 @@ extern "C" int pp_nms_dev(int kind, const float* boxes, int box_stride, const fl
         const int limit = post_max_size > 0 ? post_max_size : 0x7fffffff;
         PP_CUDA(cudaMemsetAsync(w.kept_cnt, 0, sizeof(int) * B, st));
         PP_CUDA(cudaMemsetAsync(w.dead, 0, (size_t)B * kStripe, st));
+        PP_CUDA(cudaMemsetAsync(w.bin_head, 0xff, (size_t)B * kGridMax * kGridMax * sizeof(int), st));
         const bool rot = kind == PP_NMS_ROTATED;
+        StripeGrid* sgrid = static_cast<StripeGrid*>(w.grid);
+        {
+            PP_TIMED("nms_grid_setup", st);
+            if (rot) nms_grid_setup_kernel<true><<<B, 1024, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, sgrid);
+            else nms_grid_setup_kernel<false><<<B, 1024, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, sgrid);
+            PP_LAUNCHED();
+        }
         for (int64_t base = 0; base < w.n_cap; base += kStripe) {
             if (base > 0) {
-                const dim3 g(kStripe / kCrossThreads, B, kCrossSplit);
+                const dim3 g(kStripe / kCrossThreads, B);
                 PP_TIMED("nms_cross", st);
-                if (rot) nms_cross_kernel<true><<<g, kCrossThreads, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, (int)base, w.kept_box, w.kept_cnt, limit, thresh, w.dead);
-                else nms_cross_kernel<false><<<g, kCrossThreads, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, (int)base, w.kept_box, w.kept_cnt, limit, thresh, w.dead);
+                if (rot) nms_cross_kernel<true><<<g, kCrossThreads, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, (int)base, w.kept_box, w.kept_cnt, limit, thresh, sgrid, w.bin_head, w.bin_next, w.dead);
+                else nms_cross_kernel<false><<<g, kCrossThreads, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, (int)base, w.kept_box, w.kept_cnt, limit, thresh, sgrid, w.bin_head, w.bin_next, w.dead);
                 PP_LAUNCHED();
             }
             {
@@ -973,8 +1068,8 @@ extern "C" int pp_nms_dev(int kind, const float* boxes, int box_stride, const fl
             }
             {
                 PP_TIMED("nms_stripe_sweep", st);
-                if (rot) nms_stripe_sweep_kernel<true><<<B, 256, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, (int)base, w.mask, w.dead, w.order, limit, w.kept_box, w.kept_cnt, keep, keep_stride);
-                else nms_stripe_sweep_kernel<false><<<B, 256, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, (int)base, w.mask, w.dead, w.order, limit, w.kept_box, w.kept_cnt, keep, keep_stride);
+                if (rot) nms_stripe_sweep_kernel<true><<<B, 256, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, (int)base, w.mask, w.dead, w.order, limit, w.kept_box, w.kept_cnt, sgrid, w.bin_head, w.bin_next, keep, keep_stride);
+                else nms_stripe_sweep_kernel<false><<<B, 256, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, (int)base, w.mask, w.dead, w.order, limit, w.kept_box, w.kept_cnt, sgrid, w.bin_head, w.bin_next, keep, keep_stride);
                 PP_LAUNCHED();
             }
         }
