@@ -25,8 +25,16 @@ class VoxelCfg(C.Structure):
                 ("reverse_index", C.c_int32), ("arith_f32", C.c_int32)]
 
 
+class PredictCfg(C.Structure):
+    _fields_ = [("num_class", C.c_int32), ("use_direction_classifier", C.c_int32), ("top_k", C.c_int32),
+                ("nms_pre_max_size", C.c_int32), ("nms_post_max_size", C.c_int32), ("nms_kind", C.c_int32),
+                ("nms_iou_threshold", C.c_float), ("nms_score_threshold", C.c_float),
+                ("anchors_per_frame", C.c_int32)]
+
+
 _vp, _i32, _i64, _f32, _f64, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_size_t
 _cfgp = C.POINTER(VoxelCfg)
+_pcfgp = C.POINTER(PredictCfg)
 
 # name -> (restype, argtypes); must list every symbol include/pp_b200.h declares
 SIGNATURES = {
@@ -54,6 +62,11 @@ SIGNATURES = {
     "pp_anchor_mask_workspace_bytes": (_sz, [C.c_int, C.c_int, C.c_int]),
     "pp_anchor_mask_dev": (C.c_int, [_vp, C.c_int, _i64, _vp, C.c_int, C.c_int, C.c_int, _vp, _i64, _f32, _vp, _vp, _vp,
                                      _vp, _vp, _sz, _vp]),
+    "pp_predict_workspace_bytes": (_sz, [C.c_int, _i64]),
+    "pp_predict_dev": (C.c_int, [_pcfgp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _i64, C.c_int, _vp, _vp, _vp, _vp,
+                                 _vp, _vp, _vp, _sz, _vp]),
+    "pp_predict_host": (C.c_int, [_vp, _pcfgp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _i64, C.c_int, _vp, _vp, _vp,
+                                  _vp, _vp, _vp]),
     "pp_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "pp_ctx_destroy": (None, [_vp]),
     "pp_ctx_stream": (_vp, [_vp]),

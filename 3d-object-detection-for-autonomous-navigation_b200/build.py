@@ -55,11 +55,25 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = os.environ.get("PP_NVCC_DEFS", "").split()
-    cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB, *sources()]
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    inc = ["-I", os.path.join(ROOT, "include"), "-I", CSRC]
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd), file=sys.stderr)
-    subprocess.run(cmd, check=True)
+        flags = ["-Xptxas=-v"] + flags
+    # one nvcc per translation unit, in parallel, then one link
+    import tempfile
+    from concurrent.futures import ThreadPoolExecutor
+    with tempfile.TemporaryDirectory(prefix="pp_b200_build_") as tmp:
+        def compile_one(src):
+            obj = os.path.join(tmp, os.path.basename(src)[:-3] + ".o")
+            cmd = [nvcc, *flags, *extra, *inc, "-c", "-o", obj, src]
+            if verbose:
+                print(" ".join(cmd), file=sys.stderr)
+            subprocess.run(cmd, check=True)
+            return obj
+        with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+            objs = list(ex.map(compile_one, sources()))
+        subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC",
+                        "-o", LIB, *objs], check=True)
     with open(LIB + ".srchash", "w") as f:
         f.write(source_hash())
     return LIB

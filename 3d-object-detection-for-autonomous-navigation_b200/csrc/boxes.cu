@@ -4,7 +4,7 @@
 // Rows are 7 floats (28 bytes), so a block stages 256 rows through shared memory with 16-byte
 // loads/stores; arithmetic uses explicit _rn intrinsics so the compiler cannot contract the
 // numpy two-step multiply/add into an FMA.
-#include "pp_common.cuh"
+#include "box_math.cuh"
 
 namespace pp {
 
@@ -52,18 +52,7 @@ box_decode_kernel(const float* __restrict__ enc, const float* __restrict__ ancho
     if ((int)threadIdx.x < m) {
         float* t = s_t + threadIdx.x * 7;
         const float* a = s_a + threadIdx.x * 7;
-        const float xa = a[0], ya = a[1], wa = a[3], la = a[4], ha = a[5], ra = a[6];
-        const float za = __fadd_rn(a[2], __fdiv_rn(ha, 2.f));
-        const float diag = __fsqrt_rn(__fadd_rn(__fmul_rn(la, la), __fmul_rn(wa, wa)));
-        const float xg = __fadd_rn(__fmul_rn(t[0], diag), xa);
-        const float yg = __fadd_rn(__fmul_rn(t[1], diag), ya);
-        float zg = __fadd_rn(__fmul_rn(t[2], ha), za);
-        const float lg = __fmul_rn(expf(t[4]), la);
-        const float wg = __fmul_rn(expf(t[3]), wa);
-        const float hg = __fmul_rn(expf(t[5]), ha);
-        const float rg = __fadd_rn(t[6], ra);
-        zg = __fsub_rn(zg, __fdiv_rn(hg, 2.f));
-        t[0] = xg; t[1] = yg; t[2] = zg; t[3] = wg; t[4] = lg; t[5] = hg; t[6] = rg;
+        box_decode_one(t, a, t);
     }
     __syncthreads();
     stage_out(out + base * 7, s_t, m * 7);
@@ -77,21 +66,7 @@ rbox_to_standup_kernel(const float* __restrict__ boxes, int stride, int64_t N, f
     float cx, cy, w, l, r;
     if (stride == 7) { cx = b[0]; cy = b[1]; w = b[3]; l = b[4]; r = b[6]; }
     else { cx = b[0]; cy = b[1]; w = b[2]; l = b[3]; r = b[4]; }
-    double ds, dc;
-    sincos((double)r, &ds, &dc);
-    const float s = (float)ds, c = (float)dc;
-    const float hx[4] = {-0.5f, -0.5f, 0.5f, 0.5f};
-    const float hy[4] = {-0.5f, 0.5f, 0.5f, -0.5f};
-    float mnx = 0.f, mny = 0.f, mxx = 0.f, mxy = 0.f;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float x = __fmul_rn(w, hx[k]), y = __fmul_rn(l, hy[k]);
-        const float xr = __fadd_rn(__fadd_rn(__fmul_rn(x, c), __fmul_rn(y, s)), cx);
-        const float yr = __fadd_rn(__fadd_rn(__fmul_rn(x, -s), __fmul_rn(y, c)), cy);
-        if (k == 0) { mnx = mxx = xr; mny = mxy = yr; }
-        else { mnx = fminf(mnx, xr); mxx = fmaxf(mxx, xr); mny = fminf(mny, yr); mxy = fmaxf(mxy, yr); }
-    }
-    reinterpret_cast<float4*>(out)[i] = make_float4(mnx, mny, mxx, mxy);
+    reinterpret_cast<float4*>(out)[i] = rbox_standup_one(cx, cy, w, l, r);
 }
 
 }  // namespace pp

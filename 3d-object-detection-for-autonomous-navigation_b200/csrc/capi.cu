@@ -374,3 +374,64 @@ extern "C" int pp_rotate_iou_host(pp_ctx* c, const float* boxes, int64_t N, cons
     PP_CUDA(cudaStreamSynchronize(st));
     return PP_OK;
 }
+
+extern "C" int pp_predict_host(pp_ctx* c, const pp_predict_cfg* cfg, const float* box_preds, const float* cls_preds,
+                               const float* dir_preds, const float* anchors, const uint8_t* anchors_mask,
+                               const float* rect, const float* Trv2c, int B, int64_t A, int K, float* box3d_lidar,
+                               double* box3d_camera, float* scores, int32_t* label_preds, int32_t* anchor_index,
+                               int32_t* count) {
+    PP_ENTER(c);
+    PP_CHECK_ARG(cfg && B > 0 && A >= 0 && K > 0 && box3d_lidar && count, "pp_predict_host: bad argument");
+    const size_t nbox = (size_t)B * A;
+    const size_t n_anch = cfg->anchors_per_frame ? nbox : (size_t)A;
+    const size_t ws_bytes = pp_predict_workspace_bytes(B, A);
+    void *d_bp, *d_cls, *d_dir = nullptr, *d_an, *d_mask = nullptr, *d_rect = nullptr, *d_trv = nullptr, *d_ws, *d_out;
+    PP_TRY(c->get(0, nbox * 28, &d_bp));
+    PP_TRY(c->get(1, nbox * 4 * cfg->num_class, &d_cls));
+    PP_TRY(c->get(3, n_anch * 28, &d_an));
+    PP_TRY(c->get(7, ws_bytes, &d_ws));
+    if (A > 0) {
+        PP_CHECK_ARG(box_preds && cls_preds && anchors, "pp_predict_host: null input");
+        PP_CUDA(cudaMemcpyAsync(d_bp, box_preds, nbox * 28, cudaMemcpyHostToDevice, st));
+        PP_CUDA(cudaMemcpyAsync(d_cls, cls_preds, nbox * 4 * cfg->num_class, cudaMemcpyHostToDevice, st));
+        PP_CUDA(cudaMemcpyAsync(d_an, anchors, n_anch * 28, cudaMemcpyHostToDevice, st));
+        if (dir_preds && cfg->use_direction_classifier) {
+            PP_TRY(c->get(2, nbox * 8, &d_dir));
+            PP_CUDA(cudaMemcpyAsync(d_dir, dir_preds, nbox * 8, cudaMemcpyHostToDevice, st));
+        }
+        if (anchors_mask) {
+            PP_TRY(c->get(4, nbox, &d_mask));
+            PP_CUDA(cudaMemcpyAsync(d_mask, anchors_mask, nbox, cudaMemcpyHostToDevice, st));
+        }
+    }
+    if (rect && Trv2c) {
+        PP_TRY(c->get(5, (size_t)B * 64, &d_rect));
+        PP_TRY(c->get(6, (size_t)B * 64, &d_trv));
+        PP_CUDA(cudaMemcpyAsync(d_rect, rect, (size_t)B * 64, cudaMemcpyHostToDevice, st));
+        PP_CUDA(cudaMemcpyAsync(d_trv, Trv2c, (size_t)B * 64, cudaMemcpyHostToDevice, st));
+    }
+    const size_t rows = (size_t)B * K;
+    Carver sz(nullptr);
+    sz.take<double>(rows * 7); sz.take<float>(rows * 7); sz.take<float>(rows); sz.take<int32_t>(rows); sz.take<int32_t>(rows);
+    sz.take<int32_t>(B);
+    PP_TRY(c->get(8, sz.used(), &d_out));
+    Carver o(d_out);
+    double* o_cam = o.take<double>(rows * 7);
+    float* o_lid = o.take<float>(rows * 7);
+    float* o_sc = o.take<float>(rows);
+    int32_t* o_lab = o.take<int32_t>(rows);
+    int32_t* o_idx = o.take<int32_t>(rows);
+    int32_t* o_cnt = o.take<int32_t>(B);
+    PP_TRY(pp_predict_dev(cfg, static_cast<float*>(d_bp), static_cast<float*>(d_cls), static_cast<float*>(d_dir),
+                          static_cast<float*>(d_an), static_cast<uint8_t*>(d_mask), static_cast<float*>(d_rect),
+                          static_cast<float*>(d_trv), B, A, K, o_lid, box3d_camera ? o_cam : nullptr, o_sc, o_lab, o_idx, o_cnt,
+                          d_ws, ws_bytes, st));
+    PP_CUDA(cudaMemcpyAsync(box3d_lidar, o_lid, rows * 28, cudaMemcpyDeviceToHost, st));
+    if (box3d_camera) PP_CUDA(cudaMemcpyAsync(box3d_camera, o_cam, rows * 56, cudaMemcpyDeviceToHost, st));
+    if (scores) PP_CUDA(cudaMemcpyAsync(scores, o_sc, rows * 4, cudaMemcpyDeviceToHost, st));
+    if (label_preds) PP_CUDA(cudaMemcpyAsync(label_preds, o_lab, rows * 4, cudaMemcpyDeviceToHost, st));
+    if (anchor_index) PP_CUDA(cudaMemcpyAsync(anchor_index, o_idx, rows * 4, cudaMemcpyDeviceToHost, st));
+    PP_CUDA(cudaMemcpyAsync(count, o_cnt, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    PP_CUDA(cudaStreamSynchronize(st));
+    return PP_OK;
+}

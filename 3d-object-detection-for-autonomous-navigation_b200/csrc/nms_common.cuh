@@ -1,0 +1,184 @@
+// Pieces shared by nms.cu and predict.cu: score ordering (radix-select top-k + bitonic sort), the
+// 64-byte prepared rotated box, and the axis-aligned "+1" IoU of the live path.
+#pragma once
+#include "pp_common.cuh"
+#include "rotated_iou.cuh"
+
+namespace pp {
+
+constexpr int kSortThreads = 1024;
+constexpr int kSelectMaxK = 1024;
+
+__device__ __forceinline__ unsigned score_key(float s) {
+    if (s != s) return 0xFFFFFFFFu;  // numpy sorts NaN last, i.e. first after the [::-1]
+    const unsigned u = __float_as_uint(s);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Top-k (k <= 1024) per frame: radix select of the k-th largest key, compaction, bitonic sort.
+// Boxes whose score is -inf are absent (pp_anchor_mask_dev writes -inf for masked-out anchors: the
+// reference gathers `box_preds[a_mask]` before scoring, model/voxelnet.py:1119-1137).  Block-wide count
+// of present scores; all threads of the block must call it.
+__device__ __forceinline__ int block_count_present(const float* __restrict__ sc, int nv) {
+    int total = 0;
+    for (int i0 = 0; i0 < nv; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        total += __syncthreads_count(i < nv && sc[i] != -INFINITY);
+    }
+    return total;
+}
+
+// Warp 0: find the digit d (255..0) where the count of keys with a larger digit is < rem <= that
+// count + hist[d]; returns d and the number still needed inside digit d.  8 bins per lane.
+__device__ __forceinline__ void select_digit(const unsigned* hist, unsigned rem, unsigned prefix, int shift,
+                                             unsigned* prefix_out, unsigned* rem_out, unsigned* cnt_out) {
+    const int lane = lane_id();
+    // lane l owns bins 255-8l .. 248-8l (descending)
+    unsigned h[8], tot = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { h[q] = hist[255 - 8 * lane - q]; tot += h[q]; }
+    unsigned inc = tot;  // inclusive prefix over lanes (descending bins)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    const unsigned before = inc - tot;  // keys in bins above this lane's range
+    const bool mine = before < rem && rem <= inc;
+    const unsigned bal = __ballot_sync(0xffffffffu, mine);
+    if (bal == 0) {  // fewer than rem keys in total: take digit 0
+        const unsigned total = __shfl_sync(0xffffffffu, inc, 31);
+        if (lane == 0) { *prefix_out = prefix; *rem_out = rem - total + hist[0]; *cnt_out = hist[0]; }
+        return;
+    }
+    if (mine) {
+        unsigned acc = before;
+        int q = 0;
+        for (; q < 7; ++q) {
+            if (acc + h[q] >= rem) break;
+            acc += h[q];
+        }
+        *prefix_out = prefix | ((unsigned)(255 - 8 * lane - q) << shift);
+        *rem_out = rem - acc;
+        *cnt_out = h[q];
+    }
+}
+
+// Block-wide: the kk (<= kSelectMaxK) best of sc[0..nv) by (score desc, index desc), sorted, as
+// (key<<32 | index) in skey[0..kk).  All kSortThreads threads of the block must call it.
+__device__ __forceinline__ void block_topk(const float* __restrict__ sc, int nv, int kk,
+                                           unsigned long long* skey /*[kSelectMaxK]*/) {
+    __shared__ unsigned hist[256];
+    __shared__ unsigned s_prefix, s_remaining, s_count, s_scratch;
+
+    unsigned T = 0, Tidx = 0;
+    if (kk < nv) {
+        // ---- k-th largest key
+        if (threadIdx.x == 0) { s_prefix = 0; s_remaining = (unsigned)kk; }
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+            __syncthreads();
+            const unsigned prefix = s_prefix;
+            // warp-aggregated histogram: scores cluster in a few top-byte bins, a plain atomicAdd
+            // would serialise the whole block on one shared-memory word
+            for (int i0 = 0; i0 < nv; i0 += kSortThreads) {
+                const int i = i0 + threadIdx.x;
+                int d = -1;
+                if (i < nv) {
+                    const unsigned key = score_key(sc[i]);
+                    if (shift == 24 || ((key ^ prefix) >> (shift + 8)) == 0) d = (int)((key >> shift) & 255u);
+                }
+                const unsigned peers = __match_any_sync(0xffffffffu, d);
+                if (d >= 0 && (int)lane_id() == __ffs(peers) - 1) atomicAdd(&hist[d], (unsigned)__popc(peers));
+            }
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                const unsigned rem = s_remaining;
+                __syncwarp();
+                select_digit(hist, rem, prefix, shift, &s_prefix, &s_remaining, &s_count);
+            }
+            __syncthreads();
+        }
+        T = s_prefix;
+        const unsigned need_eq = s_remaining, have_eq = s_count;
+        __syncthreads();
+        if (have_eq > need_eq) {
+            // ---- among keys == T keep the need_eq largest indices (tie rule: descending index)
+            if (threadIdx.x == 0) { s_prefix = 0; s_remaining = need_eq; }
+            for (int shift = 24; shift >= 0; shift -= 8) {
+                if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+                __syncthreads();
+                const unsigned prefix = s_prefix;
+                for (int i = threadIdx.x; i < nv; i += kSortThreads) {
+                    if (score_key(sc[i]) != T) continue;
+                    const unsigned key = (unsigned)i;
+                    if (shift == 24 || ((key ^ prefix) >> (shift + 8)) == 0) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+                }
+                __syncthreads();
+                if (threadIdx.x < 32) {
+                    const unsigned rem = s_remaining;
+                    __syncwarp();
+                    select_digit(hist, rem, prefix, shift, &s_prefix, &s_remaining, &s_scratch);
+                }
+                __syncthreads();
+            }
+            Tidx = s_prefix;
+            __syncthreads();
+        }
+    }
+    // ---- compaction (arbitrary order) + bitonic sort, descending on (key, index)
+    if (threadIdx.x == 0) s_count = 0;
+    int np2 = 1;
+    while (np2 < kk) np2 <<= 1;
+    for (int i = threadIdx.x; i < np2; i += kSortThreads) skey[i] = 0ull;
+    __syncthreads();
+    for (int i = threadIdx.x; i < nv; i += kSortThreads) {
+        const unsigned key = score_key(sc[i]);
+        if (kk == nv || key > T || (key == T && (unsigned)i >= Tidx)) {
+            const unsigned pos = atomicAdd(&s_count, 1u);
+            if (pos < (unsigned)kSelectMaxK) skey[pos] = ((unsigned long long)key << 32) | (unsigned)i;
+        }
+    }
+    __syncthreads();
+    for (int size = 2; size <= np2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < (np2 >> 1); t += kSortThreads) {
+                const int lo = 2 * t - (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool desc = ((lo & size) == 0);
+                const unsigned long long a = skey[lo], c = skey[hi];
+                if ((a < c) == desc) { skey[lo] = c; skey[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct __align__(16) RBoxG {  // 64 bytes in global / shared memory
+    float c[8];
+    float area, mnx, mny, mxx, mxy, pad0, pad1, pad2;
+};
+
+__device__ __forceinline__ void load_rbox(const RBoxG* g, RBox& r) {
+    const float4* p = reinterpret_cast<const float4*>(g);
+    const float4 a = p[0], b = p[1], c = p[2], d = p[3];
+    r.c[0] = a.x; r.c[1] = a.y; r.c[2] = a.z; r.c[3] = a.w;
+    r.c[4] = b.x; r.c[5] = b.y; r.c[6] = b.z; r.c[7] = b.w;
+    r.area = c.x; r.mnx = c.y; r.mny = c.z; r.mxx = c.w; r.mxy = d.x;
+}
+
+// iou_device, eval_helper_functions.py:553-564: float32 differences, then "+ 1" onwards in float64
+__device__ __forceinline__ double standup_iou(const float4& a, const float4& b) {
+    const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
+    const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
+    const double width = fmax((double)__fsub_rn(right, left) + 1.0, 0.0);
+    const double height = fmax((double)__fsub_rn(bottom, top) + 1.0, 0.0);
+    const double interS = width * height;
+    const double Sa = ((double)__fsub_rn(a.z, a.x) + 1.0) * ((double)__fsub_rn(a.w, a.y) + 1.0);
+    const double Sb = ((double)__fsub_rn(b.z, b.x) + 1.0) * ((double)__fsub_rn(b.w, b.y) + 1.0);
+    return interS / (Sa + Sb - interS);
+}
+
+}  // namespace pp

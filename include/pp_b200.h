@@ -203,6 +203,39 @@ PP_API int pp_anchor_mask_dev(const int32_t* coors, int coors_cols, int64_t M, c
                        float* area, uint8_t* mask, float* masked_scores, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* ---- predict glue ("next" row N2) ---------------------------------------------------------------
+ * Replaces the per-frame body of VoxelNet.predict, model/voxelnet.py:1105-1326, for a batch of frames:
+ * anchor-mask gather (1119-1137), dir argmax (1143), sigmoid_array (722-723, 1150), optional score
+ * threshold (1190-1198), top-k by score (hard-coded 100, 1207), second_box_decode of the selected
+ * boxes (1227), standup boxes (1233-1249) and nms (1259-1265) -- or rotated NMS when nms_kind is
+ * PP_NMS_ROTATED --, `box_preds[selected]` (1281-1287), direction flip (1301-1306) and
+ * box_lidar_to_camera (1319, load_data.py:1511-1523).  One launch for the scores, one CTA per frame for
+ * the rest; min(top_k, nms_pre_max_size) must be <= 128.
+ *   box_preds [B,A,7], cls_preds [B,A,num_class], dir_preds [B,A,2] (NULL without direction classifier),
+ *   anchors [A,7] shared (anchors_per_frame 0) or [B,A,7], anchors_mask [B,A] uint8 or NULL,
+ *   rect, Trv2c [B,4,4] float32 or both NULL (then box3d_camera is not written)
+ *   outputs, K rows per frame, zero padded after count[b]:
+ *   box3d_lidar [B,K,7] f32, box3d_camera [B,K,7] f64 (x,y,z,l,h,w,r: float64 like the reference's
+ *   concatenate of float64 xyz with float32 columns), scores [B,K] f32, label_preds [B,K] int32,
+ *   anchor_index [B,K] int32 (index into the frame's A anchors, -1 padded), count [B] (0 = the reference's None). */
+typedef struct pp_predict_cfg {
+    int32_t num_class;                /* columns of cls_preds (encode_background_as_zeros) */
+    int32_t use_direction_classifier;
+    int32_t top_k;                    /* 100 in the reference */
+    int32_t nms_pre_max_size;         /* <= 0: none */
+    int32_t nms_post_max_size;        /* <= 0: none */
+    int32_t nms_kind;                 /* PP_NMS_STANDUP (the live path) or PP_NMS_ROTATED */
+    float nms_iou_threshold;
+    float nms_score_threshold;        /* <= 0: off */
+    int32_t anchors_per_frame;
+} pp_predict_cfg;
+PP_API size_t pp_predict_workspace_bytes(int B, int64_t A);
+PP_API int pp_predict_dev(const pp_predict_cfg* cfg, const float* box_preds, const float* cls_preds,
+                   const float* dir_preds, const float* anchors, const uint8_t* anchors_mask, const float* rect,
+                   const float* Trv2c, int B, int64_t A, int K, float* box3d_lidar, double* box3d_camera,
+                   float* scores, int32_t* label_preds, int32_t* anchor_index, int32_t* count, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
 /* ---- context + host-buffer layer ----------------------------------------------------------- */
 typedef struct pp_ctx pp_ctx;
 PP_API int pp_ctx_create(int device, pp_ctx** out);
@@ -238,6 +271,11 @@ PP_API int pp_d3_box_overlap_host(pp_ctx* ctx, const double* boxes, int64_t N, c
                            int criterion, float* out);
 PP_API int pp_rotate_iou_host(pp_ctx* ctx, const float* boxes, int64_t N, const float* query_boxes,
                        int64_t K, int criterion, float* out);
+/* VoxelNet.predict(example, preds_dict) per-frame body on host arrays (see pp_predict_dev). */
+PP_API int pp_predict_host(pp_ctx* ctx, const pp_predict_cfg* cfg, const float* box_preds, const float* cls_preds,
+                    const float* dir_preds, const float* anchors, const uint8_t* anchors_mask, const float* rect,
+                    const float* Trv2c, int B, int64_t A, int K, float* box3d_lidar, double* box3d_camera,
+                    float* scores, int32_t* label_preds, int32_t* anchor_index, int32_t* count);
 
 #ifdef __cplusplus
 }

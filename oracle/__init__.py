@@ -255,3 +255,36 @@ def full_path_batch(points, frame_off, voxel_size, coors_range, max_points, max_
                               C.c_int64(A), int(pre_max), int(post_max), C.c_float(thresh),
                               int(rotated), int(nthreads), _p(det), _p(cnt), _p(vc))
     return det, cnt, vc
+
+
+def predict_frame(box_preds, cls_preds, dir_preds, anchors, a_mask, rect, Trv2c, top_k=100, pre_max_size=100,
+                  post_max_size=50, iou_threshold=0.5, score_threshold=0.0, rotated=False,
+                  use_direction_classifier=True):
+    """Per-frame body of VoxelNet.predict, model/voxelnet.py:1105-1326 -> dict with the reference's keys
+    (+ 'anchor_index'), or all-None boxes when nothing is kept."""
+    bp = np.ascontiguousarray(box_preds, np.float32).reshape(-1, 7)
+    A = bp.shape[0]
+    cl = np.ascontiguousarray(cls_preds, np.float32).reshape(A, -1)
+    dp = None if dir_preds is None else np.ascontiguousarray(dir_preds, np.float32).reshape(A, 2)
+    an = np.ascontiguousarray(anchors, np.float32).reshape(A, 7)
+    am = None if a_mask is None else np.ascontiguousarray(a_mask, np.uint8).reshape(A)
+    rc = None if rect is None else np.ascontiguousarray(rect, np.float32).reshape(16)
+    tv = None if Trv2c is None else np.ascontiguousarray(Trv2c, np.float32).reshape(16)
+    cap = min(A, top_k) if A else 1
+    lid = np.zeros((cap, 7), np.float32)
+    cam = np.zeros((cap, 7), np.float64)
+    sc = np.zeros((cap,), np.float32)
+    lab = np.zeros((cap,), np.int32)
+    idx = np.zeros((cap,), np.int32)
+    pn = lambda a: None if a is None else _p(a)  # noqa: E731
+    with np.errstate(all="ignore"):
+        k = lib().ppo_predict_frame(_p(bp), _p(cl), pn(dp), _p(an), pn(am), pn(rc), pn(tv), C.c_int64(A), cl.shape[1],
+                                    int(bool(use_direction_classifier)), int(top_k),
+                                    -1 if pre_max_size is None else int(pre_max_size),
+                                    -1 if post_max_size is None else int(post_max_size), C.c_float(iou_threshold),
+                                    C.c_float(score_threshold), int(bool(rotated)), cap, _p(lid), _p(cam), _p(sc),
+                                    _p(lab), _p(idx))
+    if k == 0:
+        return {"box3d_lidar": None, "box3d_camera": None, "scores": None, "label_preds": None, "anchor_index": None}
+    return {"box3d_lidar": lid[:k], "box3d_camera": cam[:k] if rc is not None else None, "scores": sc[:k],
+            "label_preds": lab[:k].astype(np.int64), "anchor_index": idx[:k]}

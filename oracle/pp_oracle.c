@@ -762,3 +762,135 @@ PPO_API int64_t ppo_full_path_batch(const void* points, int is_f64, const int64_
     }
     return total;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * "Next" row N2 -- the per-frame body of VoxelNet.predict, model/voxelnet.py:1105-1326.
+ *   1112-1137  a_mask_as_indices = np.where(a_mask == 1); gather box/cls/dir/anchors
+ *   1143       dir_labels = np.argmax(dir_preds, -1)
+ *   1150       total_scores = sigmoid_array(cls_preds)  (722-723: 1 / (1 + np.exp(-x)), float32)
+ *   1176-1184  one class: top_scores = squeeze, labels 0 (more classes: max / argmax)
+ *   1190-1198  optional `top_scores >= nms_score_threshold`
+ *   1207       top min(len,100) by np.argpartition (a set; ties at the cut are undefined in the
+ *              reference -- fixed here as everywhere: descending score, then descending index)
+ *   1227       second_box_decode of the selected rows
+ *   1233-1249  boxes_for_nms = standup boxes of (x,y,w,l,r)
+ *   1259-1265  nms(boxes, scores, pre_max, post_max, iou_thr)  (eval_helper_functions.py:463-492),
+ *              or rotate NMS on (x,y,w,l,r) when `rotated`
+ *   1281-1287  box_preds[selected], dir_labels[selected], top_scores[selected]
+ *   1301-1306  opp = (r > 0) ^ dir_label; r += where(opp, pi, 0)   (float32 += float64: one rounding)
+ *   1319       box_lidar_to_camera (load_data.py:1511-1523): xyz1 (float64) @ (rect @ Trv2c (float32)).T,
+ *              concat [xyz, l, h, w, r] -> float64
+ * Outputs hold `cap` rows; returns the number of detections (0 = the reference's None branch).
+ * ------------------------------------------------------------------------------------------ */
+static float ppo_sigmoid(float x) { const float e = expf(-x); const float d = 1.f + e; return 1.f / d; }
+
+PPO_API int ppo_predict_frame(const float* box_preds, const float* cls_preds, const float* dir_preds,
+                              const float* anchors, const uint8_t* a_mask, const float* rect, const float* trv2c,
+                              int64_t A, int num_class, int use_dir, int top_k, int pre_max, int post_max,
+                              float iou_thr, float score_thr, int rotated, int cap, float* box3d_lidar,
+                              double* box3d_camera, float* scores_out, int32_t* labels_out, int32_t* index_out) {
+    if (A <= 0) return 0;
+    int32_t* idx = (int32_t*)malloc(sizeof(int32_t) * (size_t)A);
+    float* sc = (float*)malloc(sizeof(float) * (size_t)A);
+    int64_t m = 0;
+    for (int64_t a = 0; a < A; ++a) {
+        if (a_mask && a_mask[a] != 1) continue;
+        float s = ppo_sigmoid(cls_preds[a * num_class]);
+        for (int c = 1; c < num_class; ++c) { const float v = ppo_sigmoid(cls_preds[a * num_class + c]); if (v > s) s = v; }
+        if (score_thr > 0.f && !(s >= score_thr)) continue;
+        idx[m] = (int32_t)a; sc[m] = s; ++m;
+    }
+    int nk = 0;
+    if (m > 0) {
+        int32_t* order = (int32_t*)malloc(sizeof(int32_t) * (size_t)m);
+        ppo_argsort_desc(sc, m, order);  /* the gather preserves index order, so ties break as on anchor index */
+        int64_t n = m < top_k ? m : top_k;
+        if (pre_max > 0 && pre_max < n) n = pre_max;
+        float* dec = (float*)malloc(sizeof(float) * 7 * (size_t)n);
+        float* te = (float*)malloc(sizeof(float) * 7 * (size_t)n);
+        float* ta = (float*)malloc(sizeof(float) * 7 * (size_t)n);
+        float* ssel = (float*)malloc(sizeof(float) * (size_t)n);
+        for (int64_t i = 0; i < n; ++i) {
+            const int64_t a = idx[order[i]];
+            memcpy(te + 7 * i, box_preds + 7 * a, 28);
+            memcpy(ta + 7 * i, anchors + 7 * a, 28);
+            ssel[i] = sc[order[i]];
+        }
+        ppo_second_box_decode(te, ta, n, dec);
+        /* the selection is already in NMS order (descending score, ties by descending anchor index):
+         * mask + sweep directly, eval_helper_functions.py:494-546 / nms_gpu.py:455-490 */
+        int32_t* keep = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+        const int64_t cb = (n + 63) / 64;
+        uint64_t* mask = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)(n * cb));
+        if (rotated) {
+            float* dets = (float*)malloc(sizeof(float) * 6 * (size_t)n);
+            for (int64_t i = 0; i < n; ++i) {
+                const float* d = dec + 7 * i;
+                float* o = dets + 6 * i;
+                o[0] = d[0]; o[1] = d[1]; o[2] = d[3]; o[3] = d[4]; o[4] = d[6]; o[5] = ssel[i];
+            }
+            ppo_rotate_mask(dets, n, iou_thr, mask);
+            free(dets);
+        } else {
+            float* rb = (float*)malloc(sizeof(float) * 5 * (size_t)n);
+            float* sb = (float*)malloc(sizeof(float) * 4 * (size_t)n);
+            for (int64_t i = 0; i < n; ++i) {
+                const float* d = dec + 7 * i;
+                float* o = rb + 5 * i;
+                o[0] = d[0]; o[1] = d[1]; o[2] = d[3]; o[3] = d[4]; o[4] = d[6];
+            }
+            ppo_rbox_to_standup(rb, n, sb);
+            ppo_standup_mask(sb, n, iou_thr, mask);
+            free(rb); free(sb);
+        }
+        nk = ppo_nms_postprocess(mask, n, keep);
+        free(mask);
+        if (post_max > 0 && nk > post_max) nk = post_max;
+        if (nk > cap) nk = cap;
+        float M[12];
+        if (rect && trv2c)
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 4; ++j) {
+                    float acc = rect[i * 4] * trv2c[j];
+                    for (int k = 1; k < 4; ++k) { const float p = rect[i * 4 + k] * trv2c[k * 4 + j]; acc = acc + p; }
+                    M[i * 4 + j] = acc;
+                }
+        for (int k = 0; k < nk; ++k) {
+            const int64_t t = keep[k];
+            const int64_t a = idx[order[t]];
+            float o[7];
+            memcpy(o, dec + 7 * t, 28);
+            int label = 0;
+            if (num_class > 1) {
+                float best = ppo_sigmoid(cls_preds[a * num_class]);
+                for (int c = 1; c < num_class; ++c) {
+                    const float v = ppo_sigmoid(cls_preds[a * num_class + c]);
+                    if (v > best) { best = v; label = c; }
+                }
+            }
+            if (use_dir && dir_preds) {
+                const int dl = dir_preds[2 * a + 1] > dir_preds[2 * a];
+                const int opp = (o[6] > 0.f) != dl;
+                o[6] = (float)((double)o[6] + (opp ? 3.141592653589793 : 0.0));
+            }
+            memcpy(box3d_lidar + 7 * k, o, 28);
+            if (box3d_camera && rect && trv2c) {
+                double* c = box3d_camera + 7 * k;
+                for (int i = 0; i < 3; ++i) {
+                    double acc = (double)o[0] * (double)M[i * 4];
+                    acc = acc + (double)o[1] * (double)M[i * 4 + 1];
+                    acc = acc + (double)o[2] * (double)M[i * 4 + 2];
+                    acc = acc + (double)M[i * 4 + 3];
+                    c[i] = acc;
+                }
+                c[3] = o[4]; c[4] = o[5]; c[5] = o[3]; c[6] = o[6];
+            }
+            if (scores_out) scores_out[k] = ssel[t];
+            if (labels_out) labels_out[k] = label;
+            if (index_out) index_out[k] = (int32_t)a;
+        }
+        free(order); free(dec); free(te); free(ta); free(ssel); free(keep);
+    }
+    free(idx); free(sc);
+    return nk;
+}

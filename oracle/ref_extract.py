@@ -16,6 +16,8 @@ CPython-3.6 `nms.so` that do not exist here.
                     for `np.empty`; bodies, operation order and numba's type inference (the
                     f32/f64 promotion map of SURVEY 3.5) are untouched.
   * standup IoU     eval_helper_functions.py:553-564, same mechanical swap.
+  * predict         model/voxelnet.py:1060-1389 (method body, run with a stand-in `self`; the numpy-1.19
+                    `x[[index_array]]` idiom is rewritten to `x[index_array]`, see _numpy119_indexing)
 """
 from __future__ import annotations
 
@@ -58,6 +60,28 @@ _LOCAL_ARRAY = re.compile(r"cuda\.local\.array\(\((\d+),\s*\),\s*dtype=numba\.fl
 def _cuda_device_to_njit(src: str) -> str:
     src = _CUDA_DECORATOR.sub('@numba.njit(error_model="numpy")', src)
     return _LOCAL_ARRAY.sub(r"np.empty(\1, np.float32)", src)
+
+
+_LIST_OF_ARRAY_INDEX = re.compile(r"\[\[(\w+)\]\]")
+
+
+def _numpy119_indexing(src: str) -> str:
+    """`x[[idx]]` with idx an index ARRAY: numpy 1.19 (the reference's pin) read the one-element list as a
+    tuple, i.e. x[idx]; numpy >= 1.23 reads it as a new leading axis.  Rewritten textually to `x[idx]`."""
+    return _LIST_OF_ARRAY_INDEX.sub(r"[\1]", src)
+
+
+def _extract_method(src: str, cls: str, name: str) -> str:
+    """Source of method `name` of top-level class `cls`, dedented to a plain function."""
+    import textwrap
+    tree = ast.parse(src)
+    lines = src.splitlines()
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name == cls:
+            for m in node.body:
+                if isinstance(m, ast.FunctionDef) and m.name == name:
+                    return textwrap.dedent("\n".join(lines[m.lineno - 1:m.end_lineno])) + "\n"
+    raise RuntimeError(f"reference method {cls}.{name} not found")
 
 
 _cache = None
@@ -203,7 +227,43 @@ def load() -> types.SimpleNamespace:
         ev["d3_box_overlap_kernel"](boxes, qboxes, rinc, criterion)
         return rinc
 
+    # ---- "next" row N2: VoxelNet.predict (model/voxelnet.py:1060-1389) run as the reference wrote it, with
+    #      self.nms_func = nms (voxelnet.py:786, eval_helper_functions.py:463-492) whose numba.cuda nms_gpu is the
+    #      CPU run of the same kernel body (standup_nms above).
+    vn = _read("model/voxelnet.py")
+    pred = {"np": np}
+    exec(_extract_defs(_read("load_data.py"), ["lidar_to_camera", "box_lidar_to_camera"]), pred)
+    pred.update(second_box_decode=ns["second_box_decode"], center_to_corner_box2d=ns["center_to_corner_box2d"],
+                corner_to_standup_nd_jit=ns["corner_to_standup_nd_jit"])
+    exec(_extract_defs(vn, ["sigmoid_array"]), pred)
+    exec(_numpy119_indexing(_extract_method(vn, "VoxelNet", "predict")), pred)
+    nmsns = {"np": np, "nms_gpu": lambda dets, thr: standup_nms(dets, thr)[0]}
+    exec(_numpy119_indexing(_extract_defs(ehf, ["nms"])), nmsns)
+
+    class _T:  # stands in for an eager tensor: only .numpy() is used (voxelnet.py:1067-1084)
+        def __init__(self, a):
+            self.a = a
+
+        def numpy(self):
+            return self.a
+
+    def predict(example, preds_dict, config):
+        """example: tuple of numpy arrays laid out as the reference's (indices 3,4,5,6,7,8 are read);
+        preds_dict: numpy arrays under box_preds / cls_preds / dir_cls_preds."""
+        sec = config["model"]["second"]
+        me = types.SimpleNamespace(
+            num_class=sec["num_class"], encode_background_as_zeros=sec["encode_background_as_zeros"], config=config,
+            box_code_size=7, use_direction_classifier=sec["use_direction_classifier"],
+            use_multi_class_nms=sec["use_multi_class_nms"], nms_score_threshold=sec["nms_score_threshold"],
+            nms_func=nmsns["nms"], nms_pre_max_size=sec["nms_pre_max_size"],
+            nms_post_max_size=sec["nms_post_max_size"], nms_iou_threshold=sec["nms_iou_threshold"],
+            measure_time_extended=False)
+        ex = [None if a is None else _T(a) for a in example]
+        pd = {k: _T(v) for k, v in preds_dict.items()}
+        return pred["predict"](me, ex, pd)
+
     _cache = types.SimpleNamespace(
+        predict=predict,
         points_to_voxel=ns["points_to_voxel"],
         second_box_decode=ns["second_box_decode"],
         nms_postprocess=ns["nms_postprocess"],

@@ -51,6 +51,40 @@ def voxel_cases(ref):
     return cases
 
 
+PREDICT_CONFIG = {"num_class": 1, "model": {"second": {
+    "num_class": 1, "encode_background_as_zeros": True, "use_direction_classifier": True, "use_multi_class_nms": False,
+    "nms_score_threshold": 0.0, "nms_pre_max_size": 100, "nms_post_max_size": 50, "nms_iou_threshold": 0.5,
+    "use_sigmoid_score": True}}}  # configs/train.yaml:121-179
+
+
+def predict_case(ref):
+    """Three D435 frames through the reference's own predict(): random-init-like RPN outputs, a 60 % anchor
+    mask, one frame with an empty mask (the None branch), a camera calibration with small random perturbation."""
+    an = synth.anchors_stride(synth.D435)
+    A, B = an.shape[0], 3
+    rng = np.random.default_rng(5)
+    bp = rng.normal(0, 0.1, (B, A, 7)).astype(np.float32)
+    cl = rng.normal(-2, 1, (B, A, 1)).astype(np.float32)
+    dr = rng.normal(0, 1, (B, A, 2)).astype(np.float32)
+    mask = (rng.random((B, A)) < 0.6).astype(np.uint8)
+    mask[2, 1000:] = 0   # few candidates: fewer than 100 survive the mask on a 80-anchor window
+    mask[2, :920] = 0
+    rect = np.tile(np.eye(4, dtype=np.float32), (B, 1, 1))
+    trv = np.tile(np.array([[0, -1, 0, 0.01], [0, 0, -1, -0.07], [1, 0, 0, -0.27], [0, 0, 0, 1]], np.float32), (B, 1, 1))
+    trv = (trv + rng.normal(0, 1e-3, (B, 4, 4))).astype(np.float32)
+    anchors = np.tile(an, (B, 1, 1))
+    example = [None, None, None, rect, trv, rect, anchors, mask, np.arange(B)]
+    res = ref.predict(example, {"box_preds": bp, "cls_preds": cl, "dir_cls_preds": dr}, PREDICT_CONFIG)
+    out = dict(box_preds=bp, cls_preds=cl, dir_cls_preds=dr, anchors=anchors, anchors_mask=mask, rect=rect, Trv2c=trv)
+    for b, r in enumerate(res):
+        out[f"count{b}"] = np.array(0 if r["box3d_lidar"] is None else r["box3d_lidar"].shape[0])
+        for k in ("box3d_lidar", "box3d_camera", "scores", "label_preds", "bbox"):
+            if r[k] is not None:
+                out[f"{k}{b}"] = np.asarray(r[k])
+        print("predict frame", b, int(out[f"count{b}"]))
+    return out
+
+
 def main():
     warnings.simplefilter("ignore")
     ref = ref_extract.load()
@@ -119,6 +153,8 @@ def main():
     for crit in (-1, 0, 1, 2):
         d3[f"d3_crit{crit}"] = ref.d3_box_overlap(b, q, crit)
     np.savez_compressed(os.path.join(OUT, "d3_overlap.npz"), **d3)
+    # VoxelNet.predict post-network half, "next" row N2 (model/voxelnet.py:1060-1389)
+    np.savez_compressed(os.path.join(OUT, "predict.npz"), **predict_case(ref))
     print("done")
 
 

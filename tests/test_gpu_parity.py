@@ -287,3 +287,97 @@ def test_d3_and_bev_overlap(pp, oracle, synth):
     bev_b, bev_q = b[:, [0, 2, 3, 5, 6]], q[:, [0, 2, 3, 5, 6]]
     np.testing.assert_allclose(pp.bev_box_overlap(bev_b, bev_q, -1), oracle.rotate_iou_gpu_eval(bev_b, bev_q, -1), rtol=0, atol=IOU_ATOL)
     assert pp.d3_box_overlap(b[:0], q, -1).shape == (0, 700)
+
+
+def _predict_inputs(synth, B, seed, num_class=1, mask_p=0.6):
+    an = synth.anchors_stride(synth.D435)
+    A = an.shape[0]
+    rng = np.random.default_rng(seed)
+    bp = rng.normal(0, 0.1, (B, A, 7)).astype(np.float32)
+    cl = rng.normal(-2, 1, (B, A, num_class)).astype(np.float32)
+    dr = rng.normal(0, 1, (B, A, 2)).astype(np.float32)
+    mask = (rng.random((B, A)) < mask_p).astype(np.uint8)
+    rect = np.tile(np.eye(4, dtype=np.float32), (B, 1, 1))
+    trv = np.tile(np.array([[0, -1, 0, 0.01], [0, 0, -1, -0.07], [1, 0, 0, -0.27], [0, 0, 0, 1]], np.float32), (B, 1, 1))
+    trv = (trv + rng.normal(0, 1e-3, (B, 4, 4))).astype(np.float32)
+    return an, bp, cl, dr, mask, rect, trv
+
+
+def _check_predict_frame(got, want):
+    if want["box3d_lidar"] is None:
+        assert got["box3d_lidar"] is None and got["scores"] is None and got["box3d_camera"] is None
+        return
+    assert got["box3d_lidar"].shape == want["box3d_lidar"].shape
+    np.testing.assert_allclose(got["box3d_lidar"], want["box3d_lidar"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(got["box3d_camera"], want["box3d_camera"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(got["scores"], want["scores"], rtol=1e-6, atol=0)
+    assert np.array_equal(got["label_preds"], want["label_preds"])
+    assert got["box3d_camera"].dtype == np.float64 and got["label_preds"].dtype == np.int64
+
+
+def test_predict_golden_reference(pp):
+    """N2: pp.predict against the reference's own VoxelNet.predict outputs (tests/golden/predict.npz)."""
+    g = golden("predict.npz")
+    B = g["box_preds"].shape[0]
+    example = [None, None, None, g["rect"], g["Trv2c"], g["rect"], g["anchors"], g["anchors_mask"], np.arange(B) + 7]
+    cfg = {"model": {"second": {"num_class": 1, "use_direction_classifier": True, "nms_pre_max_size": 100,
+                                "nms_post_max_size": 50, "nms_iou_threshold": 0.5, "nms_score_threshold": 0.0}}}
+    res = pp.predict(example, {"box_preds": g["box_preds"], "cls_preds": g["cls_preds"],
+                               "dir_cls_preds": g["dir_cls_preds"]}, cfg)
+    assert len(res) == B
+    for b, r in enumerate(res):
+        k = int(g[f"count{b}"])
+        assert r["batch_idx"] == b + 7 and r["box3d_lidar"].shape == (k, 7)
+        np.testing.assert_allclose(r["box3d_lidar"], g[f"box3d_lidar{b}"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(r["box3d_camera"], g[f"box3d_camera{b}"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(r["scores"], g[f"scores{b}"], rtol=1e-6, atol=0)
+        assert np.array_equal(r["label_preds"], g[f"label_preds{b}"])
+        assert np.array_equal(r["bbox"], g[f"bbox{b}"])
+
+
+@pytest.mark.parametrize("rotated", [False, True])
+def test_predict_vs_oracle(pp, oracle, synth, rotated):
+    B = 5
+    an, bp, cl, dr, mask, rect, trv = _predict_inputs(synth, B, 11)
+    mask[3] = 0               # nothing present: the reference's None branch
+    mask[4, 50:] = 0          # fewer candidates than top_k
+    lid, cam, sc, lab, idx, cnt = pp.predict_arrays(bp, cl, dr, an, mask, rect, trv, rotated=rotated)
+    assert cnt[3] == 0 and np.all(idx[3] == -1) and np.all(lid[3] == 0)
+    for b in range(B):
+        want = oracle.predict_frame(bp[b], cl[b], dr[b], an, mask[b], rect[b], trv[b], rotated=rotated)
+        k = int(cnt[b])
+        if want["box3d_lidar"] is None:
+            assert k == 0
+            continue
+        assert np.array_equal(idx[b, :k], want["anchor_index"])  # integer outputs: bit-exact
+        assert np.all(idx[b, k:] == -1) and np.all(lid[b, k:] == 0) and np.all(cam[b, k:] == 0)
+        np.testing.assert_allclose(lid[b, :k], want["box3d_lidar"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(cam[b, :k], want["box3d_camera"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(sc[b, :k], want["scores"], rtol=1e-6, atol=0)
+    res = pp.predict([None, None, None, rect, trv, None, np.tile(an, (B, 1, 1)), mask, np.arange(B)],
+                     {"box_preds": bp, "cls_preds": cl, "dir_cls_preds": dr}, None, rotated=rotated)
+    for b in range(B):
+        _check_predict_frame(res[b], {**oracle.predict_frame(bp[b], cl[b], dr[b], an, mask[b], rect[b], trv[b], rotated=rotated)})
+
+
+def test_predict_options(pp, oracle, synth):
+    """Score threshold, more than one class, no mask, no direction classifier, no calibration, caps."""
+    B = 2
+    an, bp, cl, dr, mask, rect, trv = _predict_inputs(synth, B, 12, num_class=3)
+    lid, cam, sc, lab, idx, cnt = pp.predict_arrays(bp, cl, dr, an, None, rect, trv, num_class=3, nms_score_threshold=0.3,
+                                                    nms_pre_max_size=60, nms_post_max_size=7, nms_iou_threshold=0.1)
+    for b in range(B):
+        want = oracle.predict_frame(bp[b], cl[b], dr[b], an, None, rect[b], trv[b], pre_max_size=60, post_max_size=7,
+                                    iou_threshold=0.1, score_threshold=0.3)
+        k = int(cnt[b])
+        assert 0 < k <= 7 and np.array_equal(idx[b, :k], want["anchor_index"])
+        assert np.array_equal(lab[b, :k], want["label_preds"]) and lab[b, :k].max() > 0
+        assert np.all(sc[b, :k] >= 0.3)
+        np.testing.assert_allclose(lid[b, :k], want["box3d_lidar"], rtol=1e-5, atol=1e-6)
+    lid2, cam2, sc2, lab2, idx2, cnt2 = pp.predict_arrays(bp[0], cl[0, :, :1], None, an, None, None, None,
+                                                          use_direction_classifier=False)
+    want = oracle.predict_frame(bp[0], cl[0, :, :1], None, an, None, None, None, use_direction_classifier=False)
+    assert cam2 is None and np.array_equal(idx2[0, :cnt2[0]], want["anchor_index"])
+    np.testing.assert_allclose(lid2[0, :cnt2[0]], want["box3d_lidar"], rtol=1e-5, atol=1e-6)
+    with pytest.raises(pp.PPError):
+        pp.predict_arrays(bp, cl, dr, an, None, rect, trv, num_class=3, top_k=500, nms_pre_max_size=None)

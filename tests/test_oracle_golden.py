@@ -146,3 +146,22 @@ def test_d3_overlap_golden(oracle):
         got = oracle.d3_box_overlap(g["boxes"], g["query"], crit)
         assert got.dtype == np.float32
         np.testing.assert_allclose(got, g[f"d3_crit{crit}"], rtol=0, atol=1e-6)
+
+
+def test_predict_golden(oracle):
+    """N2: the oracle's per-frame predict against the reference's own VoxelNet.predict (model/voxelnet.py:1060-1389)."""
+    g = golden("predict.npz")
+    B = g["box_preds"].shape[0]
+    for b in range(B):
+        o = oracle.predict_frame(g["box_preds"][b], g["cls_preds"][b], g["dir_cls_preds"][b], g["anchors"][b],
+                                 g["anchors_mask"][b], g["rect"][b], g["Trv2c"][b])
+        k = int(g[f"count{b}"])
+        assert k > 0 and o["box3d_lidar"].shape == (k, 7)
+        assert o["box3d_camera"].dtype == np.float64 and o["label_preds"].dtype == np.int64
+        # decode goes through exp (numpy SIMD vs libm: 1 ulp), the camera matrix through a float32 matmul
+        np.testing.assert_allclose(o["box3d_lidar"], g[f"box3d_lidar{b}"], rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(o["box3d_camera"], g[f"box3d_camera{b}"], rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(o["scores"], g[f"scores{b}"], rtol=1e-6, atol=0)
+        assert np.array_equal(o["label_preds"], g[f"label_preds{b}"])
+        # the kept set is the same set of anchors: decoded x,y identify them
+        assert np.all(np.diff(o["scores"]) <= 0)
