@@ -67,6 +67,11 @@ SIGNATURES = {
                                  _vp, _vp, _vp, _sz, _vp]),
     "pp_predict_host": (C.c_int, [_vp, _pcfgp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _i64, C.c_int, _vp, _vp, _vp,
                                   _vp, _vp, _vp]),
+    "pp_ingest_workspace_bytes": (_sz, [C.c_int, _i64]),
+    "pp_ingest_dev": (C.c_int, [_vp, C.c_int, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp,
+                                _vp, _i64, _vp, _vp, _sz, _vp]),
+    "pp_ingest_host": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp,
+                                 _vp, _i64, C.POINTER(_i32)]),
     "pp_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "pp_ctx_destroy": (None, [_vp]),
     "pp_ctx_stream": (_vp, [_vp]),

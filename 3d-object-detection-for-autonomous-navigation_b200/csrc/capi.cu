@@ -435,3 +435,28 @@ extern "C" int pp_predict_host(pp_ctx* c, const pp_predict_cfg* cfg, const float
     PP_CUDA(cudaStreamSynchronize(st));
     return PP_OK;
 }
+
+extern "C" int pp_ingest_host(pp_ctx* c, const void* cloud, int64_t n_in, int point_step, int off_x, int off_y, int off_z,
+                              int start, int step, const double* rotations, int n_rot, const double* translation,
+                              double* points_out, int64_t cap, int32_t* n_out) {
+    PP_ENTER(c);
+    PP_CHECK_ARG(n_in >= 0 && point_step > 0 && cap >= 0 && n_out && (points_out || cap == 0), "pp_ingest_host: bad argument");
+    const size_t ws_bytes = pp_ingest_workspace_bytes(1, n_in);
+    void *d_c, *d_o, *d_n, *d_ws;
+    PP_TRY(c->get(0, (size_t)n_in * point_step, &d_c));
+    PP_TRY(c->get(1, (size_t)cap * 24, &d_o));
+    PP_TRY(c->get(2, 256, &d_n));
+    PP_TRY(c->get(3, ws_bytes, &d_ws));
+    if (n_in > 0) PP_CUDA(cudaMemcpyAsync(d_c, cloud, (size_t)n_in * point_step, cudaMemcpyHostToDevice, st));
+    PP_TRY(pp_ingest_dev(d_c, 1, n_in, point_step, off_x, off_y, off_z, start, step, rotations, n_rot, translation,
+                         static_cast<double*>(d_o), cap, static_cast<int32_t*>(d_n), d_ws, ws_bytes, st));
+    int32_t n = 0;
+    PP_CUDA(cudaMemcpyAsync(&n, d_n, 4, cudaMemcpyDeviceToHost, st));
+    PP_CUDA(cudaStreamSynchronize(st));
+    *n_out = n;
+    if (n > 0) {
+        PP_CUDA(cudaMemcpyAsync(points_out, d_o, (size_t)n * 24, cudaMemcpyDeviceToHost, st));
+        PP_CUDA(cudaStreamSynchronize(st));
+    }
+    return PP_OK;
+}

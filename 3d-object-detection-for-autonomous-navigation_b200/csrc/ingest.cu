@@ -57,8 +57,6 @@ ingest_count_kernel(const unsigned char* __restrict__ cloud, int64_t n_in, int p
             c += finite3(x, y, z);
         }
     }
-    const int total = __syncthreads_count(0) + 0;  // barrier only; counts are reduced below
-    (void)total;
     __shared__ int s_w[kIngestThreads / 32];
 #pragma unroll
     for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);

@@ -30,7 +30,7 @@ class FramePipeline:
 
     def __init__(self, cfg, device=0, max_frames=64, max_total_points=None, rotated_nms=True,
                  layout="NCHW", fused_decorate=True, keep_voxels=True, anchors=None, overlap_post=True,
-                 anchor_area_threshold=None):
+                 anchor_area_threshold=None, production=False, sensor_points=None):
         self.cfg = cfg
         self.dev = torch.device("cuda", device)
         self.B = int(max_frames)
@@ -52,7 +52,8 @@ class FramePipeline:
         self.post = cfg["nms_post_max_size"]
         self.thr = cfg["nms_iou_threshold"]
         if max_total_points is None:
-            max_total_points = self.B * 410_000
+            max_total_points = self.B * (410_000 if not production else
+                                         ((sensor_points or 848 * 480) + 3) // 4)
         self.max_pts = int(max_total_points)
         L = _lib.lib()
         with torch.cuda.device(self.dev):
@@ -98,6 +99,32 @@ class FramePipeline:
                 _lib.check(L.pp_anchor_cells_dev(_p(self.anchors), self.A, vs3, pcr6, _p(self.anchor_cells),
                                                  C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)))
                 overlap_post = False  # the post stage now depends on the voxelizer's coors
+            # "next" rows N2 / N3: the live production chain (sensor cloud in, camera boxes out)
+            self.production = production
+            if production:
+                from . import ingest as _ingest
+                from .predict import make_cfg as _make_predict_cfg
+                self.n_sensor = int(sensor_points if sensor_points is not None else 848 * 480)
+                self.in_start, self.in_step = 1, 4  # load_data.py:2434
+                self.in_cap = max(0, (self.n_sensor - self.in_start + self.in_step - 1) // self.in_step)
+                self.in_points = torch.empty((B, self.in_cap, 3), dtype=torch.float64, **e)
+                self.in_count = torch.zeros((B,), dtype=torch.int32, **e)
+                self.in_off = (torch.arange(B + 1, dtype=torch.int64) * self.in_cap).to(self.dev)
+                self.in_rot = np.ascontiguousarray(np.stack([_ingest.R_Y_NEG90, _ingest.R_X_POS90]))
+                self.in_lift = np.ascontiguousarray(_ingest.LIFT)
+                self.ws_in_bytes = int(L.pp_ingest_workspace_bytes(B, self.n_sensor))
+                self.ws_in = torch.empty((self.ws_in_bytes,), dtype=torch.uint8, **e)
+                self.pcfg = _make_predict_cfg(1, True, 100, self.pre, self.post, self.thr, 0.0, rotated_nms, False)
+                self.ws_pr_bytes = int(L.pp_predict_workspace_bytes(B, self.A))
+                self.ws_pr = torch.empty((self.ws_pr_bytes,), dtype=torch.uint8, **e)
+                self.box3d_lidar = torch.empty((B, self.post, 7), dtype=torch.float32, **e)
+                self.box3d_camera = torch.empty((B, self.post, 7), dtype=torch.float64, **e)
+                self.det_scores = torch.empty((B, self.post), dtype=torch.float32, **e)
+                self.det_labels = torch.empty((B, self.post), dtype=torch.int32, **e)
+                self.det_index = torch.empty((B, self.post), dtype=torch.int32, **e)
+                self.cam_host = torch.empty((B, self.post, 7), dtype=torch.float64).pin_memory()
+                self.lidar_host = torch.empty((B, self.post, 7), dtype=torch.float32).pin_memory()
+                self.score_host = torch.empty((B, self.post), dtype=torch.float32).pin_memory()
             self.post_stream = torch.cuda.Stream(device=self.dev) if overlap_post else None
             self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
             self.dets_host = torch.empty((B, self.post, 8), dtype=torch.float32).pin_memory()
@@ -138,6 +165,49 @@ class FramePipeline:
                                     _p(self.ws_nms), self.ws_nms_bytes, stream))
         _lib.check(L.pp_gather_dets_dev(_p(self.boxes), 7, _p(scores), n_frames, A, _p(self.keep), self.post,
                                         _p(self.keep_count), self.post, _p(self.dets), stream))
+
+    # ---- "next" rows: sensor ingest (N3) and the predict glue (N2) -------------------------------
+    def ingest(self, cloud, n_frames, point_step, offsets, stream):
+        """cloud: device uint8/float32 tensor holding [n_frames, n_sensor] PointCloud2 records
+        (load_data.py:2434-2443).  -> (points [n_frames*cap,3] f64, frame_off, total, cap)"""
+        ox, oy, oz = offsets
+        _lib.check(_lib.lib().pp_ingest_dev(
+            _p(cloud), n_frames, self.n_sensor, point_step, ox, oy, oz, self.in_start, self.in_step,
+            _lib.ptr(self.in_rot), 2, _lib.ptr(self.in_lift), _p(self.in_points), self.in_cap, _p(self.in_count),
+            _p(self.ws_in), self.ws_in_bytes, stream))
+        return self.in_points, self.in_off, n_frames * self.in_cap, self.in_cap
+
+    def predict(self, box_preds, cls_preds, dir_preds, rect, trv2c, anchors_mask, n_frames, stream):
+        """VoxelNet.predict's post-network half (model/voxelnet.py:1105-1326) on device tensors."""
+        _lib.check(_lib.lib().pp_predict_dev(
+            C.byref(self.pcfg), _p(box_preds), _p(cls_preds), _p(dir_preds), _p(self.anchors), _p(anchors_mask),
+            _p(rect), _p(trv2c), n_frames, self.A, self.post, _p(self.box3d_lidar), _p(self.box3d_camera),
+            _p(self.det_scores), _p(self.det_labels), _p(self.det_index), _p(self.keep_count), _p(self.ws_pr),
+            self.ws_pr_bytes, stream))
+
+    def run_production(self, cloud, n_frames, point_step, offsets, pfn_feats, box_preds, cls_preds, dir_preds, rect, trv2c):
+        """The reference's live chain for a batch of sensor frames, all on the current stream:
+        ingest -> voxelize(+decorate) -> scatter -> anchor mask -> predict (the TF layers in between are
+        stand-in tensors)."""
+        st = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        pts, off, total, cap = self.ingest(cloud, n_frames, point_step, offsets, st)
+        self.voxelize(pts, off, n_frames, total, cap, st)
+        self.scatter(pfn_feats, n_frames, st)
+        mask = None
+        if self.area_thr is not None:
+            _lib.check(_lib.lib().pp_anchor_mask_dev(
+                _p(self.coors), 4, self.cap_rows, C.c_void_p(self.voxel_base.data_ptr() + 4 * n_frames), n_frames,
+                self.ny, self.nx, _p(self.anchor_cells), self.A, float(self.area_thr), None, None,
+                _p(self.anchor_mask), None, _p(self.ws_am), self.ws_am_bytes, st))
+            mask = self.anchor_mask
+        self.predict(box_preds, cls_preds, dir_preds, rect, trv2c, mask, n_frames, st)
+
+    def fetch_production(self, n_frames):
+        self.cam_host[:n_frames].copy_(self.box3d_camera[:n_frames], non_blocking=True)
+        self.lidar_host[:n_frames].copy_(self.box3d_lidar[:n_frames], non_blocking=True)
+        self.score_host[:n_frames].copy_(self.det_scores[:n_frames], non_blocking=True)
+        self.keep_count_host[:n_frames].copy_(self.keep_count[:n_frames], non_blocking=True)
+        return self.lidar_host, self.cam_host, self.score_host, self.keep_count_host
 
     # ---- whole path ---------------------------------------------------------------------------
     def run(self, points, frame_off, n_frames, total_points, max_frame_points, pfn_feats, box_enc, scores):

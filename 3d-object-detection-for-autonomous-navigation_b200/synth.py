@@ -70,6 +70,19 @@ def d435_cloud(seed=0, subsample=False):
     return np.ascontiguousarray(pts[1::4]) if subsample else pts
 
 
+def d435_sensor_cloud(seed=0, invalid=0.1):
+    """The same scene as d435_cloud as the sensor publishes it (sensor_msgs/PointCloud2 xyz, float32, camera
+    optical frame, invalid pixels NaN): float32 [407040,3] such that the reference's ingest
+    (load_data.py:2434-2443: finite rows, [1::4], two rotations, +1 m) maps it into the D435 grid."""
+    lidar = d435_cloud(seed)
+    x, y, z = lidar[:, 0], lidar[:, 1], lidar[:, 2] - 1.0
+    # inverse of p @ R_y(-90) @ R_x(+90): lidar (x,y,z) = (s2, s0, -s1) -> sensor (s0,s1,s2) = (y, -z, x)
+    sensor = np.stack([y, -z, x], axis=1).astype(np.float32)
+    rng = np.random.default_rng(seed + 77_000)
+    sensor[rng.random(sensor.shape[0]) < invalid] = np.nan
+    return np.ascontiguousarray(sensor)
+
+
 def kitti_cloud(seed=0, shuffled=False):
     """HDL-64-like: 64 rings x 1875 azimuth steps, float32 [120000,4] ring-major."""
     rng = np.random.default_rng(seed)

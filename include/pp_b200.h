@@ -236,6 +236,27 @@ PP_API int pp_predict_dev(const pp_predict_cfg* cfg, const float* box_preds, con
                    float* scores, int32_t* label_preds, int32_t* anchor_index, int32_t* count, void* workspace,
                    size_t workspace_bytes, void* stream);
 
+/* ---- sensor ingest ("next" row N3) ---------------------------------------------------------------
+ * Replaces the production branch of dataLoader.__getitem__, load_data.py:2434-2443 (same sequence in
+ * scripts/realsense_make_dataset.py:382-414):
+ *     ros_numpy.point_cloud2.pointcloud2_to_xyz_array(pc)   rows with finite x,y,z only, as float64
+ *     [start::step]                                          ([1::4] in the reference)
+ *     np.dot(points, r), np.dot(points, r2)                  n_rot float64 3x3 matrices, row vectors
+ *     points + [0, 0, 1]                                     translation
+ * cloud  [B, n_in] records of point_step bytes (sensor_msgs/PointCloud2 data), float32 fields at byte
+ *        offsets off_x, off_y, off_z; a plain [N,3] float32 array is point_step 12, offsets 0,4,8
+ * rotations  HOST pointer, n_rot (<= 4) row-major 3x3 float64; translation HOST pointer [3] or NULL
+ * points_out [B, cap, 3] float64; rows at and after n_out[b] are NaN (the voxelizer drops NaN points), so
+ *        the batch feeds pp_voxelize_dev with frame_offsets b*cap.  cap >= ceil((n_in - start)/step) never
+ *        truncates.  n_out [B] int32.
+ * Bit-identical to numpy for matrices whose entries are 0, +-1, +-2^k (the reference's from_euler(+-90 deg)
+ * matrices); within 1 ulp per product-sum otherwise (BLAS summation order is unspecified). */
+PP_API size_t pp_ingest_workspace_bytes(int B, int64_t n_in);
+PP_API int pp_ingest_dev(const void* cloud, int B, int64_t n_in, int point_step, int off_x, int off_y, int off_z,
+                  int start, int step, const double* rotations, int n_rot, const double* translation,
+                  double* points_out, int64_t cap, int32_t* n_out, void* workspace, size_t workspace_bytes,
+                  void* stream);
+
 /* ---- context + host-buffer layer ----------------------------------------------------------- */
 typedef struct pp_ctx pp_ctx;
 PP_API int pp_ctx_create(int device, pp_ctx** out);
@@ -271,6 +292,10 @@ PP_API int pp_d3_box_overlap_host(pp_ctx* ctx, const double* boxes, int64_t N, c
                            int criterion, float* out);
 PP_API int pp_rotate_iou_host(pp_ctx* ctx, const float* boxes, int64_t N, const float* query_boxes,
                        int64_t K, int criterion, float* out);
+/* One host cloud in, host float64 points [*n_out, 3] out (points_out holds cap rows). */
+PP_API int pp_ingest_host(pp_ctx* ctx, const void* cloud, int64_t n_in, int point_step, int off_x, int off_y, int off_z,
+                   int start, int step, const double* rotations, int n_rot, const double* translation,
+                   double* points_out, int64_t cap, int32_t* n_out);
 /* VoxelNet.predict(example, preds_dict) per-frame body on host arrays (see pp_predict_dev). */
 PP_API int pp_predict_host(pp_ctx* ctx, const pp_predict_cfg* cfg, const float* box_preds, const float* cls_preds,
                     const float* dir_preds, const float* anchors, const uint8_t* anchors_mask, const float* rect,

@@ -288,3 +288,19 @@ def predict_frame(box_preds, cls_preds, dir_preds, anchors, a_mask, rect, Trv2c,
         return {"box3d_lidar": None, "box3d_camera": None, "scores": None, "label_preds": None, "anchor_index": None}
     return {"box3d_lidar": lid[:k], "box3d_camera": cam[:k] if rc is not None else None, "scores": sc[:k],
             "label_preds": lab[:k].astype(np.int64), "anchor_index": idx[:k]}
+
+
+def pointcloud2_to_lidar(xyz, rotations, translation, start=1, step=4):
+    """load_data.py:2434-2443 restated with numpy (the reference's own expressions; numpy is the arithmetic it
+    uses).  `pointcloud2_to_xyz_array` belongs to ros_numpy (third party, not vendored, unpinned in
+    configs/pip/requirements_short.txt); its published algorithm -- get_xyz_points(remove_nans=True, dtype=float):
+    keep rows whose x, y and z are all finite, widen to float64 -- is restated in the first two lines.
+    xyz: [N,3] float32 sensor points."""
+    xyz = np.asarray(xyz, np.float32)
+    mask = np.isfinite(xyz[:, 0]) & np.isfinite(xyz[:, 1]) & np.isfinite(xyz[:, 2])
+    points = xyz[mask].astype(np.float64)[start::step]
+    for r in rotations:
+        points = np.dot(points, np.asarray(r, np.float64))
+    if translation is not None:
+        points = points + np.asarray(translation, np.float64)
+    return points

@@ -381,3 +381,59 @@ def test_predict_options(pp, oracle, synth):
     np.testing.assert_allclose(lid2[0, :cnt2[0]], want["box3d_lidar"], rtol=1e-5, atol=1e-6)
     with pytest.raises(pp.PPError):
         pp.predict_arrays(bp, cl, dr, an, None, rect, trv, num_class=3, top_k=500, nms_pre_max_size=None)
+
+
+def _sensor_cloud(n, seed, nan_frac=0.2):
+    rng = np.random.default_rng(seed)
+    xyz = np.stack([rng.uniform(-3, 3, n), rng.uniform(-3, 3, n), rng.uniform(0.3, 8, n)], axis=1).astype(np.float32)
+    bad = rng.random(n) < nan_frac
+    xyz[bad] = np.nan
+    if n > 10:
+        xyz[7, 2] = np.inf
+        xyz[9, 0] = -np.inf
+    return xyz
+
+
+def test_ingest_bit_exact(pp, oracle):
+    """N3 (load_data.py:2434-2443): finite-row compaction, [1::4], two rotations, lift -- bit-identical float64."""
+    from importlib import import_module
+    ing = import_module(pp.__name__ + ".ingest")
+    rots, lift = (ing.R_Y_NEG90, ing.R_X_POS90), ing.LIFT
+    for n, frac in ((407040, 0.2), (1000, 0.0), (1025, 0.9), (3, 0.0), (1, 0.0), (0, 0.0), (5000, 1.0)):
+        xyz = _sensor_cloud(n, n, frac) if n else np.zeros((0, 3), np.float32)
+        want = oracle.pointcloud2_to_lidar(xyz, rots, lift, 1, 4)
+        got = pp.pointcloud2_to_lidar(xyz)
+        assert got.dtype == np.float64 and got.shape == want.shape, (n, got.shape, want.shape)
+        assert np.array_equal(got, want), n
+    # PointCloud2 records as the RealSense driver publishes them: x,y,z float32 + padding + rgb, point_step 20
+    xyz = _sensor_cloud(50000, 1)
+    rec = np.zeros(50000, dtype=np.dtype({"names": ["x", "y", "z", "rgb"], "formats": ["<f4", "<f4", "<f4", "<f4"],
+                                          "offsets": [0, 4, 8, 16], "itemsize": 20}))
+    rec["x"], rec["y"], rec["z"] = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+    want = oracle.pointcloud2_to_lidar(xyz, rots, lift, 1, 4)
+    assert np.array_equal(pp.pointcloud2_to_lidar(rec), want)
+    assert np.array_equal(pp.pointcloud2_to_lidar(rec.tobytes(), point_step=20, offsets=(0, 4, 8)), want)
+    # other slices, no rotation, general rotation (BLAS order unspecified: 1 ulp per dot)
+    assert np.array_equal(pp.pointcloud2_to_lidar(xyz, rotations=(), translation=None, start=0, step=1),
+                          oracle.pointcloud2_to_lidar(xyz, (), None, 0, 1))
+    assert np.array_equal(pp.pointcloud2_to_lidar(xyz, start=3, step=7), oracle.pointcloud2_to_lidar(xyz, rots, lift, 3, 7))
+    from scipy.spatial.transform import Rotation as R
+    rr = R.from_euler("xyz", [10, 20, 30], degrees=True).as_matrix()
+    np.testing.assert_allclose(pp.pointcloud2_to_lidar(xyz, rotations=(rr,)), oracle.pointcloud2_to_lidar(xyz, (rr,), lift, 1, 4),
+                               rtol=0, atol=1e-14)
+
+
+def test_ingest_feeds_voxelizer(pp, oracle, synth):
+    """Sensor cloud -> ingest -> points_to_voxel equals the reference sequence on the host."""
+    cfg = synth.D435
+    xyz = _sensor_cloud(120000, 21, 0.15)
+    # camera optical frame -> the reference's rotations put depth on x: scale so points fall in the grid
+    pts = pp.pointcloud2_to_lidar(xyz)
+    vs, pcr = np.array(cfg["voxel_size"]), np.array(cfg["point_cloud_range"])
+    v, c, n = pp.points_to_voxel(pts, vs, pcr, cfg["max_points"], True, cfg["max_voxels"])
+    from importlib import import_module
+    ing = import_module(pp.__name__ + ".ingest")
+    opts = oracle.pointcloud2_to_lidar(xyz, (ing.R_Y_NEG90, ing.R_X_POS90), ing.LIFT, 1, 4)
+    ov, oc, on = oracle.points_to_voxel(opts, vs, pcr, cfg["max_points"], True, cfg["max_voxels"])
+    assert c.shape[0] > 100
+    assert np.array_equal(c, oc) and np.array_equal(n, on) and np.array_equal(v, ov)

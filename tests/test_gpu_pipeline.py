@@ -134,3 +134,57 @@ def test_profiler_and_launch_count(pp, synth):
     assert names == ["vox_memset"] + kernels
     assert all(t >= 0 for _, t in rec)
     assert pp.launch_count() == len(kernels)
+
+
+@pytest.mark.parametrize("rotated", [False, True])
+def test_production_chain(synth, oracle, rotated):
+    """N3 + a1-a5 + N1 + N2 chained on the device for a batch of sensor frames (the reference's live loop:
+    load_data.py:2434-2443 -> 2966 -> 3043-3072 -> model/voxelnet.py:1060-1389) against the per-frame oracle."""
+    import torch
+    pipeline = importlib.import_module(PKG + ".pipeline")
+    ing = importlib.import_module(PKG + ".ingest")
+    cfg = synth.D435
+    n_sensor = 848 * 480
+    clouds = [synth.d435_sensor_cloud(60), synth.d435_sensor_cloud(61, invalid=0.5), synth.d435_sensor_cloud(62, invalid=0.0)]
+    clouds[1][:200000] = np.nan          # a frame whose valid pixels are all in the lower half of the image
+    B = len(clouds)
+    pipe = pipeline.FramePipeline(cfg, device=0, max_frames=B, rotated_nms=rotated, anchor_area_threshold=1,
+                                  production=True, sensor_points=n_sensor)
+    A = pipe.A
+    an = synth.anchors_stride(cfg)
+    rng = np.random.default_rng(9)
+    bp = rng.normal(0, 0.1, (B, A, 7)).astype(np.float32)
+    cl = rng.normal(-2, 1, (B, A, 1)).astype(np.float32)
+    dr = rng.normal(0, 1, (B, A, 2)).astype(np.float32)
+    rect = np.tile(np.eye(4, dtype=np.float32), (B, 1, 1))
+    trv = np.tile(np.array([[0, -1, 0, 0.01], [0, 0, -1, -0.07], [1, 0, 0, -0.27], [0, 0, 0, 1]], np.float32), (B, 1, 1))
+    feats = synth.pfn_standin(pipe.cap_rows, cfg["num_filters"], 3)
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    pipe.run_production(t(np.stack(clouds)), B, 12, (0, 4, 8), t(feats), t(bp), t(cl), t(dr), t(rect), t(trv))
+    lid_h, cam_h, sc_h, cnt_h = pipe.fetch_production(B)
+    torch.cuda.synchronize()
+    vbase = pipe.voxel_base[:B + 1].cpu().numpy()
+    coors = pipe.coors[:int(vbase[B])].cpu().numpy()
+    num = pipe.num_points[:int(vbase[B])].cpu().numpy()
+    n_in = pipe.in_count[:B].cpu().numpy()
+    idx = pipe.det_index[:B].cpu().numpy()
+    gm = pipe.anchor_mask[:B].cpu().numpy()
+    vs, pcr = np.array(cfg["voxel_size"]), np.array(cfg["point_cloud_range"])
+    for b in range(B):
+        pts = oracle.pointcloud2_to_lidar(clouds[b], (ing.R_Y_NEG90, ing.R_X_POS90), ing.LIFT, 1, 4)
+        assert n_in[b] == pts.shape[0]
+        got_pts = pipe.in_points[b].cpu().numpy()
+        assert np.array_equal(got_pts[:n_in[b]], pts) and np.isnan(got_pts[n_in[b]:]).all()
+        _, oc, on = oracle.points_to_voxel(pts, vs, pcr, cfg["max_points"], True, cfg["max_voxels"])
+        lo, hi = int(vbase[b]), int(vbase[b + 1])
+        assert np.array_equal(coors[lo:hi, 1:], oc) and np.array_equal(num[lo:hi], on)
+        _, mask = oracle.anchors_mask(oc, an, vs, pcr, 1)
+        assert np.array_equal(gm[b].astype(bool), mask)
+        want = oracle.predict_frame(bp[b], cl[b], dr[b], an, mask.astype(np.uint8), rect[b], trv[b], rotated=rotated)
+        k = int(cnt_h[b])
+        assert want["box3d_lidar"] is not None and k == want["box3d_lidar"].shape[0]
+        assert np.array_equal(idx[b, :k], want["anchor_index"])
+        np.testing.assert_allclose(lid_h[b, :k].numpy(), want["box3d_lidar"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(cam_h[b, :k].numpy(), want["box3d_camera"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(sc_h[b, :k].numpy(), want["scores"], rtol=1e-6, atol=0)

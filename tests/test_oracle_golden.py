@@ -165,3 +165,22 @@ def test_predict_golden(oracle):
         assert np.array_equal(o["label_preds"], g[f"label_preds{b}"])
         # the kept set is the same set of anchors: decoded x,y identify them
         assert np.all(np.diff(o["scores"]) <= 0)
+
+
+def test_ingest_oracle_matches_reference_expressions(oracle):
+    """N3: load_data.py:2434-2443 evaluated with scipy/numpy exactly as written, against the oracle restatement,
+    on a D435-like organised cloud with invalid (NaN / inf) pixels."""
+    from scipy.spatial.transform import Rotation as R
+    rng = np.random.default_rng(3)
+    xyz = rng.normal(0, 2, (20000, 3)).astype(np.float32)
+    xyz[rng.random(20000) < 0.2] = np.nan
+    xyz[5, 1] = np.inf
+    r = R.from_euler('y', -90, degrees=True).as_matrix()    # `as_dcm` before scipy 1.4
+    r2 = R.from_euler('x', 90, degrees=True).as_matrix()
+    finite = xyz[np.isfinite(xyz).all(axis=1)].astype(np.float64)   # ros_numpy get_xyz_points(remove_nans=True)
+    points = finite[1::4]
+    points = np.dot(points, r)
+    points = np.dot(points, r2)
+    points = points + [0.0, 0.0, 1.0]
+    got = oracle.pointcloud2_to_lidar(xyz, (r, r2), [0.0, 0.0, 1.0], 1, 4)
+    assert got.dtype == np.float64 and np.array_equal(got, points)
