@@ -8,8 +8,9 @@
 // ros_numpy (third party, not vendored by the reference) drops every row with a non-finite x, y or z
 // BEFORE the [1::4] slice, so the subsample is a slice of an ordered stream compaction.  Three launches
 // for a batch of frames: per-tile finite counts, a scan over tiles per frame, and a pass that ranks the
-// finite rows (ballot + popc), keeps rank = start + j*step, applies the rotations and the translation
-// in float64 (k = 0,1,2 in order, separate multiply and add) and stores row j.  Rows past the frame's
+// finite rows (four consecutive records per thread, one block scan per 1024-record tile), keeps
+// rank = start + j*step, applies the rotations and the translation in float64 (k = 0,1,2 in order,
+// separate multiply and add) and stores row j.  Rows past the frame's
 // count are filled with NaN, which the voxelizer drops, so the [B, cap, 3] output feeds pp_voxelize_dev
 // with fixed frame offsets and no host round trip for the counts.
 //
@@ -34,29 +35,45 @@ __device__ __forceinline__ bool finite3(float x, float y, float z) {
     return isfinite(x) && isfinite(y) && isfinite(z);
 }
 
-__device__ __forceinline__ void load_xyz(const unsigned char* __restrict__ cloud, int64_t row, int point_step, int ox,
-                                         int oy, int oz, float& x, float& y, float& z) {
-    const unsigned char* p = cloud + row * point_step;
-    x = *reinterpret_cast<const float*>(p + ox);
-    y = *reinterpret_cast<const float*>(p + oy);
-    z = *reinterpret_cast<const float*>(p + oz);
+// Thread t of a tile owns the four consecutive records 4t..4t+3.  PACKED (point_step 12, 16-byte aligned
+// frames): they are 48 contiguous bytes = three 16-byte loads; otherwise twelve 4-byte loads.
+template <bool PACKED>
+__device__ __forceinline__ void load_rows4(const unsigned char* __restrict__ fc, int64_t row0, int64_t n_in, int point_step,
+                                           int ox, int oy, int oz, float (&x)[4], float (&y)[4], float (&z)[4],
+                                           unsigned& okmask) {
+    okmask = 0;
+    if (PACKED && row0 + 4 <= n_in) {
+        const float4* p = reinterpret_cast<const float4*>(fc + row0 * 12);
+        const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+        x[0] = a.x; y[0] = a.y; z[0] = a.z; x[1] = a.w; y[1] = b.x; z[1] = b.y;
+        x[2] = b.z; y[2] = b.w; z[2] = c.x; x[3] = c.y; y[3] = c.z; z[3] = c.w;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) okmask |= finite3(x[k], y[k], z[k]) ? 1u << k : 0u;
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        x[k] = y[k] = z[k] = 0.f;
+        if (row0 + k < n_in) {
+            const unsigned char* p = fc + (row0 + k) * point_step;
+            x[k] = *reinterpret_cast<const float*>(p + ox);
+            y[k] = *reinterpret_cast<const float*>(p + oy);
+            z[k] = *reinterpret_cast<const float*>(p + oz);
+            okmask |= finite3(x[k], y[k], z[k]) ? 1u << k : 0u;
+        }
+    }
 }
 
+template <bool PACKED>
 __global__ void __launch_bounds__(kIngestThreads)
 ingest_count_kernel(const unsigned char* __restrict__ cloud, int64_t n_in, int point_step, int ox, int oy, int oz,
                     int tiles_per_frame, int* __restrict__ tile_count) {
     const int b = blockIdx.y, tile = blockIdx.x;
     const unsigned char* fc = cloud + (int64_t)b * n_in * point_step;
-    int c = 0;
-#pragma unroll
-    for (int q = 0; q < kIngestTile / kIngestThreads; ++q) {
-        const int64_t i = (int64_t)tile * kIngestTile + q * kIngestThreads + threadIdx.x;
-        if (i < n_in) {
-            float x, y, z;
-            load_xyz(fc, i, point_step, ox, oy, oz, x, y, z);
-            c += finite3(x, y, z);
-        }
-    }
+    float x[4], y[4], z[4];
+    unsigned ok;
+    load_rows4<PACKED>(fc, (int64_t)tile * kIngestTile + 4 * threadIdx.x, n_in, point_step, ox, oy, oz, x, y, z, ok);
+    int c = __popc(ok);
     __shared__ int s_w[kIngestThreads / 32];
 #pragma unroll
     for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -98,62 +115,51 @@ ingest_scan_kernel(int* __restrict__ tile_count, int tiles_per_frame, int start,
     }
 }
 
+template <bool PACKED>
 __global__ void __launch_bounds__(kIngestThreads)
 ingest_write_kernel(const unsigned char* __restrict__ cloud, int64_t n_in, int point_step, int ox, int oy, int oz,
                     int tiles_per_frame, const int* __restrict__ tile_base, int start, int step, IngestXform xf,
-                    double* __restrict__ out, int64_t cap) {
-    __shared__ int s_w[kIngestThreads / 32];
+                    double* __restrict__ out, int64_t cap, const int* __restrict__ n_out) {
+    __shared__ int sm[33];
     const int b = blockIdx.y, tile = blockIdx.x;
     const unsigned char* fc = cloud + (int64_t)b * n_in * point_step;
     double* fo = out + (int64_t)b * cap * 3;
-    int base = tile_base[(int64_t)b * tiles_per_frame + tile];
-    const int lane = lane_id(), w = threadIdx.x >> 5;
-#pragma unroll 1
-    for (int q = 0; q < kIngestTile / kIngestThreads; ++q) {
-        const int64_t i = (int64_t)tile * kIngestTile + q * kIngestThreads + threadIdx.x;
-        float x = 0.f, y = 0.f, z = 0.f;
-        bool ok = false;
-        if (i < n_in) {
-            load_xyz(fc, i, point_step, ox, oy, oz, x, y, z);
-            ok = finite3(x, y, z);
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, ok);
-        if (lane == 0) s_w[w] = __popc(bal);
-        __syncthreads();
-        int woff = 0, tot = 0;
+    float x[4], y[4], z[4];
+    unsigned ok;
+    load_rows4<PACKED>(fc, (int64_t)tile * kIngestTile + 4 * threadIdx.x, n_in, point_step, ox, oy, oz, x, y, z, ok);
+    int tot;
+    int rank = tile_base[(int64_t)b * tiles_per_frame + tile] + block_excl_scan(__popc(ok), &tot, sm);
 #pragma unroll
-        for (int k = 0; k < kIngestThreads / 32; ++k) {
-            const int c = s_w[k];
-            woff += k < w ? c : 0;
-            tot += c;
-        }
-        if (ok) {
-            const int rank = base + woff + __popc(bal & lanemask_lt());
-            const int rel = rank - start;
-            if (rel >= 0 && rel % step == 0) {
-                const int64_t j = rel / step;
-                if (j < cap) {
-                    double p[3] = {(double)x, (double)y, (double)z};
-                    for (int m = 0; m < xf.n_rot; ++m) {
-                        const double* r = xf.r[m];
-                        double o[3];
+    for (int k = 0; k < 4; ++k) {
+        if (!((ok >> k) & 1u)) continue;
+        const int rel = rank - start;
+        ++rank;
+        if (rel < 0 || rel % step != 0) continue;
+        const int64_t j = rel / step;
+        if (j >= cap) continue;
+        double p[3] = {(double)x[k], (double)y[k], (double)z[k]};
+        for (int m = 0; m < xf.n_rot; ++m) {
+            const double* r = xf.r[m];
+            double o[3];
 #pragma unroll
-                        for (int c = 0; c < 3; ++c)
-                            o[c] = __dadd_rn(__dadd_rn(__dmul_rn(p[0], r[c]), __dmul_rn(p[1], r[3 + c])), __dmul_rn(p[2], r[6 + c]));
-                        p[0] = o[0]; p[1] = o[1]; p[2] = o[2];
-                    }
-                    fo[j * 3 + 0] = __dadd_rn(p[0], xf.t[0]);
-                    fo[j * 3 + 1] = __dadd_rn(p[1], xf.t[1]);
-                    fo[j * 3 + 2] = __dadd_rn(p[2], xf.t[2]);
-                }
-            }
+            for (int c = 0; c < 3; ++c)
+                o[c] = __dadd_rn(__dadd_rn(__dmul_rn(p[0], r[c]), __dmul_rn(p[1], r[3 + c])), __dmul_rn(p[2], r[6 + c]));
+            p[0] = o[0]; p[1] = o[1]; p[2] = o[2];
         }
-        base += tot;
-        __syncthreads();
+        fo[j * 3 + 0] = __dadd_rn(p[0], xf.t[0]);
+        fo[j * 3 + 1] = __dadd_rn(p[1], xf.t[1]);
+        fo[j * 3 + 2] = __dadd_rn(p[2], xf.t[2]);
+    }
+    // rows [n_out[b], cap) = NaN (dropped by the voxelizer): every CTA of the frame pads an equal slice
+    const int64_t first = (int64_t)n_out[b] * 3, len = cap * 3 - first;
+    if (len > 0) {
+        const int64_t per = (len + tiles_per_frame - 1) / tiles_per_frame;
+        const int64_t lo = first + (int64_t)tile * per, hi = min(lo + per, cap * 3);
+        for (int64_t k = lo + threadIdx.x; k < hi; k += kIngestThreads) fo[k] = __longlong_as_double(0x7ff8000000000000ll);
     }
 }
 
-// rows [n_out[b], cap) of every frame = NaN (dropped by the voxelizer)
+// n_in == 0: every row of the output is padding
 __global__ void __launch_bounds__(256)
 ingest_pad_kernel(double* __restrict__ out, int64_t cap, const int* __restrict__ n_out) {
     const int b = blockIdx.y;
@@ -202,10 +208,13 @@ extern "C" int pp_ingest_dev(const void* cloud, int B, int64_t n_in, int point_s
         for (int k = 0; k < 9; ++k) xf.r[m][k] = rotations[m * 9 + k];
     for (int k = 0; k < 3; ++k) xf.t[k] = translation ? translation[k] : 0.0;
     const unsigned char* cl = static_cast<const unsigned char*>(cloud);
+    const bool packed = point_step == 12 && off_x == 0 && off_y == 4 && off_z == 8 &&
+                        (reinterpret_cast<uintptr_t>(cloud) & 15) == 0 && ((n_in * 12) & 15) == 0;
     if (tiles > 0) {
         PP_CHECK_ARG(cloud, "pp_ingest_dev: null cloud");
         PP_TIMED("ingest_count", st);
-        ingest_count_kernel<<<dim3(tiles, B), kIngestThreads, 0, st>>>(cl, n_in, point_step, off_x, off_y, off_z, tiles, tile_count);
+        if (packed) ingest_count_kernel<true><<<dim3(tiles, B), kIngestThreads, 0, st>>>(cl, n_in, point_step, off_x, off_y, off_z, tiles, tile_count);
+        else ingest_count_kernel<false><<<dim3(tiles, B), kIngestThreads, 0, st>>>(cl, n_in, point_step, off_x, off_y, off_z, tiles, tile_count);
         PP_LAUNCHED();
     }
     {
@@ -215,11 +224,10 @@ extern "C" int pp_ingest_dev(const void* cloud, int B, int64_t n_in, int point_s
     }
     if (tiles > 0 && cap > 0) {
         PP_TIMED("ingest_write", st);
-        ingest_write_kernel<<<dim3(tiles, B), kIngestThreads, 0, st>>>(cl, n_in, point_step, off_x, off_y, off_z, tiles, tile_count,
-                                                                      start, step, xf, points_out, cap);
+        if (packed) ingest_write_kernel<true><<<dim3(tiles, B), kIngestThreads, 0, st>>>(cl, n_in, point_step, off_x, off_y, off_z, tiles, tile_count, start, step, xf, points_out, cap, n_out);
+        else ingest_write_kernel<false><<<dim3(tiles, B), kIngestThreads, 0, st>>>(cl, n_in, point_step, off_x, off_y, off_z, tiles, tile_count, start, step, xf, points_out, cap, n_out);
         PP_LAUNCHED();
-    }
-    if (cap > 0) {
+    } else if (cap > 0) {
         PP_TIMED("ingest_pad", st);
         ingest_pad_kernel<<<dim3((unsigned)ceil_div(cap * 3, 256), B), 256, 0, st>>>(points_out, cap, n_out);
         PP_LAUNCHED();

@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--frames", type=int, default=64, help="frames per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=2)
+    ap.add_argument("--no-production", action="store_true", help="skip the sensor-to-camera-boxes production chain")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -331,6 +332,112 @@ def main():
               "launches_per_frame": pp.launch_count(reset=True) / n_single,
               "note": "one d435i frame per step, device-resident, same kernels; latency-bound (SURVEY 8d config 2)"}
 
+    # ---- the reference's live production chain ("next" rows N3, N1, N2 around the path): raw sensor cloud
+    #      (float32 PointCloud2 xyz, invalid pixels NaN) -> ingest -> voxelize+decorate -> scatter -> anchor mask ->
+    #      predict (sigmoid, top-100, decode, standup NMS, direction flip, camera boxes).  Reported beside the headline.
+    production = None
+    if not args.no_production:
+        n_sensor = 848 * 480
+        pipeP = pipeline.FramePipeline(cfg, device=local_rank, max_frames=F, rotated_nms=False, anchor_area_threshold=1,
+                                       production=True, sensor_points=n_sensor)
+        sens = [synth.d435_sensor_cloud(1000 * rank + i) for i in range(min(F, 4))]
+        host_sens = torch.empty((F, n_sensor, 3), dtype=torch.float32).pin_memory()
+        for i in range(F):
+            host_sens[i] = torch.from_numpy(sens[i % len(sens)])
+        d_sens = host_sens.to(dev)
+        stageP = [torch.empty_like(d_sens), torch.empty_like(d_sens)]
+        rngp = np.random.default_rng(7 + rank)
+        d_bp = torch.from_numpy(rngp.normal(0, 0.1, (F, A, 7)).astype(np.float32)).to(dev)
+        d_cl = torch.from_numpy(rngp.normal(-2, 1, (F, A, 1)).astype(np.float32)).to(dev)
+        d_dr = torch.from_numpy(rngp.normal(0, 1, (F, A, 2)).astype(np.float32)).to(dev)
+        d_rect = torch.eye(4, dtype=torch.float32).repeat(F, 1, 1).to(dev)
+        d_trv = torch.tensor([[0, -1, 0, 0.01], [0, 0, -1, -0.07], [1, 0, 0, -0.27], [0, 0, 0, 1]],
+                             dtype=torch.float32).repeat(F, 1, 1).to(dev)
+        d_featsP = torch.from_numpy(synth.pfn_standin(pipeP.cap_rows, cfg["num_filters"], rank)).to(dev)
+        pstate = {"i": 0}
+
+        def step_prod():
+            pipeP.run_production(d_sens, F, 12, (0, 4, 8), d_featsP, d_bp, d_cl, d_dr, d_rect, d_trv)
+
+        def step_prod_e2e():
+            k = pstate["i"] & 1
+            pstate["i"] += 1
+            main = torch.cuda.current_stream(dev)
+            copy_stream.wait_event(ev_consumed[k])
+            with torch.cuda.stream(copy_stream):
+                stageP[k].copy_(host_sens, non_blocking=True)
+                ev_copied[k].record(copy_stream)
+            main.wait_event(ev_copied[k])
+            pipeP.run_production(stageP[k], F, 12, (0, 4, 8), d_featsP, d_bp, d_cl, d_dr, d_rect, d_trv)
+            ev_consumed[k].record(main)
+            pipeP.fetch_production(F)
+        for _ in range(3):
+            step_prod()
+        torch.cuda.synchronize()
+        if int(pipeP.keep_count[:F].sum().item()) == 0:
+            raise SystemExit("bench.py: the production chain produced no detections")
+        n_prod = max(10, args.steps // 2)
+        pp.launch_count(reset=True)
+        ms_p = timed(step_prod, n_prod)
+        l_prod = pp.launch_count(reset=True) / n_prod
+        ev_consumed[0].record(); ev_consumed[1].record()
+        for _ in range(2):
+            step_prod_e2e()
+
+        def timed_prod_e2e(steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            copy_stream.wait_event(e0)
+            for _ in range(steps):
+                step_prod_e2e()
+            torch.cuda.current_stream(dev).wait_stream(copy_stream)
+            e1.record()
+            barrier()
+            m = e0.elapsed_time(e1)
+            if world > 1:
+                tt = torch.tensor([m], dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                m = float(tt.item())
+            return m
+        ms_pe = timed_prod_e2e(n_prod)
+        production = {
+            "workload": "sensor cloud 848x480 float32 xyz (10 % invalid) -> ingest [1::4] + 2 rotations + lift -> voxelize+decorate "
+                        "-> scatter -> anchor mask -> predict (top-100, decode, standup NMS pre 100/post 50, flip, camera boxes)",
+            "frames_per_s": world * F * n_prod / (ms_p / 1e3), "ms_per_step": ms_p / n_prod, "launches_per_step": l_prod,
+            "e2e_frames_per_s": world * F * n_prod / (ms_pe / 1e3), "e2e_ms_per_step": ms_pe / n_prod,
+            "h2d_bytes_per_step": F * n_sensor * 12, "d2h_bytes_per_step": F * pipeP.post * (7 * 8 + 7 * 4 + 4) + F * 4,
+            "sensor_points_per_s": world * F * n_prod / (ms_p / 1e3) * n_sensor}
+        if world == 1 and not args.no_cpu_baseline:
+            import oracle
+            ing = importlib.import_module(PKG + ".ingest")
+            an_h = synth.anchors_stride(cfg)
+            vs_h, pcr_h = np.array(cfg["voxel_size"]), np.array(cfg["point_cloud_range"])
+            feats_hp = synth.pfn_standin(cfg["max_voxels"], cfg["num_filters"], 0)
+            bp_h, cl_h, dr_h = d_bp[0].cpu().numpy(), d_cl[0].cpu().numpy(), d_dr[0].cpu().numpy()
+
+            def cpu_frame(cloud):
+                pts_ = oracle.pointcloud2_to_lidar(cloud, (ing.R_Y_NEG90, ing.R_X_POS90), ing.LIFT, 1, 4)
+                v_, c_, n_ = oracle.points_to_voxel(pts_, vs_h, pcr_h, cfg["max_points"], True, cfg["max_voxels"])
+                c4_ = np.concatenate([np.zeros((c_.shape[0], 1), np.int32), c_], axis=1)
+                oracle.decorate(v_.astype(np.float32), n_, c4_, pipeP.vx, pipeP.vy, pipeP.xo, pipeP.yo)
+                oracle.scatter(feats_hp[:c_.shape[0]], c4_, 1, pipeP.ny, pipeP.nx)
+                _, m_ = oracle.anchors_mask(c_, an_h, vs_h, pcr_h, 1)
+                return oracle.predict_frame(bp_h, cl_h, dr_h, an_h, m_.astype(np.uint8), np.eye(4, dtype=np.float32),
+                                            d_trv[0].cpu().numpy())
+            want = cpu_frame(sens[0])
+            t0 = time.perf_counter()
+            reps = 0
+            while time.perf_counter() - t0 < 3.0:
+                cpu_frame(sens[reps % len(sens)])
+                reps += 1
+            production["cpu_port_single_thread_frames_per_s"] = reps / (time.perf_counter() - t0)
+            k0 = int(pipeP.keep_count[0].item())
+            production["detections_match"] = bool(
+                want["box3d_lidar"] is not None and k0 == want["box3d_lidar"].shape[0] and
+                np.array_equal(pipeP.det_index[0, :k0].cpu().numpy(), want["anchor_index"]))
+        del pipeP, d_sens, stageP, host_sens
+
     # ---- per-kernel device times (CUDA events on the launching stream, outside the timed region) ----
     per_kernel = {}
     if args.profile_steps > 0:
@@ -422,6 +529,7 @@ def main():
         "roofline": roof,
         "cpu_baseline": cpu,
         "single_frame": single,
+        "production": production,
         "path": {"pillars_per_frame": m_pillars, "detections_per_step": n_dets,
                  "algorithmic_bytes_per_frame": ab["total"],
                  "path_gbs_per_gpu": ab["total"] * F / (ms / args.steps * 1e-3) / 1e9,
