@@ -309,28 +309,35 @@ rotate_iou_matrix_kernel(const float* __restrict__ boxes, int64_t N, const float
 }
 
 // ---------------------------------------------------------------------------------------------
-// Stripe-sequential NMS for large box counts (> kStripeMin after pre_max_size).
+// Alive-stripe NMS for large box counts (> kStripeMin after pre_max_size).
 //
 // Greedy NMS keeps box j iff no KEPT box of higher score overlaps it.  The all-pairs bitmask of the
 // reference (N^2/128 bytes: 1.25 GB at 100 k boxes) spends most of its work on rows of boxes that
-// end up suppressed.  Here the score-ordered boxes are processed in stripes of kStripe:
-//   cross   every box of the stripe against the boxes kept so far -- only those in the 3x3 neighbourhood of
-//           its bin in a uniform grid over box centres (bin edge >= the largest hull), early exit on the
-//           first suppressor -- no mask, only a dead flag per box
-//   mask    the usual upper-triangle bitmask, but only inside the stripe and only for live rows
-//   sweep   greedy sweep of the stripe seeded with the dead flags; kept boxes are appended to the
-//           compact kept array (and to the output) for the following stripes
-// The result is identical to the all-pairs algorithm (same IoU function, same argument order
-// (higher score first), same strict > test).
-constexpr int kStripe = 2048;           // boxes per stripe = kMaskGroup * 64
+// end up suppressed.  Here every box carries a dead flag, all boxes are binned ONCE into a uniform
+// grid over their centres (bin edge >= the largest hull, so overlapping boxes sit in the same or in
+// adjacent bins), and the score-ordered boxes are consumed in stripes of the next kAlive boxes that
+// are still ALIVE:
+//   select  per frame: the next <= kAlive alive positions after the frame's cursor
+//   mask    upper-triangle bitmask inside the stripe (every row is alive)
+//   sweep   greedy sweep of the stripe; kept boxes go to the output and to the new-kept list
+//   push    one warp per newly kept box: the boxes of its 3x3 bin neighbourhood that lie after the
+//           cursor and are still alive are tested (hull pre-reject, survivors queued per warp so
+//           the polygon clips run with full lanes) and flagged dead
+// Every (kept, later) pair is looked at once at most; suppressed boxes never enter a stripe, so the
+// number of stripes follows the number of boxes alive at their turn (about a third of 100 k random
+// boxes), not N.  The result is identical to the all-pairs algorithm (same IoU function, same argument
+// order (higher score first), same strict > test).
+constexpr int kStripe = 2048;           // mask rows per frame = kMaskGroup * 64
+#ifndef PP_NMS_ALIVE
+#define PP_NMS_ALIVE 1024
+#endif
+constexpr int kAlive = PP_NMS_ALIVE;    // alive boxes per stripe (<= kStripe): the in-stripe mask costs kAlive/2 tests per box
 constexpr int kStripeMin = 16384;       // use the stripe path above this many boxes per frame
-constexpr int kCrossThreads = 128;
+constexpr int kPushWarps = 8;
 
-// Uniform grid over the box centres of one frame.  Bin edge >= the largest hull extent (+ margin), so two
-// boxes whose hulls touch have centres in the same or in adjacent bins: the cross stage only has to look
-// at the kept boxes of a 3x3 neighbourhood instead of the whole kept list.
 struct StripeGrid { float ox, oy, inv_s; int gx, gy; };
-constexpr int kGridMax = 512;
+constexpr int kGridMax = 64;            // bins per axis (bin table: kGridMax^2 + 1 ints per frame)
+constexpr int kGridBins = kGridMax * kGridMax;
 
 template <bool ROTATED>
 __device__ __forceinline__ void box_centre_extent(const void* sorted, int64_t i, float& cx, float& cy, float& ext) {
@@ -345,11 +352,24 @@ __device__ __forceinline__ void box_centre_extent(const void* sorted, int64_t i,
     }
 }
 
+__device__ __forceinline__ void grid_bin(const StripeGrid& g, float cx, float cy, int& bx, int& by) {
+    // NaN / out-of-bounds centres clamp into the grid (NaN boxes can neither suppress nor be suppressed)
+    const float fx = (cx - g.ox) * g.inv_s, fy = (cy - g.oy) * g.inv_s;
+    bx = fx >= 0.f ? min((int)fx, g.gx - 1) : 0;
+    by = fy >= 0.f ? min((int)fy, g.gy - 1) : 0;
+}
+
+// one CTA per frame: bounds of the centres and the largest extent -> grid; counting sort of the
+// frame's boxes by bin (bin_start[kGridBins+1], bin_items[n] = score-order positions)
 template <bool ROTATED>
 __global__ void __launch_bounds__(1024)
-nms_grid_setup_kernel(const void* __restrict__ sorted, int64_t sorted_stride, const int* __restrict__ n_sorted,
-                      StripeGrid* __restrict__ grid) {
+nms_bin_build_kernel(const void* __restrict__ sorted, int64_t sorted_stride, const int* __restrict__ n_sorted,
+                     StripeGrid* __restrict__ grid, int* __restrict__ bin_start, int* __restrict__ bin_items,
+                     float4* __restrict__ bin_hull, int* __restrict__ slot_of) {
     __shared__ float s_red[5][32];
+    __shared__ int s_hist[kGridBins];
+    __shared__ int sm[33];
+    __shared__ StripeGrid s_g;
     const int b = blockIdx.x;
     const int n = n_sorted[b];
     using BoxG = typename std::conditional<ROTATED, RBoxG, float4>::type;
@@ -370,6 +390,7 @@ nms_grid_setup_kernel(const void* __restrict__ sorted, int64_t sorted_stride, co
     }
     const int lane = lane_id(), w = threadIdx.x >> 5;
     if (lane == 0) { s_red[0][w] = mnx; s_red[1][w] = mny; s_red[2][w] = mxx; s_red[3][w] = mxy; s_red[4][w] = ext; }
+    for (int k = threadIdx.x; k < kGridBins; k += 1024) s_hist[k] = 0;
     __syncthreads();
     if (w == 0) {
         mnx = s_red[0][lane]; mny = s_red[1][lane]; mxx = s_red[2][lane]; mxy = s_red[3][lane]; ext = s_red[4][lane];
@@ -390,98 +411,123 @@ nms_grid_setup_kernel(const void* __restrict__ sorted, int64_t sorted_stride, co
             g.gx = min(kGridMax, (int)((mxx - mnx) * g.inv_s) + 2);
             g.gy = min(kGridMax, (int)((mxy - mny) * g.inv_s) + 2);
             grid[b] = g;
+            s_g = g;
         }
     }
-}
-
-__device__ __forceinline__ void grid_bin(const StripeGrid& g, float cx, float cy, int& bx, int& by) {
-    // NaN / out-of-bounds centres clamp into the grid (NaN boxes can neither suppress nor be suppressed)
-    const float fx = (cx - g.ox) * g.inv_s, fy = (cy - g.oy) * g.inv_s;
-    bx = fx >= 0.f ? min((int)fx, g.gx - 1) : 0;
-    by = fy >= 0.f ? min((int)fy, g.gy - 1) : 0;
-}
-
-// cross stage: one thread per box of the stripe; walks the kept boxes of the 3x3 bin neighbourhood
-template <bool ROTATED>
-__global__ void __launch_bounds__(kCrossThreads)
-nms_cross_kernel(const void* __restrict__ sorted, int64_t sorted_stride, const int* __restrict__ n_sorted, int base,
-                 const void* __restrict__ kept_box, const int* __restrict__ kept_cnt, int limit, float thresh,
-                 const StripeGrid* __restrict__ grid, const int* __restrict__ bin_head, const int* __restrict__ bin_next,
-                 unsigned char* __restrict__ dead /*[B][kStripe]*/) {
-    using BoxG = typename std::conditional<ROTATED, RBoxG, float4>::type;
-    const int b = blockIdx.y;
-    const int n = n_sorted[b];
-    if (kept_cnt[b] >= limit) return;  // post_max_size reached: nothing more will be kept
-    const int j = blockIdx.x * kCrossThreads + threadIdx.x;  // box inside the stripe
-    if (base + j >= n) return;
-    const BoxG* sb = static_cast<const BoxG*>(sorted) + (int64_t)b * sorted_stride;
-    const BoxG* kb = static_cast<const BoxG*>(kept_box) + (int64_t)b * sorted_stride;
-    const int* head = bin_head + (int64_t)b * kGridMax * kGridMax;
-    const int* next = bin_next + (int64_t)b * sorted_stride;
-    const StripeGrid g = grid[b];
-    RBox me; float4 mef = make_float4(0.f, 0.f, 0.f, 0.f);
-    float cx, cy, e;
-    box_centre_extent<ROTATED>(sb, base + j, cx, cy, e);
-    if constexpr (ROTATED) load_rbox(reinterpret_cast<const RBoxG*>(sb) + base + j, me);
-    else mef = reinterpret_cast<const float4*>(sb)[base + j];
-    int bx, by;
-    grid_bin(g, cx, cy, bx, by);
-    const double th = (double)thresh;
-    for (int dy = -1; dy <= 1; ++dy) {
-        const int yy = by + dy;
-        if (yy < 0 || yy >= g.gy) continue;
-        for (int dx = -1; dx <= 1; ++dx) {
-            const int xx = bx + dx;
-            if (xx < 0 || xx >= g.gx) continue;
-            for (int k = head[yy * kGridMax + xx]; k >= 0; k = next[k]) {
-                bool sup;
-                if constexpr (ROTATED) {
-                    RBox kbx;
-                    load_rbox(reinterpret_cast<const RBoxG*>(kb) + k, kbx);
-                    const float scale = fmaxf(fmaxf(fabsf(kbx.mxx), fabsf(kbx.mnx)), fmaxf(fabsf(kbx.mxy), fabsf(kbx.mny)));
-                    const float eps = 1e-4f * fmaxf(1.f, scale);
-                    if (kbx.mnx > me.mxx + eps || me.mnx > kbx.mxx + eps || kbx.mny > me.mxy + eps || me.mny > kbx.mxy + eps) continue;
-                    const double ai = rbox_inter(kbx.c, me.c);  // devRotateIoU(higher score, lower score)
-                    sup = ai / ((double)__fadd_rn(kbx.area, me.area) - ai) > th;
-                } else {
-                    sup = standup_iou(reinterpret_cast<const float4*>(kb)[k], mef) > th;
-                }
-                if (sup) { dead[(int64_t)b * kStripe + j] = 1; return; }
+    __syncthreads();
+    const StripeGrid g = s_g;
+    for (int i = threadIdx.x; i < n; i += 1024) {
+        float cx, cy, e;
+        box_centre_extent<ROTATED>(sb, i, cx, cy, e);
+        int bx, by;
+        grid_bin(g, cx, cy, bx, by);
+        atomicAdd(&s_hist[by * kGridMax + bx], 1);
+    }
+    __syncthreads();
+    // exclusive scan of the histogram, four bins per thread
+    int* bs = bin_start + (int64_t)b * (kGridBins + 1);
+    {
+        int v[4], t = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { v[q] = s_hist[threadIdx.x * 4 + q]; t += v[q]; }
+        int tot;
+        int ex = block_excl_scan(t, &tot, sm);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { s_hist[threadIdx.x * 4 + q] = ex; bs[threadIdx.x * 4 + q] = ex; ex += v[q]; }
+        if (threadIdx.x == 0) bs[kGridBins] = tot;
+    }
+    __syncthreads();
+    // scatter in chunks of 1024 score positions with a barrier in between: inside a bin the items are then
+    // ordered by chunk, so the push stage can skip everything before the cursor's chunk with a binary search
+    int* items = bin_items + (int64_t)b * sorted_stride;
+    float4* hull = bin_hull + (int64_t)b * sorted_stride;
+    int* slots = slot_of + (int64_t)b * sorted_stride;
+    for (int i0 = 0; i0 < n; i0 += 1024) {
+        const int i = i0 + threadIdx.x;
+        if (i < n) {
+            float cx, cy, e;
+            box_centre_extent<ROTATED>(sb, i, cx, cy, e);
+            int bx, by;
+            grid_bin(g, cx, cy, bx, by);
+            const int t = atomicAdd(&s_hist[by * kGridMax + bx], 1);
+            items[t] = i;
+            slots[i] = t;
+            if constexpr (ROTATED) {
+                const RBoxG* gb = reinterpret_cast<const RBoxG*>(sb) + i;
+                hull[t] = make_float4(gb->mnx, gb->mny, gb->mxx, gb->mxy);
+            } else {
+                hull[t] = reinterpret_cast<const float4*>(sb)[i];
             }
         }
+        __syncthreads();
     }
 }
 
-// upper-triangle mask inside one stripe, live rows only (layout [kStripe][kMaskGroup] words per frame)
+// per frame: the next <= kAlive alive positions at or after the cursor
+__global__ void __launch_bounds__(1024)
+nms_select_kernel(const int* __restrict__ n_sorted, const unsigned char* __restrict__ dead,
+                  const int* __restrict__ slot_of, int64_t sorted_stride, const int* __restrict__ kept_cnt, int limit,
+                  int* __restrict__ cursor, int* __restrict__ s_idx, int* __restrict__ s_n) {
+    __shared__ int sm[33];
+    __shared__ int s_stop;
+    const int b = blockIdx.x;
+    const int n = n_sorted[b];
+    int cur = cursor[b];
+    if (kept_cnt[b] >= limit || cur >= n) {
+        if (threadIdx.x == 0) { s_n[b] = 0; cursor[b] = n; }
+        return;
+    }
+    const unsigned char* df = dead + (int64_t)b * sorted_stride;   // indexed by bin slot
+    const int* slots = slot_of + (int64_t)b * sorted_stride;
+    int* out = s_idx + (int64_t)b * kStripe;
+    int have = 0;
+    while (cur < n && have < kAlive) {
+        const int pos = cur + threadIdx.x;
+        const int alive = pos < n && !df[slots[pos]];
+        int tot;
+        const int r = block_excl_scan(alive, &tot, sm);
+        if (threadIdx.x == 0) s_stop = min(n, cur + 1024);
+        __syncthreads();
+        if (alive && have + r < kAlive) {
+            out[have + r] = pos;
+            if (have + r == kAlive - 1) s_stop = pos + 1;  // the stripe is full: the cursor stops right behind it
+        }
+        __syncthreads();
+        have = min(kAlive, have + tot);
+        cur = s_stop;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { s_n[b] = have; cursor[b] = cur; }
+}
+
+// upper-triangle mask inside one stripe of alive boxes (layout [kStripe][kMaskGroup] words per frame)
 template <bool ROTATED>
 __global__ void __launch_bounds__(64 * kMaskQ)
-nms_stripe_mask_kernel(const void* __restrict__ sorted, int64_t sorted_stride, const int* __restrict__ n_sorted, int base,
-                       const int* __restrict__ kept_cnt, int limit, const unsigned char* __restrict__ dead, float thresh,
-                       unsigned long long* __restrict__ mask) {
+nms_stripe_mask_kernel(const void* __restrict__ sorted, int64_t sorted_stride, const int* __restrict__ s_idx,
+                       const int* __restrict__ s_n, float thresh, unsigned long long* __restrict__ mask) {
     using BoxG = typename std::conditional<ROTATED, RBoxG, float4>::type;
     __shared__ BoxG s_col[kMaskQ * 64];
     const int b = blockIdx.y, rb = blockIdx.x;
-    if (kept_cnt[b] >= limit) return;
-    const int n = min(kStripe, n_sorted[b] - base);
+    const int n = s_n[b];
     const int cb = (n + 63) >> 6;
     if (n <= 0 || rb >= cb) return;
     const int r = threadIdx.x & 63, q = threadIdx.x >> 6;
     const int row = rb * 64 + r;
-    const BoxG* sb = static_cast<const BoxG*>(sorted) + (int64_t)b * sorted_stride + base;
-    const unsigned char* df = dead + (int64_t)b * kStripe;
+    const BoxG* sb = static_cast<const BoxG*>(sorted) + (int64_t)b * sorted_stride;
+    const int* idx = s_idx + (int64_t)b * kStripe;
     unsigned long long* mb = mask + (int64_t)b * kStripe * kMaskGroup;
     const double th = (double)thresh;
-    const bool live = row < n && !df[row];
+    const bool live = row < n;
     RBox rrow; float4 frow = make_float4(0.f, 0.f, 0.f, 0.f);
     if (live) {
-        if constexpr (ROTATED) load_rbox(reinterpret_cast<const RBoxG*>(sb) + row, rrow);
-        else frow = reinterpret_cast<const float4*>(sb)[row];
+        if constexpr (ROTATED) load_rbox(reinterpret_cast<const RBoxG*>(sb) + idx[row], rrow);
+        else frow = reinterpret_cast<const float4*>(sb)[idx[row]];
     }
     for (int cbase = rb & ~(kMaskQ - 1); cbase < cb; cbase += kMaskQ) {
         __syncthreads();
         {
             const int col = cbase * 64 + threadIdx.x;
-            if (col < n) s_col[threadIdx.x] = sb[col];
+            if (col < n) s_col[threadIdx.x] = sb[idx[col]];
         }
         __syncthreads();
         const int cbk = cbase + q;
@@ -490,7 +536,6 @@ nms_stripe_mask_kernel(const void* __restrict__ sorted, int64_t sorted_stride, c
             const int jn = min(64, n - cbk * 64);
             const int j0 = (cbk == rb) ? r + 1 : 0;
             for (int jj = j0; jj < jn; ++jj) {
-                if (df[cbk * 64 + jj]) continue;  // a dead column can never be kept: its bit is irrelevant
                 bool sup;
                 if constexpr (ROTATED) {
                     const RBoxG& c = s_col[q * 64 + jj];
@@ -511,48 +556,35 @@ nms_stripe_mask_kernel(const void* __restrict__ sorted, int64_t sorted_stride, c
     }
 }
 
-// sweep of one stripe seeded with the dead flags; appends the kept boxes
-template <bool ROTATED>
+// greedy sweep of one stripe; kept boxes go to the output and to the new-kept list of the push stage
 __global__ void __launch_bounds__(256)
-nms_stripe_sweep_kernel(const void* __restrict__ sorted, int64_t sorted_stride, const int* __restrict__ n_sorted, int base,
-                        const unsigned long long* __restrict__ mask, unsigned char* __restrict__ dead,
-                        const int* __restrict__ order, int limit, void* __restrict__ kept_box, int* __restrict__ kept_cnt,
-                        const StripeGrid* __restrict__ grid, int* __restrict__ bin_head, int* __restrict__ bin_next,
+nms_stripe_sweep_kernel(const int* __restrict__ s_idx, const int* __restrict__ s_n, int64_t sorted_stride,
+                        const unsigned long long* __restrict__ mask, const int* __restrict__ order, int limit,
+                        int* __restrict__ kept_cnt, int* __restrict__ new_kept, int* __restrict__ n_new,
                         int* __restrict__ keep, int64_t keep_stride) {
-    using BoxG = typename std::conditional<ROTATED, RBoxG, float4>::type;
-    __shared__ unsigned long long remv[kMaskGroup];
     __shared__ int s_list[kStripe];
     __shared__ int s_nk;
     const int b = blockIdx.x;
-    const int n = min(kStripe, n_sorted[b] - base);
-    unsigned char* df = dead + (int64_t)b * kStripe;
+    const int n = s_n[b];
     const int nk0 = kept_cnt[b];
     if (n <= 0 || nk0 >= limit) {
-        for (int k = threadIdx.x; k < kStripe; k += 256) df[k] = 0;
+        if (threadIdx.x == 0) n_new[b] = 0;
         return;
     }
     const int cb = (n + 63) >> 6;
     const unsigned long long* mb = mask + (int64_t)b * kStripe * kMaskGroup;
-    // seed the removed-set with the dead flags (and clear them for the next stripe)
-    if (threadIdx.x < kMaskGroup) remv[threadIdx.x] = 0ull;
-    __syncthreads();
-    for (int k = threadIdx.x; k < kStripe; k += 256) {
-        if (df[k]) atomicOr(&remv[k >> 6], 1ull << (k & 63));
-        df[k] = 0;
-    }
-    __syncthreads();
     if (threadIdx.x < 32) {
         // one warp: lane w owns removed-word w; the kept test is broadcast from the owning lane
         const int lane = threadIdx.x;
-        unsigned long long rm = lane < kMaskGroup ? remv[lane] : 0ull;
+        unsigned long long rm = 0ull;
         int nk = 0;
         // rows are fetched eight at a time ahead of the (serial) keep test, so the L2 latency of a kept
-        // row's mask is not on the dependency chain; rows of dead boxes hold stale words and are never used
+        // row's mask is not on the dependency chain
         for (int i0 = 0; i0 < n && nk0 + nk < limit; i0 += 8) {
             unsigned long long rows[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u)
-                rows[u] = (i0 + u < n && lane < cb) ? mb[(int64_t)(i0 + u) * kMaskGroup + lane] : 0ull;
+                rows[u] = (i0 + u < n && lane < cb && lane >= ((i0 + u) >> 6)) ? mb[(int64_t)(i0 + u) * kMaskGroup + lane] : 0ull;
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int i = i0 + u;
@@ -561,7 +593,7 @@ nms_stripe_sweep_kernel(const void* __restrict__ sorted, int64_t sorted_stride, 
                     if (!((wv >> (i & 63)) & 1ull)) {
                         if (lane == 0) s_list[nk] = i;
                         ++nk;
-                        if (lane >= (i >> 6)) rm |= rows[u];
+                        rm |= rows[u];
                     }
                 }
             }
@@ -570,25 +602,102 @@ nms_stripe_sweep_kernel(const void* __restrict__ sorted, int64_t sorted_stride, 
     }
     __syncthreads();
     const int nk = s_nk;
-    const BoxG* sb = static_cast<const BoxG*>(sorted) + (int64_t)b * sorted_stride + base;
-    BoxG* kb = static_cast<BoxG*>(kept_box) + (int64_t)b * sorted_stride + nk0;
-    const int* ord = order + (int64_t)b * sorted_stride + base;
+    const int* idx = s_idx + (int64_t)b * kStripe;
+    const int* ord = order + (int64_t)b * sorted_stride;
     int* kp = keep + (int64_t)b * keep_stride;
-    const StripeGrid g = grid[b];
-    int* head = bin_head + (int64_t)b * kGridMax * kGridMax;
-    int* next = bin_next + (int64_t)b * sorted_stride;
+    int* nkp = new_kept + (int64_t)b * kStripe;
     for (int k = threadIdx.x; k < nk; k += 256) {
-        const int i = s_list[k];
-        kb[k] = sb[i];
-        if (nk0 + k < keep_stride) kp[nk0 + k] = ord[i];
-        // publish the kept box in its grid bin for the cross stage of the following stripes
-        float cx, cy, e;
-        box_centre_extent<ROTATED>(sb, i, cx, cy, e);
-        int bx, by;
-        grid_bin(g, cx, cy, bx, by);
-        next[nk0 + k] = atomicExch(&head[by * kGridMax + bx], nk0 + k);
+        const int pos = idx[s_list[k]];
+        nkp[k] = pos;
+        if (nk0 + k < keep_stride) kp[nk0 + k] = ord[pos];
     }
-    if (threadIdx.x == 0) kept_cnt[b] = nk0 + nk;
+    if (threadIdx.x == 0) { kept_cnt[b] = nk0 + nk; n_new[b] = nk; }
+}
+
+// push stage: one warp per newly kept box flags the later, still alive boxes it suppresses.  Everything it
+// scans (item positions, dead flags, hulls) is stored in bin order, so the scan is coalesced.
+template <bool ROTATED>
+__global__ void __launch_bounds__(kPushWarps * 32)
+nms_push_kernel(const void* __restrict__ sorted, int64_t sorted_stride, const int* __restrict__ new_kept,
+                const int* __restrict__ n_new, const int* __restrict__ cursor, const int* __restrict__ n_sorted,
+                const int* __restrict__ kept_cnt, int limit, float thresh, const StripeGrid* __restrict__ grid,
+                const int* __restrict__ bin_start, const int* __restrict__ bin_items,
+                const float4* __restrict__ bin_hull, unsigned char* __restrict__ dead) {
+    using BoxG = typename std::conditional<ROTATED, RBoxG, float4>::type;
+    __shared__ int s_q[kPushWarps][64];
+    const int b = blockIdx.y;
+    const int lane = lane_id(), w = threadIdx.x >> 5;
+    const int k = blockIdx.x * kPushWarps + w;
+    const int cur = cursor[b];
+    if (k >= n_new[b] || cur >= n_sorted[b] || kept_cnt[b] >= limit) return;  // warp-uniform
+    const BoxG* sb = static_cast<const BoxG*>(sorted) + (int64_t)b * sorted_stride;
+    const int* bs = bin_start + (int64_t)b * (kGridBins + 1);
+    const int* items = bin_items + (int64_t)b * sorted_stride;
+    const float4* hull = bin_hull + (int64_t)b * sorted_stride;
+    unsigned char* df = dead + (int64_t)b * sorted_stride;
+    const StripeGrid g = grid[b];
+    const int pos = new_kept[(int64_t)b * kStripe + k];
+    RBox me; float4 mef = make_float4(0.f, 0.f, 0.f, 0.f);
+    float cx, cy, e;
+    box_centre_extent<ROTATED>(sb, pos, cx, cy, e);
+    if constexpr (ROTATED) load_rbox(reinterpret_cast<const RBoxG*>(sb) + pos, me);
+    else mef = reinterpret_cast<const float4*>(sb)[pos];
+    int bx, by;
+    grid_bin(g, cx, cy, bx, by);
+    const double th = (double)thresh;
+    const int cur_chunk = cur & ~1023;  // items of a bin are ordered by 1024-position chunk (nms_bin_build_kernel)
+    int qn = 0;
+    int* q = s_q[w];
+    float eps = 0.f;
+    if constexpr (ROTATED) eps = 1e-4f * fmaxf(1.f, fmaxf(fmaxf(fabsf(me.mxx), fabsf(me.mnx)), fmaxf(fabsf(me.mxy), fabsf(me.mny))));
+    auto clip = [&](int t) {  // full test of the candidate in slot t (this kept box has the higher score: first argument)
+        RBox c;
+        load_rbox(reinterpret_cast<const RBoxG*>(sb) + items[t], c);
+        const double ai = rbox_inter(me.c, c.c);
+        if (ai / ((double)__fadd_rn(me.area, c.area) - ai) > th) df[t] = 1;
+    };
+    for (int dy = -1; dy <= 1; ++dy) {
+        const int yy = by + dy;
+        if (yy < 0 || yy >= g.gy) continue;
+        for (int xx = max(bx - 1, 0); xx <= min(bx + 1, g.gx - 1); ++xx) {
+            int t0 = bs[yy * kGridMax + xx];
+            const int t1 = bs[yy * kGridMax + xx + 1];
+            // first item whose chunk is not before the cursor's
+            {
+                int lo = t0, hi = t1;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (items[mid] < cur_chunk) lo = mid + 1; else hi = mid;
+                }
+                t0 = lo;
+            }
+            for (int tb = t0; tb < t1; tb += 32) {
+                const int t = tb + lane;
+                bool cand = false;
+                if (t < t1) cand = items[t] >= cur && !df[t];
+                if constexpr (ROTATED) {
+                    if (cand) {
+                        const float4 h = hull[t];  // mnx, mny, mxx, mxy
+                        cand = !(h.x > me.mxx + eps || me.mnx > h.z + eps || h.y > me.mxy + eps || me.mny > h.w + eps);
+                    }
+                    const unsigned bal = __ballot_sync(0xffffffffu, cand);
+                    if (cand) q[qn + __popc(bal & lanemask_lt())] = t;
+                    qn += __popc(bal);
+                    __syncwarp();
+                    if (qn >= 32) {
+                        clip(q[qn - 32 + lane]);
+                        qn -= 32;
+                        __syncwarp();
+                    }
+                } else {
+                    if (cand && standup_iou(mef, hull[t]) > th) df[t] = 1;
+                }
+            }
+        }
+    }
+    if constexpr (ROTATED) {
+        if (lane < qn) clip(q[lane]);
+    }
 }
 
 __global__ void nms_stripe_finish_kernel(const int* __restrict__ kept_cnt, int limit, int64_t keep_stride, int B,
@@ -773,7 +882,8 @@ extern "C" int pp_gather_dets_dev(const float* boxes, int box_dim, const float* 
 namespace {
 struct NmsWs {
     int* order; int* n_sorted; void* sorted; unsigned long long* mask; unsigned* kbuf; int* ibuf;
-    void* kept_box; int* kept_cnt; unsigned char* dead; void* grid; int* bin_head; int* bin_next;
+    int* kept_cnt; unsigned char* dead; void* grid; int* bin_start; int* bin_items; float4* bin_hull; int* slot_of;
+    int* cursor; int* s_idx; int* s_n; int* new_kept; int* n_new;
     int64_t n_cap, cb_cap; size_t total; bool full_sort, stripes;
 };
 NmsWs nms_carve(void* ws, int kind, int B, int64_t N, int pre_max) {
@@ -787,16 +897,22 @@ NmsWs nms_carve(void* ws, int kind, int B, int64_t N, int pre_max) {
     if (kind == PP_NMS_ROTATED) w.sorted = c.take<RBoxG>((size_t)B * w.n_cap + 1);
     else w.sorted = c.take<float4>((size_t)B * w.n_cap + 1);
     w.stripes = w.n_cap > kStripeMin;
-    w.kept_box = nullptr; w.kept_cnt = nullptr; w.dead = nullptr; w.grid = nullptr; w.bin_head = nullptr; w.bin_next = nullptr;
+    w.kept_cnt = nullptr; w.dead = nullptr; w.grid = nullptr; w.bin_start = nullptr; w.bin_items = nullptr; w.bin_hull = nullptr; w.slot_of = nullptr;
+    w.cursor = nullptr; w.s_idx = nullptr; w.s_n = nullptr; w.new_kept = nullptr; w.n_new = nullptr;
     if (w.stripes) {
         w.mask = c.take<unsigned long long>((size_t)B * kStripe * kMaskGroup + 1);
-        if (kind == PP_NMS_ROTATED) w.kept_box = c.take<RBoxG>((size_t)B * w.n_cap + 1);
-        else w.kept_box = c.take<float4>((size_t)B * w.n_cap + 1);
         w.kept_cnt = c.take<int>(B);
-        w.dead = c.take<unsigned char>((size_t)B * kStripe);
+        w.cursor = c.take<int>(B);
+        w.s_n = c.take<int>(B);
+        w.n_new = c.take<int>(B);
+        w.dead = c.take<unsigned char>((size_t)B * w.n_cap + 1);
         w.grid = c.take<StripeGrid>(B);
-        w.bin_head = c.take<int>((size_t)B * kGridMax * kGridMax);
-        w.bin_next = c.take<int>((size_t)B * w.n_cap + 1);
+        w.bin_start = c.take<int>((size_t)B * (kGridBins + 1));
+        w.bin_items = c.take<int>((size_t)B * w.n_cap + 1);
+        w.bin_hull = c.take<float4>((size_t)B * w.n_cap + 1);
+        w.slot_of = c.take<int>((size_t)B * w.n_cap + 1);
+        w.s_idx = c.take<int>((size_t)B * kStripe);
+        w.new_kept = c.take<int>((size_t)B * kStripe);
     } else {
         w.mask = c.take<unsigned long long>((size_t)B * w.n_cap * w.cb_cap + 1);
     }
@@ -868,35 +984,42 @@ extern "C" int pp_nms_dev(int kind, const float* boxes, int box_stride, const fl
     if (w.stripes) {
         const int limit = post_max_size > 0 ? post_max_size : 0x7fffffff;
         PP_CUDA(cudaMemsetAsync(w.kept_cnt, 0, sizeof(int) * B, st));
-        PP_CUDA(cudaMemsetAsync(w.dead, 0, (size_t)B * kStripe, st));
-        PP_CUDA(cudaMemsetAsync(w.bin_head, 0xff, (size_t)B * kGridMax * kGridMax * sizeof(int), st));
+        PP_CUDA(cudaMemsetAsync(w.cursor, 0, sizeof(int) * B, st));
+        PP_CUDA(cudaMemsetAsync(w.dead, 0, (size_t)B * w.n_cap, st));
         const bool rot = kind == PP_NMS_ROTATED;
         StripeGrid* sgrid = static_cast<StripeGrid*>(w.grid);
         {
-            PP_TIMED("nms_grid_setup", st);
-            if (rot) nms_grid_setup_kernel<true><<<B, 1024, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, sgrid);
-            else nms_grid_setup_kernel<false><<<B, 1024, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, sgrid);
+            PP_TIMED("nms_bin_build", st);
+            if (rot) nms_bin_build_kernel<true><<<B, 1024, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, sgrid, w.bin_start, w.bin_items, w.bin_hull, w.slot_of);
+            else nms_bin_build_kernel<false><<<B, 1024, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, sgrid, w.bin_start, w.bin_items, w.bin_hull, w.slot_of);
             PP_LAUNCHED();
         }
-        for (int64_t base = 0; base < w.n_cap; base += kStripe) {
-            if (base > 0) {
-                const dim3 g(kStripe / kCrossThreads, B);
-                PP_TIMED("nms_cross", st);
-                if (rot) nms_cross_kernel<true><<<g, kCrossThreads, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, (int)base, w.kept_box, w.kept_cnt, limit, thresh, sgrid, w.bin_head, w.bin_next, w.dead);
-                else nms_cross_kernel<false><<<g, kCrossThreads, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, (int)base, w.kept_box, w.kept_cnt, limit, thresh, sgrid, w.bin_head, w.bin_next, w.dead);
+        // at most ceil(n/kAlive) stripes: every stripe moves the cursor past kAlive alive boxes or to the end;
+        // frames that are done (or reached post_max_size) make their CTAs exit at once
+        for (int64_t base = 0; base < w.n_cap; base += kAlive) {
+            {
+                PP_TIMED("nms_select", st);
+                nms_select_kernel<<<B, 1024, 0, st>>>(w.n_sorted, w.dead, w.slot_of, w.n_cap, w.kept_cnt, limit, w.cursor, w.s_idx, w.s_n);
                 PP_LAUNCHED();
             }
             {
-                const dim3 g(kMaskGroup, B);
+                const dim3 g(kAlive / 64, B);
                 PP_TIMED("nms_stripe_mask", st);
-                if (rot) nms_stripe_mask_kernel<true><<<g, 64 * kMaskQ, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, (int)base, w.kept_cnt, limit, w.dead, thresh, w.mask);
-                else nms_stripe_mask_kernel<false><<<g, 64 * kMaskQ, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, (int)base, w.kept_cnt, limit, w.dead, thresh, w.mask);
+                if (rot) nms_stripe_mask_kernel<true><<<g, 64 * kMaskQ, 0, st>>>(w.sorted, w.n_cap, w.s_idx, w.s_n, thresh, w.mask);
+                else nms_stripe_mask_kernel<false><<<g, 64 * kMaskQ, 0, st>>>(w.sorted, w.n_cap, w.s_idx, w.s_n, thresh, w.mask);
                 PP_LAUNCHED();
             }
             {
                 PP_TIMED("nms_stripe_sweep", st);
-                if (rot) nms_stripe_sweep_kernel<true><<<B, 256, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, (int)base, w.mask, w.dead, w.order, limit, w.kept_box, w.kept_cnt, sgrid, w.bin_head, w.bin_next, keep, keep_stride);
-                else nms_stripe_sweep_kernel<false><<<B, 256, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, (int)base, w.mask, w.dead, w.order, limit, w.kept_box, w.kept_cnt, sgrid, w.bin_head, w.bin_next, keep, keep_stride);
+                nms_stripe_sweep_kernel<<<B, 256, 0, st>>>(w.s_idx, w.s_n, w.n_cap, w.mask, w.order, limit, w.kept_cnt, w.new_kept,
+                                                           w.n_new, keep, keep_stride);
+                PP_LAUNCHED();
+            }
+            if (base + kAlive < w.n_cap) {
+                const dim3 g(kAlive / kPushWarps, B);
+                PP_TIMED("nms_push", st);
+                if (rot) nms_push_kernel<true><<<g, kPushWarps * 32, 0, st>>>(w.sorted, w.n_cap, w.new_kept, w.n_new, w.cursor, w.n_sorted, w.kept_cnt, limit, thresh, sgrid, w.bin_start, w.bin_items, w.bin_hull, w.dead);
+                else nms_push_kernel<false><<<g, kPushWarps * 32, 0, st>>>(w.sorted, w.n_cap, w.new_kept, w.n_new, w.cursor, w.n_sorted, w.kept_cnt, limit, thresh, sgrid, w.bin_start, w.bin_items, w.bin_hull, w.dead);
                 PP_LAUNCHED();
             }
         }
