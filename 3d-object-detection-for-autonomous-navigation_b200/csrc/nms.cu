@@ -365,7 +365,7 @@ template <bool ROTATED>
 __global__ void __launch_bounds__(1024)
 nms_bin_build_kernel(const void* __restrict__ sorted, int64_t sorted_stride, const int* __restrict__ n_sorted,
                      StripeGrid* __restrict__ grid, int* __restrict__ bin_start, int* __restrict__ bin_items,
-                     float4* __restrict__ bin_hull, int* __restrict__ slot_of) {
+                     float4* __restrict__ bin_hull, float* __restrict__ bin_area, int* __restrict__ slot_of) {
     __shared__ float s_red[5][32];
     __shared__ int s_hist[kGridBins];
     __shared__ int sm[33];
@@ -441,6 +441,7 @@ nms_bin_build_kernel(const void* __restrict__ sorted, int64_t sorted_stride, con
     // ordered by chunk, so the push stage can skip everything before the cursor's chunk with a binary search
     int* items = bin_items + (int64_t)b * sorted_stride;
     float4* hull = bin_hull + (int64_t)b * sorted_stride;
+    float* area = bin_area + (int64_t)b * sorted_stride;
     int* slots = slot_of + (int64_t)b * sorted_stride;
     for (int i0 = 0; i0 < n; i0 += 1024) {
         const int i = i0 + threadIdx.x;
@@ -455,6 +456,7 @@ nms_bin_build_kernel(const void* __restrict__ sorted, int64_t sorted_stride, con
             if constexpr (ROTATED) {
                 const RBoxG* gb = reinterpret_cast<const RBoxG*>(sb) + i;
                 hull[t] = make_float4(gb->mnx, gb->mny, gb->mxx, gb->mxy);
+                area[t] = gb->area;
             } else {
                 hull[t] = reinterpret_cast<const float4*>(sb)[i];
             }
@@ -517,6 +519,7 @@ nms_stripe_mask_kernel(const void* __restrict__ sorted, int64_t sorted_stride, c
     const int* idx = s_idx + (int64_t)b * kStripe;
     unsigned long long* mb = mask + (int64_t)b * kStripe * kMaskGroup;
     const double th = (double)thresh;
+    const float need_frac = thresh / (1.f + thresh);
     const bool live = row < n;
     RBox rrow; float4 frow = make_float4(0.f, 0.f, 0.f, 0.f);
     if (live) {
@@ -544,6 +547,7 @@ nms_stripe_mask_kernel(const void* __restrict__ sorted, int64_t sorted_stride, c
                     if (rrow.mnx > c.mxx + eps || c.mnx > rrow.mxx + eps || rrow.mny > c.mxy + eps || c.mny > rrow.mxy + eps) continue;
                     RBox cbx;
                     load_rbox(&s_col[q * 64 + jj], cbx);
+                    if (rbox_cannot_exceed(rrow, cbx, need_frac)) continue;
                     const double ai = rbox_inter(rrow.c, cbx.c);
                     sup = ai / ((double)__fadd_rn(rrow.area, cbx.area) - ai) > th;
                 } else {
@@ -616,13 +620,17 @@ nms_stripe_sweep_kernel(const int* __restrict__ s_idx, const int* __restrict__ s
 
 // push stage: one warp per newly kept box flags the later, still alive boxes it suppresses.  Everything it
 // scans (item positions, dead flags, hulls) is stored in bin order, so the scan is coalesced.
+#ifndef PP_PUSH_MINBLOCKS
+#define PP_PUSH_MINBLOCKS 4
+#endif
 template <bool ROTATED>
-__global__ void __launch_bounds__(kPushWarps * 32)
+__global__ void __launch_bounds__(kPushWarps * 32, PP_PUSH_MINBLOCKS)
 nms_push_kernel(const void* __restrict__ sorted, int64_t sorted_stride, const int* __restrict__ new_kept,
                 const int* __restrict__ n_new, const int* __restrict__ cursor, const int* __restrict__ n_sorted,
                 const int* __restrict__ kept_cnt, int limit, float thresh, const StripeGrid* __restrict__ grid,
                 const int* __restrict__ bin_start, const int* __restrict__ bin_items,
-                const float4* __restrict__ bin_hull, unsigned char* __restrict__ dead) {
+                const float4* __restrict__ bin_hull, const float* __restrict__ bin_area,
+                unsigned char* __restrict__ dead) {
     using BoxG = typename std::conditional<ROTATED, RBoxG, float4>::type;
     __shared__ int s_q[kPushWarps][64];
     const int b = blockIdx.y;
@@ -634,6 +642,7 @@ nms_push_kernel(const void* __restrict__ sorted, int64_t sorted_stride, const in
     const int* bs = bin_start + (int64_t)b * (kGridBins + 1);
     const int* items = bin_items + (int64_t)b * sorted_stride;
     const float4* hull = bin_hull + (int64_t)b * sorted_stride;
+    const float* area = bin_area + (int64_t)b * sorted_stride;
     unsigned char* df = dead + (int64_t)b * sorted_stride;
     const StripeGrid g = grid[b];
     const int pos = new_kept[(int64_t)b * kStripe + k];
@@ -645,6 +654,7 @@ nms_push_kernel(const void* __restrict__ sorted, int64_t sorted_stride, const in
     int bx, by;
     grid_bin(g, cx, cy, bx, by);
     const double th = (double)thresh;
+    const float need_frac = thresh / (1.f + thresh);
     const int cur_chunk = cur & ~1023;  // items of a bin are ordered by 1024-position chunk (nms_bin_build_kernel)
     int qn = 0;
     int* q = s_q[w];
@@ -653,6 +663,7 @@ nms_push_kernel(const void* __restrict__ sorted, int64_t sorted_stride, const in
     auto clip = [&](int t) {  // full test of the candidate in slot t (this kept box has the higher score: first argument)
         RBox c;
         load_rbox(reinterpret_cast<const RBoxG*>(sb) + items[t], c);
+        if (rbox_cannot_exceed(me, c, need_frac)) return;
         const double ai = rbox_inter(me.c, c.c);
         if (ai / ((double)__fadd_rn(me.area, c.area) - ai) > th) df[t] = 1;
     };
@@ -674,11 +685,22 @@ nms_push_kernel(const void* __restrict__ sorted, int64_t sorted_stride, const in
             for (int tb = t0; tb < t1; tb += 32) {
                 const int t = tb + lane;
                 bool cand = false;
-                if (t < t1) cand = items[t] >= cur && !df[t];
                 if constexpr (ROTATED) {
-                    if (cand) {
+                    if (t < t1) {
+                        // the four loads are independent: one round trip per 32 items
+                        const int it = items[t];
+                        const unsigned char dd = df[t];
                         const float4 h = hull[t];  // mnx, mny, mxx, mxy
-                        cand = !(h.x > me.mxx + eps || me.mnx > h.z + eps || h.y > me.mxy + eps || me.mny > h.w + eps);
+                        const float ar = area[t];
+                        cand = it >= cur && !dd &&
+                               !(h.x > me.mxx + eps || me.mnx > h.z + eps || h.y > me.mxy + eps || me.mny > h.w + eps);
+                        if (cand) {
+                            // the candidate lies inside its hull: IoU > thresh needs more intersection than this
+                            // kept box has with the hull (measured along the kept box's own axes)
+                            const float hc[8] = {h.x, h.y, h.x, h.w, h.z, h.w, h.z, h.y};
+                            const float asum = me.area + ar;
+                            cand = !(rect_inter_bound(me.c, hc) * 1.002f + 1e-6f * asum < need_frac * asum);
+                        }
                     }
                     const unsigned bal = __ballot_sync(0xffffffffu, cand);
                     if (cand) q[qn + __popc(bal & lanemask_lt())] = t;
@@ -690,6 +712,7 @@ nms_push_kernel(const void* __restrict__ sorted, int64_t sorted_stride, const in
                         __syncwarp();
                     }
                 } else {
+                    if (t < t1) cand = items[t] >= cur && !df[t];
                     if (cand && standup_iou(mef, hull[t]) > th) df[t] = 1;
                 }
             }
@@ -882,7 +905,7 @@ extern "C" int pp_gather_dets_dev(const float* boxes, int box_dim, const float* 
 namespace {
 struct NmsWs {
     int* order; int* n_sorted; void* sorted; unsigned long long* mask; unsigned* kbuf; int* ibuf;
-    int* kept_cnt; unsigned char* dead; void* grid; int* bin_start; int* bin_items; float4* bin_hull; int* slot_of;
+    int* kept_cnt; unsigned char* dead; void* grid; int* bin_start; int* bin_items; float4* bin_hull; float* bin_area; int* slot_of;
     int* cursor; int* s_idx; int* s_n; int* new_kept; int* n_new;
     int64_t n_cap, cb_cap; size_t total; bool full_sort, stripes;
 };
@@ -897,7 +920,7 @@ NmsWs nms_carve(void* ws, int kind, int B, int64_t N, int pre_max) {
     if (kind == PP_NMS_ROTATED) w.sorted = c.take<RBoxG>((size_t)B * w.n_cap + 1);
     else w.sorted = c.take<float4>((size_t)B * w.n_cap + 1);
     w.stripes = w.n_cap > kStripeMin;
-    w.kept_cnt = nullptr; w.dead = nullptr; w.grid = nullptr; w.bin_start = nullptr; w.bin_items = nullptr; w.bin_hull = nullptr; w.slot_of = nullptr;
+    w.kept_cnt = nullptr; w.dead = nullptr; w.grid = nullptr; w.bin_start = nullptr; w.bin_items = nullptr; w.bin_hull = nullptr; w.bin_area = nullptr; w.slot_of = nullptr;
     w.cursor = nullptr; w.s_idx = nullptr; w.s_n = nullptr; w.new_kept = nullptr; w.n_new = nullptr;
     if (w.stripes) {
         w.mask = c.take<unsigned long long>((size_t)B * kStripe * kMaskGroup + 1);
@@ -910,6 +933,7 @@ NmsWs nms_carve(void* ws, int kind, int B, int64_t N, int pre_max) {
         w.bin_start = c.take<int>((size_t)B * (kGridBins + 1));
         w.bin_items = c.take<int>((size_t)B * w.n_cap + 1);
         w.bin_hull = c.take<float4>((size_t)B * w.n_cap + 1);
+        w.bin_area = c.take<float>((size_t)B * w.n_cap + 1);
         w.slot_of = c.take<int>((size_t)B * w.n_cap + 1);
         w.s_idx = c.take<int>((size_t)B * kStripe);
         w.new_kept = c.take<int>((size_t)B * kStripe);
@@ -990,8 +1014,8 @@ extern "C" int pp_nms_dev(int kind, const float* boxes, int box_stride, const fl
         StripeGrid* sgrid = static_cast<StripeGrid*>(w.grid);
         {
             PP_TIMED("nms_bin_build", st);
-            if (rot) nms_bin_build_kernel<true><<<B, 1024, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, sgrid, w.bin_start, w.bin_items, w.bin_hull, w.slot_of);
-            else nms_bin_build_kernel<false><<<B, 1024, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, sgrid, w.bin_start, w.bin_items, w.bin_hull, w.slot_of);
+            if (rot) nms_bin_build_kernel<true><<<B, 1024, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, sgrid, w.bin_start, w.bin_items, w.bin_hull, w.bin_area, w.slot_of);
+            else nms_bin_build_kernel<false><<<B, 1024, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, sgrid, w.bin_start, w.bin_items, w.bin_hull, w.bin_area, w.slot_of);
             PP_LAUNCHED();
         }
         // at most ceil(n/kAlive) stripes: every stripe moves the cursor past kAlive alive boxes or to the end;
@@ -1018,8 +1042,8 @@ extern "C" int pp_nms_dev(int kind, const float* boxes, int box_stride, const fl
             if (base + kAlive < w.n_cap) {
                 const dim3 g(kAlive / kPushWarps, B);
                 PP_TIMED("nms_push", st);
-                if (rot) nms_push_kernel<true><<<g, kPushWarps * 32, 0, st>>>(w.sorted, w.n_cap, w.new_kept, w.n_new, w.cursor, w.n_sorted, w.kept_cnt, limit, thresh, sgrid, w.bin_start, w.bin_items, w.bin_hull, w.dead);
-                else nms_push_kernel<false><<<g, kPushWarps * 32, 0, st>>>(w.sorted, w.n_cap, w.new_kept, w.n_new, w.cursor, w.n_sorted, w.kept_cnt, limit, thresh, sgrid, w.bin_start, w.bin_items, w.bin_hull, w.dead);
+                if (rot) nms_push_kernel<true><<<g, kPushWarps * 32, 0, st>>>(w.sorted, w.n_cap, w.new_kept, w.n_new, w.cursor, w.n_sorted, w.kept_cnt, limit, thresh, sgrid, w.bin_start, w.bin_items, w.bin_hull, w.bin_area, w.dead);
+                else nms_push_kernel<false><<<g, kPushWarps * 32, 0, st>>>(w.sorted, w.n_cap, w.new_kept, w.n_new, w.cursor, w.n_sorted, w.kept_cnt, limit, thresh, sgrid, w.bin_start, w.bin_items, w.bin_hull, w.bin_area, w.dead);
                 PP_LAUNCHED();
             }
         }
