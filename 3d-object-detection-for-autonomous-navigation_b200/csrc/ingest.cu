@@ -128,27 +128,46 @@ ingest_write_kernel(const unsigned char* __restrict__ cloud, int64_t n_in, int p
     unsigned ok;
     load_rows4<PACKED>(fc, (int64_t)tile * kIngestTile + 4 * threadIdx.x, n_in, point_step, ox, oy, oz, x, y, z, ok);
     int tot;
-    int rank = tile_base[(int64_t)b * tiles_per_frame + tile] + block_excl_scan(__popc(ok), &tot, sm);
+    const int rank0 = tile_base[(int64_t)b * tiles_per_frame + tile] + block_excl_scan(__popc(ok), &tot, sm);
+    // Ranks of this thread's finite rows are rank0, rank0+1, ...: one division finds the first kept rank
+    // (start + j*step) at or after rank0, the rest is counting.  The kept rows (at most one per thread when
+    // step >= 4) are then transformed in a loop all lanes walk together -- running the float64 transform
+    // inside the four-row loop would execute it four times per warp with a quarter of the lanes each.
+    const int rel0 = rank0 - start;
+    int64_t j = rel0 <= 0 ? 0 : (rel0 + step - 1) / step;
+    int next_sel = start + (int)j * step;
+    unsigned sel = 0;
+    {
+        int rank = rank0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (!((ok >> k) & 1u)) continue;
-        const int rel = rank - start;
-        ++rank;
-        if (rel < 0 || rel % step != 0) continue;
-        const int64_t j = rel / step;
-        if (j >= cap) continue;
-        double p[3] = {(double)x[k], (double)y[k], (double)z[k]};
-        for (int m = 0; m < xf.n_rot; ++m) {
-            const double* r = xf.r[m];
-            double o[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-                o[c] = __dadd_rn(__dadd_rn(__dmul_rn(p[0], r[c]), __dmul_rn(p[1], r[3 + c])), __dmul_rn(p[2], r[6 + c]));
-            p[0] = o[0]; p[1] = o[1]; p[2] = o[2];
+        for (int k = 0; k < 4; ++k) {
+            if ((ok >> k) & 1u) {
+                if (rank == next_sel) { sel |= 1u << k; next_sel += step; }
+                ++rank;
+            }
         }
-        fo[j * 3 + 0] = __dadd_rn(p[0], xf.t[0]);
-        fo[j * 3 + 1] = __dadd_rn(p[1], xf.t[1]);
-        fo[j * 3 + 2] = __dadd_rn(p[2], xf.t[2]);
+    }
+    while (sel) {
+        const int k = __ffs(sel) - 1;
+        sel &= sel - 1;
+        if (j < cap) {
+            const float xs = k == 0 ? x[0] : k == 1 ? x[1] : k == 2 ? x[2] : x[3];
+            const float ys = k == 0 ? y[0] : k == 1 ? y[1] : k == 2 ? y[2] : y[3];
+            const float zs = k == 0 ? z[0] : k == 1 ? z[1] : k == 2 ? z[2] : z[3];
+            double p[3] = {(double)xs, (double)ys, (double)zs};
+            for (int m = 0; m < xf.n_rot; ++m) {
+                const double* r = xf.r[m];
+                double o[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    o[c] = __dadd_rn(__dadd_rn(__dmul_rn(p[0], r[c]), __dmul_rn(p[1], r[3 + c])), __dmul_rn(p[2], r[6 + c]));
+                p[0] = o[0]; p[1] = o[1]; p[2] = o[2];
+            }
+            fo[j * 3 + 0] = __dadd_rn(p[0], xf.t[0]);
+            fo[j * 3 + 1] = __dadd_rn(p[1], xf.t[1]);
+            fo[j * 3 + 2] = __dadd_rn(p[2], xf.t[2]);
+        }
+        ++j;
     }
     // rows [n_out[b], cap) = NaN (dropped by the voxelizer): every CTA of the frame pads an equal slice
     const int64_t first = (int64_t)n_out[b] * 3, len = cap * 3 - first;
