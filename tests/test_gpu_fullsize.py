@@ -144,3 +144,21 @@ def test_stripe_nms_equals_all_pairs_nms(pp, oracle, synth):
         k_all = pp.nms(sb[top[:16000]], d[top[:16000], 5], None, None, 0.5)
         k_str = pp.nms(sb, d[:, 5], None, None, 0.5)
         assert k_str[:len(k_all)].tolist() == [int(top[i]) for i in k_all]
+
+
+@pytest.mark.parametrize("thr", [0.05, 0.3, 0.7])
+def test_stripe_nms_thresholds(pp, oracle, synth, thr):
+    """The large-N path skips polygon clips whose intersection-area upper bound cannot reach thr/(1+thr)*(a1+a2);
+    the keep list must not depend on that (all-pairs path on the 16 000 best boxes, CPU oracle on the 3 000 best),
+    for loose and tight thresholds and for boxes of very different sizes."""
+    n = 24_000
+    rng = np.random.default_rng(int(thr * 100))
+    d = synth.rotated_boxes(n, 300 + int(thr * 100), clustered=True)
+    d[:, 2] *= rng.uniform(0.3, 3.0, n).astype(np.float32)     # widths and lengths over an order of magnitude
+    d[:, 3] *= rng.uniform(0.3, 3.0, n).astype(np.float32)
+    got = pp.rotate_nms_gpu(d, thr)
+    top = oracle.argsort_desc(d[:, 5])
+    prefix = [int(top[i]) for i in pp.rotate_nms_gpu(d[top[:16000]], thr)]
+    assert got[:len(prefix)] == prefix
+    want = [int(top[i]) for i in oracle.rotate_nms_gpu(d[top[:3000]], thr)]
+    assert got[:len(want)] == want
