@@ -244,6 +244,26 @@ class FramePipeline:
         return self.dets_host, self.keep_count_host
 
 
+def capture_graph(step, device=None, warmup=3):
+    """Capture `step()` (a closure that only issues pipeline stages on the current stream: kernel launches,
+    memsets, event fork/join -- no host synchronisation) into a CUDA graph and return it; `graph.replay()`
+    then re-issues the whole chain with one driver call.  A single frame is 11-17 small launches, so the
+    per-launch host cost dominates its latency; the replay removes it.  Inputs and outputs are the static
+    device tensors the closure captured (copy new data into them before replay)."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):          # warm-up on a side stream, as torch's capture rules require
+        for _ in range(warmup):
+            step()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize(dev)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        step()
+    return graph
+
+
 def shard_frames(n_frames, world_size, rank):
     """Contiguous block sharding of independent frames across ranks: no collective
     on the data path.  Returns (first, count)."""

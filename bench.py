@@ -331,6 +331,18 @@ def main():
     single = {"us_per_frame": ms_single / n_single * 1e3, "frames_per_s": world * n_single / (ms_single / 1e3),
               "launches_per_frame": pp.launch_count(reset=True) / n_single,
               "note": "one d435i frame per step, device-resident, same kernels; latency-bound (SURVEY 8d config 2)"}
+    try:  # the same step replayed from a CUDA graph: one driver call instead of 11 launches
+        graph1 = pipeline.capture_graph(step_single, dev)
+        for _ in range(5):
+            graph1.replay()
+        ms_g = timed(graph1.replay, n_single)
+        single["graph_us_per_frame"] = ms_g / n_single * 1e3
+        single["graph_frames_per_s"] = world * n_single / (ms_g / 1e3)
+        c1 = int(pipe1.keep_count[0].item())
+        single["graph_detections_match"] = bool(c1 > 0 and torch.equal(pipe1.dets[0], pipe.dets[0]))
+        del graph1
+    except Exception as e:  # noqa: BLE001
+        single["graph_error"] = str(e)[:200]
 
     # ---- the reference's live production chain ("next" rows N3, N1, N2 around the path): raw sensor cloud
     #      (float32 PointCloud2 xyz, invalid pixels NaN) -> ingest -> voxelize+decorate -> scatter -> anchor mask ->
