@@ -103,6 +103,41 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def bind_to_gpu_numa(local_rank):
+    """Pin this rank to the CPUs next to its GPU before any pinned host buffer is allocated, so the buffer's pages
+    land on that NUMA node: with 8 ranks streaming 55 GB/s each, remote-socket pinned memory is what bounds the
+    end-to-end number.  Best effort: NVML's ideal affinity, else the PCI device's numa_node from sysfs."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = f"{getattr(pr, 'pci_domain_id', 0):08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        allowed = os.sched_getaffinity(0)
+        cpus = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = {64 * i + b for i, wv in enumerate(words) for b in range(64) if (int(wv) >> b) & 1}
+        except Exception:  # noqa: BLE001
+            node_path = f"/sys/bus/pci/devices/{bus[4:]}/numa_node"
+            if os.path.exists(node_path):
+                node = int(open(node_path).read().strip())
+                if node >= 0:
+                    cpus = set()
+                    for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                        lo, _, hi = part.partition("-")
+                        cpus.update(range(int(lo), int(hi or lo) + 1))
+        if cpus:
+            use = cpus & allowed
+            if use:
+                os.sched_setaffinity(0, use)
+                return {"cpus": len(use), "first": min(use)}
+    except Exception as e:  # noqa: BLE001
+        log("numa binding skipped:", e)
+    return None
+
+
 def make_frames(synth, cfg, n_distinct, seed0):
     return [synth.d435_cloud(seed0 + i) for i in range(n_distinct)]
 
@@ -198,6 +233,8 @@ def main():
         # CPU scalars also keeps stdout to the single JSON line.
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("gloo")
+
+    numa = bind_to_gpu_numa(local_rank) if world > 1 else None
 
     pp = importlib.import_module(PKG)
     pipeline = importlib.import_module(PKG + ".pipeline")
@@ -537,6 +574,7 @@ def main():
         "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps, "points_per_s": fps_e2e * n_pts},
         "gpu_launches": int(launches),
+        "host_binding": numa,
         "clocks": clocks,
         "roofline": roof,
         "cpu_baseline": cpu,
