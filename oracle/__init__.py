@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE ONLY -- the parity checker and the "port" CPU baseline.  Only `tests/`,
 `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs may import
-this package; the product package never does (tests/test_no_oracle_in_product.py enforces it).
+this package; the product package never does (tests/test_abi_exports.py::test_product_never_imports_oracle enforces it).
 
 Function names and argument meaning mirror the reference (file:line in pp_oracle.c).
 """

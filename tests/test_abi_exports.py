@@ -74,6 +74,27 @@ def test_argument_validation_needs_no_gpu(pp):
     assert L.pp_scatter_dev(one, one, 10, None, 64, 0, 4, 4, 0, one, one, 1 << 20, None) == -1
     assert L.pp_nms_dev(7, one, 5, one, None, 1, 10, -1, -1, 0.5, one, 10, one, one, 1 << 20, None) == -1
     assert L.pp_rotate_iou_dev(one, 4, one, 4, 9, one, None) == -1
+    # "next" rows: predict glue and sensor ingest
+    pc = _lib.PredictCfg(1, 1, 100, 100, 50, 0, 0.5, 0.0, 1)
+    pargs = [C.byref(pc), one, one, one, one, None, None, None, 2, 100, 50, one, None, one, one, one, one, one, 1 << 20, None]
+    bad = list(pargs); bad[0] = C.byref(_lib.PredictCfg(1, 1, 500, -1, 50, 0, 0.5, 0.0, 1))   # 500 boxes into the fused NMS
+    assert L.pp_predict_dev(*bad) == -1 and b"exceeds 128" in L.pp_last_error_string()
+    bad = list(pargs); bad[6] = one                                                             # rect without Trv2c
+    assert L.pp_predict_dev(*bad) == -1
+    bad = list(pargs); bad[18] = 16
+    assert L.pp_predict_dev(*bad) == -3
+    rot = (C.c_double * 9)(1, 0, 0, 0, 1, 0, 0, 0, 1)
+    iargs = [one, 1, 1000, 12, 0, 4, 8, 1, 4, rot, 1, None, one, 250, one, one, 1 << 20, None]
+    bad = list(iargs); bad[3] = 10                                                              # point_step not a multiple of 4
+    assert L.pp_ingest_dev(*bad) == -1
+    bad = list(iargs); bad[6] = 12                                                              # z field outside the record
+    assert L.pp_ingest_dev(*bad) == -1
+    bad = list(iargs); bad[8] = 0                                                               # step 0
+    assert L.pp_ingest_dev(*bad) == -1
+    bad = list(iargs); bad[10] = 5                                                              # too many rotations
+    assert L.pp_ingest_dev(*bad) == -1
+    bad = list(iargs); bad[16] = 8
+    assert L.pp_ingest_dev(*bad) == -3
     with pytest.raises(pp.PPError):
         _lib.check(-1)
     assert L.pp_voxelize_workspace_bytes(C.byref(cfg), 120000, 64) > 64 * 214272 * 16

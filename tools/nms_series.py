@@ -1,6 +1,7 @@
+"""Per-launch CUDA-event times of the large-N NMS stripe kernels (select / mask / sweep / push) for 100 000 boxes x 32 frames."""
 import ctypes as C, importlib, json, os, sys
 import numpy as np, torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 PKG = "3d-object-detection-for-autonomous-navigation_b200"
 pp = importlib.import_module(PKG); _lib = importlib.import_module(PKG + "._lib")
 N, B = 100000, 32
