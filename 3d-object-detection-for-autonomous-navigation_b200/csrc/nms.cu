@@ -161,6 +161,7 @@ nms_mask_kernel(const void* __restrict__ sorted, int64_t sorted_stride, const in
     const int row = rb * 64 + r;
     const BoxG* sb = static_cast<const BoxG*>(sorted) + (int64_t)b * sorted_stride;
     const double th = (double)thresh;
+    const float need_frac = thresh / (1.f + thresh);
 
     RBox rrow; float4 frow = make_float4(0.f, 0.f, 0.f, 0.f);
     if (row < n) {
@@ -195,6 +196,8 @@ nms_mask_kernel(const void* __restrict__ sorted, int64_t sorted_stride, const in
                     cand &= cand - 1;
                     RBox cbx;
                     load_rbox(&s_col[q * 64 + j], cbx);
+                    // a pair whose intersection-area upper bound cannot reach thresh/(1+thresh)*(a1+a2) is not clipped
+                    if (rbox_cannot_exceed(rrow, cbx, need_frac)) continue;
                     // devRotateIoU(row box, col box), nms_gpu.py:445-449
                     const double ai = rbox_inter(rrow.c, cbx.c);
                     const double iou = ai / ((double)__fadd_rn(rrow.area, cbx.area) - ai);
