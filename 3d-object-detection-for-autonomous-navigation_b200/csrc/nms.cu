@@ -14,6 +14,7 @@
 //   mask    upper-triangle tiles only, 64 rows x 32 col-blocks per CTA, hull pre-reject, candidate
 //           bits first then polygon clips, rows of the tile stored as 256-byte runs.
 //   sweep   one CTA per frame, removed-bitmap in shared memory, early exit at post_max_size.
+#include <cooperative_groups.h>
 #include <type_traits>
 
 #include "nms_common.cuh"
@@ -33,6 +34,183 @@ nms_topk_kernel(const float* __restrict__ scores, const int* __restrict__ n_vali
     if (kk == 0) return;
     block_topk(sc, nv, kk, skey);
     for (int i = threadIdx.x; i < kk; i += kSortThreads)
+        order[(int64_t)b * order_stride + i] = (int)(skey[i] & 0xffffffffu);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Top-k of a long score list (KITTI: 107 k anchors per frame) by a thread-block CLUSTER: the frame is
+// split over kTopkCluster CTAs, every CTA histograms its slice in its own shared memory, and after a
+// cluster barrier each CTA sums the eight histograms through distributed shared memory and picks the
+// digit -- all CTAs reach the same decision, so nothing has to be broadcast back.  The selected
+// (key, index) pairs are appended to the rank-0 CTA's shared-memory list with DSMEM atomics and sorted
+// there.  Same total order and tie rule as block_topk (descending score, then descending index).
+constexpr int kTopkCluster = 8;
+// 256 threads per CTA: at 64 registers a 1024-thread CTA owns a whole SM's register file, i.e. 16 clusters in flight
+// on the chip and four waves for 64 frames (198 us); with 256 threads 74 clusters are resident and 64 frames are one wave
+#ifndef PP_TOPK_THREADS
+#define PP_TOPK_THREADS 256
+#endif
+constexpr int kTopkThreads = PP_TOPK_THREADS;
+
+__global__ void __cluster_dims__(kTopkCluster, 1, 1) __launch_bounds__(kTopkThreads)
+nms_topk_cluster_kernel(const float* __restrict__ scores, const int* __restrict__ n_valid, int64_t N, int k,
+                        int* __restrict__ order, int64_t order_stride, int* __restrict__ n_sorted) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ unsigned long long skey[kSelectMaxK];   // used on rank 0
+    __shared__ unsigned hist[256];                      // this CTA's slice
+    __shared__ unsigned tot[256];                       // cluster-wide
+    __shared__ unsigned s_prefix, s_remaining, s_count, s_scratch, s_fill, s_present;
+    const unsigned rank = cluster.block_rank();
+    const int b = blockIdx.x / kTopkCluster;
+    const float* sc = scores + (int64_t)b * N;
+    const int nv = n_valid ? max(0, min(n_valid[b], (int)N)) : (int)N;
+    const int per = (nv + kTopkCluster - 1) / kTopkCluster;
+    const int lo = min(nv, (int)rank * per), hi = min(nv, lo + per);
+
+    // cluster-wide histogram step: local -> DSMEM sum -> digit choice (identical in every CTA)
+    auto reduce_and_select = [&](unsigned prefix, int shift, unsigned* cnt_out) {
+        cluster.sync();  // every slice histogram is complete
+        if (threadIdx.x < 256) {
+            unsigned t = 0;
+#pragma unroll
+            for (int r = 0; r < kTopkCluster; ++r) t += cluster.map_shared_rank(hist, r)[threadIdx.x];
+            tot[threadIdx.x] = t;
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const unsigned rem = s_remaining;
+            __syncwarp();
+            select_digit(tot, rem, prefix, shift, &s_prefix, &s_remaining, cnt_out);
+        }
+        cluster.sync();  // remote reads done before any CTA clears its histogram again
+    };
+
+    // present scores (not -inf) over the whole frame
+    if (threadIdx.x == 0) s_present = 0;
+    if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+    __syncthreads();
+    {
+        int c = 0;
+#pragma unroll 4
+        for (int i = lo + threadIdx.x; i < hi; i += kTopkThreads) c += sc[i] != -INFINITY;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane_id() == 0 && c) atomicAdd(&hist[0], (unsigned)c);
+    }
+    __syncthreads();
+    cluster.sync();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+        for (int r = 0; r < kTopkCluster; ++r) t += cluster.map_shared_rank(hist, r)[0];
+        s_present = t;
+    }
+    __syncthreads();
+    cluster.sync();
+    const int kk = min(k, (int)s_present);
+    if (kk == 0) {  // uniform over the cluster
+        if (rank == 0 && threadIdx.x == 0) n_sorted[b] = 0;
+        return;
+    }
+
+    unsigned T = 0, Tidx = 0;
+    if (kk < nv) {
+        if (threadIdx.x == 0) { s_prefix = 0; s_remaining = (unsigned)kk; }
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+            __syncthreads();
+            const unsigned prefix = s_prefix;
+            // four independent loads per trip: the scan is bound by the L2 latency of its one dependent load otherwise
+            for (int i0 = lo; i0 < hi; i0 += 4 * kTopkThreads) {
+                float v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * kTopkThreads + threadIdx.x;
+                    v[u] = i < hi ? sc[i] : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * kTopkThreads + threadIdx.x;
+                    int d = -1;
+                    if (i < hi) {
+                        const unsigned key = score_key(v[u]);
+                        if (shift == 24 || ((key ^ prefix) >> (shift + 8)) == 0) d = (int)((key >> shift) & 255u);
+                    }
+                    const unsigned peers = __match_any_sync(0xffffffffu, d);
+                    if (d >= 0 && (int)lane_id() == __ffs(peers) - 1) atomicAdd(&hist[d], (unsigned)__popc(peers));
+                }
+            }
+            __syncthreads();
+            reduce_and_select(prefix, shift, &s_count);
+        }
+        T = s_prefix;
+        const unsigned need_eq = s_remaining, have_eq = s_count;
+        __syncthreads();
+        if (have_eq > need_eq) {  // uniform over the cluster
+            // among keys == T keep the need_eq largest indices (tie rule: descending index)
+            if (threadIdx.x == 0) { s_prefix = 0; s_remaining = need_eq; }
+            for (int shift = 24; shift >= 0; shift -= 8) {
+                if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+                __syncthreads();
+                const unsigned prefix = s_prefix;
+                for (int i = lo + threadIdx.x; i < hi; i += kTopkThreads) {
+                    if (score_key(sc[i]) != T) continue;
+                    const unsigned key = (unsigned)i;
+                    if (shift == 24 || ((key ^ prefix) >> (shift + 8)) == 0) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+                }
+                __syncthreads();
+                reduce_and_select(prefix, shift, &s_scratch);
+            }
+            Tidx = s_prefix;
+            __syncthreads();
+        }
+    }
+    // compaction into rank 0's list (arbitrary order), then bitonic sort there
+    int np2 = 1;
+    while (np2 < kk) np2 <<= 1;
+    if (rank == 0) {
+        if (threadIdx.x == 0) s_fill = 0;
+        for (int i = threadIdx.x; i < np2; i += kTopkThreads) skey[i] = 0ull;
+    }
+    cluster.sync();
+    {
+        unsigned long long* rkey = cluster.map_shared_rank(skey, 0);
+        unsigned* rfill = cluster.map_shared_rank(&s_fill, 0);
+        for (int i0 = lo; i0 < hi; i0 += 4 * kTopkThreads) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * kTopkThreads + threadIdx.x;
+                v[u] = i < hi ? sc[i] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * kTopkThreads + threadIdx.x;
+                if (i >= hi) continue;
+                const unsigned key = score_key(v[u]);
+                if (kk == nv || key > T || (key == T && (unsigned)i >= Tidx)) {
+                    const unsigned pos = atomicAdd(rfill, 1u);
+                    if (pos < (unsigned)kSelectMaxK) rkey[pos] = ((unsigned long long)key << 32) | (unsigned)i;
+                }
+            }
+        }
+    }
+    cluster.sync();
+    if (rank != 0) return;
+    for (int size = 2; size <= np2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < (np2 >> 1); t += kTopkThreads) {
+                const int l = 2 * t - (t & (stride - 1));
+                const int h = l + stride;
+                const bool desc = ((l & size) == 0);
+                const unsigned long long a = skey[l], c = skey[h];
+                if ((a < c) == desc) { skey[l] = c; skey[h] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) n_sorted[b] = kk;
+    for (int i = threadIdx.x; i < kk; i += kTopkThreads)
         order[(int64_t)b * order_stride + i] = (int)(skey[i] & 0xffffffffu);
 }
 
@@ -996,7 +1174,10 @@ extern "C" int pp_nms_dev(int kind, const float* boxes, int box_stride, const fl
     } else {
         const int k = (int)w.n_cap;
         PP_TIMED("nms_topk", st);
-        nms_topk_kernel<<<B, kSortThreads, 0, st>>>(scores, n_valid, N, k, w.order, w.n_cap, w.n_sorted);
+        if (N >= 16384)  // long score lists: one 8-CTA cluster per frame (DSMEM histograms)
+            nms_topk_cluster_kernel<<<B * kTopkCluster, kTopkThreads, 0, st>>>(scores, n_valid, N, k, w.order, w.n_cap, w.n_sorted);
+        else
+            nms_topk_kernel<<<B, kSortThreads, 0, st>>>(scores, n_valid, N, k, w.order, w.n_cap, w.n_sorted);
     }
     PP_LAUNCHED();
     {

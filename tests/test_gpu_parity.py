@@ -437,3 +437,24 @@ def test_ingest_feeds_voxelizer(pp, oracle, synth):
     ov, oc, on = oracle.points_to_voxel(opts, vs, pcr, cfg["max_points"], True, cfg["max_voxels"])
     assert c.shape[0] > 100
     assert np.array_equal(c, oc) and np.array_equal(n, on) and np.array_equal(v, ov)
+
+
+def test_topk_cluster_ties_and_absent(pp, oracle, synth):
+    """Score lists of >= 16 384 entries take the 8-CTA cluster top-k (DSMEM histograms): same total order as the
+    single-CTA select -- descending score, ties by descending index, -inf scores absent, fewer present than k."""
+    n = 40_000
+    d = synth.rotated_boxes(n, 123, clustered=False)
+    rng = np.random.default_rng(4)
+    d[:, 5] = np.round(rng.random(n) * 200).astype(np.float32) / 200          # ~200 distinct scores: massive ties at the cut
+    for pre, post in ((1000, 300), (100, 50), (777, None)):
+        got = pp.rotate_nms_gpu(d, 0.5, pre_max_size=pre, post_max_size=post)
+        assert got == oracle.rotate_nms_gpu(d, 0.5, pre, post)
+    d2 = d.copy()
+    d2[:, 5] = rng.random(n).astype(np.float32)
+    d2[rng.random(n) < 0.99, 5] = -np.inf                                      # ~400 present: fewer than pre_max
+    got = pp.rotate_nms_gpu(d2, 0.5, pre_max_size=1000, post_max_size=300)
+    present = np.nonzero(np.isfinite(d2[:, 5]))[0]
+    want = [int(present[i]) for i in oracle.rotate_nms_gpu(d2[present], 0.5, 1000, 300)]
+    assert got == want and len(got) > 50
+    d2[:, 5] = -np.inf
+    assert pp.rotate_nms_gpu(d2, 0.5, pre_max_size=1000, post_max_size=300) == []
