@@ -55,6 +55,8 @@ SIGNATURES = {
     "pp_nms_workspace_bytes": (_sz, [C.c_int, C.c_int, _i64, C.c_int]),
     "pp_nms_dev": (C.c_int, [C.c_int, _vp, C.c_int, _vp, _vp, C.c_int, _i64, C.c_int, C.c_int, _f32, _vp, _i64,
                              _vp, _vp, _sz, _vp]),
+    "pp_decode_nms_dev": (C.c_int, [C.c_int, _vp, _vp, _i64, _vp, _vp, C.c_int, _i64, C.c_int, C.c_int, _f32, _vp, _i64, _vp,
+                                    _vp, C.c_int, _vp, _sz, _vp]),
     "pp_gather_dets_dev": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _i64, _vp, _i64, _vp, C.c_int, _vp, _vp]),
     "pp_rotate_iou_dev": (C.c_int, [_vp, _i64, _vp, _i64, C.c_int, _vp, _vp]),
     "pp_d3_box_overlap_dev": (C.c_int, [_vp, _i64, _vp, _i64, C.c_int, _vp, _vp]),

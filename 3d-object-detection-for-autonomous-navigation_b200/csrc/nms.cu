@@ -17,6 +17,7 @@
 #include <cooperative_groups.h>
 #include <type_traits>
 
+#include "box_math.cuh"
 #include "nms_common.cuh"
 
 namespace pp {
@@ -291,21 +292,56 @@ nms_sort_kernel(const float* __restrict__ scores, const int* __restrict__ n_vali
 }
 
 
+// Where NMS reads a box from.  anchors == nullptr: `boxes` holds boxes (stride floats per row: 4 standup, 5 BEV,
+// 7 decoded).  anchors != nullptr: `boxes` holds box ENCODINGS [B,N,7] and the box is decoded on the fly
+// (second_box_decode, then BEV columns 0,1,3,4,6 / their standup box): only boxes that reach NMS are ever decoded,
+// the order of the reference's live path (top-k at model/voxelnet.py:1207, decode at 1227, NMS at 1259).
+struct BoxSrc {
+    const float* boxes;
+    int stride;
+    const float* anchors;
+    int64_t period;  // > 0: anchors hold `period` rows reused cyclically over the batch
+};
+
+__device__ __forceinline__ void src_decoded(const BoxSrc& s, int64_t row, float* d /*7*/) {
+    const int64_t ar = s.period > 0 ? row % s.period : row;
+    box_decode_one(s.boxes + row * 7, s.anchors + ar * 7, d);
+}
+__device__ __forceinline__ void src_bev(const BoxSrc& s, int64_t row, float* r /*x,y,w,l,angle*/) {
+    if (s.anchors) {
+        float d[7];
+        src_decoded(s, row, d);
+        r[0] = d[0]; r[1] = d[1]; r[2] = d[3]; r[3] = d[4]; r[4] = d[6];
+        return;
+    }
+    const float* src = s.boxes + row * s.stride;
+    const bool dec7 = s.stride == 7;  // decoded boxes (x,y,z,w,l,h,r) -> BEV columns 0,1,3,4,6 (model/voxelnet.py:1233)
+    r[0] = src[0]; r[1] = src[1]; r[2] = dec7 ? src[3] : src[2]; r[3] = dec7 ? src[4] : src[3]; r[4] = dec7 ? src[6] : src[4];
+}
+__device__ __forceinline__ float4 src_standup(const BoxSrc& s, int64_t row) {
+    if (s.anchors) {
+        float d[7];
+        src_decoded(s, row, d);
+        return rbox_standup_one(d[0], d[1], d[3], d[4], d[6]);  // model/voxelnet.py:1233-1249
+    }
+    const float* src = s.boxes + row * s.stride;
+    return make_float4(src[0], src[1], src[2], src[3]);
+}
+
 // gather boxes into score order; rotated: corners/area/hull once per box
 template <bool ROTATED>
 __global__ void __launch_bounds__(256)
-nms_prep_kernel(const float* __restrict__ boxes, int box_stride, int64_t N, const int* __restrict__ order,
+nms_prep_kernel(BoxSrc bs, int64_t N, const int* __restrict__ order,
                 int64_t order_stride, const int* __restrict__ n_sorted, void* __restrict__ sorted,
                 int64_t sorted_stride) {
     const int b = blockIdx.y;
     const int n = n_sorted[b];
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
-    const float* src = boxes + ((int64_t)b * N + order[(int64_t)b * order_stride + i]) * box_stride;
+    const int64_t row = (int64_t)b * N + order[(int64_t)b * order_stride + i];
     if (ROTATED) {
-        // box_stride 7: decoded boxes (x,y,z,w,l,h,r) -> BEV columns 0,1,3,4,6 (model/voxelnet.py:1233)
-        const bool dec7 = box_stride == 7;
-        const float r[5] = {src[0], src[1], dec7 ? src[3] : src[2], dec7 ? src[4] : src[3], dec7 ? src[6] : src[4]};
+        float r[5];
+        src_bev(bs, row, r);
         RBox rb;
         rbox_prepare(r, rb);
         float4* dst = reinterpret_cast<float4*>(static_cast<RBoxG*>(sorted) + (int64_t)b * sorted_stride + i);
@@ -314,7 +350,7 @@ nms_prep_kernel(const float* __restrict__ boxes, int box_stride, int64_t N, cons
         dst[2] = make_float4(rb.area, rb.mnx, rb.mny, rb.mxx);
         dst[3] = make_float4(rb.mxy, 0.f, 0.f, 0.f);
     } else {
-        static_cast<float4*>(sorted)[(int64_t)b * sorted_stride + i] = make_float4(src[0], src[1], src[2], src[3]);
+        static_cast<float4*>(sorted)[(int64_t)b * sorted_stride + i] = src_standup(bs, row);
     }
 }
 
@@ -918,7 +954,7 @@ __global__ void nms_stripe_finish_kernel(const int* __restrict__ kept_cnt, int l
 constexpr int kSmallN = 128;
 template <bool ROTATED>
 __global__ void __launch_bounds__(kSortThreads)
-nms_small_kernel(const float* __restrict__ boxes, int box_stride, const float* __restrict__ scores,
+nms_small_kernel(BoxSrc bs, const float* __restrict__ scores,
                  const int* __restrict__ n_valid, int64_t N, int k, int post_max, float thresh,
                  int* __restrict__ keep, int64_t keep_stride, int* __restrict__ keep_count) {
     using BoxG = typename std::conditional<ROTATED, RBoxG, float4>::type;
@@ -935,10 +971,10 @@ nms_small_kernel(const float* __restrict__ boxes, int box_stride, const float* _
     }
     block_topk(sc, nv, n, skey);
     if (threadIdx.x < n) {
-        const float* src = boxes + ((int64_t)b * N + (int)(skey[threadIdx.x] & 0xffffffffu)) * box_stride;
+        const int64_t row = (int64_t)b * N + (int)(skey[threadIdx.x] & 0xffffffffu);
         if constexpr (ROTATED) {
-            const bool dec7 = box_stride == 7;
-            const float r[5] = {src[0], src[1], dec7 ? src[3] : src[2], dec7 ? src[4] : src[3], dec7 ? src[6] : src[4]};
+            float r[5];
+            src_bev(bs, row, r);
             RBox rb;
             rbox_prepare(r, rb);
             RBoxG& d = s_box[threadIdx.x];
@@ -946,7 +982,7 @@ nms_small_kernel(const float* __restrict__ boxes, int box_stride, const float* _
             for (int i = 0; i < 8; ++i) d.c[i] = rb.c[i];
             d.area = rb.area; d.mnx = rb.mnx; d.mny = rb.mny; d.mxx = rb.mxx; d.mxy = rb.mxy;
         } else {
-            s_box[threadIdx.x] = make_float4(src[0], src[1], src[2], src[3]);
+            s_box[threadIdx.x] = src_standup(bs, row);
         }
         s_mask[threadIdx.x][0] = 0ull;
         s_mask[threadIdx.x][1] = 0ull;
@@ -1001,6 +1037,24 @@ gather_dets_kernel(const float* __restrict__ boxes, int box_dim, const float* __
         v = d < box_dim ? boxes[i * box_dim + d] : scores[i];
     }
     out[((int64_t)b * K + k) * od + d] = v;
+}
+
+// same with the boxes decoded on the fly (pp_decode_nms_dev)
+__global__ void __launch_bounds__(256)
+decode_gather_dets_kernel(BoxSrc bs, const float* __restrict__ scores, int64_t N, const int* __restrict__ keep,
+                          int64_t keep_stride, const int* __restrict__ keep_count, int K, float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= K) return;
+    float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (k < min(keep_count[b], K)) {
+        const int64_t row = (int64_t)b * N + keep[(int64_t)b * keep_stride + k];
+        src_decoded(bs, row, o);
+        o[7] = scores[row];
+    }
+    float4* dst = reinterpret_cast<float4*>(out + ((int64_t)b * K + k) * 8);
+    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
 }
 
 // d3_box_overlap (second/utils/eval.py:131-163): BEV intersection of camera boxes (columns 0,2,3,5,6, float32,
@@ -1135,10 +1189,11 @@ extern "C" size_t pp_nms_workspace_bytes(int kind, int B, int64_t N, int pre_max
     return nms_carve(nullptr, kind, B, N > 0 ? N : 1, pre_max_size).total + 256;
 }
 
-extern "C" int pp_nms_dev(int kind, const float* boxes, int box_stride, const float* scores,
-                          const int32_t* n_valid, int B, int64_t N, int pre_max_size, int post_max_size,
-                          float thresh, int32_t* keep, int64_t keep_stride, int32_t* keep_count,
-                          void* workspace, size_t workspace_bytes, void* stream) {
+static int nms_run(int kind, const float* boxes, int box_stride, const float* anchors, int64_t anchor_period,
+                   const float* scores, const int32_t* n_valid, int B, int64_t N, int pre_max_size, int post_max_size,
+                   float thresh, int32_t* keep, int64_t keep_stride, int32_t* keep_count, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+    const BoxSrc bsrc{boxes, box_stride, anchors, anchor_period};
     PP_CHECK_ARG(kind == PP_NMS_STANDUP || kind == PP_NMS_ROTATED, "pp_nms_dev: bad kind");
     PP_CHECK_ARG(B > 0 && B <= 65535 && N >= 0 && N < ((int64_t)1 << 31), "pp_nms_dev: bad B/N");
     PP_CHECK_ARG(keep && keep_count && workspace && keep_stride > 0, "pp_nms_dev: null argument");
@@ -1159,10 +1214,10 @@ extern "C" int pp_nms_dev(int kind, const float* boxes, int box_stride, const fl
     if (w.n_cap <= kSmallN) {
         PP_TIMED("nms_small", st);
         if (kind == PP_NMS_ROTATED)
-            nms_small_kernel<true><<<B, kSortThreads, 0, st>>>(boxes, box_stride, scores, n_valid, N, (int)w.n_cap,
+            nms_small_kernel<true><<<B, kSortThreads, 0, st>>>(bsrc, scores, n_valid, N, (int)w.n_cap,
                                                               post_max_size, thresh, keep, keep_stride, keep_count);
         else
-            nms_small_kernel<false><<<B, kSortThreads, 0, st>>>(boxes, box_stride, scores, n_valid, N, (int)w.n_cap,
+            nms_small_kernel<false><<<B, kSortThreads, 0, st>>>(bsrc, scores, n_valid, N, (int)w.n_cap,
                                                                post_max_size, thresh, keep, keep_stride, keep_count);
         PP_LAUNCHED();
         return PP_OK;
@@ -1184,9 +1239,9 @@ extern "C" int pp_nms_dev(int kind, const float* boxes, int box_stride, const fl
         const dim3 g((unsigned)ceil_div(w.n_cap, 256), B);
         PP_TIMED("nms_prep", st);
         if (kind == PP_NMS_ROTATED)
-            nms_prep_kernel<true><<<g, 256, 0, st>>>(boxes, box_stride, N, w.order, w.n_cap, w.n_sorted, w.sorted, w.n_cap);
+            nms_prep_kernel<true><<<g, 256, 0, st>>>(bsrc, N, w.order, w.n_cap, w.n_sorted, w.sorted, w.n_cap);
         else
-            nms_prep_kernel<false><<<g, 256, 0, st>>>(boxes, box_stride, N, w.order, w.n_cap, w.n_sorted, w.sorted, w.n_cap);
+            nms_prep_kernel<false><<<g, 256, 0, st>>>(bsrc, N, w.order, w.n_cap, w.n_sorted, w.sorted, w.n_cap);
         PP_LAUNCHED();
     }
     if (w.stripes) {
@@ -1254,6 +1309,38 @@ extern "C" int pp_nms_dev(int kind, const float* boxes, int box_stride, const fl
                                                         post_max_size, keep, keep_stride, keep_count);
         PP_LAUNCHED();
     }
+    return PP_OK;
+}
+
+extern "C" int pp_nms_dev(int kind, const float* boxes, int box_stride, const float* scores,
+                          const int32_t* n_valid, int B, int64_t N, int pre_max_size, int post_max_size,
+                          float thresh, int32_t* keep, int64_t keep_stride, int32_t* keep_count,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+    return nms_run(kind, boxes, box_stride, nullptr, 0, scores, n_valid, B, N, pre_max_size, post_max_size, thresh, keep,
+                   keep_stride, keep_count, workspace, workspace_bytes, stream);
+}
+
+extern "C" int pp_decode_nms_dev(int kind, const float* box_encodings, const float* anchors, int64_t anchor_period,
+                                 const float* scores, const int32_t* n_valid, int B, int64_t N, int pre_max_size,
+                                 int post_max_size, float thresh, int32_t* keep, int64_t keep_stride,
+                                 int32_t* keep_count, float* dets, int K, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+    PP_CHECK_ARG(N == 0 || anchors, "pp_decode_nms_dev: null anchors");
+    PP_CHECK_ARG(anchor_period >= 0, "pp_decode_nms_dev: bad anchor_period");
+    PP_CHECK_ARG(!dets || (K > 0 && (reinterpret_cast<uintptr_t>(dets) & 15) == 0), "pp_decode_nms_dev: dets needs K > 0 and 16-byte alignment");
+    const int rc = nms_run(kind, box_encodings, 7, anchors, anchor_period, scores, n_valid, B, N, pre_max_size, post_max_size,
+                           thresh, keep, keep_stride, keep_count, workspace, workspace_bytes, stream);
+    if (rc || !dets) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (N == 0) {
+        PP_CUDA(cudaMemsetAsync(dets, 0, (size_t)B * K * 8 * sizeof(float), st));
+        return PP_OK;
+    }
+    const BoxSrc bsrc{box_encodings, 7, anchors, anchor_period};
+    const dim3 g((unsigned)ceil_div(K, 256), B);
+    PP_TIMED("gather_dets", st);
+    decode_gather_dets_kernel<<<g, 256, 0, st>>>(bsrc, scores, N, keep, keep_stride, keep_count, K, dets);
+    PP_LAUNCHED();
     return PP_OK;
 }
 

@@ -30,8 +30,9 @@ class FramePipeline:
 
     def __init__(self, cfg, device=0, max_frames=64, max_total_points=None, rotated_nms=True,
                  layout="NCHW", fused_decorate=True, keep_voxels=True, anchors=None, overlap_post=True,
-                 anchor_area_threshold=None, production=False, sensor_points=None):
+                 anchor_area_threshold=None, production=False, sensor_points=None, fused_post=True):
         self.cfg = cfg
+        self.fused_post = fused_post
         self.dev = torch.device("cuda", device)
         self.B = int(max_frames)
         self.D = cfg["num_point_features"]
@@ -153,6 +154,12 @@ class FramePipeline:
     def postprocess(self, box_enc, scores, n_frames, stream):
         L = _lib.lib()
         A = self.A
+        if self.fused_post:
+            # top-k on the scores first, decode only what reaches NMS (the reference's own order, voxelnet.py:1207-1265)
+            _lib.check(L.pp_decode_nms_dev(self.nms_kind, _p(box_enc), _p(self.anchors), A, _p(scores), None, n_frames, A,
+                                           self.pre, self.post, self.thr, _p(self.keep), self.post, _p(self.keep_count),
+                                           _p(self.dets), self.post, _p(self.ws_nms), self.ws_nms_bytes, stream))
+            return
         _lib.check(L.pp_box_decode_dev(_p(box_enc), _p(self.anchors), n_frames * A, A, _p(self.boxes), stream))
         if self.rotated:
             _lib.check(L.pp_nms_dev(self.nms_kind, _p(self.boxes), 7, _p(scores), None, n_frames, A, self.pre,

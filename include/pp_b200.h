@@ -166,6 +166,18 @@ PP_API int pp_nms_dev(int kind, const float* boxes, int box_stride, const float*
                float thresh, int32_t* keep, int64_t keep_stride, int32_t* keep_count,
                void* workspace, size_t workspace_bytes, void* stream);
 
+/* Decode + NMS in one call: box_encodings [B,N,7] and anchors ([anchor_period,7] reused cyclically, or [B*N,7]
+ * with anchor_period 0) instead of boxes.  second_box_decode (eval_helper_functions.py:388-461) is applied only to
+ * the boxes NMS looks at -- the order of the reference's live path: top-k (model/voxelnet.py:1207), decode (1227),
+ * standup boxes (1233-1249, kind PP_NMS_STANDUP) or BEV boxes (kind PP_NMS_ROTATED), NMS (1259) -- so a batch never
+ * materialises all decoded anchors.  keep / keep_count as pp_nms_dev; dets optional [B,K,8] (16-byte aligned):
+ * decoded box + score of each kept box, zero padded (what pp_gather_dets_dev returns).  Workspace:
+ * pp_nms_workspace_bytes. */
+PP_API int pp_decode_nms_dev(int kind, const float* box_encodings, const float* anchors, int64_t anchor_period,
+                      const float* scores, const int32_t* n_valid, int B, int64_t N, int pre_max_size,
+                      int post_max_size, float thresh, int32_t* keep, int64_t keep_stride, int32_t* keep_count,
+                      float* dets, int K, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Final detections of a batch (the only tensor the pipeline copies back to the host):
  * out[b,k,:] = (boxes[b,keep[b,k],0:box_dim], scores[b,keep[b,k]]) for k < keep_count[b], zeros
  * after.  Mirrors `box_preds[selected]`, `top_scores[selected]`, model/voxelnet.py:1281-1287. */

@@ -225,3 +225,35 @@ def test_cuda_graph_replay_matches_direct_launches(synth):
         assert want[0].shape[0] > 1000 and int(want[5][0]) > 0
         for a, b in zip(want, got):
             assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("name,rotated", [("d435", True), ("d435", False), ("kitti", True), ("kitti", False)])
+def test_decode_nms_fused_equals_decode_then_nms(synth, name, rotated):
+    """pp_decode_nms_dev (top-k, decode of the selected boxes only, NMS, decoded detections) must return bit for bit
+    what box_decode on every anchor -> (standup) -> pp_nms_dev -> gather returns."""
+    import torch
+    pipeline = importlib.import_module(PKG + ".pipeline")
+    cfg = synth.D435 if name == "d435" else synth.KITTI
+    B = 3
+    dev = torch.device("cuda", 0)
+    outs = []
+    for fused in (True, False):
+        pipe = pipeline.FramePipeline(cfg, device=0, max_frames=B, max_total_points=1000, rotated_nms=rotated, fused_post=fused)
+        A = pipe.A
+        box = torch.from_numpy(np.stack([synth.rpn_standin(A, 90 + i)[0] for i in range(B)])).to(dev)
+        sco = np.stack([synth.rpn_standin(A, 90 + i)[1] for i in range(B)])
+        sco[2, ::3] = -np.inf     # absent anchors
+        sco = torch.from_numpy(sco).to(dev)
+        pipe.postprocess(box, sco, B, C_void(torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        outs.append((pipe.keep_count[:B].cpu().numpy().copy(), pipe.keep[:B].cpu().numpy().copy(), pipe.dets[:B].cpu().numpy().copy()))
+    (c0, k0, d0), (c1, k1, d1) = outs
+    assert np.array_equal(c0, c1) and c0.min() > 0
+    for b in range(B):
+        assert np.array_equal(k0[b, :c0[b]], k1[b, :c1[b]])
+    assert np.array_equal(d0, d1)
+
+
+def C_void(x):
+    import ctypes
+    return ctypes.c_void_p(x)
