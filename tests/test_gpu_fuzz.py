@@ -64,3 +64,59 @@ def test_scatter_and_nms_random(pp, oracle, synth, seed):
     g2 = pp.nms(sb, d[:, 5], pre, post, thr)
     w2 = oracle.nms(sb, d[:, 5], pre, post, thr)
     assert (g2 is None and w2 is None) or g2.tolist() == w2.tolist()
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_predict_fuzz(pp, oracle, synth, seed):
+    """N2: random shapes / options of the predict glue against the oracle (anchor indices bit-exact)."""
+    rng = np.random.default_rng(1000 + seed)
+    A = int(rng.integers(1, 3000))
+    B = int(rng.integers(1, 5))
+    nc = int(rng.integers(1, 4))
+    an = synth.anchors_stride(synth.D435)[rng.choice(10240, A, replace=A > 10240)]
+    bp = rng.normal(0, 0.2, (B, A, 7)).astype(np.float32)
+    cl = rng.normal(-1, 1.5, (B, A, nc)).astype(np.float32)
+    dr = rng.normal(0, 1, (B, A, 2)).astype(np.float32)
+    mask = (rng.random((B, A)) < rng.uniform(0.05, 1.0)).astype(np.uint8) if rng.random() < 0.7 else None
+    rect = rng.normal(0, 1, (B, 4, 4)).astype(np.float32)
+    trv = rng.normal(0, 1, (B, 4, 4)).astype(np.float32)
+    opts = dict(top_k=int(rng.integers(1, 129)), nms_pre_max_size=int(rng.integers(1, 200)), nms_post_max_size=int(rng.integers(1, 80)),
+                nms_iou_threshold=float(rng.uniform(0.05, 0.8)), nms_score_threshold=float(rng.choice([0.0, 0.1, 0.3])),
+                rotated=bool(rng.integers(0, 2)))
+    lid, cam, sc, lab, idx, cnt = pp.predict_arrays(bp, cl, dr, an, mask, rect, trv, num_class=nc, **opts)
+    for b in range(B):
+        want = oracle.predict_frame(bp[b], cl[b], dr[b], an, None if mask is None else mask[b], rect[b], trv[b],
+                                    top_k=opts["top_k"], pre_max_size=opts["nms_pre_max_size"], post_max_size=opts["nms_post_max_size"],
+                                    iou_threshold=opts["nms_iou_threshold"], score_threshold=opts["nms_score_threshold"],
+                                    rotated=opts["rotated"])
+        k = int(cnt[b])
+        if want["box3d_lidar"] is None:
+            assert k == 0
+            continue
+        assert np.array_equal(idx[b, :k], want["anchor_index"]), (seed, b, opts)
+        assert np.array_equal(lab[b, :k], want["label_preds"])
+        np.testing.assert_allclose(lid[b, :k], want["box3d_lidar"], rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(cam[b, :k], want["box3d_camera"], rtol=1e-5, atol=1e-4)
+        np.testing.assert_allclose(sc[b, :k], want["scores"], rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_ingest_fuzz(pp, oracle, seed):
+    """N3: random record layouts, slices and NaN patterns; reference matrices => bit-identical."""
+    from importlib import import_module
+    ing = import_module(pp.__name__ + ".ingest")
+    rng = np.random.default_rng(2000 + seed)
+    n = int(rng.integers(0, 70000))
+    ps = int(rng.choice([12, 16, 20, 32]))
+    offs = sorted(rng.choice(np.arange(0, ps, 4), 3, replace=False).tolist())
+    xyz = rng.normal(0, 3, (n, 3)).astype(np.float32)
+    xyz[rng.random(n) < rng.uniform(0, 0.6)] = np.nan
+    if n:
+        xyz[rng.integers(0, n, 5), rng.integers(0, 3, 5)] = np.inf
+    raw = rng.integers(0, 255, (n, ps), dtype=np.uint8)
+    for j, o in enumerate(offs):
+        raw[:, o:o + 4] = xyz[:, j:j + 1].view(np.uint8)
+    start, step = int(rng.integers(0, 6)), int(rng.integers(1, 7))
+    got = pp.pointcloud2_to_lidar(raw.tobytes(), start=start, step=step, point_step=ps, offsets=tuple(offs))
+    want = oracle.pointcloud2_to_lidar(xyz, (ing.R_Y_NEG90, ing.R_X_POS90), ing.LIFT, start, step)
+    assert got.shape == want.shape and np.array_equal(got, want), (seed, n, ps, offs, start, step)
