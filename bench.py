@@ -210,6 +210,7 @@ def main():
     ap.add_argument("--frames", type=int, default=64, help="frames per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=2)
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the bounded KITTI-batch and NMS-stress measurements")
     ap.add_argument("--no-production", action="store_true", help="skip the sensor-to-camera-boxes production chain")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -487,6 +488,68 @@ def main():
                 np.array_equal(pipeP.det_index[0, :k0].cpu().numpy(), want["anchor_index"]))
         del pipeP, d_sens, stageP, host_sens
 
+    # ---- the other BASELINE.json configs, bounded: configs[2] KITTI-shaped batch and configs[3] rotated-NMS stress ----
+    extra = None
+    if not args.no_extra_configs:
+        import ctypes as C
+        _libm = importlib.import_module(PKG + "._lib")
+        extra = {}
+        try:
+            kc = synth.KITTI
+            Fk = min(F, 64)
+            kfr = [synth.kitti_cloud(1000 * rank + i, shuffled=bool(i & 1)) for i in range(4)]
+            nk = kfr[0].shape[0]
+            kp = torch.from_numpy(np.concatenate([kfr[i % 4] for i in range(Fk)])).to(dev)
+            koff = (torch.arange(Fk + 1, dtype=torch.int64) * nk).to(dev)
+            pk = pipeline.FramePipeline(kc, device=local_rank, max_frames=Fk, max_total_points=Fk * nk, overlap_post=False)
+            kbox = torch.from_numpy(np.stack([synth.rpn_standin(pk.A, i % 4)[0] for i in range(Fk)])).to(dev)
+            ksco = torch.from_numpy(np.stack([synth.rpn_standin(pk.A, i % 4)[1] for i in range(Fk)])).to(dev)
+            kfe = torch.from_numpy(synth.pfn_standin(pk.cap_rows, kc["num_filters"], 0)).to(dev)
+            stepk = lambda: pk.run(kp, koff, Fk, Fk * nk, nk, kfe, kbox, ksco)  # noqa: E731
+            for _ in range(3):
+                stepk()
+            nks = max(5, args.steps // 10)
+            msk = timed(stepk, nks)
+            Mk = int(pk.voxel_base[Fk].item()) / Fk
+            gk = synth.grid_size(kc)
+            abk = algorithmic_bytes(kc, nk, Mk, pk.A, kc["nms_pre_max_size"], gk, 4)
+            extra["kitti_batch"] = {
+                "workload": f"BASELINE configs[2]: {nk} float32 points/frame, 432x496 BEV, cap 12 000 pillars, C=64, {pk.A} anchors, "
+                            f"rotated NMS pre 1000 / post 300, batch {Fk}",
+                "frames_per_s": world * Fk * nks / (msk / 1e3), "ms_per_step": msk / nks, "pillars_per_frame": Mk,
+                "path_gbs_per_gpu": abk["total"] * Fk / (msk / nks * 1e-3) / 1e9,
+                "points_per_s": world * Fk * nks / (msk / 1e3) * nk}
+            del pk, kp, kbox, ksco, kfe
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            extra["kitti_batch"] = {"error": str(e)[:200]}
+        try:
+            Nn, Bn = 100_000, 32
+            dn = np.stack([synth.rotated_boxes(Nn, 500 + i, False) for i in range(2)])
+            dn = np.concatenate([dn] * (Bn // 2))
+            nb_ = torch.from_numpy(np.ascontiguousarray(dn[:, :, :5])).to(dev)
+            ns_ = torch.from_numpy(np.ascontiguousarray(dn[:, :, 5])).to(dev)
+            Ln = _libm.lib()
+            wsb = int(Ln.pp_nms_workspace_bytes(_libm.PP_NMS_ROTATED, Bn, Nn, -1))
+            wsn = torch.empty(wsb, dtype=torch.uint8, device=dev)
+            keepn = torch.empty((Bn, Nn), dtype=torch.int32, device=dev)
+            cntn = torch.zeros(Bn, dtype=torch.int32, device=dev)
+
+            def stepn():
+                _libm.check(Ln.pp_nms_dev(_libm.PP_NMS_ROTATED, C.c_void_p(nb_.data_ptr()), 5, C.c_void_p(ns_.data_ptr()), None, Bn, Nn,
+                                          -1, -1, 0.5, C.c_void_p(keepn.data_ptr()), Nn, C.c_void_p(cntn.data_ptr()),
+                                          C.c_void_p(wsn.data_ptr()), wsb, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+            stepn()
+            msn = timed(stepn, 3)
+            extra["nms_stress"] = {"workload": f"BASELINE configs[3]: rotated NMS, {Nn} boxes/frame, IoU 0.5, batch {Bn}",
+                                   "ms_per_frame": msn / 3 / Bn, "frames_per_s": world * Bn * 3 / (msn / 1e3),
+                                   "kept_per_frame": float(cntn.float().mean().item()),
+                                   "reference_pairs_per_s": Nn * (Nn - 1) / 2 * Bn * 3 / (msn / 1e3)}
+            del nb_, ns_, wsn, keepn
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            extra["nms_stress"] = {"error": str(e)[:200]}
+
     # ---- per-kernel device times (CUDA events on the launching stream, outside the timed region) ----
     per_kernel = {}
     if args.profile_steps > 0:
@@ -580,6 +643,7 @@ def main():
         "cpu_baseline": cpu,
         "single_frame": single,
         "production": production,
+        "other_configs": extra,
         "path": {"pillars_per_frame": m_pillars, "detections_per_step": n_dets,
                  "algorithmic_bytes_per_frame": ab["total"],
                  "path_gbs_per_gpu": ab["total"] * F / (ms / args.steps * 1e-3) / 1e9,
