@@ -459,13 +459,15 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask, int64_t mask_strid
         const int cnt = min(64, n - base);
         if (threadIdx.x < 64) s_diag[threadIdx.x] = threadIdx.x < cnt ? mb[(int64_t)(base + threadIdx.x) * cb + k] : 0ull;
         __syncthreads();
+        const int nk_before = s_nkeep;
         if (threadIdx.x == 0) {
+            // the serial part touches shared memory only (a global load of order[] per kept box sat on this chain)
             unsigned long long rm = remv[k], kept = 0ull;
-            int nk = s_nkeep;
+            int nk = nk_before;
             for (int i = 0; i < cnt && nk < limit; ++i) {
                 if (!((rm >> i) & 1ull)) {
                     kept |= 1ull << i;
-                    kp[nk++] = ord[base + i];
+                    ++nk;
                     rm |= s_diag[i];
                 }
             }
@@ -474,6 +476,8 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask, int64_t mask_strid
         }
         __syncthreads();
         const unsigned long long kept = s_kept;
+        if (threadIdx.x < 64 && ((kept >> threadIdx.x) & 1ull))  // kept box i of this block is output nk_before + rank(i)
+            kp[nk_before + __popcll(kept & ((1ull << threadIdx.x) - 1ull))] = ord[base + threadIdx.x];
         if (s_nkeep >= limit) break;
         if (kept) {
             for (int j = k + 1 + threadIdx.x; j < cb; j += kSweepThreads) {
@@ -489,6 +493,47 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask, int64_t mask_strid
         __syncthreads();
     }
     if (threadIdx.x == 0) keep_count[b] = s_nkeep;
+}
+
+// Sweep for at most 1024 boxes (16 mask words per row): the frame's whole mask (<= 128 KB) is copied into shared
+// memory with one coalesced pass, then one warp walks the rows -- lane w owns removed-word w -- without touching
+// global memory again.  (nms_sweep_kernel pays an L2 round trip per 64-row block and more for the propagation.)
+constexpr int kSweepSmemWords = 16;
+__global__ void __launch_bounds__(512)
+nms_sweep_smem_kernel(const unsigned long long* __restrict__ mask, int64_t mask_stride, int cb_stride,
+                      const int* __restrict__ n_sorted, const int* __restrict__ order, int64_t order_stride,
+                      int post_max, int* __restrict__ keep, int64_t keep_stride, int* __restrict__ keep_count) {
+    extern __shared__ unsigned long long s_m[];  // [n][cb_stride] then the kept list
+    __shared__ int s_nk;
+    const int b = blockIdx.x;
+    const int n = n_sorted[b];
+    const int cb = (n + 63) >> 6;
+    int* s_list = reinterpret_cast<int*>(s_m + (size_t)kSweepSmemWords * 64 * cb_stride);
+    const unsigned long long* mb = mask + (int64_t)b * mask_stride;
+    // rows are packed with the frame's own word count cb (nms_mask_kernel), not with the capacity
+    for (int k = threadIdx.x; k < n * cb; k += 512) s_m[k] = mb[k];
+    __syncthreads();
+    const int limit = (int)min((int64_t)(post_max > 0 ? post_max : n), keep_stride);
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        unsigned long long rm = 0ull;
+        int nk = 0;
+        for (int i = 0; i < n && nk < limit; ++i) {
+            const unsigned long long wv = __shfl_sync(0xffffffffu, rm, i >> 6);
+            if (!((wv >> (i & 63)) & 1ull)) {
+                if (lane == 0) s_list[nk] = i;
+                ++nk;
+                if (lane < cb && lane >= (i >> 6)) rm |= s_m[(size_t)i * cb + lane];
+            }
+        }
+        if (lane == 0) s_nk = nk;
+    }
+    __syncthreads();
+    const int nk = s_nk;
+    const int* ord = order + (int64_t)b * order_stride;
+    int* kp = keep + (int64_t)b * keep_stride;
+    for (int k = threadIdx.x; k < nk; k += 512) kp[k] = ord[s_list[k]];
+    if (threadIdx.x == 0) keep_count[b] = nk;
 }
 
 // rotate_iou_kernel(_eval), nms_gpu.py:493-523 / 579-615: out[n,k] = f(query k, box n)
@@ -1300,7 +1345,15 @@ static int nms_run(int kind, const float* boxes, int box_stride, const float* an
             nms_mask_kernel<false><<<g, 64 * kMaskQ, 0, st>>>(w.sorted, w.n_cap, w.n_sorted, thresh, w.mask, w.n_cap * w.cb_cap);
         PP_LAUNCHED();
     }
-    {
+    if (w.cb_cap <= kSweepSmemWords) {
+        const size_t smem = (size_t)kSweepSmemWords * 64 * w.cb_cap * 8 + (size_t)kSweepSmemWords * 64 * 4;
+        if (smem > 48 * 1024)
+            PP_CUDA(cudaFuncSetAttribute(nms_sweep_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PP_TIMED("nms_sweep", st);
+        nms_sweep_smem_kernel<<<B, 512, smem, st>>>(w.mask, w.n_cap * w.cb_cap, (int)w.cb_cap, w.n_sorted, w.order, w.n_cap,
+                                                    post_max_size, keep, keep_stride, keep_count);
+        PP_LAUNCHED();
+    } else {
         const size_t smem = (size_t)w.cb_cap * 8 + 8;
         if (smem > 48 * 1024)
             PP_CUDA(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

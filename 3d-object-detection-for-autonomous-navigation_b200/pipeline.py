@@ -73,8 +73,9 @@ class FramePipeline:
             self.voxel_base = torch.zeros((B + 1,), dtype=torch.int32, **e)
             self.canvas = torch.empty((B, Cc, self.ny, self.nx) if layout == "NCHW" else (B, self.ny, self.nx, Cc),
                                       dtype=torch.float32, **e)
-            self.boxes = torch.empty((B, self.A, 7), dtype=torch.float32, **e)
-            self.standup = torch.empty((B, self.A, 4), dtype=torch.float32, **e)
+            # all-anchor decoded / standup tensors exist only on the unfused path (decode -> standup -> NMS -> gather)
+            self.boxes = None if fused_post else torch.empty((B, self.A, 7), dtype=torch.float32, **e)
+            self.standup = None if (fused_post or rotated_nms) else torch.empty((B, self.A, 4), dtype=torch.float32, **e)
             self.keep = torch.empty((B, self.post), dtype=torch.int32, **e)
             self.keep_count = torch.zeros((B,), dtype=torch.int32, **e)
             self.dets = torch.empty((B, self.post, 8), dtype=torch.float32, **e)
