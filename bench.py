@@ -513,11 +513,24 @@ def main():
             Mk = int(pk.voxel_base[Fk].item()) / Fk
             gk = synth.grid_size(kc)
             abk = algorithmic_bytes(kc, nk, Mk, pk.A, kc["nms_pre_max_size"], gk, 4)
+            _libm.profile_start()
+            stepk(); stepk()
+            kk_ms = {}
+            for name, t in _libm.profile_stop():
+                kk_ms.setdefault(name, []).append(t)
+            kk_ms = {k_: float(np.mean(v_)) for k_, v_ in kk_ms.items()}
+            vs_ms = sum(v_ for k_, v_ in kk_ms.items() if k_.startswith("vox_") or k_.startswith("scatter_"))
+            vs_gbs_k = (abk["voxelize"] + abk["decorate"] + abk["scatter"]) * Fk / max(1e-9, vs_ms * 1e-3) / 1e9
+            peak_k = 6500.3
+            if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+                peak_k = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
             extra["kitti_batch"] = {
                 "workload": f"BASELINE configs[2]: {nk} float32 points/frame, 432x496 BEV, cap 12 000 pillars, C=64, {pk.A} anchors, "
                             f"rotated NMS pre 1000 / post 300, batch {Fk}",
                 "frames_per_s": world * Fk * nks / (msk / 1e3), "ms_per_step": msk / nks, "pillars_per_frame": Mk,
                 "path_gbs_per_gpu": abk["total"] * Fk / (msk / nks * 1e-3) / 1e9,
+                "voxelize_scatter_gbs": vs_gbs_k, "voxelize_scatter_frac_of_peak": vs_gbs_k / peak_k,
+                "kernel_ms_per_launch": kk_ms,
                 "points_per_s": world * Fk * nks / (msk / 1e3) * nk}
             del pk, kp, kbox, ksco, kfe
             torch.cuda.empty_cache()
@@ -589,7 +602,7 @@ def main():
             if tj.get("frames") == F and dom in tj.get("kernels", {}):
                 traffic = tj["kernels"][dom]  # dram bytes per launch from the committed ncu --set full capture
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved / peak, "frac_of_8tbs_spec": achieved / 8000.0, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_launch, "launch_ms": cand[dom],
                 "kernel_share_of_step": cand[dom] / step_kernel_ms if step_kernel_ms else None}
     path_gbs = ab["total"] * F * args.steps / (ms * 1e-3) / 1e9 / world * world  # per GPU == aggregate/world
