@@ -257,3 +257,51 @@ def test_decode_nms_fused_equals_decode_then_nms(synth, name, rotated):
 def C_void(x):
     import ctypes
     return ctypes.c_void_p(x)
+
+
+def test_production_chain_empty_and_tiny_frames(synth, oracle):
+    """Edge frames through the whole device chain: a frame whose every pixel is invalid (no points, no pillars, no
+    anchors in the mask, no detections -- the reference's None branch) next to a normal one and one with a handful of points."""
+    import torch
+    pipeline = importlib.import_module(PKG + ".pipeline")
+    ing = importlib.import_module(PKG + ".ingest")
+    cfg = synth.D435
+    n_sensor = 848 * 480
+    dead = np.full((n_sensor, 3), np.nan, np.float32)
+    tiny = dead.copy()
+    tiny[1000:1040] = synth.d435_sensor_cloud(70, invalid=0.0)[200000:200040]
+    clouds = [dead, synth.d435_sensor_cloud(71), tiny]
+    B = len(clouds)
+    pipe = pipeline.FramePipeline(cfg, device=0, max_frames=B, rotated_nms=False, anchor_area_threshold=1,
+                                  production=True, sensor_points=n_sensor)
+    A = pipe.A
+    an = synth.anchors_stride(cfg)
+    rng = np.random.default_rng(19)
+    bp = rng.normal(0, 0.1, (B, A, 7)).astype(np.float32)
+    cl = rng.normal(-2, 1, (B, A, 1)).astype(np.float32)
+    dr = rng.normal(0, 1, (B, A, 2)).astype(np.float32)
+    eye = np.tile(np.eye(4, dtype=np.float32), (B, 1, 1))
+    feats = synth.pfn_standin(pipe.cap_rows, cfg["num_filters"], 3)
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    pipe.run_production(t(np.stack(clouds)), B, 12, (0, 4, 8), t(feats), t(bp), t(cl), t(dr), t(eye), t(eye))
+    lid_h, cam_h, sc_h, cnt_h = pipe.fetch_production(B)
+    torch.cuda.synchronize()
+    vnum = pipe.voxel_num[:B].cpu().numpy()
+    n_in = pipe.in_count[:B].cpu().numpy()
+    assert n_in[0] == 0 and vnum[0] == 0 and int(cnt_h[0]) == 0 and not pipe.anchor_mask[0].any().item()
+    vs, pcr = np.array(cfg["voxel_size"]), np.array(cfg["point_cloud_range"])
+    for b in (1, 2):
+        pts = oracle.pointcloud2_to_lidar(clouds[b], (ing.R_Y_NEG90, ing.R_X_POS90), ing.LIFT, 1, 4)
+        assert n_in[b] == pts.shape[0]
+        _, oc, _ = oracle.points_to_voxel(pts, vs, pcr, cfg["max_points"], True, cfg["max_voxels"])
+        assert vnum[b] == oc.shape[0]
+        _, mask = oracle.anchors_mask(oc, an, vs, pcr, 1)
+        want = oracle.predict_frame(bp[b], cl[b], dr[b], an, mask.astype(np.uint8), eye[b], eye[b])
+        k = int(cnt_h[b])
+        if want["box3d_lidar"] is None:
+            assert k == 0
+        else:
+            assert k == want["box3d_lidar"].shape[0]
+            assert np.array_equal(pipe.det_index[b, :k].cpu().numpy(), want["anchor_index"])
+    assert n_in[2] == 10 and 0 < vnum[2] <= 10
