@@ -98,3 +98,22 @@ def test_argument_validation_needs_no_gpu(pp):
     with pytest.raises(pp.PPError):
         _lib.check(-1)
     assert L.pp_voxelize_workspace_bytes(C.byref(cfg), 120000, 64) > 64 * 214272 * 16
+
+
+def test_header_is_plain_c_and_exports_match():
+    """include/pp_b200.h compiles as C99 (no C++ / CUDA / torch types at the boundary) and the library exports no
+    pp_* symbol the header does not declare."""
+    import subprocess
+    import tempfile
+    hdr = os.path.join(ROOT, "include", "pp_b200.h")
+    with tempfile.TemporaryDirectory() as tmp:
+        src = os.path.join(tmp, "t.c")
+        with open(src, "w") as f:
+            f.write('#include "pp_b200.h"\nint main(void) { pp_voxel_cfg c; pp_predict_cfg p; (void)c; (void)p; return PP_OK; }\n')
+        r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.dirname(hdr), src],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    build = importlib.import_module(PKG + ".build")
+    out = subprocess.run(["nm", "-D", "--defined-only", build.build()], capture_output=True, text=True).stdout
+    exported = sorted({ln.split()[-1] for ln in out.splitlines() if ln.split() and ln.split()[-1].startswith("pp_")})
+    assert exported == header_symbols()
