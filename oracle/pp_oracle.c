@@ -8,11 +8,16 @@
  *
  * Every function cites the reference file:line (paths relative to the reference checkout)
  * whose algorithm it follows.  Pinning status (see DESIGN.md "Oracle"):
- *   - voxelizer, box decode, standup prep, NMS sweep, rotated IoU: pinned against the
- *     reference's own source executed in the build container (oracle/ref_extract.py,
- *     tests/golden/ fixtures, tests/test_oracle_vs_reference.py).
- *   - decoration and scatter: the reference implements them with TensorFlow ops; TensorFlow
- *     is not installable here, the reference has no tests => "parity unpinned" for those two.
+ *   - voxelizer, box decode, standup prep, NMS sweep, rotated IoU, anchor mask, eval overlaps,
+ *     predict glue: pinned against the reference's own source executed in the build container
+ *     (oracle/ref_extract.py, tests/golden/ fixtures, tests/test_oracle_vs_reference.py).
+ *   - decoration and scatter: the reference implements them with TensorFlow ops and TensorFlow is
+ *     not installable here; its two method bodies are executed unmodified over a numpy stand-in
+ *     for those ops (oracle/tf_shim.py) and the oracle matches bit for bit.  Pinned to the
+ *     reference's op sequence; TensorFlow's internal float32 summation order is not
+ *     ("parity unpinned" in that one respect, covered by the 1e-5 tolerance).
+ *   - sensor ingest: numpy/scipy expressions of the reference as written; the ros_numpy step
+ *     (third party, not vendored) is restated from its published algorithm.
  *
  * Build: plain C99, `gcc -O2 -ffp-contract=off -fno-fast-math` (no FMA contraction: the numba
  * CPU oracle derived from the reference source does not contract either).

@@ -16,6 +16,8 @@ CPython-3.6 `nms.so` that do not exist here.
                     for `np.empty`; bodies, operation order and numba's type inference (the
                     f32/f64 promotion map of SURVEY 3.5) are untouched.
   * standup IoU     eval_helper_functions.py:553-564, same mechanical swap.
+  * decoration, scatter   model/pointpillars.py:23-49, 128-203, 285-341: the method bodies run unmodified with
+                    oracle/tf_shim.py (numpy) bound to `tf` -- TensorFlow itself cannot be installed here
   * predict         model/voxelnet.py:1060-1389 (method body, run with a stand-in `self`; the numpy-1.19
                     `x[[index_array]]` idiom is rewritten to `x[index_array]`, see _numpy119_indexing)
 """
@@ -262,7 +264,38 @@ def load() -> types.SimpleNamespace:
         pd = {k: _T(v) for k, v in preds_dict.items()}
         return pred["predict"](me, ex, pd)
 
+    # ---- a4 / a5: PillarFeatureNet.call lines 143-203 and PointPillarsScatter.call (model/pointpillars.py) executed
+    #      as written, with oracle/tf_shim.py (numpy) standing in for the dozen TensorFlow ops they call
+    from . import tf_shim
+    ppsrc = _read("model/pointpillars.py")
+    pfn = {"np": np, "tf": tf_shim}
+    exec(_extract_defs(ppsrc, ["get_paddings_indicator"]), pfn)
+    exec(_extract_method(ppsrc, "PillarFeatureNet", "call"), pfn)
+    pfn["pfn_call"] = pfn.pop("call")
+    exec(_extract_method(ppsrc, "PointPillarsScatter", "call"), pfn)
+    pfn["scatter_call"] = pfn.pop("call")
+
+    def pillar_decorate(voxels, num_points, coors, voxel_size, point_cloud_range):
+        """The tensor PillarFeatureNet.call hands to self.pfn_layer (model/pointpillars.py:211), i.e. the decorated and
+        masked [M,P,D+5] features; constants as __init__ computes them (121-124)."""
+        captured = {}
+
+        def pfn_layer(x, training=False):
+            captured["x"] = np.array(x)
+            return x
+        vx, vy = voxel_size[0], voxel_size[1]
+        me = types.SimpleNamespace(vx=vx, vy=vy, x_offset=vx / 2 + point_cloud_range[0], y_offset=vy / 2 + point_cloud_range[1],
+                                   with_distance=False, pfn_layer=pfn_layer, training=False)
+        pfn["pfn_call"](me, tf_shim.convert(voxels), tf_shim.convert(num_points), tf_shim.convert(coors))
+        return captured["x"]
+
+    def pointpillars_scatter(voxel_features, coords, batch_size, nchannels, ny, nx):
+        me = types.SimpleNamespace(batch_size=batch_size, nchannels=nchannels, ny=ny, nx=nx)
+        return np.array(pfn["scatter_call"](me, tf_shim.convert(voxel_features), tf_shim.convert(coords)))
+
     _cache = types.SimpleNamespace(
+        pillar_decorate=pillar_decorate,
+        pointpillars_scatter=pointpillars_scatter,
         predict=predict,
         points_to_voxel=ns["points_to_voxel"],
         second_box_decode=ns["second_box_decode"],

@@ -85,6 +85,28 @@ def predict_case(ref):
     return out
 
 
+def decorate_scatter_case(ref):
+    out = {}
+    for cfg, pts in ((synth.D435, synth.d435_cloud(2, True)[::6]), (synth.KITTI, synth.kitti_cloud(2)[::12])):
+        n_ = cfg["name"]
+        vs, pcr = np.array(cfg["voxel_size"]), np.array(cfg["point_cloud_range"])
+        v, c, num = ref.points_to_voxel(pts, vs, pcr, cfg["max_points"], True, cfg["max_voxels"])
+        v = v[:600].astype(np.float32); c = c[:600]; num = num[:600]
+        c4 = np.concatenate([np.zeros((c.shape[0], 1), np.int32), c], axis=1)
+        dec = ref.pillar_decorate(v, num, c4, cfg["voxel_size"], cfg["point_cloud_range"])
+        nx, ny, _ = synth.grid_size(cfg)
+        half = c.shape[0] // 2
+        c4b = np.concatenate([c4, np.concatenate([np.ones((half, 1), np.int32), c[:half]], axis=1)])
+        c4b[-1, 2:] = c4b[-2, 2:]          # an exact duplicate (b,y,x): scatter_nd adds
+        feats = synth.pfn_standin(c4b.shape[0], 8, 1)
+        canvas = ref.pointpillars_scatter(feats, c4b, 2, 8, ny, nx)
+        out.update({f"{n_}_voxels": v, f"{n_}_num": num.copy(), f"{n_}_coors": c4, f"{n_}_decorated": dec,
+                    f"{n_}_voxel_size": vs, f"{n_}_range": pcr, f"{n_}_feats": feats, f"{n_}_coords": c4b,
+                    f"{n_}_canvas": canvas})
+        print("decorate/scatter", n_, dec.shape, canvas.shape, int((canvas != 0).sum()))
+    return out
+
+
 def main():
     warnings.simplefilter("ignore")
     ref = ref_extract.load()
@@ -153,6 +175,8 @@ def main():
     for crit in (-1, 0, 1, 2):
         d3[f"d3_crit{crit}"] = ref.d3_box_overlap(b, q, crit)
     np.savez_compressed(os.path.join(OUT, "d3_overlap.npz"), **d3)
+    # decoration + scatter: the reference's own method bodies over oracle/tf_shim.py (model/pointpillars.py:128-203, 285-341)
+    np.savez_compressed(os.path.join(OUT, "decorate_scatter.npz"), **decorate_scatter_case(ref))
     # VoxelNet.predict post-network half, "next" row N2 (model/voxelnet.py:1060-1389)
     np.savez_compressed(os.path.join(OUT, "predict.npz"), **predict_case(ref))
     print("done")

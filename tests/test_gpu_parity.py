@@ -458,3 +458,16 @@ def test_topk_cluster_ties_and_absent(pp, oracle, synth):
     assert got == want and len(got) > 50
     d2[:, 5] = -np.inf
     assert pp.rotate_nms_gpu(d2, 0.5, pre_max_size=1000, post_max_size=300) == []
+
+
+def test_decorate_scatter_golden_reference(pp, synth):
+    """a4 / a5 against fixtures produced by the reference's own method bodies (tests/golden/decorate_scatter.npz)."""
+    g = golden("decorate_scatter.npz")
+    for cfg in (synth.D435, synth.KITTI):
+        n = cfg["name"]
+        vs, pcr = g[f"{n}_voxel_size"], g[f"{n}_range"]
+        dec = pp.pillar_decorate(g[f"{n}_voxels"], g[f"{n}_num"], g[f"{n}_coors"], vs[0], vs[1], vs[0] / 2 + pcr[0], vs[1] / 2 + pcr[1])
+        np.testing.assert_allclose(dec, g[f"{n}_decorated"], rtol=1e-5, atol=1e-5)
+        nx, ny, _ = synth.grid_size(cfg)
+        canvas = pp.scatter(g[f"{n}_feats"], g[f"{n}_coords"], 2, ny, nx)
+        assert np.array_equal(canvas, g[f"{n}_canvas"])

@@ -184,3 +184,18 @@ def test_ingest_oracle_matches_reference_expressions(oracle):
     points = points + [0.0, 0.0, 1.0]
     got = oracle.pointcloud2_to_lidar(xyz, (r, r2), [0.0, 0.0, 1.0], 1, 4)
     assert got.dtype == np.float64 and np.array_equal(got, points)
+
+
+def test_decorate_scatter_golden(oracle, synth):
+    """a4 / a5: the oracle against the reference's own PillarFeatureNet.call (143-203) and PointPillarsScatter.call
+    (285-341) executed over a numpy stand-in for TensorFlow (oracle/tf_shim.py; fixtures from make_golden.py)."""
+    g = golden("decorate_scatter.npz")
+    for cfg in (synth.D435, synth.KITTI):
+        n = cfg["name"]
+        vs, pcr = g[f"{n}_voxel_size"], g[f"{n}_range"]
+        dec = oracle.decorate(g[f"{n}_voxels"], g[f"{n}_num"], g[f"{n}_coors"], vs[0], vs[1], vs[0] / 2 + pcr[0], vs[1] / 2 + pcr[1])
+        assert dec.dtype == np.float32 and dec.shape == g[f"{n}_decorated"].shape
+        np.testing.assert_allclose(dec, g[f"{n}_decorated"], rtol=1e-5, atol=1e-6)
+        nx, ny, _ = synth.grid_size(cfg)
+        canvas = oracle.scatter(g[f"{n}_feats"], g[f"{n}_coords"], 2, ny, nx)
+        assert canvas.shape == g[f"{n}_canvas"].shape and np.array_equal(canvas, g[f"{n}_canvas"])

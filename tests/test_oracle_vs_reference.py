@@ -80,3 +80,21 @@ def test_d3_box_overlap(ref, oracle, synth):
     b, q = synth.camera_boxes(300, 7), synth.camera_boxes(180, 8)
     for crit in (-1, 0, 1, 2):
         np.testing.assert_allclose(oracle.d3_box_overlap(b, q, crit), ref.d3_box_overlap(b, q, crit), rtol=0, atol=1e-6)
+
+
+def test_decorate_scatter_full_size(ref, oracle, synth):
+    """a4 / a5 at full size: the reference's PillarFeatureNet.call (143-203) / PointPillarsScatter.call (285-341)
+    bodies over the numpy TF stand-in vs the C oracle -- decoration to 1e-6, canvas bit for bit."""
+    for cfg, pts in ((synth.D435, synth.d435_cloud(5)), (synth.KITTI, synth.kitti_cloud(5))):
+        vs, pcr = np.array(cfg["voxel_size"]), np.array(cfg["point_cloud_range"])
+        v, c, n = oracle.points_to_voxel(pts, vs, pcr, cfg["max_points"], True, cfg["max_voxels"])
+        v = v.astype(np.float32)
+        c4 = np.concatenate([np.zeros((c.shape[0], 1), np.int32), c], axis=1)
+        want = ref.pillar_decorate(v, n, c4, cfg["voxel_size"], cfg["point_cloud_range"])
+        got = oracle.decorate(v, n, c4, vs[0], vs[1], vs[0] / 2 + pcr[0], vs[1] / 2 + pcr[1])
+        np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6)
+        nx, ny, _ = synth.grid_size(cfg)
+        c4b = np.concatenate([c4, np.concatenate([np.ones((c.shape[0], 1), np.int32), c], axis=1)])
+        feats = synth.pfn_standin(c4b.shape[0], cfg["num_filters"], 2)
+        assert np.array_equal(oracle.scatter(feats, c4b, 2, ny, nx),
+                              ref.pointpillars_scatter(feats, c4b, 2, cfg["num_filters"], ny, nx))
