@@ -294,6 +294,7 @@ def load() -> types.SimpleNamespace:
         return np.array(pfn["scatter_call"](me, tf_shim.convert(voxel_features), tf_shim.convert(coords)))
 
     _cache = types.SimpleNamespace(
+        nms=nmsns["nms"],
         pillar_decorate=pillar_decorate,
         pointpillars_scatter=pointpillars_scatter,
         predict=predict,

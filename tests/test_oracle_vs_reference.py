@@ -98,3 +98,17 @@ def test_decorate_scatter_full_size(ref, oracle, synth):
         feats = synth.pfn_standin(c4b.shape[0], cfg["num_filters"], 2)
         assert np.array_equal(oracle.scatter(feats, c4b, 2, ny, nx),
                               ref.pointpillars_scatter(feats, c4b, 2, cfg["num_filters"], ny, nx))
+
+
+def test_live_nms_wrapper(ref, oracle, synth):
+    """a7 wrapper: nms(bboxes, scores, pre_max_size, post_max_size, iou_threshold), eval_helper_functions.py:463-492,
+    run as written (its numba.cuda kernel replaced by the CPU run of the same body): index arrays and the None sentinel."""
+    d = synth.rotated_boxes(600, 9, clustered=True)
+    sb = oracle.rbox_to_standup(d[:, :5]) * np.float32(10)
+    sc = d[:, 5].copy()
+    for pre, post, thr in ((100, 50, 0.5), (None, None, 0.3), (600, 7, 0.7), (17, 100, 0.1)):
+        want = ref.nms(sb, sc, pre_max_size=pre, post_max_size=post, iou_threshold=thr)
+        got = oracle.nms(sb, sc, pre, post, thr)
+        assert got.dtype == np.int64 and np.array_equal(got, np.asarray(want, np.int64)), (pre, post, thr)
+    assert ref.nms(sb[:0], sc[:0], pre_max_size=None, post_max_size=50, iou_threshold=0.5) is None
+    assert oracle.nms(sb[:0], sc[:0], None, 50, 0.5) is None
