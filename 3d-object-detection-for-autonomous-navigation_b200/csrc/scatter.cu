@@ -150,7 +150,22 @@ scatter_canvas_kernel(const float* __restrict__ feats, const int* __restrict__ h
     } else {
         // NCHW: channel c row segment at ((b*C + c)*ny + y)*nx + x0, wx floats
         const bool vec = ((nx & 3) == 0) && ((wx & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-        if (vec) {
+        if (vec && wx == kTileX) {
+            // full tile: 8 float4 per channel row; thread -> (channel c0 + j*step, float4 i) with no division and one
+            // pointer bump per store (ncu: the generic loop below made this pass 75 % issue-active on KITTI)
+            const int i = threadIdx.x & 7;
+            const int64_t plane = (int64_t)ny * nx;
+            float* dst = out + (((int64_t)b * C + (threadIdx.x >> 3)) * ny + y) * nx + x0 + (i << 2);
+            const float* t = tile + (threadIdx.x >> 3) * 33 + (i << 2);
+            constexpr int kStep = kScThreads >> 3;
+            if (any) {
+                for (int c = threadIdx.x >> 3; c < C; c += kStep, dst += kStep * plane, t += kStep * 33)
+                    *reinterpret_cast<float4*>(dst) = make_float4(t[0], t[1], t[2], t[3]);
+            } else {
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int c = threadIdx.x >> 3; c < C; c += kStep, dst += kStep * plane) *reinterpret_cast<float4*>(dst) = z;
+            }
+        } else if (vec) {
             const int q = wx >> 2;  // float4 per channel row
             for (int k = threadIdx.x; k < C * q; k += kScThreads) {
                 const int c = k / q, i = k - c * q;
