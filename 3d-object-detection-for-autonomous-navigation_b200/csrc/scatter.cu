@@ -17,7 +17,8 @@ namespace pp {
 constexpr int kTileX = 32;
 // The canvas pass is bound by its dependent loads (head -> next -> feature row) before any store: more,
 // smaller CTAs keep more of those chains in flight.  Measured on B200, 64 frames: KITTI (C=64, 8 KB of
-// output per tile) 1170 us at 256 threads, 865 at 128, 822 at 64; D435 (C=128) 90 / 97 / 121 us.
+// output per tile) 1170 us at 256 threads, 865 at 128, 822 at 64 (765 with the division-free store loop, 838 at 32);
+// D435 (C=128) 90 / 97 / 121 us.
 constexpr int kScThreadsWide = 256;    // C > 64
 constexpr int kScThreadsNarrow = 64;   // C <= 64
 constexpr int kChainMax = 4;
