@@ -142,6 +142,15 @@ scatter_canvas_kernel(const float* __restrict__ feats, const int* __restrict__ h
             } else {
                 for (int k = threadIdx.x; k < n; k += kScThreads) dst[k] = 0.f;
             }
+        } else if ((C & 3) == 0 && (C & (C - 1)) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+            // power-of-two channel count: float4 over channels, no division
+            const int sh = 31 - __clz(C >> 2);  // log2(C / 4)
+            float4* d4 = reinterpret_cast<float4*>(dst);
+            for (int k = threadIdx.x; k < (n >> 2); k += kScThreads) {
+                const int x = k >> sh, c = (k - (x << sh)) << 2;
+                const float* t = tile + c * 33 + x;
+                d4[k] = make_float4(t[0], t[33], t[66], t[99]);
+            }
         } else {
             for (int k = threadIdx.x; k < n; k += kScThreads) {
                 const int x = k / C, c = k - x * C;
