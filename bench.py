@@ -532,7 +532,18 @@ def main():
                 "voxelize_scatter_gbs": vs_gbs_k, "voxelize_scatter_frac_of_peak": vs_gbs_k / peak_k,
                 "kernel_ms_per_launch": kk_ms,
                 "points_per_s": world * Fk * nks / (msk / 1e3) * nk}
-            del pk, kp, kbox, ksco, kfe
+            # the same batch with the canvas in NHWC (the layout RPN.call transposes to, model/voxelnet.py:697, and the one
+            # the north star names for the scatter stage): one contiguous run per tile instead of 64 channel-row segments
+            del pk
+            torch.cuda.empty_cache()
+            pk2 = pipeline.FramePipeline(kc, device=local_rank, max_frames=Fk, max_total_points=Fk * nk, overlap_post=False,
+                                         layout="NHWC")
+            stepk2 = lambda: pk2.run(kp, koff, Fk, Fk * nk, nk, kfe, kbox, ksco)  # noqa: E731
+            for _ in range(3):
+                stepk2()
+            msk2 = timed(stepk2, nks)
+            extra["kitti_batch"]["nhwc_canvas"] = {"frames_per_s": world * Fk * nks / (msk2 / 1e3), "ms_per_step": msk2 / nks}
+            del pk2, kp, kbox, ksco, kfe
             torch.cuda.empty_cache()
         except Exception as e:  # noqa: BLE001
             extra["kitti_batch"] = {"error": str(e)[:200]}
