@@ -120,3 +120,26 @@ def test_ingest_fuzz(pp, oracle, seed):
     got = pp.pointcloud2_to_lidar(raw.tobytes(), start=start, step=step, point_step=ps, offsets=tuple(offs))
     want = oracle.pointcloud2_to_lidar(xyz, (ing.R_Y_NEG90, ing.R_X_POS90), ing.LIFT, start, step)
     assert got.shape == want.shape and np.array_equal(got, want), (seed, n, ps, offs, start, step)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_large_n_nms_fuzz(pp, oracle, synth, seed):
+    """The alive-stripe path (> 16 384 boxes) against the all-pairs path on the 16 000 best boxes: random size, threshold,
+    box scale / aspect, clustering, post_max_size; rotated and standup kinds."""
+    rng = np.random.default_rng(4242 + seed)
+    n = int(rng.integers(16500, 50000))
+    thr = float(rng.uniform(0.02, 0.85))
+    d = synth.rotated_boxes(n, 3000 + seed, clustered=bool(rng.integers(0, 2)))
+    d[:, :4] *= np.float32(rng.choice([0.3, 1.0, 4.0]))
+    if seed % 2 == 0:
+        d[:, 2] *= rng.uniform(0.2, 5.0, n).astype(np.float32)
+        d[:, 3] *= rng.uniform(0.2, 5.0, n).astype(np.float32)
+    post = None if seed == 1 else int(rng.integers(50, 5000))
+    top = oracle.argsort_desc(d[:, 5])
+    got = pp.rotate_nms_gpu(d, thr, post_max_size=post)
+    want = [int(top[i]) for i in pp.rotate_nms_gpu(d[top[:16000]], thr, post_max_size=post)]
+    assert got[:len(want)] == want
+    sb = oracle.rbox_to_standup(d[:, :5]) * np.float32(10)
+    ks = pp.nms(sb, d[:, 5], None, post, thr)
+    ka = pp.nms(sb[top[:16000]], d[top[:16000], 5], None, post, thr)
+    assert ks[:len(ka)].tolist() == [int(top[i]) for i in ka]
