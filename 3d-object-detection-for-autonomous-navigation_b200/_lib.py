@@ -44,7 +44,7 @@ SIGNATURES = {
     "pp_profile_start": (C.c_int, []),
     "pp_profile_stop": (C.c_int, [C.c_char_p, _sz, C.POINTER(_f32), C.c_int]),
     "pp_grid_size": (C.c_int, [C.POINTER(_f64), C.POINTER(_f64), C.c_int, C.POINTER(_i32)]),
-    "pp_voxelize_workspace_bytes": (_sz, [_cfgp, _i64, C.c_int]),
+    "pp_voxelize_workspace_bytes": (_sz, [_cfgp, _i64, C.c_int, _i64, C.c_int, C.c_int]),
     "pp_voxelize_dev": (C.c_int, [_cfgp, _vp, C.c_int, C.c_int, _vp, C.c_int, _i64, _i64, C.c_int, _vp, _vp,
                                   _vp, C.c_int, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pp_decorate_dev": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int, C.c_int, _f64, _f64, _f64, _f64, _vp, _vp]),

@@ -25,7 +25,7 @@ def sources():
 
 
 def _deps():
-    return sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(ROOT, "include", "pp_b200.h")]
+    return sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + sorted(glob.glob(os.path.join(CSRC, "*.h"))) + [os.path.join(ROOT, "include", "pp_b200.h")]
 
 
 def source_hash() -> str:

@@ -155,7 +155,7 @@ extern "C" int pp_anchor_mask_dev(const int32_t* coors, int coors_cols, int64_t 
     PP_CUDA(cudaMemsetAsync(map, 0, (size_t)B * ny * nx * sizeof(int), st));
     if (M > 0) {
         int64_t blocks = ceil_div(M, 256);
-        if (blocks > (int64_t)kNumSM * 16) blocks = (int64_t)kNumSM * 16;
+        if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
         PP_TIMED("amask_hist", st);
         amask_hist_kernel<<<(unsigned)blocks, 256, 0, st>>>(coors, coors_cols, M, M_dev, B, ny, nx, map);
         PP_LAUNCHED();

@@ -1,6 +1,9 @@
 // C-ABI glue: thread-local error string, launch counter, pp_ctx (stream + device arena) and
 // the host-buffer entry points the reference's numpy call sites bind (include/pp_b200.h).
+#include <map>
+#include <mutex>
 #include <new>
+#include <tuple>
 #include <vector>
 #include <stdarg.h>
 #include <stdlib.h>
@@ -35,6 +38,47 @@ LaunchTimer::LaunchTimer(const char* name, cudaStream_t st) : st_(st), slot_(-1)
 }
 LaunchTimer::~LaunchTimer() {
     if (slot_ >= 0) cudaEventRecord((*g_prof)[slot_].e1, st_);
+}
+
+// ---- launch-configuration cache ------------------------------------------------------------------
+static std::mutex g_cfg_mu;
+static int g_sm_count[64] = {0};
+
+int num_sms() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int n = g_sm_count[dev];
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        g_sm_count[dev] = n;
+    }
+    return n;
+}
+
+struct KernelKey {
+    const void* k; int dev, threads; size_t smem;
+    bool operator<(const KernelKey& o) const { return std::tie(k, dev, threads, smem) < std::tie(o.k, o.dev, o.threads, o.smem); }
+};
+static std::map<KernelKey, int> g_kernel_cfg;
+static std::map<std::pair<const void*, int>, size_t> g_kernel_smem;  // largest dynamic smem opted into so far
+
+int kernel_config(const void* kernel, int threads, size_t smem, int* ctas_per_sm) {
+    int dev = 0;
+    PP_CUDA(cudaGetDevice(&dev));
+    const KernelKey key{kernel, dev, threads, smem};
+    std::lock_guard<std::mutex> lock(g_cfg_mu);
+    auto it = g_kernel_cfg.find(key);
+    if (it != g_kernel_cfg.end()) { *ctas_per_sm = it->second; return PP_OK; }
+    size_t& opted = g_kernel_smem[{kernel, dev}];
+    if (smem > 48 * 1024 && smem > opted) {
+        PP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        opted = smem;
+    }
+    int per_sm = 0;
+    PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    g_kernel_cfg[key] = per_sm;
+    *ctas_per_sm = per_sm;
+    return PP_OK;
 }
 
 }  // namespace pp
@@ -164,7 +208,7 @@ extern "C" int pp_points_to_voxel_host(pp_ctx* c, const pp_voxel_cfg* cfg, const
     PP_CHECK_ARG(point_dtype == PP_F32 || point_dtype == PP_F64, "bad point_dtype");
     const size_t esz = point_dtype == PP_F64 ? 8 : 4;
     const int P = cfg->max_points, MV = cfg->max_voxels;
-    const size_t ws_bytes = pp_voxelize_workspace_bytes(cfg, N, 1);
+    const size_t ws_bytes = pp_voxelize_workspace_bytes(cfg, N, 1, N, D, point_dtype);
     PP_CHECK_ARG(ws_bytes > 0, "pp_points_to_voxel_host: bad config");
     void *d_pts, *d_vox, *d_coors, *d_num, *d_misc, *d_ws, *d_slot = nullptr;
     PP_TRY(c->get(0, (size_t)N * D * esz, &d_pts));

@@ -75,7 +75,7 @@ extern "C" int pp_decorate_dev(const float* voxels, const int32_t* num_points, c
     if (smem > 48 * 1024)
         PP_CUDA(cudaFuncSetAttribute(decorate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t blocks = ceil_div(M, kDecWarps);
-    if (blocks > (int64_t)kNumSM * 8) blocks = (int64_t)kNumSM * 8;
+    if (blocks > (int64_t)num_sms() * 8) blocks = (int64_t)num_sms() * 8;
     PP_TIMED("decorate", static_cast<cudaStream_t>(stream));
     decorate_kernel<<<(unsigned)blocks, kDecWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
         voxels, num_points, coors, M, P, D, (float)vx, (float)vy, (float)x_offset, (float)y_offset, out);

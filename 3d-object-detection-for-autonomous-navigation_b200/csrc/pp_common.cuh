@@ -51,7 +51,18 @@ struct LaunchTimer {
         }                                                                                    \
     } while (0)
 
-constexpr int kNumSM = 148;  // B200
+// Multiprocessor count of the current device (148 on B200), queried once per device.
+int num_sms();
+// Per-process cache of a kernel's launch configuration: raises the dynamic shared-memory limit when `smem`
+// needs it and returns the resident CTAs per SM for (threads, smem).  cudaFuncSetAttribute and the occupancy
+// query cost microseconds each, which matters on the single-frame path; they run once per (kernel, smem, device).
+int kernel_config(const void* kernel, int threads, size_t smem, int* ctas_per_sm);
+
+#define PP_TRY_RC(expr)        \
+    do {                       \
+        int rc__ = (expr);     \
+        if (rc__) return rc__; \
+    } while (0)
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -213,6 +213,9 @@ extern "C" int pp_scatter_dev(const float* feats, const int32_t* coords, int64_t
     PP_CHECK_ARG(layout == PP_LAYOUT_NCHW || layout == PP_LAYOUT_NHWC, "pp_scatter_dev: bad layout");
     PP_CHECK_ARG(out && workspace && (M == 0 || (feats && coords)), "pp_scatter_dev: null argument");
     PP_CHECK_ARG(M < ((int64_t)1 << 31), "pp_scatter_dev: M must be < 2^31");
+    // coords rows are read as int4 and the canvas is stored with 16-byte vectors
+    PP_CHECK_ARG((reinterpret_cast<uintptr_t>(coords) & 15) == 0, "pp_scatter_dev: coords must be 16-byte aligned");
+    PP_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "pp_scatter_dev: out must be 16-byte aligned");
     const size_t smem = (size_t)C * 33 * sizeof(float);
     PP_CHECK_ARG(smem <= 200 * 1024, "pp_scatter_dev: C=%d too large", C);
     if (pp_scatter_workspace_bytes(B, ny, nx, M) > workspace_bytes) {
@@ -225,11 +228,14 @@ extern "C" int pp_scatter_dev(const float* feats, const int32_t* coords, int64_t
     int* head = cv.take<int>((size_t)B * ny * nx);
     int* next = cv.take<int>((size_t)M + 1);
     unsigned char* multi = cv.take<unsigned char>((size_t)B * ny * nx);
-    PP_CUDA(cudaMemsetAsync(head, 0xff, (size_t)B * ny * nx * sizeof(int), st));
-    PP_CUDA(cudaMemsetAsync(multi, 0, (size_t)B * ny * nx, st));
+    {
+        PP_TIMED("scatter_memset", st);
+        PP_CUDA(cudaMemsetAsync(head, 0xff, (size_t)B * ny * nx * sizeof(int), st));
+        PP_CUDA(cudaMemsetAsync(multi, 0, (size_t)B * ny * nx, st));
+    }
     if (M > 0) {
         int64_t blocks = ceil_div(M, 256);
-        if (blocks > (int64_t)kNumSM * 16) blocks = (int64_t)kNumSM * 16;
+        if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
         PP_TIMED("scatter_link", st);
         scatter_link_kernel<<<(unsigned)blocks, 256, 0, st>>>(coords, M, M_dev, B, ny, nx, head, next, multi);
         PP_LAUNCHED();
@@ -239,7 +245,8 @@ extern "C" int pp_scatter_dev(const float* feats, const int32_t* coords, int64_t
 #define PP_CANVAS(NHWC_, T_)                                                                                          \
     do {                                                                                                              \
         auto k = scatter_canvas_kernel<NHWC_, T_>;                                                                    \
-        if (smem > 48 * 1024) PP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        int per_sm__ = 0;                                                                                             \
+        PP_TRY_RC(kernel_config(reinterpret_cast<const void*>(k), T_, smem, &per_sm__));                              \
         k<<<g, T_, smem, st>>>(feats, head, next, multi, C, ny, nx, out);                                             \
     } while (0)
     const bool nhwc = layout == PP_LAYOUT_NHWC;

@@ -23,33 +23,10 @@
 #include <stdlib.h>
 
 #include "pp_common.cuh"
+#include "vox_common.cuh"
+#include "vox_internal.h"
 
 namespace pp {
-
-// n / d for 0 <= n < 2^31 with one 32x32->64 multiply (Granlund-Montgomery round-up magic)
-struct FastDiv {
-    unsigned d, m, s;
-    __host__ __device__ FastDiv() : d(1), m(0x80000000u), s(31) {}
-    __host__ explicit FastDiv(unsigned dd) : d(dd) {
-        unsigned l = 0;
-        while ((1ull << l) < dd) ++l;
-        s = 31 + l;
-        m = (unsigned)(((1ull << s) + dd - 1) / dd);
-    }
-    __device__ __forceinline__ int div(int n) const { return (int)(((unsigned long long)(unsigned)n * m) >> s); }
-};
-
-struct VoxParams {
-    double lo[3], vs[3], inv[3];
-    float lo32[3], vs32[3], inv32[3];
-    int grid[3];  // nx, ny, nz
-    int ncell;
-    FastDiv div_nx, div_nxny;
-    int max_points, max_voxels, reverse_index, arith_f32;
-    int D;
-    // decoration constants (model/pointpillars.py:121-124), float32 like TF constants
-    float vx, vy, x_off, y_off;
-};
 
 constexpr int kMarkThreads = 256;
 constexpr int kCellThreads = 256;
@@ -64,48 +41,6 @@ constexpr int kGatherWarps = PP_GATHER_WARPS;
 
 __device__ __forceinline__ int64_t word_base(const int64_t* frame_off, int b) {
     return (frame_off[b] >> 5) + b;
-}
-
-// ---------------------------------------------------------------------------------------------
-// cell id in the reference's arithmetic (load_data.py:620-626).  -1: outside the grid or NaN.
-// floor((p - lo) / vs) must equal the reference's correctly rounded IEEE division.
-// The quotient is first formed with a reciprocal multiply (relative error < 2^-51 in float64,
-// < 2^-22 in float32); only when it lands within a 2^-48 (2^-20) relative band of an integer --
-// where the two roundings could fall on different sides -- is the exact division evaluated.
-template <typename T, bool A32>
-__device__ __forceinline__ int cell_of(const T* q, const VoxParams& p) {
-    int c[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        if (A32) {
-            const float d = __fsub_rn((float)q[j], p.lo32[j]);
-            const float qq = __fmul_rn(d, p.inv32[j]);
-            float v = floorf(qq);
-            const float frac = __fsub_rn(qq, v), tol = fabsf(qq) * 0x1p-20f + 1e-30f;
-            if (frac < tol || frac > 1.f - tol) v = floorf(__fdiv_rn(d, p.vs32[j]));
-            if (!(v >= 0.f) || !((double)v < (double)p.grid[j])) return -1;
-            c[j] = (int)v;
-        } else {
-            const double d = __dsub_rn((double)q[j], p.lo[j]);
-            const double qq = __dmul_rn(d, p.inv[j]);
-            if (!(fabs(qq) < 2.0e9)) return -1;  // far outside any grid, inf or NaN
-            // floor without the conversion (XU) pipe: qq + 1.5*2^52 rounded down leaves floor(qq) in the
-            // low mantissa bits (two's complement), and subtracting the constant gives it back as a double
-            const double kMagic = 6755399441055744.0;
-            const double t = __dadd_rd(qq, kMagic);
-            int ci = __double2loint(t);
-            const double fl = __dsub_rn(t, kMagic);
-            const double frac = __dsub_rn(qq, fl), tol = fabs(qq) * 0x1p-48 + 1e-300;
-            if (frac < tol || frac > 1.0 - tol) {
-                const double v = floor(__ddiv_rn(d, p.vs[j]));  // the reference's exact quotient (rare path)
-                if (!(v >= 0.0) || !(v < (double)p.grid[j])) return -1;
-                ci = (int)v;
-            }
-            if (ci < 0 || ci >= p.grid[j]) return -1;
-            c[j] = ci;
-        }
-    }
-    return (c[2] * p.grid[1] + c[1]) * p.grid[0] + c[0];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -437,42 +372,6 @@ vox_bucket_kernel(const int2* __restrict__ cellpos, const int64_t* __restrict__ 
 // stores.  DS = compile-time point width (3, 4) or 0 for a runtime width.
 constexpr int kSegRegs = 8;  // register path handles buckets up to 32*kSegRegs indices
 constexpr int kIdxInf = 0x7fffffff;
-
-__device__ __forceinline__ void warp_store_row(float* __restrict__ dst, const float* __restrict__ src, int n, int lane) {
-    // dst: global, src: shared (16-byte aligned); n floats
-    const uintptr_t a = reinterpret_cast<uintptr_t>(dst);
-    if ((a & 15) == 0 && (n & 3) == 0) {
-        for (int k = lane; k < (n >> 2); k += 32)
-            reinterpret_cast<float4*>(dst)[k] = reinterpret_cast<const float4*>(src)[k];
-    } else if ((a & 7) == 0 && (n & 1) == 0) {
-        for (int k = lane; k < (n >> 1); k += 32)
-            reinterpret_cast<float2*>(dst)[k] = reinterpret_cast<const float2*>(src)[k];
-    } else {
-        for (int k = lane; k < n; k += 32) dst[k] = src[k];
-    }
-}
-
-// same, but elements at or past `lim` are stored as zero (src need not be initialised there)
-__device__ __forceinline__ void warp_store_row_padded(float* __restrict__ dst, const float* __restrict__ src, int n, int lim, int lane) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(dst);
-    if ((a & 15) == 0 && (n & 3) == 0) {
-        for (int k = lane; k < (n >> 2); k += 32) {
-            float4 v = reinterpret_cast<const float4*>(src)[k];
-            const int e = k << 2;
-            v.x = e < lim ? v.x : 0.f; v.y = e + 1 < lim ? v.y : 0.f; v.z = e + 2 < lim ? v.z : 0.f; v.w = e + 3 < lim ? v.w : 0.f;
-            reinterpret_cast<float4*>(dst)[k] = v;
-        }
-    } else if ((a & 7) == 0 && (n & 1) == 0) {
-        for (int k = lane; k < (n >> 1); k += 32) {
-            float2 v = reinterpret_cast<const float2*>(src)[k];
-            const int e = k << 1;
-            v.x = e < lim ? v.x : 0.f; v.y = e + 1 < lim ? v.y : 0.f;
-            reinterpret_cast<float2*>(dst)[k] = v;
-        }
-    } else {
-        for (int k = lane; k < n; k += 32) dst[k] = k < lim ? src[k] : 0.f;
-    }
-}
 
 // Zero the floats [begin, end) of a global row with TMA bulk stores (BULK instantiation of the gather pass).
 // Pillar rows are mostly padding (D435 46 % of the slots, KITTI 95 %).  For long rows the padding is not pushed
@@ -854,286 +753,18 @@ vox_gather_kernel(const T* __restrict__ points, const int64_t* __restrict__ fram
 }
 
 // ---------------------------------------------------------------------------------------------
-// Pass 5, asynchronous variant (float32 output rows, max_points <= 64, point width 3 or 4).
-// Same algorithm as vox_gather_kernel, restructured as a three-stage cp.async pipeline per warp so
-// that no global-memory round trip is exposed:
-//     iteration i:  H  cp.async the bucket head (first 64 indices) of pillar i+2       -> hd[(i+2)%3]
-//                   S  pillar i+1: head from shared memory -> register bitonic sort -> slot order;
-//                      cp.async the selected point rows                                 -> raw[(i+1)%2]
-//                   F  pillar i: point rows from shared memory -> float32 row, mean, decoration,
-//                      16-byte streaming stores
-// Descriptors are read 32 pillars at a time (lane k keeps the descriptor of pillar i+k) and handed
-// around with shuffles.  Buckets longer than 64 indices fetch their tail synchronously in stage S.
-__device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src, int bytes) {
-    const unsigned d = smem_u32(smem_dst);
-    if (bytes == 16) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-    else if (bytes == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
-    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-template <typename T, int DS>
-__global__ void __launch_bounds__(kGatherWarps * 32, PP_GATHER_MINBLOCKS)
-vox_gather_async_kernel(const T* __restrict__ points, const int64_t* __restrict__ frame_off, VoxParams p, int b0, int nb,
-                        const int4* __restrict__ occ_desc, const int* __restrict__ occ_base,
-                        const int* __restrict__ bucket, const int* __restrict__ cutoff,
-                        const int* __restrict__ voxel_base, float* __restrict__ voxels, float* __restrict__ decorated,
-                        int* __restrict__ num_points, int* __restrict__ point_slot) {
-    extern __shared__ __align__(16) unsigned char gsm_raw[];
-    constexpr int D = DS, Do = DS + 5;
-    constexpr int kRowBytes = DS * (int)sizeof(T);
-    constexpr int kCopy = (kRowBytes % 16 == 0) ? 16 : (kRowBytes % 8 == 0) ? 8 : 4;
-    const int P = p.max_points;  // <= 64
-    const int lane = lane_id(), w = threadIdx.x >> 5;
-    // per-warp carve (bytes): hd[3][64] int | so[2][64] int | raw[2][64*kRowBytes] | vrow[64*D] float
-    constexpr int kWarpBytes = 3 * 64 * 4 + 2 * 64 * 4 + 2 * 64 * kRowBytes + 64 * D * 4;
-    unsigned char* base = gsm_raw + (size_t)w * kWarpBytes;
-    int* hd = reinterpret_cast<int*>(base);
-    int* so = hd + 3 * 64;
-    unsigned char* raw = reinterpret_cast<unsigned char*>(so + 2 * 64);
-    float* vrow = reinterpret_cast<float*>(raw + 2 * 64 * kRowBytes);
-
-    const int nocc = occ_base[nb];
-    const int nwarps = gridDim.x * kGatherWarps;
-    const int e0 = blockIdx.x * kGatherWarps + w;
-    if (e0 >= nocc) return;
-    const int niter = (nocc - e0 + nwarps - 1) / nwarps;
-
-    // descriptor window: lane k holds pillar (win + k); refilled every 32 iterations
-    int4 dwin = make_int4(0, -1, 0, 0);
-    int dwin_bl = 0, bl_fill = 0;  // frame of the lane's descriptor; monotone frame pointer for the fills
-    auto fill = [&](int it0) {
-        // lanes look up consecutive pillars of this warp: it0 + lane
-        const int it = it0 + lane;
-        dwin = make_int4(0, -1, 0, 0);
-        int bl = bl_fill;
-        if (it < niter) {
-            const int ee = e0 + it * nwarps;
-            while (ee >= occ_base[bl + 1]) ++bl;
-            dwin = occ_desc[(size_t)(b0 + bl) * p.ncell + (ee - occ_base[bl])];
-        }
-        dwin_bl = bl;
-        bl_fill = __shfl_sync(0xffffffffu, bl, 0);  // later fills (same or later window) start from lane 0's frame
-    };
-    auto desc_of = [&](int it, int4& d, int& bl) {
-        const int k = it & 31;
-        d.x = __shfl_sync(0xffffffffu, dwin.x, k); d.y = __shfl_sync(0xffffffffu, dwin.y, k);
-        d.z = __shfl_sync(0xffffffffu, dwin.z, k); d.w = __shfl_sync(0xffffffffu, dwin.w, k);
-        bl = __shfl_sync(0xffffffffu, dwin_bl, k);
-    };
-    // stage H: bucket head of pillar `it` -> hd[it % 3]
-    auto stage_head = [&](int it, const int4& d) {
-        if (it < niter && d.y >= 0) {
-            const int* seg = bucket + d.w;
-            int* dst = hd + (it % 3) * 64;
-            if (lane < d.z) cp_async(dst + lane, seg + lane, 4);
-            if (lane + 32 < d.z) cp_async(dst + lane + 32, seg + lane + 32, 4);
-        }
-        cp_async_commit();
-    };
-
-    // per-stage state carried from S(i+1) to F(i+1)
-    int s_nsel = 0, s_row = -1, s_cell = 0, s_b = 0;
-    int64_t s_f0 = 0;
-    // stage S for pillar `it` (descriptor d, frame bl): slot order -> so[it&1], point rows -> raw[it&1]
-    auto stage_sort = [&](int it, const int4& d, int bl) {
-        s_row = -1;
-        if (it < niter && d.y >= 0) {
-            const int L = d.z, b = b0 + bl;
-            const int* seg = bucket + d.w;
-            const int cut = cutoff[b];
-            const int64_t f0 = frame_off[b];
-            const int* h = hd + (it % 3) * 64;
-            int* o = so + (it & 1) * 64;
-            int nsel;
-            if (L <= 32) {
-                int v[1] = {lane < L ? h[lane] : kIdxInf};
-                nsel = sort_bucket_regs<1>(cut, lane, v);
-                o[lane] = v[0];
-            } else if (L <= 64) {
-                int v[2] = {h[lane], lane + 32 < L ? h[lane + 32] : kIdxInf};
-                nsel = sort_bucket_regs<2>(cut, lane, v);
-                o[lane] = v[0]; o[lane + 32] = v[1];
-            } else if (L <= 128) {
-                int v[4];
-                nsel = load_sort_bucket<4>(seg, L, cut, lane, v);
-                o[lane] = v[0]; o[lane + 32] = v[1];
-            } else if (L <= 32 * kSegRegs) {
-                int v[kSegRegs];
-                nsel = load_sort_bucket<kSegRegs>(seg, L, cut, lane, v);
-                o[lane] = v[0]; o[lane + 32] = v[1];
-            } else {
-                // long bucket (heavy skew): threshold search streaming the bucket, then rank by counting;
-                // vrow is free here (stage F of the previous pillar has finished with it)
-                int* sel = reinterpret_cast<int*>(vrow);
-                int Lc = 0;
-                for (int k = lane; k < L; k += 32) Lc += seg[k] < cut;
-#pragma unroll
-                for (int q = 16; q; q >>= 1) Lc += __shfl_xor_sync(0xffffffffu, Lc, q);
-                int thr = cut;
-                if (Lc > P) {
-                    int lo = 0, hi = cut;
-                    while (lo < hi) {
-                        const int mid = lo + ((hi - lo) >> 1);
-                        int g = 0;
-                        for (int k = lane; k < L; k += 32) g += seg[k] < mid;
-#pragma unroll
-                        for (int q = 16; q; q >>= 1) g += __shfl_xor_sync(0xffffffffu, g, q);
-                        if (g >= P) hi = mid; else lo = mid + 1;
-                    }
-                    thr = lo;
-                }
-                nsel = min(Lc, P);
-                int nb_ = 0;
-                for (int k0 = 0; k0 < L; k0 += 32) {
-                    const int k = k0 + lane;
-                    const int x = k < L ? seg[k] : kIdxInf;
-                    const bool pr = x < thr;
-                    const unsigned bal = __ballot_sync(0xffffffffu, pr);
-                    if (pr) sel[nb_ + __popc(bal & lanemask_lt())] = x;
-                    nb_ += __popc(bal);
-                }
-                __syncwarp();
-                for (int j = lane; j < nsel; j += 32) {
-                    const int x = sel[j];
-                    int r = 0;
-                    for (int q = 0; q < nsel; ++q) r += sel[q] < x;
-                    o[r] = x;
-                }
-            }
-            nsel = min(nsel, P);
-            __syncwarp();
-            // point rows of the selected slots, asynchronously
-            unsigned char* rdst = raw + (size_t)(it & 1) * 64 * kRowBytes;
-            const unsigned char* psrc = reinterpret_cast<const unsigned char*>(points) + f0 * kRowBytes;
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int sidx = r * 32 + lane;
-                if (sidx < nsel) {
-                    const int pi = o[sidx];
-                    const unsigned char* src = psrc + (int64_t)pi * kRowBytes;
-#pragma unroll
-                    for (int c = 0; c < kRowBytes / kCopy; ++c) cp_async(rdst + sidx * kRowBytes + c * kCopy, src + c * kCopy, kCopy);
-                }
-            }
-            s_nsel = nsel; s_row = d.y; s_cell = d.x; s_b = b; s_f0 = f0;
-        }
-        cp_async_commit();
-    };
-
-    // ---- prologue: descriptors, heads of pillars 0 and 1, sort of pillar 0
-    fill(0);
-    {
-        int4 d; int bl;
-        desc_of(0, d, bl); stage_head(0, d);
-        if (niter > 1) { desc_of(1, d, bl); stage_head(1, d); } else cp_async_commit();
-        cp_async_wait<1>();  // head 0 landed
-        __syncwarp();
-        desc_of(0, d, bl);
-        stage_sort(0, d, bl);
-    }
-    for (int it = 0; it < niter; ++it) {
-        // state of pillar `it` (produced by its stage S)
-        const int nsel = s_nsel, cell = s_cell, b = s_b;
-        const int64_t row = s_row, f0 = s_f0;
-        // window refill happens when pillar it+2 moves into a new 32-block; pillars it+1 / it+2 may
-        // straddle the refill, so fetch their descriptors before refilling
-        int4 d1, d2; int bl1, bl2;
-        if (((it + 1) & 31) == 0) { fill(it + 1); }
-        desc_of(it + 1, d1, bl1);
-        if (((it + 2) & 31) == 0 && ((it + 1) & 31) != 0) {
-            // pillar it+2 is the first of the next window: it needs the refill, but it+1 (already fetched) does not
-            fill(it + 2);
-        }
-        desc_of(it + 2, d2, bl2);
-        stage_head(it + 2, d2);          // group H(it+2)
-        cp_async_wait<1>();              // everything except H(it+2): H(it+1) and P(it) are complete
-        __syncwarp();
-        stage_sort(it + 1, d1, bl1);     // group P(it+1); overwrites the carried state for the next iteration
-
-        if (row >= 0) {
-            // ---- stage F: raw point rows -> float32 row (+ sums)
-            const unsigned char* rsrc = raw + (size_t)(it & 1) * 64 * kRowBytes;
-            const int* o = so + (it & 1) * 64;
-            float sx = 0.f, sy = 0.f, sz = 0.f;
-            const int rank = point_slot ? (int)(row - voxel_base[b]) : 0;
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int sidx = r * 32 + lane;
-                if (sidx < nsel) {
-                    const T* q = reinterpret_cast<const T*>(rsrc + sidx * kRowBytes);
-                    float c[DS];
-#pragma unroll
-                    for (int dd = 0; dd < DS; ++dd) c[dd] = (float)q[dd];
-#pragma unroll
-                    for (int dd = 0; dd < DS; ++dd) vrow[sidx * DS + dd] = c[dd];
-                    sx += c[0]; sy += c[1]; sz += c[2];
-                    if (point_slot) point_slot[f0 + o[sidx]] = rank * P + sidx;
-                }
-            }
-            if (lane == 0) num_points[row] = nsel;
-            __syncwarp();
-            if (voxels) warp_store_row_padded(voxels + row * (int64_t)P * D, vrow, P * D, nsel * D, lane);
-            if (decorated) {
-#pragma unroll
-                for (int q = 16; q; q >>= 1) {
-                    sx += __shfl_xor_sync(0xffffffffu, sx, q);
-                    sy += __shfl_xor_sync(0xffffffffu, sy, q);
-                    sz += __shfl_xor_sync(0xffffffffu, sz, q);
-                }
-                const float nf = (float)nsel;
-                const float mx = __fdiv_rn(sx, nf), my = __fdiv_rn(sy, nf), mz = __fdiv_rn(sz, nf);
-                const int rem = cell - p.div_nxny.div(cell) * p.grid[0] * p.grid[1];
-                const int cy = p.div_nx.div(rem), cx = rem - cy * p.grid[0];
-                const float ex = __fadd_rn(__fmul_rn((float)cx, p.vx), p.x_off);
-                const float ey = __fadd_rn(__fmul_rn((float)cy, p.vy), p.y_off);
-                float* drow = decorated + row * (int64_t)P * Do;
-                if (DS == 3 && (reinterpret_cast<uintptr_t>(decorated) & 15) == 0) {
-                    float4* d4 = reinterpret_cast<float4*>(drow);
-                    for (int s2 = lane; s2 < P; s2 += 32) {
-                        float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
-                        if (s2 < nsel) {
-                            const float q0 = vrow[s2 * 3], q1 = vrow[s2 * 3 + 1], q2 = vrow[s2 * 3 + 2];
-                            o0 = make_float4(q0, q1, q2, q0 - mx);
-                            o1 = make_float4(q1 - my, q2 - mz, q0 - ex, q1 - ey);
-                        }
-                        d4[2 * s2] = o0;
-                        d4[2 * s2 + 1] = o1;
-                    }
-                } else {
-                    for (int k = lane; k < P * Do; k += 32) {
-                        const int s2 = k / Do, dd = k - s2 * Do;
-                        float ov = 0.f;
-                        if (s2 < nsel) {
-                            const float* q = vrow + s2 * D;
-                            ov = dd < D ? q[dd] : dd == D ? q[0] - mx : dd == D + 1 ? q[1] - my : dd == D + 2 ? q[2] - mz
-                                 : dd == D + 3 ? q[0] - ex : q[1] - ey;
-                        }
-                        drow[k] = ov;
-                    }
-                }
-            }
-            __syncwarp();
-        }
-    }
-    cp_async_wait<0>();
-}
-
-// ---------------------------------------------------------------------------------------------
 struct VoxWorkspace {
     unsigned* first_idx;  // [B*ncell]  0xff init
     int* cnt;             // [B*ncell]  zero init   -- zero region starts here
     unsigned* bitmap;     // [nwords]
     int* frame_cursor;    // [B]
     int* frame_occ;       // [B] occupied cells per frame
-    int* done_counter;    // [B]        -- zero region ends here
+    int* done_counter;    // [1]        -- zero region ends here
     unsigned* word_prefix;  // [nwords]
     int* cell_off;        // [B*ncell]
     int4* occ_desc;       // [B*ncell] descriptors of occupied cells, frame-major
     int* cutoff;          // [B]
-    int* occ_base;        // [2B+1] per-chunk exclusive scans of frame_occ
+    int* occ_base;        // [B+1] exclusive scan of frame_occ
     int2* cellpos;        // [total_points]
     int* bucket;          // [total_points]
     size_t zero_begin, zero_end, total;
@@ -1144,21 +775,19 @@ static VoxWorkspace carve(void* ws, int64_t ncell, int64_t total_points, int B) 
     Carver c(ws);
     const size_t nc = (size_t)B * ncell;
     const size_t nwords = (size_t)(total_points >> 5) + B + 2;
-    const size_t nocc = nc < (size_t)total_points ? nc : (size_t)total_points;
     w.first_idx = c.take<unsigned>(nc);
     w.zero_begin = c.used();
     w.cnt = c.take<int>(nc);
     w.bitmap = c.take<unsigned>(nwords);
     w.frame_cursor = c.take<int>(B);
     w.frame_occ = c.take<int>(B);
-    w.done_counter = c.take<int>(B);
+    w.done_counter = c.take<int>(1);
     w.zero_end = c.used();
     w.word_prefix = c.take<unsigned>(nwords);
     w.cell_off = c.take<int>(nc);
-    (void)nocc;
     w.occ_desc = c.take<int4>(nc + 1);
     w.cutoff = c.take<int>(B);
-    w.occ_base = c.take<int>(2 * (size_t)B + 2);
+    w.occ_base = c.take<int>((size_t)B + 2);
     w.cellpos = c.take<int2>((size_t)total_points + 1);
     w.bucket = c.take<int>((size_t)total_points + 1);
     w.total = c.used();
@@ -1188,63 +817,43 @@ extern "C" int pp_grid_size(const double voxel_size[3], const double coors_range
     return PP_OK;
 }
 
-extern "C" size_t pp_voxelize_workspace_bytes(const pp_voxel_cfg* cfg, int64_t total_points,
-                                              int n_frames) {
-    if (!cfg || total_points < 0 || n_frames <= 0) return 0;
+extern "C" size_t pp_voxelize_workspace_bytes(const pp_voxel_cfg* cfg, int64_t total_points, int n_frames,
+                                              int64_t max_frame_points, int D, int out_dtype) {
+    if (!cfg || total_points < 0 || n_frames <= 0 || max_frame_points < 0 || D < 3) return 0;
     int32_t grid[3];
     const int64_t ncell = ncell_of(cfg, grid);
     if (ncell <= 0) return 0;
-    return carve(nullptr, ncell, total_points, n_frames).total + 256;
+    if (max_frame_points > total_points) max_frame_points = total_points;
+    // both paths are bit-identical; the call takes the shared-memory path when the workspace allows it, so size for both
+    size_t need = carve(nullptr, ncell, total_points, n_frames).total;
+    if (vox_small_eligible(cfg, ncell, n_frames, total_points, max_frame_points, D)) {
+        const size_t small = vox_small_workspace_bytes(cfg, ncell, n_frames, total_points, max_frame_points, D, out_dtype);
+        if (small > need) need = small;
+    }
+    return need + 256;
 }
 
 template <typename T, typename TO, int DS>
 static int launch_gather(const VoxParams& p, const VoxWorkspace& w, const void* points,
                          const int64_t* frame_off, void* voxels, float* decorated, int32_t* num_points,
-                         const int32_t* voxel_base, int32_t* point_slot, int b0, int nb, const int* occ_base,
-                         int64_t max_occ, cudaStream_t st) {
+                         const int32_t* voxel_base, int32_t* point_slot, int nb, int64_t max_occ, cudaStream_t st) {
     const int P_ = p.max_points, D_ = p.D;
     const size_t per_warp = (size_t)(((P_ + 3) & ~3) + ((P_ * D_ + 3) & ~3) + (DS == 3 ? 0 : ((P_ * (D_ + 5) + 3) & ~3))) * 4;
     const size_t smem = (size_t)kGatherWarps * per_warp;
     PP_CHECK_ARG(smem <= 200 * 1024, "pp_voxelize_dev: max_points * D too large for the gather pass");
     // long float32 rows: the instantiation that writes the padding with TMA bulk stores
-    static const bool no_bulk = getenv("PP_VOX_NO_BULK") != nullptr;
-    const bool bulk = sizeof(TO) == 4 && !no_bulk && (size_t)P_ * (D_ + 5) * 4 >= (size_t)kBulkMinRowBytes;
+    const bool bulk = sizeof(TO) == 4 && (size_t)P_ * (D_ + 5) * 4 >= (size_t)kBulkMinRowBytes;
     auto kern = bulk ? vox_gather_kernel<T, TO, DS, true> : vox_gather_kernel<T, TO, DS, false>;
-    if (smem > 48 * 1024) PP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t blocks = ceil_div(max_occ, kGatherWarps);
     int per_sm = 0;
-    PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kGatherWarps * 32, smem));
-    const int64_t cap = (int64_t)kNumSM * (per_sm > 0 ? per_sm : 1);  // persistent: one resident wave
+    PP_TRY_RC(kernel_config(reinterpret_cast<const void*>(kern), kGatherWarps * 32, smem, &per_sm));
+    int64_t blocks = ceil_div(max_occ, kGatherWarps);
+    const int64_t cap = (int64_t)num_sms() * (per_sm > 0 ? per_sm : 1);  // persistent: one resident wave
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     PP_TIMED("vox_gather", st);
     kern<<<(unsigned)blocks, kGatherWarps * 32, smem, st>>>(
-        static_cast<const T*>(points), frame_off, p, b0, nb, w.occ_desc, occ_base, w.bucket, w.cutoff, voxel_base,
+        static_cast<const T*>(points), frame_off, p, 0, nb, w.occ_desc, w.occ_base, w.bucket, w.cutoff, voxel_base,
         static_cast<TO*>(voxels), decorated, num_points, point_slot);
-    PP_LAUNCHED();
-    return PP_OK;
-}
-
-template <typename T, int DS>
-static int launch_gather_async(const VoxParams& p, const VoxWorkspace& w, const void* points,
-                               const int64_t* frame_off, float* voxels, float* decorated, int32_t* num_points,
-                               const int32_t* voxel_base, int32_t* point_slot, int b0, int nb, const int* occ_base,
-                               int64_t max_occ, cudaStream_t st) {
-    constexpr int kRowBytes = DS * (int)sizeof(T);
-    constexpr size_t kWarpBytes = 3 * 64 * 4 + 2 * 64 * 4 + 2 * 64 * kRowBytes + 64 * DS * 4;
-    const size_t smem = (size_t)kGatherWarps * kWarpBytes;
-    auto kern = vox_gather_async_kernel<T, DS>;
-    if (smem > 48 * 1024) PP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t blocks = ceil_div(max_occ, kGatherWarps);
-    int per_sm = 0;
-    PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kGatherWarps * 32, smem));
-    const int64_t cap = (int64_t)kNumSM * (per_sm > 0 ? per_sm : 1);
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    PP_TIMED("vox_gather", st);
-    kern<<<(unsigned)blocks, kGatherWarps * 32, smem, st>>>(
-        static_cast<const T*>(points), frame_off, p, b0, nb, w.occ_desc, occ_base, w.bucket, w.cutoff, voxel_base,
-        voxels, decorated, num_points, point_slot);
     PP_LAUNCHED();
     return PP_OK;
 }
@@ -1278,11 +887,6 @@ extern "C" int pp_voxelize_dev(const pp_voxel_cfg* cfg, const void* points, int 
     PP_CHECK_ARG(grid[0] > 0 && grid[1] > 0 && grid[2] > 0, "empty grid %d x %d x %d", grid[0], grid[1], grid[2]);
     PP_CHECK_ARG(ncell * n_frames < ((int64_t)1 << 31), "n_frames * cells must be < 2^31");
     PP_CHECK_ARG(total_points < ((int64_t)1 << 31), "a batch may hold < 2^31 points (bucket offsets are int32)");
-    const VoxWorkspace w = carve(workspace, ncell, total_points, n_frames);
-    if (w.total > workspace_bytes) {
-        set_error("pp_voxelize_dev: workspace %zu < required %zu", workspace_bytes, w.total);
-        return PP_E_WORKSPACE;
-    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
     VoxParams p;
@@ -1299,123 +903,101 @@ extern "C" int pp_voxelize_dev(const pp_voxel_cfg* cfg, const void* points, int 
     p.x_off = (float)(cfg->voxel_size[0] / 2 + cfg->coors_range[0]);
     p.y_off = (float)(cfg->voxel_size[1] / 2 + cfg->coors_range[1]);
 
+    const int esz = point_dtype == PP_F64 ? 8 : 4;
+    // Grids whose per-cell tables fit in shared memory (the d435i grid: 10 240 cells) take the
+    // chunk-privatised path of voxelize_small.cu: no global atomics, no bucket pass, no sort.
+    if (vox_small_eligible(cfg, ncell, n_frames, total_points, max_frame_points, D) &&
+        vox_small_workspace_bytes(cfg, ncell, n_frames, total_points, max_frame_points, D, out_dtype) <= workspace_bytes)
+        return vox_small_run(cfg, p, points, point_dtype, frame_offsets, n_frames, total_points, max_frame_points,
+                             out_dtype, voxels, decorated, coors, coors_cols, num_points, cap_rows, voxel_num,
+                             voxel_base, point_slot, cell_voxel, workspace, workspace_bytes, st);
+
+    const VoxWorkspace w = carve(workspace, ncell, total_points, n_frames);
+    if (w.total > workspace_bytes) {
+        set_error("pp_voxelize_dev: workspace %zu < required %zu", workspace_bytes, w.total);
+        return PP_E_WORKSPACE;
+    }
     const size_t nc = (size_t)n_frames * ncell;
     {
         PP_TIMED("vox_memset", st);
         PP_CUDA(cudaMemsetAsync(w.first_idx, 0xff, nc * sizeof(unsigned), st));
         PP_CUDA(cudaMemsetAsync(static_cast<char*>(workspace) + w.zero_begin, 0, w.zero_end - w.zero_begin, st));
     }
-
-    // Frames are processed in chunks small enough that a chunk's points and its intermediates
-    // (cell/pos, buckets) stay resident in the 126 MB L2 between the five passes: the points are
-    // then read from HBM once, by the mark pass; the gather pass finds them in L2.
-    const int esz = point_dtype == PP_F64 ? 8 : 4;
-    int chunk_frames = n_frames;
-    {
-        const char* env = getenv("PP_VOX_CHUNK_MB");
-        const double chunk_mb = env ? atof(env) : 0.0;  // measured on B200: per-chunk launch tails cost more than the L2 hits save (profiles/r01_notes.md)
-        const double frame_mb = (double)max_frame_points * D * esz / 1e6;
-        if (chunk_mb > 0 && frame_mb > 0) {
-            chunk_frames = (int)(chunk_mb / frame_mb);
-            if (chunk_frames < 1) chunk_frames = 1;
-            if (chunk_frames > n_frames) chunk_frames = n_frames;
-        }
-    }
+    // (Processing the frames in L2-sized chunks was measured and rejected: per-chunk launch tails cost more
+    //  than the L2 hits save, profiles/r01_notes.md.)
+    const int nb = n_frames;
     const size_t mark_smem = 2 * ((size_t)kMarkTile * D * esz + 32);  // two pipeline stages
-    int mark_ctas_per_sm = (int)((size_t)(220 * 1024) / (mark_smem + 1024));
-    if (mark_ctas_per_sm > 8) mark_ctas_per_sm = 8;
-    if (mark_ctas_per_sm < 1) mark_ctas_per_sm = 1;
     const int aligned16 = (reinterpret_cast<uintptr_t>(points) & 15) == 0;
     PP_CHECK_ARG(mark_smem <= 200 * 1024, "pp_voxelize_dev: D too large for the mark pass");
-    if (mark_smem > 48 * 1024) {
-        PP_CUDA(cudaFuncSetAttribute(vox_mark_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mark_smem));
-        PP_CUDA(cudaFuncSetAttribute(vox_mark_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mark_smem));
-        PP_CUDA(cudaFuncSetAttribute(vox_mark_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mark_smem));
+    if (max_frame_points > 0) {
+        const void* kern = point_dtype == PP_F64 ? reinterpret_cast<const void*>(vox_mark_kernel<double, false>)
+                           : cfg->arith_f32     ? reinterpret_cast<const void*>(vox_mark_kernel<float, true>)
+                                                : reinterpret_cast<const void*>(vox_mark_kernel<float, false>);
+        int mark_ctas_per_sm = 0;
+        PP_TRY_RC(kernel_config(kern, kMarkThreads, mark_smem, &mark_ctas_per_sm));
+        if (mark_ctas_per_sm > 8) mark_ctas_per_sm = 8;
+        if (mark_ctas_per_sm < 1) mark_ctas_per_sm = 1;
+        const int tpf = (int)ceil_div(max_frame_points, kMarkTile);
+        const int64_t tiles = (int64_t)tpf * nb;
+        int64_t g = (int64_t)num_sms() * mark_ctas_per_sm;
+        if (g > tiles) g = tiles;
+        PP_TIMED("vox_mark", st);
+        if (point_dtype == PP_F64)
+            vox_mark_kernel<double, false><<<(unsigned)g, kMarkThreads, mark_smem, st>>>(
+                static_cast<const double*>(points), frame_offsets, p, total_points, aligned16, 0, nb, tpf,
+                w.first_idx, w.cnt, w.cellpos, point_slot);
+        else if (cfg->arith_f32)
+            vox_mark_kernel<float, true><<<(unsigned)g, kMarkThreads, mark_smem, st>>>(
+                static_cast<const float*>(points), frame_offsets, p, total_points, aligned16, 0, nb, tpf,
+                w.first_idx, w.cnt, w.cellpos, point_slot);
+        else
+            vox_mark_kernel<float, false><<<(unsigned)g, kMarkThreads, mark_smem, st>>>(
+                static_cast<const float*>(points), frame_offsets, p, total_points, aligned16, 0, nb, tpf,
+                w.first_idx, w.cnt, w.cellpos, point_slot);
+        PP_LAUNCHED();
     }
-    int chunk_id = 0;
-    for (int b0 = 0; b0 < n_frames; b0 += chunk_frames, ++chunk_id) {
-        const int nb = n_frames - b0 < chunk_frames ? n_frames - b0 : chunk_frames;
-        int* occ_base = w.occ_base + b0 + chunk_id;  // this chunk's [nb+1] slice
-        if (max_frame_points > 0) {
-            const int tpf = (int)ceil_div(max_frame_points, kMarkTile);
-            const int64_t tiles = (int64_t)tpf * nb;
-            int64_t g = (int64_t)kNumSM * mark_ctas_per_sm;
-            if (g > tiles) g = tiles;
-            PP_TIMED("vox_mark", st);
-            if (point_dtype == PP_F64)
-                vox_mark_kernel<double, false><<<(unsigned)g, kMarkThreads, mark_smem, st>>>(
-                    static_cast<const double*>(points), frame_offsets, p, total_points, aligned16, b0, nb, tpf,
-                    w.first_idx, w.cnt, w.cellpos, point_slot);
-            else if (cfg->arith_f32)
-                vox_mark_kernel<float, true><<<(unsigned)g, kMarkThreads, mark_smem, st>>>(
-                    static_cast<const float*>(points), frame_offsets, p, total_points, aligned16, b0, nb, tpf,
-                    w.first_idx, w.cnt, w.cellpos, point_slot);
-            else
-                vox_mark_kernel<float, false><<<(unsigned)g, kMarkThreads, mark_smem, st>>>(
-                    static_cast<const float*>(points), frame_offsets, p, total_points, aligned16, b0, nb, tpf,
-                    w.first_idx, w.cnt, w.cellpos, point_slot);
-            PP_LAUNCHED();
-        }
-        {
-            const dim3 g((unsigned)ceil_div(ncell, kCellThreads * kCellPerThread), nb);
-            PP_TIMED("vox_cell", st);
-            vox_cell_kernel<<<g, kCellThreads, 0, st>>>(w.first_idx, w.cnt, frame_offsets, (int)ncell, b0,
-                                                        w.bitmap, w.cell_off, w.frame_cursor, w.occ_desc,
-                                                        w.frame_occ, cell_voxel);
-            PP_LAUNCHED();
-        }
-        {
-            PP_TIMED("vox_rank", st);
-            vox_rank_kernel<<<nb, kRankThreads, 0, st>>>(w.bitmap, w.word_prefix, frame_offsets, b0, nb,
-                                                         cfg->max_voxels, voxel_num, w.cutoff, voxel_base,
-                                                         w.frame_occ, occ_base, w.done_counter + chunk_id);
-            PP_LAUNCHED();
-        }
-        const int64_t chunk_pts = (int64_t)nb * max_frame_points;
-        const int64_t frame_occ_max = ncell < max_frame_points ? ncell : max_frame_points;
-        if (frame_occ_max > 0) {
-            const dim3 g((unsigned)ceil_div(frame_occ_max, 256), nb);
-            PP_TIMED("vox_rowmap", st);
-            vox_rowmap_kernel<<<g, 256, 0, st>>>(w.occ_desc, occ_base, frame_offsets, p, b0, w.bitmap, w.word_prefix,
-                                                 voxel_base, cap_rows, coors, coors_cols, cell_voxel);
-            PP_LAUNCHED();
-        }
-        if (max_frame_points > 0) {
-            // (a variant that staged the frame's offset table in shared memory was measured slower: 185 vs 113 us)
-            const dim3 g((unsigned)ceil_div(max_frame_points, 256 * kBucketPPT), nb);
-            PP_TIMED("vox_bucket", st);
-            vox_bucket_kernel<<<g, 256, 0, st>>>(w.cellpos, frame_offsets, (int)ncell, b0, w.cell_off, w.bucket);
-            PP_LAUNCHED();
-        }
-        const int64_t max_occ = (int64_t)nb * ncell < chunk_pts ? (int64_t)nb * ncell : chunk_pts;
-        if (max_occ > 0 && cap_rows > 0) {
-            int rc;
-            // cp.async pipeline variant: float32 rows, at most two slots per lane, 3- or 4-wide points
-            const int row_bytes = D * esz;
-            const int copy = row_bytes % 16 == 0 ? 16 : row_bytes % 8 == 0 ? 8 : 4;
-            const bool use_async = out_dtype == PP_F32 && cfg->max_points <= 64 && (D == 3 || D == 4) &&
-                                   (reinterpret_cast<uintptr_t>(points) % copy) == 0 && getenv("PP_VOX_ASYNC_GATHER");
-            // (measured on B200: the cp.async variant is correct but slower, 0.74 vs 0.47 ms -- it trades the exposed
-            //  point-gather latency for shared-memory/shuffle (MIO) pressure; kept behind PP_VOX_ASYNC_GATHER=1)
-#define PP_GATHER_A(T, DS)                                                                                     \
-    launch_gather_async<T, DS>(p, w, points, frame_offsets, static_cast<float*>(voxels), decorated, num_points, \
-                               voxel_base, point_slot, b0, nb, occ_base, max_occ, st)
-            if (use_async) {
-                if (point_dtype == PP_F64) rc = D == 3 ? PP_GATHER_A(double, 3) : PP_GATHER_A(double, 4);
-                else rc = D == 3 ? PP_GATHER_A(float, 3) : PP_GATHER_A(float, 4);
-                if (rc) return rc;
-                continue;
-            }
-#undef PP_GATHER_A
+    {
+        const dim3 g((unsigned)ceil_div(ncell, kCellThreads * kCellPerThread), nb);
+        PP_TIMED("vox_cell", st);
+        vox_cell_kernel<<<g, kCellThreads, 0, st>>>(w.first_idx, w.cnt, frame_offsets, (int)ncell, 0,
+                                                    w.bitmap, w.cell_off, w.frame_cursor, w.occ_desc,
+                                                    w.frame_occ, cell_voxel);
+        PP_LAUNCHED();
+    }
+    {
+        PP_TIMED("vox_rank", st);
+        vox_rank_kernel<<<nb, kRankThreads, 0, st>>>(w.bitmap, w.word_prefix, frame_offsets, 0, nb,
+                                                     cfg->max_voxels, voxel_num, w.cutoff, voxel_base,
+                                                     w.frame_occ, w.occ_base, w.done_counter);
+        PP_LAUNCHED();
+    }
+    const int64_t chunk_pts = (int64_t)nb * max_frame_points;
+    const int64_t frame_occ_max = ncell < max_frame_points ? ncell : max_frame_points;
+    if (frame_occ_max > 0) {
+        const dim3 g((unsigned)ceil_div(frame_occ_max, 256), nb);
+        PP_TIMED("vox_rowmap", st);
+        vox_rowmap_kernel<<<g, 256, 0, st>>>(w.occ_desc, w.occ_base, frame_offsets, p, 0, w.bitmap, w.word_prefix,
+                                             voxel_base, cap_rows, coors, coors_cols, cell_voxel);
+        PP_LAUNCHED();
+    }
+    if (max_frame_points > 0) {
+        // (a variant that staged the frame's offset table in shared memory was measured slower: 185 vs 113 us)
+        const dim3 g((unsigned)ceil_div(max_frame_points, 256 * kBucketPPT), nb);
+        PP_TIMED("vox_bucket", st);
+        vox_bucket_kernel<<<g, 256, 0, st>>>(w.cellpos, frame_offsets, (int)ncell, 0, w.cell_off, w.bucket);
+        PP_LAUNCHED();
+    }
+    const int64_t max_occ = (int64_t)nb * ncell < chunk_pts ? (int64_t)nb * ncell : chunk_pts;
+    if (max_occ > 0 && cap_rows > 0) {
+        int rc;
 #define PP_GATHER(T, TO, DS)                                                                                   \
     launch_gather<T, TO, DS>(p, w, points, frame_offsets, voxels, decorated, num_points, voxel_base,          \
-                             point_slot, b0, nb, occ_base, max_occ, st)
-            if (point_dtype == PP_F64 && out_dtype == PP_F64) rc = PP_GATHER(double, double, 0);
-            else if (point_dtype == PP_F64) rc = D == 3 ? PP_GATHER(double, float, 3) : D == 4 ? PP_GATHER(double, float, 4) : PP_GATHER(double, float, 0);
-            else rc = D == 3 ? PP_GATHER(float, float, 3) : D == 4 ? PP_GATHER(float, float, 4) : PP_GATHER(float, float, 0);
+                             point_slot, nb, max_occ, st)
+        if (point_dtype == PP_F64 && out_dtype == PP_F64) rc = PP_GATHER(double, double, 0);
+        else if (point_dtype == PP_F64) rc = D == 3 ? PP_GATHER(double, float, 3) : D == 4 ? PP_GATHER(double, float, 4) : PP_GATHER(double, float, 0);
+        else rc = D == 3 ? PP_GATHER(float, float, 3) : D == 4 ? PP_GATHER(float, float, 4) : PP_GATHER(float, float, 0);
 #undef PP_GATHER
-            if (rc) return rc;
-        }
+        if (rc) return rc;
     }
     return PP_OK;
 }

@@ -93,7 +93,7 @@ def points_to_voxel(points, voxel_size, coors_range, max_points, reverse_index, 
     )
     if decorate:
         out["decorated"] = torch.empty((cap, max_points, D + 5), dtype=torch.float32, device=dev)
-    ws_bytes = int(L.pp_voxelize_workspace_bytes(C.byref(cfg), N, B))
+    ws_bytes = int(L.pp_voxelize_workspace_bytes(C.byref(cfg), N, B, max_frame, D, _lib.PP_F64 if f64_out else _lib.PP_F32))
     ws = _scratch.get(dev, "vox", ws_bytes)
     _lib.check(L.pp_voxelize_dev(
         C.byref(cfg), _p(pts), _lib.PP_F64 if pts.dtype == torch.float64 else _lib.PP_F32, D, _p(off), B, N, max_frame,

@@ -30,7 +30,8 @@ class FramePipeline:
 
     def __init__(self, cfg, device=0, max_frames=64, max_total_points=None, rotated_nms=True,
                  layout="NCHW", fused_decorate=True, keep_voxels=True, anchors=None, overlap_post=True,
-                 anchor_area_threshold=None, production=False, sensor_points=None, fused_post=True):
+                 anchor_area_threshold=None, production=False, sensor_points=None, fused_post=True,
+                 max_frame_points=None):
         self.cfg = cfg
         self.fused_post = fused_post
         self.dev = torch.device("cuda", device)
@@ -53,9 +54,14 @@ class FramePipeline:
         self.post = cfg["nms_post_max_size"]
         self.thr = cfg["nms_iou_threshold"]
         if max_total_points is None:
-            max_total_points = self.B * (410_000 if not production else
-                                         ((sensor_points or 848 * 480) + 3) // 4)
+            per_frame = 410_000 if not production else ((sensor_points or 848 * 480) + 3) // 4
+            max_total_points = self.B * per_frame
+            if max_frame_points is None:
+                max_frame_points = per_frame
         self.max_pts = int(max_total_points)
+        # largest single frame the workspaces are sized for.  Default: the batch capacity (always enough); callers
+        # that know their frames are of similar size pass the real bound, which keeps the small-grid workspace small
+        self.max_frame_pts = int(max_frame_points) if max_frame_points is not None else self.max_pts
         L = _lib.lib()
         with torch.cuda.device(self.dev):
             an = _synth.anchors_stride(cfg) if anchors is None else np.asarray(anchors, np.float32)
@@ -79,7 +85,8 @@ class FramePipeline:
             self.keep = torch.empty((B, self.post), dtype=torch.int32, **e)
             self.keep_count = torch.zeros((B,), dtype=torch.int32, **e)
             self.dets = torch.empty((B, self.post, 8), dtype=torch.float32, **e)
-            self.ws_vox_bytes = int(L.pp_voxelize_workspace_bytes(C.byref(self.vcfg), self.max_pts, B))
+            self.ws_vox_bytes = int(L.pp_voxelize_workspace_bytes(C.byref(self.vcfg), self.max_pts, B, self.max_frame_pts,
+                                                                  self.D, _lib.PP_F32))
             self.ws_sc_bytes = int(L.pp_scatter_workspace_bytes(B, self.ny, self.nx, self.cap_rows))
             kind = _lib.PP_NMS_ROTATED if rotated_nms else _lib.PP_NMS_STANDUP
             self.nms_kind = kind

@@ -45,8 +45,9 @@ def algorithmic_bytes(cfg, n_points, m_pillars, n_anchors, pre_max, grid, s_in):
     return dict(voxelize=vox, decorate=dec, scatter=sca, decode=dcd, nms=nms,
                 total=vox + dec + sca + dcd + nms,
                 # per-kernel split used for the dominant-kernel roofline
-                vox_mark=n_points * D * s_in,
+                vox_mark=n_points * D * s_in, vox_scan=n_points * D * s_in,
                 vox_gather=m_pillars * P * D * 4 + m_pillars * 4 + dec,  # voxel rows + num_points + decorated rows
+                vox_finish=m_pillars * P * D * 4 + m_pillars * 4 + m_pillars * 3 * 4 + dec,  # + coors
                 scatter_canvas=sca)
 
 
@@ -255,7 +256,7 @@ def main():
         hp[i * n_pts:(i + 1) * n_pts] = distinct[i % n_distinct]
     frame_off = torch.arange(F + 1, dtype=torch.int64) * n_pts
     pipe = pipeline.FramePipeline(cfg, device=local_rank, max_frames=F, max_total_points=total, rotated_nms=True,
-                                  layout="NCHW", fused_decorate=True, keep_voxels=True)
+                                  layout="NCHW", fused_decorate=True, keep_voxels=True, max_frame_points=n_pts)
     A = pipe.A
     box = np.stack([synth.rpn_standin(A, 100 * rank + (i % n_distinct))[0] for i in range(F)])
     sco = np.stack([synth.rpn_standin(A, 100 * rank + (i % n_distinct))[1] for i in range(F)])
@@ -601,7 +602,7 @@ def main():
         peak = 6650.0; peak_src = "fallback (B200_PROFILING.md 6.65 TB/s)"
     ab = algorithmic_bytes(cfg, n_pts, m_pillars, A, cfg["nms_pre_max_size"], grid, 8)
     roof = None
-    cand = {k: kern_ms[k] for k in ("vox_mark", "vox_gather", "scatter_canvas") if k in kern_ms}
+    cand = {k: kern_ms[k] for k in ("vox_mark", "vox_gather", "vox_scan", "vox_finish", "scatter_canvas") if k in kern_ms}
     if cand:
         dom = max(cand, key=cand.get)
         bytes_launch = ab[dom] * F
@@ -618,8 +619,7 @@ def main():
                 "kernel_share_of_step": cand[dom] / step_kernel_ms if step_kernel_ms else None}
     path_gbs = ab["total"] * F * args.steps / (ms * 1e-3) / 1e9 / world * world  # per GPU == aggregate/world
     vs_gbs = (ab["voxelize"] + ab["decorate"] + ab["scatter"]) * F / max(1e-9, sum(
-        kern_ms.get(k, 0.0) for k in ("vox_memset", "vox_mark", "vox_cell", "vox_rank", "vox_rowmap", "vox_bucket", "vox_gather",
-                                      "scatter_link", "scatter_canvas")) * 1e-3) / 1e9
+        v for k, v in kern_ms.items() if k.startswith("vox_") or k.startswith("scatter_")) * 1e-3) / 1e9
 
     # ---- CPU baseline (oracle port, bounded sample) ----------------------------------------------
     cpu = None

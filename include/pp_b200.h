@@ -10,8 +10,10 @@
  *   *_dev   device pointers in, device pointers out, asynchronous on the caller's stream,
  *           caller-provided workspace.  This is what a DLPack / __cuda_array_interface__
  *           consumer (TensorFlow via tf.experimental.dlpack, torch, cupy) binds.
- *   *_host  host (numpy) buffers in and out through a pp_ctx that owns a stream, a device
- *           arena and pinned staging.  Synchronous, like the reference's numpy functions.
+ *   *_host  host (numpy) buffers in and out through a pp_ctx that owns a stream, a grow-only device
+ *           arena and grow-only pinned staging buffers (pageable caller memory is copied through them
+ *           in pieces so that the host copy overlaps the transfer).  Synchronous, like the
+ *           reference's numpy functions.
  *           This is what the reference's call sites bind through ctypes.
  *
  * Conventions
@@ -84,7 +86,11 @@ typedef struct pp_voxel_cfg {
     int32_t arith_f32;     /* 1 only when points AND voxel_size/coors_range were float32 */
 } pp_voxel_cfg;
 
-PP_API size_t pp_voxelize_workspace_bytes(const pp_voxel_cfg* cfg, int64_t total_points, int n_frames);
+/* Workspace of pp_voxelize_dev for a batch of n_frames frames, total_points points in all, at most
+ * max_frame_points in one frame (the batch total is a valid bound when the largest frame is not known),
+ * D values per point, voxels of out_dtype.  A call with smaller counts fits in the same workspace. */
+PP_API size_t pp_voxelize_workspace_bytes(const pp_voxel_cfg* cfg, int64_t total_points, int n_frames,
+                                   int64_t max_frame_points, int D, int out_dtype);
 
 /*  points         [total_points, D] point_dtype, frames concatenated
  *  frame_offsets  device int64 [n_frames+1], frame b = rows [off[b], off[b+1])
@@ -123,7 +129,7 @@ PP_API int pp_decorate_dev(const float* voxels, const int32_t* num_points, const
  * Replaces PointPillarsScatter.call, model/pointpillars.py:285-341: out[b,:,y,x] = SUM of the
  * feature rows with coords (b,*,y,x) (z ignored, duplicates added, lines 302,317); everything
  * else zero.  `out` is fully written (no memset needed).  Rows with b outside [0,B) or (y,x)
- * outside the canvas are ignored.  M may be read from device (`M_dev`, e.g. voxel_base+n_frames)
+ * outside the canvas are ignored.  `coords` and `out` must be 16-byte aligned.  M may be read from device (`M_dev`, e.g. voxel_base+n_frames)
  * when the host does not know it; then M is the capacity. */
 PP_API size_t pp_scatter_workspace_bytes(int B, int ny, int nx, int64_t M);
 PP_API int pp_scatter_dev(const float* feats, const int32_t* coords, int64_t M, const int32_t* M_dev, int C,

@@ -97,7 +97,7 @@ def test_argument_validation_needs_no_gpu(pp):
     assert L.pp_ingest_dev(*bad) == -3
     with pytest.raises(pp.PPError):
         _lib.check(-1)
-    assert L.pp_voxelize_workspace_bytes(C.byref(cfg), 120000, 64) > 64 * 214272 * 16
+    assert L.pp_voxelize_workspace_bytes(C.byref(cfg), 120000 * 64, 64, 120000, 4, 0) > 64 * 214272 * 16
 
 
 def test_header_is_plain_c_and_exports_match():

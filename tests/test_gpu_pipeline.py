@@ -130,9 +130,19 @@ def test_profiler_and_launch_count(pp, synth):
     pp.points_to_voxel(pts, np.array(synth.D435["voxel_size"]), np.array(synth.D435["point_cloud_range"]), 50, True, 12000)
     rec = _lib.profile_stop()
     names = [n for n, _ in rec]
+    # the d435i grid (10 240 cells) takes the shared-memory path: four launches, no memset
+    kernels = ["vox_scan", "vox_prefix", "vox_place", "vox_finish"]
+    assert names == kernels
+    assert all(t >= 0 for _, t in rec)
+    assert pp.launch_count() == len(kernels)
+    # a KITTI-sized grid (214 272 cells) takes the any-grid path
+    kp = synth.kitti_cloud(0)
+    pp.launch_count(reset=True)
+    _lib.profile_start()
+    pp.points_to_voxel(kp, np.array(synth.KITTI["voxel_size"]), np.array(synth.KITTI["point_cloud_range"]), 100, True, 12000)
+    names = [n for n, _ in _lib.profile_stop()]
     kernels = ["vox_mark", "vox_cell", "vox_rank", "vox_rowmap", "vox_bucket", "vox_gather"]
     assert names == ["vox_memset"] + kernels
-    assert all(t >= 0 for _, t in rec)
     assert pp.launch_count() == len(kernels)
 
 

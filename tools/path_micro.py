@@ -13,7 +13,7 @@ fr = [gen(i) for i in range(8)]; n = fr[0].shape[0]
 pts = torch.from_numpy(np.concatenate([fr[i % 8] for i in range(F)])).cuda()
 off = (torch.arange(F + 1, dtype=torch.int64) * n).cuda()
 amask = len(sys.argv) > 3 and sys.argv[3] == "amask"
-pipe = pipeline.FramePipeline(cfg, max_frames=F, max_total_points=F * n, overlap_post=False, anchor_area_threshold=1 if amask else None)
+pipe = pipeline.FramePipeline(cfg, max_frames=F, max_total_points=F * n, max_frame_points=n, overlap_post=False, anchor_area_threshold=1 if amask else None)
 A = pipe.A
 box = torch.from_numpy(np.stack([synth.rpn_standin(A, i % 8)[0] for i in range(F)])).cuda()
 sco = torch.from_numpy(np.stack([synth.rpn_standin(A, i % 8)[1] for i in range(F)])).cuda()

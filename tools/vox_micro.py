@@ -8,7 +8,7 @@ synth = pp.synth; cfg = synth.D435; F = int(sys.argv[1]) if len(sys.argv) > 1 el
 fr = [synth.d435_cloud(i) for i in range(4)]; n = fr[0].shape[0]
 pts = torch.from_numpy(np.concatenate([fr[i % 4] for i in range(F)])).cuda()
 off = (torch.arange(F + 1, dtype=torch.int64) * n).cuda()
-pipe = pipeline.FramePipeline(cfg, max_frames=F, max_total_points=F * n)
+pipe = pipeline.FramePipeline(cfg, max_frames=F, max_total_points=F * n, max_frame_points=n)
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 for _ in range(3): pipe.voxelize(pts, off, F, F * n, n, st)
 torch.cuda.synchronize(); _lib.profile_start()
