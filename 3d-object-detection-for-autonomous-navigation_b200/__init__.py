@@ -15,7 +15,7 @@ Drop-in Python surface (same names, argument meaning and return types as the ref
 
 The compute lives in libpp_b200.so (csrc/*.cu, include/pp_b200.h).  There is no CPU fallback.
 """
-from ._lib import PPError, Ctx, ctx, grid_size, launch_count, lib, set_device  # noqa: F401
+from ._lib import PPError, Ctx, ctx, grid_size, launch_count, lib, pinned_empty, set_device  # noqa: F401
 from .anchors import anchors_mask  # noqa: F401
 from .boxes import rbox_to_standup, second_box_decode  # noqa: F401
 from .nms import (bev_box_overlap, d3_box_overlap, nms, nms_gpu, rotate_iou_gpu, rotate_iou_gpu_eval,  # noqa: F401

@@ -79,6 +79,8 @@ SIGNATURES = {
     "pp_ctx_stream": (_vp, [_vp]),
     "pp_ctx_device": (C.c_int, [_vp]),
     "pp_ctx_sync": (C.c_int, [_vp]),
+    "pp_host_alloc": (C.c_int, [_sz, C.POINTER(_vp)]),
+    "pp_host_free": (None, [_vp]),
     "pp_points_to_voxel_host": (C.c_int, [_vp, _cfgp, _vp, C.c_int, _i64, C.c_int, _vp, _vp, _vp, C.POINTER(_i32), _vp]),
     "pp_decorate_host": (C.c_int, [_vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int, _f64, _f64, _f64, _f64, _vp]),
     "pp_scatter_host": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
@@ -188,6 +190,33 @@ def ctx(device=None) -> Ctx:
     if c is None:
         c = cache[device] = Ctx(device)
     return c
+
+
+class _PinnedBlock:
+    """Owner of one pp_host_alloc block (freed when the last numpy view dies)."""
+
+    def __init__(self, nbytes):
+        h = _vp()
+        check(lib().pp_host_alloc(int(nbytes), C.byref(h)))
+        self.ptr, self.nbytes = h.value, int(nbytes)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().pp_host_free(_vp(self.ptr))
+                self.ptr = None
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
+    """numpy array in page-locked host memory: the *_host entry points DMA straight from / into it."""
+    dt = np.dtype(dtype)
+    shape = tuple(int(x) for x in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+    n = int(np.prod(shape)) * dt.itemsize
+    blk = _PinnedBlock(max(n, 1))
+    blk.__array_interface__ = {"shape": shape, "typestr": dt.str, "data": (blk.ptr, False), "version": 3}
+    return np.asarray(blk)   # the array's base keeps the block alive
 
 
 def make_cfg(voxel_size, coors_range, max_points, max_voxels, reverse_index, arith_f32) -> VoxelCfg:

@@ -15,7 +15,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "-fmad=false",            # float parity with the reference: no FMA contraction anywhere
-    "-Xcompiler", "-fPIC,-fvisibility=hidden",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden,-fopenmp",   # OpenMP: host-side staging copies of the *_host layer
     "-shared",
 ]
 
@@ -72,8 +72,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             return obj
         with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
             objs = list(ex.map(compile_one, sources()))
-        subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC",
-                        "-o", LIB, *objs], check=True)
+        subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC,-fopenmp",
+                        "-o", LIB, *objs, "-lgomp"], check=True)
     with open(LIB + ".srchash", "w") as f:
         f.write(source_hash())
     return LIB

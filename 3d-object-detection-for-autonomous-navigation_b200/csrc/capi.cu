@@ -130,11 +130,40 @@ extern "C" int pp_profile_stop(char* names, size_t names_cap, float* ms, int max
 }
 
 // ---- context ----------------------------------------------------------------------------------
+// Host <-> device transfers of the *_host layer.  Caller memory that is already page-locked (cudaHostAlloc /
+// cudaHostRegister / torch pinned tensors / pp_host_alloc) is handed to the copy engine directly.  Pageable memory
+// (a fresh numpy array, the reference's case) is moved through the context's own pinned ring in pieces: a few host
+// threads copy piece k+1 into the ring while the DMA of piece k is in flight, so the host copy overlaps the transfer
+// instead of preceding it (a pageable cudaMemcpyAsync does the same inside the driver with one thread).
+constexpr size_t kPiece = (size_t)2 << 20;   // bytes per staged piece
+constexpr int kRing = 4;                      // pieces in flight
+constexpr int kCopyThreads = 4;
+
+static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+    if (bytes < ((size_t)256 << 10)) { memcpy(dst, src, bytes); return; }
+    const size_t per = (bytes / kCopyThreads + 4095) & ~(size_t)4095;
+#pragma omp parallel for num_threads(kCopyThreads) schedule(static, 1)
+    for (int t = 0; t < kCopyThreads; ++t) {
+        const size_t o = (size_t)t * per;
+        if (o < bytes) memcpy(static_cast<char*>(dst) + o, static_cast<const char*>(src) + o, bytes - o < per ? bytes - o : per);
+    }
+}
+
+static bool is_page_locked(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 struct pp_ctx {
     int device;
     cudaStream_t stream;
     struct Buf { void* p = nullptr; size_t cap = 0; };
     Buf dev[12];
+    void* ring = nullptr;            // kRing pinned pieces of kPiece bytes
+    cudaEvent_t ring_ev[kRing] = {};  // the DMA that last used the piece
+    bool ring_busy[kRing] = {};
+    void* small = nullptr;           // pinned scratch for scalars read back
     // grow-only device buffers, one per slot
     int get(int slot, size_t bytes, void** out) {
         Buf& b = dev[slot];
@@ -147,6 +176,71 @@ struct pp_ctx {
             b.cap = want;
         }
         *out = b.p;
+        return PP_OK;
+    }
+    int ensure_ring() {
+        if (ring) return PP_OK;
+        PP_CUDA(cudaHostAlloc(&ring, kRing * kPiece, cudaHostAllocDefault));
+        PP_CUDA(cudaHostAlloc(&small, 4096, cudaHostAllocDefault));
+        for (int k = 0; k < kRing; ++k) PP_CUDA(cudaEventCreateWithFlags(&ring_ev[k], cudaEventDisableTiming));
+        return PP_OK;
+    }
+    char* piece(int k) { return static_cast<char*>(ring) + (size_t)k * kPiece; }
+    int wait_piece(int k) {
+        if (ring_busy[k]) { PP_CUDA(cudaEventSynchronize(ring_ev[k])); ring_busy[k] = false; }
+        return PP_OK;
+    }
+    // host -> device, asynchronous on the context stream; `src` may be reused as soon as this returns
+    int h2d(void* dst_dev, const void* src, size_t bytes) {
+        if (bytes == 0) return PP_OK;
+        if (is_page_locked(src)) {
+            PP_CUDA(cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyHostToDevice, stream));
+            return PP_OK;
+        }
+        PP_TRY_RC(ensure_ring());
+        int k = 0;
+        for (size_t o = 0; o < bytes; o += kPiece, k = (k + 1) % kRing) {
+            const size_t nb = bytes - o < kPiece ? bytes - o : kPiece;
+            PP_TRY_RC(wait_piece(k));
+            parallel_memcpy(piece(k), static_cast<const char*>(src) + o, nb);
+            PP_CUDA(cudaMemcpyAsync(static_cast<char*>(dst_dev) + o, piece(k), nb, cudaMemcpyHostToDevice, stream));
+            PP_CUDA(cudaEventRecord(ring_ev[k], stream));
+            ring_busy[k] = true;
+        }
+        return PP_OK;
+    }
+    // device -> host; `dst` is complete when this returns (the stream has been drained up to the copy)
+    int d2h(void* dst, const void* src_dev, size_t bytes) {
+        if (bytes == 0) return PP_OK;
+        if (is_page_locked(dst)) {
+            PP_CUDA(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, stream));
+            PP_CUDA(cudaStreamSynchronize(stream));
+            return PP_OK;
+        }
+        PP_TRY_RC(ensure_ring());
+        const size_t np = (bytes + kPiece - 1) / kPiece;
+        for (int k = 0; k < kRing; ++k) PP_TRY_RC(wait_piece(k));
+        size_t issued = 0;
+        for (size_t done = 0; done < np; ++done) {
+            for (; issued < np && issued < done + kRing; ++issued) {  // keep kRing DMAs in flight
+                const int k = (int)(issued % kRing);
+                const size_t o = issued * kPiece, nb = bytes - o < kPiece ? bytes - o : kPiece;
+                PP_CUDA(cudaMemcpyAsync(piece(k), static_cast<const char*>(src_dev) + o, nb, cudaMemcpyDeviceToHost, stream));
+                PP_CUDA(cudaEventRecord(ring_ev[k], stream));
+            }
+            const int k = (int)(done % kRing);
+            const size_t o = done * kPiece, nb = bytes - o < kPiece ? bytes - o : kPiece;
+            PP_CUDA(cudaEventSynchronize(ring_ev[k]));
+            parallel_memcpy(static_cast<char*>(dst) + o, piece(k), nb);
+        }
+        return PP_OK;
+    }
+    // one small value back (voxel counts): pinned scratch + event wait, no full-stream drain semantics needed
+    int read_back(void* dst, const void* src_dev, size_t bytes) {
+        PP_TRY_RC(ensure_ring());
+        PP_CUDA(cudaMemcpyAsync(small, src_dev, bytes, cudaMemcpyDeviceToHost, stream));
+        PP_CUDA(cudaStreamSynchronize(stream));
+        memcpy(dst, small, bytes);
         return PP_OK;
     }
 };
@@ -176,6 +270,11 @@ extern "C" void pp_ctx_destroy(pp_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (auto& b : c->dev)
         if (b.p) cudaFree(b.p);
+    if (c->ring) {
+        cudaFreeHost(c->ring);
+        cudaFreeHost(c->small);
+        for (int k = 0; k < kRing; ++k) cudaEventDestroy(c->ring_ev[k]);
+    }
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -185,6 +284,17 @@ extern "C" int pp_ctx_sync(pp_ctx* c) {
     PP_CHECK_ARG(c, "null ctx");
     PP_CUDA(cudaStreamSynchronize(c->stream));
     return PP_OK;
+}
+
+// Page-locked host memory for callers that want the direct-DMA path of the *_host functions
+// (numpy: np.frombuffer over the returned block).
+extern "C" int pp_host_alloc(size_t bytes, void** out) {
+    PP_CHECK_ARG(out, "pp_host_alloc: null out");
+    PP_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return PP_OK;
+}
+extern "C" void pp_host_free(void* p) {
+    if (p) cudaFreeHost(p);
 }
 
 #define PP_TRY(expr)          \
@@ -222,21 +332,23 @@ extern "C" int pp_points_to_voxel_host(pp_ctx* c, const pp_voxel_cfg* cfg, const
     int32_t* d_vnum = reinterpret_cast<int32_t*>(d_off + 2);
     int32_t* d_vbase = d_vnum + 1;
     const int64_t off[2] = {0, N};
-    PP_CUDA(cudaMemcpyAsync(d_off, off, sizeof(off), cudaMemcpyHostToDevice, st));
-    if (N > 0) PP_CUDA(cudaMemcpyAsync(d_pts, points, (size_t)N * D * esz, cudaMemcpyHostToDevice, st));
+    PP_CUDA(cudaMemcpyAsync(d_off, off, sizeof(off), cudaMemcpyHostToDevice, st));  // 16 bytes: copied at enqueue time
+    PP_TRY(c->h2d(d_pts, points, (size_t)N * D * esz));
     PP_TRY(pp_voxelize_dev(cfg, d_pts, point_dtype, D, d_off, 1, N, N, point_dtype, d_vox, nullptr,
                            static_cast<int32_t*>(d_coors), 3, static_cast<int32_t*>(d_num), MV, d_vnum,
                            d_vbase, static_cast<int32_t*>(d_slot), nullptr, d_ws, ws_bytes, st));
     int32_t m = 0;
-    PP_CUDA(cudaMemcpyAsync(&m, d_vnum, 4, cudaMemcpyDeviceToHost, st));
-    PP_CUDA(cudaStreamSynchronize(st));
+    PP_TRY(c->read_back(&m, d_vnum, 4));
     *voxel_num_out = m;
+    // the three result arrays leave in one stream; the last copy drains it
     if (m > 0) {
-        PP_CUDA(cudaMemcpyAsync(voxels, d_vox, (size_t)m * P * D * esz, cudaMemcpyDeviceToHost, st));
+        if (point_slot && N > 0) PP_CUDA(cudaMemcpyAsync(point_slot, d_slot, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
         PP_CUDA(cudaMemcpyAsync(coors, d_coors, (size_t)m * 12, cudaMemcpyDeviceToHost, st));
         PP_CUDA(cudaMemcpyAsync(num_points, d_num, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+        PP_TRY(c->d2h(voxels, d_vox, (size_t)m * P * D * esz));
+    } else if (point_slot && N > 0) {
+        PP_TRY(c->d2h(point_slot, d_slot, (size_t)N * 4));
     }
-    if (point_slot && N > 0) PP_CUDA(cudaMemcpyAsync(point_slot, d_slot, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
     PP_CUDA(cudaStreamSynchronize(st));
     return PP_OK;
 }

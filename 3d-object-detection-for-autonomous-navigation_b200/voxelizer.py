@@ -21,12 +21,32 @@ def _arith_is_f32(points, voxel_size, coors_range) -> bool:
     return (points.dtype == np.float32 and dt(voxel_size) == np.float32 and dt(coors_range) == np.float32)
 
 
+_OUT_RING = 3  # pinned result sets per (thread, shape): a returned view stays valid for the next two calls
+
+
+def _pinned_out(c, max_voxels, max_points, D, dtype):
+    """Reusable page-locked result buffers of the calling thread's context (round robin)."""
+    ring = c.__dict__.setdefault("_vox_out", {})
+    key = (int(max_voxels), int(max_points), int(D), np.dtype(dtype).str)
+    ent = ring.get(key)
+    if ent is None:
+        ent = ring[key] = {"i": 0, "sets": [(_lib.pinned_empty((max_voxels, max_points, D), dtype),
+                                             _lib.pinned_empty((max_voxels, 3), np.int32),
+                                             _lib.pinned_empty((max_voxels,), np.int32)) for _ in range(_OUT_RING)]}
+    ent["i"] = (ent["i"] + 1) % _OUT_RING
+    return ent["sets"][ent["i"]]
+
+
 def points_to_voxel(points, voxel_size, coors_range, max_points, reverse_index, max_voxels,
-                    return_point_slots=False, device=None):
+                    return_point_slots=False, device=None, out="fresh"):
     """points [N,D] float32/float64 -> (voxels [M,max_points,D], coors [M,3], num_points [M]).
 
     `return_point_slots` additionally returns the point-to-slot assignment [N] int32
-    (voxel*max_points+slot, -1 for dropped points); `device` picks the GPU (default: thread's)."""
+    (voxel*max_points+slot, -1 for dropped points); `device` picks the GPU (default: thread's).
+    `out`: "fresh" (the reference's behaviour: new arrays every call) or "pinned": views of a small ring of
+    page-locked buffers owned by the calling thread's context -- the results are DMA-ed straight into them (no
+    staging copy, no page faults on 14 MB of fresh memory); a returned view is overwritten three calls later.
+    Page-locked `points` (`pinned_empty`, torch pinned tensors) are likewise read by the copy engine directly."""
     points = np.asarray(points)
     if points.dtype not in (np.float32, np.float64):
         raise TypeError(f"points must be float32 or float64, got {points.dtype}")
@@ -40,16 +60,21 @@ def points_to_voxel(points, voxel_size, coors_range, max_points, reverse_index, 
         coors_range = np.array(coors_range, dtype=points.dtype)
     cfg = _lib.make_cfg(voxel_size, coors_range, max_points, max_voxels, reverse_index, f32)
     N, D = points.shape
-    voxels = np.empty((max_voxels, max_points, D), points.dtype)
-    coors = np.empty((max_voxels, 3), np.int32)
-    num = np.empty((max_voxels,), np.int32)
+    c = _lib.ctx(device)
+    if out == "pinned":
+        voxels, coors, num = _pinned_out(c, max_voxels, max_points, D, points.dtype)
+    elif out == "fresh":
+        voxels = np.empty((max_voxels, max_points, D), points.dtype)
+        coors = np.empty((max_voxels, 3), np.int32)
+        num = np.empty((max_voxels,), np.int32)
+    else:
+        raise ValueError("out must be 'fresh' or 'pinned'")
     slots = np.empty((N,), np.int32) if return_point_slots else None
     m = C.c_int32(0)
-    c = _lib.ctx(device)
     _lib.check(_lib.lib().pp_points_to_voxel_host(
         c.handle, C.byref(cfg), _lib.ptr(points), _lib.PP_F64 if points.dtype == np.float64 else _lib.PP_F32,
         N, D, _lib.ptr(voxels), _lib.ptr(coors), _lib.ptr(num), C.byref(m),
         _lib.ptr(slots) if return_point_slots else None))
     M = m.value
-    out = (voxels[:M], coors[:M], num[:M])
-    return out + (slots,) if return_point_slots else out
+    res = (voxels[:M], coors[:M], num[:M])
+    return res + (slots,) if return_point_slots else res

@@ -282,6 +282,11 @@ PP_API void pp_ctx_destroy(pp_ctx* ctx);
 PP_API void* pp_ctx_stream(pp_ctx* ctx);
 PP_API int pp_ctx_device(pp_ctx* ctx);
 PP_API int pp_ctx_sync(pp_ctx* ctx);
+/* Page-locked host memory.  The *_host functions hand caller buffers that are page-locked (these, cudaHostAlloc /
+ * cudaHostRegister memory, torch pinned tensors) straight to the copy engine; pageable buffers go through the
+ * context's pinned ring. */
+PP_API int pp_host_alloc(size_t bytes, void** out);
+PP_API void pp_host_free(void* p);
 
 /* points_to_voxel(points, voxel_size, coors_range, max_points, reverse_index, max_voxels),
  * load_data.py:695-771: host points [N,D] -> host voxels [max_voxels,max_points,D] in the

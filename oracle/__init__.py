@@ -190,6 +190,12 @@ def rotate_iou_gpu_eval(boxes, query_boxes, criterion=-1):
     return out
 
 
+def set_exact_trig(on: bool):
+    """Evaluate the box rotation's sin/cos in float64 and round (what the CUDA path does) instead of the host libm's
+    sinf/cosf (1 ulp off in ~1 % of the arguments): isolates that one source of float difference."""
+    lib().ppo_set_exact_trig(int(bool(on)))
+
+
 def rotate_iou_pair(r1, r2, criterion=-1) -> float:
     a = np.ascontiguousarray(r1, np.float32)
     b = np.ascontiguousarray(r2, np.float32)

@@ -34,6 +34,19 @@
 
 #define PPO_API __attribute__((visibility("default")))
 
+/* cosf/sinf of the host libm are within 1 ulp but not always correctly rounded (glibc: 1.3 % of the arguments in
+ * [-pi, pi] differ from RN(cos(double))), and neither is the libm behind the reference (numba -> llvm.cos.f32 ->
+ * libm on the CPU, libdevice on the GPU).  One ulp on a corner at 70 m moves a car-sized IoU by ~4e-6.  The CUDA
+ * path evaluates sincos in float64 and rounds; ppo_set_exact_trig(1) makes the oracle do the same, which isolates
+ * that one source of difference in the parity tests. */
+static int g_exact_trig = 0;
+PPO_API void ppo_set_exact_trig(int on) { g_exact_trig = on; }
+static inline void ppo_sincosf(float a, float* s, float* c) {
+    if (g_exact_trig) { *s = (float)sin((double)a); *c = (float)cos((double)a); }
+    else { *s = sinf(a); *c = cosf(a); }
+}
+
+
 /* ------------------------------------------------------------------------------------------
  * Grid size: load_data.py:612-615 / 722-731 (np.round == round-half-to-even, then int32).
  * arith_f32 != 0 reproduces the case where the caller handed python lists, which the wrapper
@@ -247,7 +260,8 @@ PPO_API void ppo_rbox_to_standup(const float* boxes, int64_t N, float* out) {
     static const float cn[4][2] = {{-0.5f, -0.5f}, {-0.5f, 0.5f}, {0.5f, 0.5f}, {0.5f, -0.5f}};
     for (int64_t i = 0; i < N; ++i) {
         const float* b = boxes + 5 * i;
-        const float s = sinf(b[4]), c = cosf(b[4]);
+        float s, c;
+        ppo_sincosf(b[4], &s, &c);
         float mnx = 0, mny = 0, mxx = 0, mxy = 0;
         for (int k = 0; k < 4; ++k) {
             const float x = b[2] * cn[k][0], y = b[3] * cn[k][1];
@@ -498,7 +512,8 @@ static int ppo_quad_inter(const float* p1, const float* p2, float* ip) {
 }
 
 static void ppo_rbbox_to_corners(float* corners, const float* r) {
-    const float a_cos = cosf(r[4]), a_sin = sinf(r[4]);
+    float a_sin, a_cos;
+    ppo_sincosf(r[4], &a_sin, &a_cos);
     const float cx = r[0], cy = r[1];
     const float hx = (float)((double)r[2] / 2.0), hy = (float)((double)r[3] / 2.0);
     const float xs[4] = {-hx, -hx, hx, hx};

@@ -2,6 +2,8 @@
 import numpy as np
 import pytest
 
+from nms_check import assert_keep_lists_agree
+
 pytestmark = pytest.mark.gpu
 
 
@@ -56,10 +58,7 @@ def test_scatter_and_nms_random(pp, oracle, synth, seed):
     post = None if post is None else int(post)
     got = pp.rotate_nms_gpu(d, thr, pre_max_size=pre, post_max_size=post)
     want = oracle.rotate_nms_gpu(d, thr, pre, post)
-    if got != want:
-        ds = d[oracle.argsort_desc(d[:, 5])]
-        iou = oracle.rotate_iou_gpu_eval(ds[:, :5], ds[:, :5], -1)
-        assert (np.abs(iou - thr) < 1e-5).any(), (n, thr, pre, post)
+    assert_keep_lists_agree(got, want, d, thr, oracle, tol=1e-6, pre_max_size=pre, post_max_size=post)
     sb = oracle.rbox_to_standup(d[:, :5]) * np.float32(rng.choice([1.0, 20.0]))
     g2 = pp.nms(sb, d[:, 5], pre, post, thr)
     w2 = oracle.nms(sb, d[:, 5], pre, post, thr)

@@ -26,6 +26,12 @@ for name, pts in (("full_407040", full), ("subsampled_101760", sub)):
     g_us, g_l, (v, c, n) = bench(lambda: pp.points_to_voxel(pts, vs, pcr, 50, True, 12000))
     c_us, _, _ = bench(lambda: oracle.points_to_voxel(pts, vs, pcr, 50, True, 12000), 5)
     out[f"points_to_voxel_{name}"] = {"gpu_us": g_us, "cpu_us": c_us, "launches": g_l}
+    # page-locked input + results into the context's pinned ring: the copy engine reads / writes caller memory directly
+    pin = pp.pinned_empty(pts.shape, pts.dtype); pin[:] = pts
+    p_us, _, (v2, c2, n2) = bench(lambda: pp.points_to_voxel(pin, vs, pcr, 50, True, 12000, out="pinned"))
+    assert np.array_equal(v2, v) and np.array_equal(c2, c) and np.array_equal(n2, n)
+    out[f"points_to_voxel_{name}"]["gpu_pinned_us"] = p_us
+    out[f"points_to_voxel_{name}"]["pcie_floor_us"] = (pts.nbytes + v.nbytes) / 55e9 * 1e6
 v32 = v.astype(np.float32); c4 = np.concatenate([np.zeros((c.shape[0], 1), np.int32), c], 1)
 feats = synth.pfn_standin(c4.shape[0], 128, 0)
 boxes = oracle.second_box_decode(be, an); top = np.argsort(sc)[-100:]
