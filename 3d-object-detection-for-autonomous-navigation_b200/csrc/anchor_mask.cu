@@ -27,11 +27,20 @@ anchor_cells_kernel(const float* __restrict__ anchors, int64_t A, double vsx, do
     const float dx = cond ? l : w, dy = cond ? w : l;
     const float hx = __fdiv_rn(dx, 2.f), hy = __fdiv_rn(dy, 2.f);
     const float b0 = __fsub_rn(x, hx), b1 = __fsub_rn(y, hy), b2 = __fadd_rn(x, hx), b3 = __fadd_rn(y, hy);
-    int c0 = (int)floor(__ddiv_rn(__dsub_rn((double)b0, lox), vsx));
-    int c1 = (int)floor(__ddiv_rn(__dsub_rn((double)b1, loy), vsy));
-    int c2 = (int)floor(__ddiv_rn(__dsub_rn((double)b2, lox), vsx));
-    int c3 = (int)floor(__ddiv_rn(__dsub_rn((double)b3, loy), vsy));
-    cells[i] = make_int4(max(c0, 0), max(c1, 0), min(c2, nx - 1), min(c3, ny - 1));
+    // The reference clips one side of each index only (load_data.py:577-580) and then indexes dense_map:
+    // an index that stays negative wraps around once (numba's negative indexing); anything else outside the
+    // map, and NaN / infinite coordinates, is undefined behaviour there.  Here those anchors get the cell
+    // rectangle (-1,-1,-1,-1), which the lookup turns into area 0.
+    const double v0 = floor(__ddiv_rn(__dsub_rn((double)b0, lox), vsx)), v1 = floor(__ddiv_rn(__dsub_rn((double)b1, loy), vsy));
+    const double v2 = floor(__ddiv_rn(__dsub_rn((double)b2, lox), vsx)), v3 = floor(__ddiv_rn(__dsub_rn((double)b3, loy), vsy));
+    int4 c = make_int4(-1, -1, -1, -1);
+    if (fabs(v0) < 2.0e9 && fabs(v1) < 2.0e9 && fabs(v2) < 2.0e9 && fabs(v3) < 2.0e9) {
+        int c0 = max((int)v0, 0), c1 = max((int)v1, 0), c2 = min((int)v2, nx - 1), c3 = min((int)v3, ny - 1);
+        c2 += c2 < 0 ? nx : 0;
+        c3 += c3 < 0 ? ny : 0;
+        if (c0 < nx && c1 < ny && c2 >= 0 && c3 >= 0) c = make_int4(c0, c1, c2, c3);
+    }
+    cells[i] = c;
 }
 
 __global__ void __launch_bounds__(256)
@@ -103,9 +112,12 @@ amask_lookup_kernel(const int* __restrict__ map, int ny, int nx, const int4* __r
     if (i >= A) return;
     const int4 c = cells[i];
     const int* m = map + (int64_t)b * ny * nx;
-    const int ID = m[(int64_t)c.w * nx + c.z], IA = m[(int64_t)c.y * nx + c.x];
-    const int IB = m[(int64_t)c.w * nx + c.x], IC = m[(int64_t)c.y * nx + c.z];
-    const float v = (float)(ID - IB - IC + IA);
+    float v = 0.f;  // anchors whose footprint the reference cannot index (anchor_cells_kernel)
+    if (c.x >= 0) {
+        const int ID = m[(int64_t)c.w * nx + c.z], IA = m[(int64_t)c.y * nx + c.x];
+        const int IB = m[(int64_t)c.w * nx + c.x], IC = m[(int64_t)c.y * nx + c.z];
+        v = (float)(ID - IB - IC + IA);
+    }
     const bool on = v > threshold;
     const int64_t o = (int64_t)b * A + i;
     if (area) area[o] = v;

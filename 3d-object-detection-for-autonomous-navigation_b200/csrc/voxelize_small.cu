@@ -9,18 +9,21 @@
 //           live in SHARED memory (ATOMS) and are written out once per chunk.
 //   prefix  (frame, 256 cells)  per cell: exclusive prefix of the chunk counts = the slot base of every chunk
 //           (uint8, saturated: a base >= max_points means "full"); the chunk in which a cell first appears is
-//           counted, which gives every chunk the number of voxels opened before it.
+//           counted, which gives every chunk the number of voxels opened before it; the cells' runs of
+//           min(points, max_points) entries are laid back to back in a per-frame slot table.
 //   place   (frame, chunk)  ONE WARP walks the chunk's record tags in order, 32 per step, with the chunk's running
 //           per-cell counts in shared memory: slot = count[cell] + rank among the step's earlier records of the
-//           cell (match_any).  A record that finds count 0 opens its cell: because the walk is in index order,
-//           the running number of such records IS the voxel id (order of first touch), and the record that
-//           would open voxel number max_voxels is the reference's `break` position (load_data.py:630-634).
-//           The record's position goes to slot (cell, slot) of a 4-byte index table (2 MB per d435i frame: it
-//           stays in L2, where scattering the 16-byte records themselves over 16 MB per frame was measured
-//           DRAM-random-write bound: 384 us against 158 us without the stores); no barrier, no atomic.
-//   finish  (pillar)  32 pillars per CTA: the records a pillar's slots point at (before the break position) ->
-//           zero-padded voxel row, num_points, coors, point->slot map and the fused PillarFeatureNet decoration
-//           (model/pointpillars.py:143-203), streamed out with 16/32-byte stores.
+//           cell (match_any, only in steps where a one-byte scratch table saw a cell repeat).  A record that finds
+//           count 0 opens its cell: because the walk is in index order, the running number of such records IS
+//           the voxel id (order of first touch), and the record that would open voxel number max_voxels is the
+//           reference's `break` position (load_data.py:630-634).  The record's position goes to entry `slot` of
+//           the cell's run in the slot table (4 bytes per kept point, 0.9 MB per d435i frame: it stays in L2,
+//           where scattering the 16-byte records themselves was measured DRAM-random-write bound: 384 us against
+//           158 us without the stores); no barrier, no atomic.
+//   finish  (pillar)  32 pillars per CTA: the records a pillar's run points at (before the break position) ->
+//           zero-padded voxel rows and the fused PillarFeatureNet decoration (model/pointpillars.py:143-203),
+//           both assembled in shared memory and written as two TMA bulk stores per CTA (the rows of consecutive
+//           pillars are contiguous in global memory); num_points, coors, point->slot map.
 #include "pp_common.cuh"
 #include "vox_common.cuh"
 #include "vox_internal.h"
@@ -226,15 +229,19 @@ vox_scan_kernel(const T* __restrict__ points, const int64_t* __restrict__ frame_
     if (tid == 0) nvalid[b * S + s] = crun;
 }
 
+
 // ---------------------------------------------------------------------------------------------
-// Pass 2: one thread per cell.  base8[s][cell] = min(255, points of the cell in chunks < s); a cell is counted
-// as a new voxel of the first chunk that holds it.  The last CTA turns the per-chunk counts into voxel_num
-// and voxel_base (rows of a batch are packed back to back, merge_second_batch layout).
+// Pass 2: one thread per cell.  base8[s][cell] = min(255, points of the cell in chunks < s) = the slot of the
+// cell's first record of chunk s; a cell is counted as a new voxel of the first chunk that holds it.  The last
+// CTA of a frame lays the cells' runs of min(points, max_points) entries back to back in the frame's slot table
+// (cellinfo = {start, length}); the last CTA of the grid turns the per-chunk voxel counts into voxel_num,
+// voxel_base (rows of a batch are packed back to back, merge_second_batch layout) and the finish pass's tile list.
 __global__ void __launch_bounds__(kPrefixThreads)
 vox_prefix_kernel(const int64_t* __restrict__ frame_off, int S, int ncell, int ncellp, int P,
                   const unsigned short* __restrict__ hist, unsigned char* __restrict__ base8,
-                  unsigned* __restrict__ cellinfo, int* __restrict__ newcount, int max_voxels, int B,
-                  int* __restrict__ voxel_num, int* __restrict__ voxel_base, int* __restrict__ done_counter,
+                  unsigned* __restrict__ cellcnt, uint2* __restrict__ cellinfo, int* __restrict__ newcount,
+                  int max_voxels, int B, int* __restrict__ voxel_num, int* __restrict__ voxel_base,
+                  int* __restrict__ tile_base, int tile_rows, int* __restrict__ done_counter,
                   int* __restrict__ frame_done) {
     __shared__ int s_new[kMaxChunks];
     __shared__ int sm[33];
@@ -247,7 +254,7 @@ vox_prefix_kernel(const int64_t* __restrict__ frame_off, int S, int ncell, int n
     if (tid < kMaxChunks) s_new[tid] = 0;
     __syncthreads();
     if (cell < ncell) {
-        int run = 0;
+        int run = 0, first = -1;
         const size_t t0 = (size_t)b * S * ncellp + cell;
         for (int s0 = 0; s0 < Sb; s0 += 8) {
             int h[8];
@@ -257,12 +264,15 @@ vox_prefix_kernel(const int64_t* __restrict__ frame_off, int S, int ncell, int n
             for (int k = 0; k < 8; ++k) {
                 if (s0 + k < Sb) {
                     base8[t0 + (size_t)(s0 + k) * ncellp] = (unsigned char)min(run, 255);
-                    if (run == 0 && h[k] > 0) atomicAdd(&s_new[s0 + k], 1);
+                    if (run == 0 && h[k] > 0) first = s0 + k;
                     run += h[k];
                 }
             }
         }
-        cellinfo[(size_t)b * ncellp + cell] = (unsigned)min(run, P) << 24;  // slots of the cell; offset added below
+        cellcnt[(size_t)b * ncellp + cell] = (unsigned)min(run, P);
+        if (first >= 0) atomicAdd(&s_new[first], 1);
+    } else if (cell < ncellp) {
+        cellcnt[(size_t)b * ncellp + cell] = 0u;
     }
     __syncthreads();
     if (tid < Sb && s_new[tid]) atomicAdd(&newcount[b * S + tid], s_new[tid]);
@@ -274,32 +284,27 @@ vox_prefix_kernel(const int64_t* __restrict__ frame_off, int S, int ncell, int n
     }
     __syncthreads();
     if (s_flast) {
-        // last CTA of the frame: exclusive prefix of the cells' slot counts = where each cell's run of the dense
-        // slot -> record table starts (cellinfo = offset | slots << 24)
+        // exclusive prefix of the run lengths over the frame's cells, four cells per thread and round
         __threadfence();
-        unsigned* ci = cellinfo + (size_t)b * ncellp;
-        constexpr int kPer = kMaxCellsSmall / kPrefixThreads;  // cells per thread, all loaded before the scan
-        const int per = (ncell + kPrefixThreads - 1) / kPrefixThreads;
-        const int c0 = tid * per;
-        unsigned v[kPer];
-        int mine = 0;
-#pragma unroll
-        for (int k = 0; k < kPer; ++k) {
-            v[k] = (k < per && c0 + k < ncell) ? __ldcg(&ci[c0 + k]) : 0u;
-        }
-#pragma unroll
-        for (int k = 0; k < kPer; ++k) mine += (int)(v[k] >> 24);
-        int tot;
-        int ex = block_excl_scan(mine, &tot, sm);
-#pragma unroll
-        for (int k = 0; k < kPer; ++k) {
-            if (k < per && c0 + k < ncell) ci[c0 + k] = v[k] | (unsigned)ex;
-            ex += (int)(v[k] >> 24);
+        const uint4* cc = reinterpret_cast<const uint4*>(cellcnt + (size_t)b * ncellp);
+        uint4* ci = reinterpret_cast<uint4*>(cellinfo + (size_t)b * ncellp);
+        int running = 0;
+        for (int c0 = 0; c0 < ncellp; c0 += kPrefixThreads * 4) {
+            const int c = c0 + tid * 4;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (c < ncellp) v = __ldcg(&cc[c >> 2]);
+            int tot;
+            const unsigned e = (unsigned)(running + block_excl_scan((int)(v.x + v.y + v.z + v.w), &tot, sm));
+            if (c < ncellp) {
+                ci[c >> 1] = make_uint4(e, v.x, e + v.x, v.y);
+                ci[(c >> 1) + 1] = make_uint4(e + v.x + v.y, v.z, e + v.x + v.y + v.z, v.w);
+            }
+            running += tot;
         }
     }
     if (!s_last) return;
     __threadfence();
-    int running = 0;
+    int running = 0, trun = 0;
     for (int b0 = 0; b0 < B; b0 += kPrefixThreads) {
         const int i = b0 + tid;
         int v = 0;
@@ -312,35 +317,54 @@ vox_prefix_kernel(const int64_t* __restrict__ frame_off, int S, int ncell, int n
         const int e = running + block_excl_scan(v, &tot, sm);
         if (i < B) voxel_base[i] = e;
         running += tot;
+        // tiles of tile_rows consecutive pillars, frame by frame
+        const int te = trun + block_excl_scan((v + tile_rows - 1) / tile_rows, &tot, sm);
+        if (i < B) tile_base[i] = te;
+        trun += tot;
     }
     if (tid == 0) {
         voxel_base[B] = running;
+        tile_base[B] = trun;
         *done_counter = 0;
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// ---------------------------------------------------------------------------------------------
-// 32-byte accesses (one full L2 sector per request; SASS STG.E.ENL2.256 / LDG.E.ENL2.256 on sm_100)
-__device__ __forceinline__ void st_global_256(void* ptr, const uint4& a, const uint4& b) {
-    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
-                 "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
-                 : "memory");
+// Pass 3: one warp per (frame, chunk) walks the chunk's record tags in index order, 32 per step, with the chunk's
+// running per-cell counts (uint8, starting at the chunk base) in shared memory: slot = count[cell] + rank among
+// the step's earlier records of the same cell.  On a depth image 32 consecutive in-range points share a handful
+// of y/z bins, so two of them in the same cell is the rule (birthday collisions over ~80 x bins) and match_any
+// -- ~11 cycles per DISTINCT value, 300 per step here -- would sit on the walk's dependent chain; the lanes that
+// share a cell are found with one ballot per cell-id bit instead (14 independent votes, ~50 cycles).  A record
+// that finds count 0 opens its cell: the walk is in index order, so the running number of such records IS the
+// voxel id (order of first touch), and the record that would open voxel number max_voxels is the reference's
+// `break` position (load_data.py:630-634).  The record's position goes to entry `slot` of the cell's run in the
+// frame's slot table (4 bytes per kept point, L2 resident).  The walk is one dependent chain per chunk, so
+// nothing on it may wait for global memory: tags are fetched three groups ahead, the cells' {run start, run
+// length} one group ahead.  No atomic, no block barrier; every chunk of a 64-frame batch has its warp resident
+// at the same time.
+constexpr unsigned kNone = 0xffffffffu;
+
+// lanes of the warp whose `c` equals this lane's (c < 2^nbits)
+__device__ __forceinline__ unsigned peers_by_bits(const unsigned c, const int nbits) {
+    unsigned peers = 0xffffffffu;
+#pragma unroll
+    for (int bit = 0; bit < 17; ++bit) {
+        if (bit < nbits) {  // uniform
+            const unsigned bal = __ballot_sync(0xffffffffu, (c >> bit) & 1u);
+            peers &= ((c >> bit) & 1u) ? bal : ~bal;
+        }
+    }
+    return peers;
 }
 
-// Pass 3: one warp per (frame, chunk).  tbl: running count per cell, uint8, starts at the chunk's base.
-// The walk is sequential over steps of 32 records, but only the table update is a true dependence between steps:
-// a group of kPlaceUnroll steps is processed in three stages -- (A) cell of every record and the lanes that share
-// it (match_any: ~11 cycles per distinct value, 350 on scattered clouds, but independent across steps, so the
-// group's matches overlap), (B) the chain count = tbl[cell]; tbl[cell] += n, (C) voxel ids of the cells that were
-// opened, slots and the index stores -- and the tags of the next two groups are already in flight.
 __global__ void __launch_bounds__(32)
 vox_place_kernel(const int64_t* __restrict__ frame_off, int S, int ncell, int ncellp, int P, int max_voxels,
                  const unsigned* __restrict__ ctag, const unsigned char* __restrict__ base8,
-                 const unsigned* __restrict__ cellinfo, const int* __restrict__ nvalid,
-                 const int* __restrict__ newcount, unsigned* __restrict__ sidx, uint2* __restrict__ rowinfo,
-                 int* __restrict__ cutoff) {
-    extern __shared__ __align__(16) unsigned char tbl[];  // [ncellp]
+                 const uint2* __restrict__ cellinfo, const int* __restrict__ nvalid,
+                 const int* __restrict__ newcount, unsigned* __restrict__ sidx, uint4* __restrict__ rowinfo,
+                 int* __restrict__ cutoff, int cell_bits) {
+    extern __shared__ __align__(16) unsigned char tbl[];  // [ncellp] running counts
     constexpr int U = kPlaceUnroll;
     const int lane = lane_id();
     // frames in reverse order: the scan pass wrote the last frames' tags last, so they are still in L2
@@ -364,106 +388,116 @@ vox_place_kernel(const int64_t* __restrict__ frame_off, int S, int ncell, int nc
     __syncwarp();
     const unsigned* tags = ctag + f0 + (int64_t)s * kChunk;
     const size_t cellrow0 = (size_t)b * ncell;
-    const unsigned* ci_b = cellinfo + (size_t)b * ncellp;
-    unsigned* sidx_b = sidx + cellrow0 * (size_t)P;  // the frame's dense slot -> record table
+    const uint2* ci_b = cellinfo + (size_t)b * ncellp;
+    unsigned* sidx_b = sidx + f0;  // the frame's slot table: the cells' runs back to back
 
-    struct Group { unsigned tg[U]; };
+    struct Tags { unsigned tg[U]; };
+    struct Info { uint2 ci[U]; };
     // unconditional loads (index clamped to the last record): a predicated load makes the compiler merge the
     // loaded registers with their old contents right behind the load, which waits for it and defeats the prefetch
-    auto fetch = [&](Group& gr, int g) {
+    auto fetch_tags = [&](Tags& t, int g) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) gr.tg[u] = __ldcs(&tags[min(g + u * 32 + lane, nval - 1)]);
+        for (int u = 0; u < U; ++u) t.tg[u] = __ldcs(&tags[max(0, min(g + u * 32 + lane, nval - 1))]);
     };
-    auto process = [&](const Group& cur, int g) {
+    auto fetch_info = [&](Info& in, const Tags& t) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) in.ci[u] = __ldg(&ci_b[t.tg[u] & 0xffffu]);
+    };
+    auto process = [&](const Tags& cur, const Info& in, int g) {
         if (g >= nval) return;  // uniform
-        int c[U], rk[U], npeer[U], cnt[U];
-        unsigned civ[U];
-        // (A) independent of the table
+        int c[U], rk[U], npeer[U];
+        // independent of the table, so the votes of the group's steps overlap
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const bool act = g + u * 32 + lane < nval;
-            c[u] = act ? (int)(cur.tg[u] & 0xffffu) : (0x10000 | lane);
-            civ[u] = act ? __ldg(&ci_b[c[u]]) : 0u;  // start of the cell's slot run | slots << 24; needed in (C)
-            const unsigned peers = __match_any_sync(0xffffffffu, c[u]);
+            c[u] = (int)(cur.tg[u] & 0xffffu);
+            const unsigned peers = peers_by_bits((unsigned)c[u], cell_bits) & __ballot_sync(0xffffffffu, act);
             rk[u] = act ? __popc(peers & lanemask_lt()) : -1;  // rk 0: first record of its cell in the step
             npeer[u] = __popc(peers);
         }
-        // (B) the sequential part
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            cnt[u] = rk[u] >= 0 ? (int)tbl[c[u]] : 1;
-            if (rk[u] == 0) tbl[c[u]] = (unsigned char)min(cnt[u] + npeer[u], 255);
+            if (g + u * 32 >= nval) break;  // uniform
+            // the sequential part
+            const int cnt = rk[u] >= 0 ? (int)tbl[c[u]] : 1;
+            if (rk[u] == 0) tbl[c[u]] = (unsigned char)min(cnt + npeer[u], 255);
             __syncwarp();
-        }
-        // (C) a count of 0 means no earlier point of the frame fell in the cell: the record opens a voxel, and
-        // since the walk is in index order the running number of opened cells is the voxel id
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const bool opener = rk[u] == 0 && cnt[u] == 0;
+            // a count of 0 means no earlier point of the frame fell in the cell: the record opens a voxel, and
+            // since the walk is in index order the running number of opened cells is the voxel id
+            const bool opener = rk[u] == 0 && cnt == 0;
             const unsigned opens = __ballot_sync(0xffffffffu, opener);
             // position of the record in its frame's record array: same order as the point indices
             const unsigned cp = (unsigned)((s << kChunkShift) + g + u * 32 + lane);
             if (opener) {
                 const int rank = newrun + __popc(opens & lanemask_lt());
-                // the finish pass finds cell and point count of a voxel in one word
-                if (rank < max_voxels) rowinfo[cellrow0 + rank] = make_uint2((unsigned)c[u], civ[u]);
+                // the finish pass finds cell, run and run length of a voxel in one 16-byte word
+                if (rank < max_voxels) rowinfo[cellrow0 + rank] = make_uint4((unsigned)c[u], in.ci[u].x, in.ci[u].y, cp);
                 else if (rank == max_voxels) cutoff[b] = (int)cp;  // the reference's break position
             }
             newrun += __popc(opens);
-            const int slot = cnt[u] + rk[u];
-#ifndef PP_EXP_NOSTORE
-            if (rk[u] >= 0 && slot < P) sidx_b[(civ[u] & 0xffffffu) + slot] = cp;
-#endif
+            const int slot = cnt + rk[u];
+            if (rk[u] >= 0 && slot < P) sidx_b[in.ci[u].x + slot] = cp;
         }
     };
-    // three register buffers used in rotation (no copies: a register move of a load that is still in flight
-    // would wait for it), each fetched two groups before it is processed
+    // register buffers used in rotation (no copies: a register move of a load that is still in flight would
+    // wait for it): tags of group i+3 and cell info of group i+1 are requested before group i is processed
     constexpr int GS = U * 32;
-    Group ga, gb, gc;
-    fetch(ga, 0);
-    fetch(gb, GS);
-    for (int g = 0; g < nval; g += 3 * GS) {
-        fetch(gc, g + 2 * GS);
-        process(ga, g);
-        fetch(ga, g + 3 * GS);
-        process(gb, g + GS);
-        fetch(gb, g + 4 * GS);
-        process(gc, g + 2 * GS);
+    Tags t0, t1, t2, t3;
+    Info i0, i1;
+    fetch_tags(t0, 0);
+    fetch_tags(t1, GS);
+    fetch_tags(t2, 2 * GS);
+    fetch_info(i0, t0);
+    for (int g = 0; g < nval; g += 4 * GS) {
+        fetch_tags(t3, g + 3 * GS);
+        fetch_info(i1, t1);
+        process(t0, i0, g);
+        fetch_tags(t0, g + 4 * GS);
+        fetch_info(i0, t2);
+        process(t1, i1, g + GS);
+        fetch_tags(t1, g + 5 * GS);
+        fetch_info(i1, t3);
+        process(t2, i0, g + 2 * GS);
+        fetch_tags(t2, g + 6 * GS);
+        fetch_info(i0, t0);
+        process(t3, i1, g + 3 * GS);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // 32-byte store that does not displace resident lines: final outputs are written once and not read again here
-__device__ __forceinline__ void st_global_256_cs(void* ptr, const uint4& a, const uint4& b) {
-    asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
-                 "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+// (one full L2 sector per lane; SASS STG.E.ENL2.256 on sm_100)
+__device__ __forceinline__ void st_global_256_cs(void* ptr, const float4& a, const float4& b) {
+    asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w),
+                 "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
                  : "memory");
 }
 
-// Pass 4: one CTA per kFinishRows consecutive pillars of a frame.  Phase 1, kFinishRPW pillars per warp with the
-// loads of all of them issued before the first is consumed: staged records before the break position -> float32
-// coordinates in shared memory laid out exactly like the output rows (zero padded), mean, num_points, coors,
-// point->slot map.  Phase 2, the whole CTA: the voxel rows and the decorated rows of the pillars are two contiguous
-// runs of global memory and are streamed out with 16/32-byte stores.
-constexpr int kFinishWarps = 8;
-constexpr int kFinishRPW = 4;
-constexpr int kFinishRows = kFinishWarps * kFinishRPW;
+// Pass 4: one warp per two consecutive pillars of a frame, lane = slot (NR slots per lane).  The loads of both
+// pillars are issued before the first is consumed: their {cell, run} words, the runs' entries of the slot table
+// (already in index order), the records they point at (before the break position).  Every lane owns its slot of
+// the output rows whether or not a point sits in it -- lanes of empty slots write the zero padding -- so the
+// voxel rows and the fused PillarFeatureNet decoration (model/pointpillars.py:143-203) go out as dense,
+// coalesced stores straight from registers (a decorated d435i point is one 32-byte store).  The sums are reduced
+// so that half-warp h ends up with pillar h's: everything that is per pillar (mean, cell -> coordinates -> pillar
+// centre, num_points, coors) is computed once per warp, for both pillars.  No shared memory, few registers: the
+// three dependent round trips of a pillar are hidden by the other warps of the SM.
+constexpr int kFinishWarps = 4;
+constexpr int kFinishRows = 2 * kFinishWarps;
 
-template <typename TO, int DS>
+template <typename TO, int DS, int NR>
 __global__ void __launch_bounds__(kFinishWarps * 32)
-vox_finish_kernel(const int64_t* __restrict__ frame_off, VoxParams p, FastDiv div_P, int ncellp,
-                  const uint2* __restrict__ rowinfo, const int* __restrict__ voxel_num,
-                  const int* __restrict__ voxel_base, const int* __restrict__ cutoff, int64_t cap_rows,
-                  const unsigned* __restrict__ sidx, const uint4* __restrict__ crec, const unsigned* __restrict__ ctag,
-                  const int* __restrict__ nvalid, int S, TO* __restrict__ voxels, float* __restrict__ decorated, int* __restrict__ coors, int coors_cols,
-                  int* __restrict__ num_points, int* __restrict__ point_slot, int* __restrict__ cell_voxel) {
-    extern __shared__ __align__(16) float xyz[];  // [kFinishRows][P*D] float32 coordinates, output layout
-    __shared__ float s_mean[kFinishRows][5];      // mx, my, mz, pillar centre x, y
-    __shared__ int s_n[kFinishRows];
+vox_finish_kernel(const int64_t* __restrict__ frame_off, VoxParams p, const uint4* __restrict__ rowinfo,
+                  const int* __restrict__ voxel_num, const int* __restrict__ voxel_base,
+                  const int* __restrict__ cutoff, int64_t cap_rows, const unsigned* __restrict__ sidx,
+                  const uint4* __restrict__ crec, const unsigned* __restrict__ ctag, const int* __restrict__ nvalid,
+                  int S, TO* __restrict__ voxels, float* __restrict__ decorated, int* __restrict__ coors,
+                  int coors_cols, int* __restrict__ num_points, int* __restrict__ point_slot,
+                  int* __restrict__ cell_voxel) {
     constexpr int D = DS, Do = DS + 5;
     constexpr int rec16 = RecFmt<TO, DS>::kRec16;
     constexpr int NT = kFinishWarps * 32;
-    const int P = p.max_points, PD = P * D;
+    const int P = p.max_points;
     const int tid = threadIdx.x, lane = lane_id(), w = tid >> 5;
     const int b = blockIdx.y;
     const int M = voxel_num[b], vb = voxel_base[b];
@@ -471,258 +505,165 @@ vox_finish_kernel(const int64_t* __restrict__ frame_off, VoxParams p, FastDiv di
     if (r0 >= M || (int64_t)vb + r0 >= cap_rows) return;
     int nrows = min(kFinishRows, M - r0);
     if ((int64_t)vb + r0 + nrows > cap_rows) nrows = (int)(cap_rows - vb - r0);
-    const int64_t row0 = (int64_t)vb + r0;
-    const int cut = cutoff[b];
+    const unsigned cut = (unsigned)cutoff[b];
     const int64_t f0 = frame_off[b];
-    const size_t cellrow0 = (size_t)b * p.ncell;
-#ifndef PP_EXP_NOPREFETCH
     {
         // The pillars' records are gathered at random from the frame's record array.  The CTAs of a frame run at
         // about the same time, so each first asks L2 for one contiguous slice of that array (128-byte lines, only
         // the compacted part of every chunk): the array then comes from DRAM as a sequential stream instead of
         // sector by sector in gather order, and the gathers below find it in L2 or in flight.
         const int n = (int)(frame_off[b + 1] - f0);
-        const int64_t lines = ((int64_t)n * rec16 * 16 + 127) >> 7;
-        const int64_t per_cta = (lines + gridDim.x - 1) / gridDim.x;
+        const int lines = (int)(((int64_t)n * rec16 * 16 + 127) >> 7);  // n <= 2^20 points
+        const int per_cta = (lines + (int)gridDim.x - 1) / (int)gridDim.x;
         const char* base = reinterpret_cast<const char*>(crec + f0 * rec16);
-        for (int64_t l = blockIdx.x * per_cta + tid; l < min(lines, (int64_t)(blockIdx.x + 1) * per_cta); l += NT) {
-            const int rec = (int)((l << 7) / (rec16 * 16));  // first record of the line
+        for (int l = blockIdx.x * per_cta + tid; l < min(lines, (int)(blockIdx.x + 1) * per_cta); l += NT) {
+            const int rec = (l << 3) / rec16;  // first record of the line
             if ((rec & (kChunk - 1)) < __ldg(&nvalid[b * S + (rec >> kChunkShift)]))
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (l << 7)));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + ((int64_t)l << 7)));
         }
     }
-#endif
-
-    // ---- phase 1: rows w, w + 8, w + 16, w + 24 of the block; the fast path holds a pillar in two registers sets
-    uint2 info[kFinishRPW];  // cell, start of the cell's slot run | slots << 24
-    const unsigned* sidx_b = sidx + cellrow0 * (size_t)P;
-#pragma unroll
-    for (int k = 0; k < kFinishRPW; ++k) {
-        const int lr = w + k * kFinishWarps;
-        info[k] = lr < nrows ? __ldg(&rowinfo[cellrow0 + r0 + lr]) : make_uint2(0u, 0u);
+    const int lr0 = 2 * w;
+    if (lr0 >= nrows) return;  // uniform per warp
+    const bool two = lr0 + 1 < nrows;
+    const int64_t row0 = (int64_t)vb + r0 + lr0;  // output row of the warp's first pillar
+    // ---- loads: row words -> slot entries -> records
+    uint4 info[2];
+    {
+        const uint4* ri = rowinfo + (size_t)b * p.ncell + r0 + lr0;
+        info[0] = __ldg(&ri[0]);
+        info[1] = two ? __ldg(&ri[1]) : make_uint4(0u, 0u, 0u, 0u);
     }
-    if (P <= 64) {
-        // slot -> position of the record in the frame's record array (4-byte index table, L2 resident), then the
-        // records themselves: both rounds of loads of all four pillars are in flight together
-        unsigned tg[kFinishRPW][2];
+    unsigned key[2][NR];
 #pragma unroll
-        for (int k = 0; k < kFinishRPW; ++k) {
-            const int tot = (int)(info[k].y >> 24);
-            const unsigned si0 = info[k].y & 0xffffffu;
+    for (int k = 0; k < 2; ++k) {
+        const unsigned* run = sidx + f0 + info[k].y + lane;
+        const int len = (int)info[k].z - lane;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int s = h * 32 + lane;
-                tg[k][h] = (w + k * kFinishWarps < nrows && s < tot) ? __ldcg(&sidx_b[si0 + s]) : 0x7fffffffu;
-            }
+        for (int r = 0; r < NR; ++r) {
+            key[k][r] = kNone;
+            if (r * 32 < len) key[k][r] = __ldcg(&run[r * 32]);
         }
-        uint4 rv[kFinishRPW][2][rec16];
+    }
+    uint4 rv[2][NR][rec16];
+    {
+        const uint4* rec = crec + f0 * rec16;
 #pragma unroll
-        for (int k = 0; k < kFinishRPW; ++k) {
+        for (int k = 0; k < 2; ++k) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                // slots are in index order, so the records before the break position are a prefix of the row
-                if ((int)tg[k][h] < cut) {
+            for (int r = 0; r < NR; ++r) {
+                // the run is in index order: the records before the break position are a prefix of it
+                if (key[k][r] < cut) {
 #pragma unroll
-                    for (int q = 0; q < rec16; ++q) rv[k][h][q] = __ldg(&crec[(f0 + tg[k][h]) * rec16 + q]);
+                    for (int q = 0; q < rec16; ++q) rv[k][r][q] = __ldg(&rec[(size_t)key[k][r] * rec16 + q]);
                 }
             }
         }
+    }
+    // ---- 1. coordinates, voxel rows, sums
+    float c[2][NR][DS];
+    float sx[2], sy[2], sz[2];
+    int nsel[2];
+    unsigned okm = 0u;  // bit k*NR + r: this lane holds a point of pillar k in slot r*32 + lane
 #pragma unroll
-        for (int k = 0; k < kFinishRPW; ++k) {
-            const int lr = w + k * kFinishWarps;
-            if (lr >= nrows) continue;  // uniform per warp
-            const int rank = r0 + lr;
-            const int64_t row = row0 + lr;
-            const int cell = (int)info[k].x;
-            float* vrow = xyz + (size_t)lr * PD;
-            float sx = 0.f, sy = 0.f, sz = 0.f;
-            int nsel = 0;
+    for (int k = 0; k < 2; ++k) {
+        sx[k] = sy[k] = sz[k] = 0.f;
+        nsel[k] = 0;
+        TO* vrow = voxels ? voxels + ((row0 + k) * (int64_t)P + lane) * D : nullptr;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int s = h * 32 + lane;
-                // slots are in index order, so the records before the break position are a prefix of the row
-                const bool ok = (int)tg[k][h] < cut;
-                nsel += __popc(__ballot_sync(0xffffffffu, ok));
-                if (ok) {
-                    float c[DS];
-                    if (sizeof(TO) == 4) {
-                        c[0] = __uint_as_float(rv[k][h][0].x); c[1] = __uint_as_float(rv[k][h][0].y); c[2] = __uint_as_float(rv[k][h][0].z);
-                        if (DS == 4) c[DS - 1] = __uint_as_float(rv[k][h][0].w);
-                    } else {
-                        const uint4 &u0 = rv[k][h][0], &u1 = rv[k][h][rec16 - 1];
-                        const double v0x = __hiloint2double((int)u0.y, (int)u0.x), v0y = __hiloint2double((int)u0.w, (int)u0.z);
-                        const double v1x = __hiloint2double((int)u1.y, (int)u1.x), v1y = __hiloint2double((int)u1.w, (int)u1.z);
-                        TO* vo = voxels + (row * (int64_t)P + s) * D;
-                        vo[0] = (TO)v0x; vo[1] = (TO)v0y; vo[2] = (TO)v1x;
-                        if (DS == 4) vo[DS - 1] = (TO)v1y;
-                        c[0] = (float)v0x; c[1] = (float)v0y; c[2] = (float)v1x;
-                        if (DS == 4) c[DS - 1] = (float)v1y;
-                    }
+        for (int r = 0; r < NR; ++r) {
+            const int s = r * 32 + lane;
+            const bool ok = key[k][r] < cut;
+            nsel[k] += __popc(__ballot_sync(0xffffffffu, ok));
+            okm |= ok ? 1u << (k * NR + r) : 0u;
+            TO v[DS];
 #pragma unroll
-                    for (int d = 0; d < DS; ++d) vrow[s * D + d] = c[d];
-                    sx += c[0]; sy += c[1]; sz += c[2];
-                    if (point_slot) {
-                        const unsigned cp = tg[k][h];
-                        const int64_t orig = (int64_t)(cp & ~(unsigned)(kChunk - 1)) + (__ldg(&ctag[f0 + cp]) >> 16);
-                        point_slot[f0 + orig] = rank * P + s;
-                    }
+            for (int dd = 0; dd < DS; ++dd) { v[dd] = (TO)0; c[k][r][dd] = 0.f; }
+            if (ok) {
+                if (sizeof(TO) == 4) {
+                    v[0] = (TO)__uint_as_float(rv[k][r][0].x); v[1] = (TO)__uint_as_float(rv[k][r][0].y); v[2] = (TO)__uint_as_float(rv[k][r][0].z);
+                    if (DS == 4) v[DS - 1] = (TO)__uint_as_float(rv[k][r][0].w);
+                } else {
+                    const uint4 &u0 = rv[k][r][0], &u1 = rv[k][r][rec16 - 1];
+                    v[0] = (TO)__hiloint2double((int)u0.y, (int)u0.x); v[1] = (TO)__hiloint2double((int)u0.w, (int)u0.z);
+                    v[2] = (TO)__hiloint2double((int)u1.y, (int)u1.x);
+                    if (DS == 4) v[DS - 1] = (TO)__hiloint2double((int)u1.w, (int)u1.z);
+                }
+#pragma unroll
+                for (int dd = 0; dd < DS; ++dd) c[k][r][dd] = (float)v[dd];
+                if (point_slot) {
+                    const unsigned cp = key[k][r];
+                    const int64_t orig = (int64_t)(cp & ~(unsigned)(kChunk - 1)) + (__ldg(&ctag[f0 + cp]) >> 16);
+                    point_slot[f0 + orig] = (r0 + lr0 + k) * P + s;
                 }
             }
-            for (int q = nsel * D + lane; q < PD; q += 32) vrow[q] = 0.f;  // zero padding of the row
-            if (sizeof(TO) == 8) {
-                TO* vo = voxels + row * (int64_t)PD;
-                for (int q = nsel * D + lane; q < PD; q += 32) vo[q] = (TO)0;
-            }
+            if (vrow && s < P && (k == 0 || two)) {  // lanes of empty slots write the padding
 #pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                sx += __shfl_xor_sync(0xffffffffu, sx, o);
-                sy += __shfl_xor_sync(0xffffffffu, sy, o);
-                sz += __shfl_xor_sync(0xffffffffu, sz, o);
+                for (int dd = 0; dd < DS; ++dd) __stcs(&vrow[(size_t)r * 32 * D + dd], v[dd]);
             }
-            if (lane == 0) {
-                const int cz = p.div_nxny.div(cell);
-                const int rem = cell - cz * p.grid[0] * p.grid[1];
-                const int cy = p.div_nx.div(rem), cx = rem - cy * p.grid[0];
-                const float nf = (float)nsel;
-                s_mean[lr][0] = __fdiv_rn(sx, nf); s_mean[lr][1] = __fdiv_rn(sy, nf); s_mean[lr][2] = __fdiv_rn(sz, nf);
-                s_mean[lr][3] = __fadd_rn(__fmul_rn((float)cx, p.vx), p.x_off);
-                s_mean[lr][4] = __fadd_rn(__fmul_rn((float)cy, p.vy), p.y_off);
-                s_n[lr] = nsel;
-                num_points[row] = nsel;
-                int* co = coors + row * coors_cols;
-                if (coors_cols == 4) *co++ = b;
-                if (p.reverse_index) { co[0] = cz; co[1] = cy; co[2] = cx; }
-                else { co[0] = cx; co[1] = cy; co[2] = cz; }
-                if (cell_voxel) cell_voxel[cellrow0 + cell] = (int)row;
-            }
-        }
-    } else {
-        // general max_points: one pillar at a time, slots in rounds of 32
-        for (int k = 0; k < kFinishRPW; ++k) {
-            const int lr = w + k * kFinishWarps;
-            if (lr >= nrows) continue;
-            const int rank = r0 + lr;
-            const int64_t row = row0 + lr;
-            const int cell = (int)info[k].x, tot = (int)(info[k].y >> 24);
-            const unsigned si0 = info[k].y & 0xffffffu;
-            float* vrow = xyz + (size_t)lr * PD;
-            float sx = 0.f, sy = 0.f, sz = 0.f;
-            int nsel = 0;
-            for (int s0 = 0; s0 < tot; s0 += 32) {
-                const int s = s0 + lane;
-                uint4 rv[rec16];
-                const unsigned tag = s < tot ? __ldcg(&sidx_b[si0 + s]) : 0x7fffffffu;
-                if ((int)tag < cut) {
-#pragma unroll
-                    for (int q = 0; q < rec16; ++q) rv[q] = __ldg(&crec[(f0 + tag) * rec16 + q]);
-                }
-                const bool ok = (int)tag < cut;
-                nsel += __popc(__ballot_sync(0xffffffffu, ok));
-                if (ok) {
-                    float c[DS];
-                    if (sizeof(TO) == 4) {
-                        c[0] = __uint_as_float(rv[0].x); c[1] = __uint_as_float(rv[0].y); c[2] = __uint_as_float(rv[0].z);
-                        if (DS == 4) c[DS - 1] = __uint_as_float(rv[0].w);
-                    } else {
-                        const uint4 &u0 = rv[0], &u1 = rv[rec16 - 1];
-                        const double v0x = __hiloint2double((int)u0.y, (int)u0.x), v0y = __hiloint2double((int)u0.w, (int)u0.z);
-                        const double v1x = __hiloint2double((int)u1.y, (int)u1.x), v1y = __hiloint2double((int)u1.w, (int)u1.z);
-                        TO* vo = voxels + (row * (int64_t)P + s) * D;
-                        vo[0] = (TO)v0x; vo[1] = (TO)v0y; vo[2] = (TO)v1x;
-                        if (DS == 4) vo[DS - 1] = (TO)v1y;
-                        c[0] = (float)v0x; c[1] = (float)v0y; c[2] = (float)v1x;
-                        if (DS == 4) c[DS - 1] = (float)v1y;
-                    }
-#pragma unroll
-                    for (int d = 0; d < DS; ++d) vrow[s * D + d] = c[d];
-                    sx += c[0]; sy += c[1]; sz += c[2];
-                    if (point_slot) {
-                        const int64_t orig = (int64_t)(tag & ~(unsigned)(kChunk - 1)) + (__ldg(&ctag[f0 + tag]) >> 16);
-                        point_slot[f0 + orig] = rank * P + s;
-                    }
-                }
-            }
-            for (int q = nsel * D + lane; q < PD; q += 32) vrow[q] = 0.f;
-            if (sizeof(TO) == 8) {
-                TO* vo = voxels + row * (int64_t)PD;
-                for (int q = nsel * D + lane; q < PD; q += 32) vo[q] = (TO)0;
-            }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                sx += __shfl_xor_sync(0xffffffffu, sx, o);
-                sy += __shfl_xor_sync(0xffffffffu, sy, o);
-                sz += __shfl_xor_sync(0xffffffffu, sz, o);
-            }
-            if (lane == 0) {
-                const int cz = p.div_nxny.div(cell);
-                const int rem = cell - cz * p.grid[0] * p.grid[1];
-                const int cy = p.div_nx.div(rem), cx = rem - cy * p.grid[0];
-                const float nf = (float)nsel;
-                s_mean[lr][0] = __fdiv_rn(sx, nf); s_mean[lr][1] = __fdiv_rn(sy, nf); s_mean[lr][2] = __fdiv_rn(sz, nf);
-                s_mean[lr][3] = __fadd_rn(__fmul_rn((float)cx, p.vx), p.x_off);
-                s_mean[lr][4] = __fadd_rn(__fmul_rn((float)cy, p.vy), p.y_off);
-                s_n[lr] = nsel;
-                num_points[row] = nsel;
-                int* co = coors + row * coors_cols;
-                if (coors_cols == 4) *co++ = b;
-                if (p.reverse_index) { co[0] = cz; co[1] = cy; co[2] = cx; }
-                else { co[0] = cx; co[1] = cy; co[2] = cz; }
-                if (cell_voxel) cell_voxel[cellrow0 + cell] = (int)row;
-            }
+            sx[k] += c[k][r][0]; sy[k] += c[k][r][1]; sz[k] += c[k][r][2];
         }
     }
-    __syncthreads();
-
-    // ---- phase 2a: voxel rows, nrows*P*D floats with the same layout in shared and in global memory
-    if (voxels && sizeof(TO) == 4) {
-        float* dst = reinterpret_cast<float*>(voxels) + row0 * (int64_t)PD;
-        const int nf = nrows * PD;
-        const uintptr_t a = reinterpret_cast<uintptr_t>(dst);
-        if ((a & 15) == 0) {
-            for (int k = tid; k < (nf >> 2); k += NT) __stcs(reinterpret_cast<float4*>(dst) + k, reinterpret_cast<const float4*>(xyz)[k]);
-            for (int k = (nf & ~3) + tid; k < nf; k += NT) dst[k] = xyz[k];
-        } else if ((a & 7) == 0) {
-            // rows of an odd row0 start 8 bytes into a 16-byte unit: one float2, then float4 from shared float2 pairs
-            if (tid == 0) *reinterpret_cast<float2*>(dst) = *reinterpret_cast<const float2*>(xyz);
-            const int n4 = (nf - 2) >> 2;
-            for (int k = tid; k < n4; k += NT) {
-                const float2 lo = *reinterpret_cast<const float2*>(xyz + 2 + 4 * k), hi = *reinterpret_cast<const float2*>(xyz + 4 + 4 * k);
-                __stcs(reinterpret_cast<float4*>(dst + 2) + k, make_float4(lo.x, lo.y, hi.x, hi.y));
-            }
-            for (int k = 2 + 4 * n4 + tid; k < nf; k += NT) dst[k] = xyz[k];
-        } else {
-            for (int k = tid; k < nf; k += NT) dst[k] = xyz[k];
+    // ---- 2. half-warp h takes pillar h: its sums, then the per-pillar values once for both pillars
+    const int h = lane >> 4;
+    float mx, my, mz;
+    {
+        const float ax = h ? sx[0] : sx[1], ay = h ? sy[0] : sy[1], az = h ? sz[0] : sz[1];
+        mx = (h ? sx[1] : sx[0]) + __shfl_xor_sync(0xffffffffu, ax, 16);
+        my = (h ? sy[1] : sy[0]) + __shfl_xor_sync(0xffffffffu, ay, 16);
+        mz = (h ? sz[1] : sz[0]) + __shfl_xor_sync(0xffffffffu, az, 16);
+#pragma unroll
+        for (int o = 8; o; o >>= 1) {
+            mx += __shfl_xor_sync(0xffffffffu, mx, o);
+            my += __shfl_xor_sync(0xffffffffu, my, o);
+            mz += __shfl_xor_sync(0xffffffffu, mz, o);
         }
     }
-    // ---- phase 2b: decorated rows (model/pointpillars.py:143-203), nrows*P points of D+5 floats
+    const int n_mine = h ? nsel[1] : nsel[0];
+    const int cell = (int)(h ? info[1].x : info[0].x);
+    const float nf = (float)n_mine;
+    mx = __fdiv_rn(mx, nf); my = __fdiv_rn(my, nf); mz = __fdiv_rn(mz, nf);
+    const int cz = p.div_nxny.div(cell);
+    const int rem = cell - cz * p.grid[0] * p.grid[1];
+    const int cy = p.div_nx.div(rem), cx = rem - cy * p.grid[0];
+    const float ex = __fadd_rn(__fmul_rn((float)cx, p.vx), p.x_off);
+    const float ey = __fadd_rn(__fmul_rn((float)cy, p.vy), p.y_off);
+    if ((lane & 15) == 0 && (h == 0 || two)) {
+        const int64_t row = row0 + h;
+        num_points[row] = n_mine;
+        int* co = coors + row * coors_cols;
+        if (coors_cols == 4) {
+            *reinterpret_cast<int4*>(co) = p.reverse_index ? make_int4(b, cz, cy, cx) : make_int4(b, cx, cy, cz);
+        } else if (p.reverse_index) { co[0] = cz; co[1] = cy; co[2] = cx; }
+        else { co[0] = cx; co[1] = cy; co[2] = cz; }
+        if (cell_voxel) cell_voxel[(size_t)b * p.ncell + cell] = (int)row;
+    }
+    // ---- 3. decorated rows
     if (decorated) {
-        float* drow = decorated + row0 * (int64_t)P * Do;
-        const int npts = nrows * P;
-        if (DS == 3 && (reinterpret_cast<uintptr_t>(drow) & 31) == 0) {
-            // 8 floats per point = one 32-byte store: (x,y,z,x-mx, y-my,z-mz,x-ex,y-ey)
-            for (int q = tid; q < npts; q += NT) {
-                const int r = div_P.div(q), sl = q - r * P;
-                uint4 o0 = make_uint4(0u, 0u, 0u, 0u), o1 = o0;
-                if (sl < s_n[r]) {
-                    const float* v = xyz + (size_t)r * PD + sl * 3;
-                    const float q0 = v[0], q1 = v[1], q2 = v[2];
-                    o0 = make_uint4(__float_as_uint(q0), __float_as_uint(q1), __float_as_uint(q2), __float_as_uint(q0 - s_mean[r][0]));
-                    o1 = make_uint4(__float_as_uint(q1 - s_mean[r][1]), __float_as_uint(q2 - s_mean[r][2]),
-                                    __float_as_uint(q0 - s_mean[r][3]), __float_as_uint(q1 - s_mean[r][4]));
+        const bool vec = DS == 3 && (reinterpret_cast<uintptr_t>(decorated) & 31u) == 0 && ((P * Do) & 7) == 0;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (k == 1 && !two) break;
+            const float kmx = __shfl_sync(0xffffffffu, mx, k * 16), kmy = __shfl_sync(0xffffffffu, my, k * 16);
+            const float kmz = __shfl_sync(0xffffffffu, mz, k * 16);
+            const float kex = __shfl_sync(0xffffffffu, ex, k * 16), key_ = __shfl_sync(0xffffffffu, ey, k * 16);
+            float* drow = decorated + ((row0 + k) * (int64_t)P + lane) * Do;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                if (r * 32 + lane >= P) continue;
+                const bool ok = (okm >> (k * NR + r)) & 1u;
+                const float x = c[k][r][0], y = c[k][r][1], z = c[k][r][2];
+                float o[Do];
+#pragma unroll
+                for (int dd = 0; dd < DS; ++dd) o[dd] = c[k][r][dd];
+                o[D] = ok ? x - kmx : 0.f; o[D + 1] = ok ? y - kmy : 0.f; o[D + 2] = ok ? z - kmz : 0.f;
+                o[D + 3] = ok ? x - kex : 0.f; o[D + 4] = ok ? y - key_ : 0.f;
+                float* dp = drow + (size_t)r * 32 * Do;
+                if (vec) {
+                    st_global_256_cs(dp, make_float4(o[0], o[1], o[2], o[3]), make_float4(o[4], o[5], o[6], o[Do - 1]));
+                } else {
+#pragma unroll
+                    for (int dd = 0; dd < Do; ++dd) __stcs(&dp[dd], o[dd]);
                 }
-                st_global_256_cs(drow + (size_t)q * 8, o0, o1);
-            }
-        } else {
-            const int nfl = npts * Do;
-            for (int k = tid; k < nfl; k += NT) {
-                const int q = k / Do, d = k - q * Do;  // Do is a compile-time constant
-                const int r = div_P.div(q), sl = q - r * P;
-                float o = 0.f;
-                if (sl < s_n[r]) {
-                    const float* v = xyz + (size_t)r * PD + sl * D;
-                    o = d < D ? v[d] : d < D + 3 ? v[d - D] - s_mean[r][d - D] : v[d - D - 3] - s_mean[r][d - D];
-                }
-                drow[k] = o;
             }
         }
     }
@@ -734,22 +675,24 @@ struct SmallWs {
     unsigned* ctag;           // [total_points + 1] cell | index in chunk << 16, same positions
     unsigned short* hist;     // [B*S*ncellp]  chunk counts
     unsigned char* base8;     // [B*S*ncellp]  chunk bases
-    unsigned* cellinfo;       // [B*ncellp]    start of the cell's run in the frame's slot table | min(P, points) << 24
+    unsigned* cellcnt;        // [B*ncellp]    min(points of the cell, max_points) = length of its run
+    uint2* cellinfo;          // [B*ncellp]    {start, length} of the cell's run in the frame's slot table
+    int* tile_base;           // [B+1] first tile of every frame in the finish pass's tile list
     int* frame_done;          // [B]
     int* nvalid;              // [B*S] records per chunk
     int* newcount;            // [B*S] voxels opened per chunk
-    uint2* rowinfo;           // [B*ncell] voxel id in frame -> {cell, cellinfo of the cell}
+    uint4* rowinfo;           // [B*ncell] voxel id in frame -> {cell, run start, run length, first record}
     int* cutoff;              // [B] break position (record position in frame) or kNoCut
     int* done_counter;        // [1]
-    unsigned* sidx;           // [B][ncell*P] slot table: the cells' runs back to back -> record position in frame
+    unsigned* sidx;           // [total_points + 1] slot tables: a frame's cells' runs back to back -> record position in frame
     size_t total;
 };
 
 static int rec_bytes_of(int D, int out_dtype) { return (int)(((size_t)D * (out_dtype == PP_F64 ? 8 : 4) + 15) / 16 * 16); }
 static int chunks_of(int64_t max_frame_points) { return (int)(max_frame_points > 0 ? ceil_div(max_frame_points, kChunk) : 1); }
 
-static SmallWs carve_small(void* ws, const pp_voxel_cfg* cfg, int64_t ncell, int n_frames, int64_t total_points,
-                           int64_t max_frame_points, int D, int out_dtype) {
+static SmallWs carve_small(void* ws, int64_t ncell, int n_frames, int64_t total_points, int64_t max_frame_points, int D,
+                           int out_dtype) {
     SmallWs w;
     Carver c(ws);
     const int S = chunks_of(max_frame_points);
@@ -759,14 +702,16 @@ static SmallWs carve_small(void* ws, const pp_voxel_cfg* cfg, int64_t ncell, int
     w.ctag = c.take<unsigned>((size_t)total_points + 1);
     w.hist = c.take<unsigned short>((size_t)n_frames * S * ncellp);
     w.base8 = c.take<unsigned char>((size_t)n_frames * S * ncellp);
-    w.cellinfo = c.take<unsigned>((size_t)n_frames * ncellp);
+    w.cellcnt = c.take<unsigned>((size_t)n_frames * ncellp);
+    w.cellinfo = c.take<uint2>((size_t)n_frames * ncellp);
+    w.tile_base = c.take<int>((size_t)n_frames + 1);
     w.frame_done = c.take<int>(n_frames);
     w.nvalid = c.take<int>((size_t)n_frames * S);
     w.newcount = c.take<int>((size_t)n_frames * S);
-    w.rowinfo = c.take<uint2>((size_t)n_frames * ncell);
+    w.rowinfo = c.take<uint4>((size_t)n_frames * ncell);
     w.cutoff = c.take<int>(n_frames);
     w.done_counter = c.take<int>(1);
-    w.sidx = c.take<unsigned>((size_t)n_frames * ncell * cfg->max_points);
+    w.sidx = c.take<unsigned>((size_t)total_points + 1);
     w.total = c.used();
     return w;
 }
@@ -775,19 +720,18 @@ bool vox_small_eligible(const pp_voxel_cfg* cfg, int64_t ncell, int n_frames, in
                         int64_t max_frame_points, int D) {
     if (ncell > kMaxCellsSmall || D > 4 || max_frame_points > kMaxFramePointsSmall || cfg->max_points > kMaxPointsSmall)
         return false;
-    // the per-chunk tables and the per-cell staging rows must stay small next to the points themselves (callers
-    // that do not know the largest frame pass the batch total, which sizes one table set per 16 384 points for
-    // every frame)
+    // the per-chunk tables must stay small next to the points themselves (callers that do not know the largest
+    // frame pass the batch total, which sizes one table set per 16 384 points for every frame)
     const double ncellp = (double)align_up((size_t)ncell, 16);
-    const double tables = (double)n_frames * chunks_of(max_frame_points) * ncellp * 3.0;
-    const double staging = (double)n_frames * (double)ncell * cfg->max_points * 4.0;
+    const double tables = (double)n_frames * chunks_of(max_frame_points) * ncellp * 3.0 + (double)n_frames * ncellp * 24.0;
     const double budget = 64.0 * (double)total_points + (double)(256 << 20);
-    return tables + staging <= budget;
+    return tables <= budget;
 }
 
 size_t vox_small_workspace_bytes(const pp_voxel_cfg* cfg, int64_t ncell, int n_frames, int64_t total_points,
                                  int64_t max_frame_points, int D, int out_dtype) {
-    return carve_small(nullptr, cfg, ncell, n_frames, total_points, max_frame_points, D, out_dtype).total;
+    (void)cfg;
+    return carve_small(nullptr, ncell, n_frames, total_points, max_frame_points, D, out_dtype).total;
 }
 
 template <typename T, bool A32, bool FAST, typename TO, int DS>
@@ -806,22 +750,16 @@ static int launch_scan(const VoxParams& p, const SmallWs& w, const void* points,
     return PP_OK;
 }
 
-template <typename TO, int DS>
-static int launch_finish(const VoxParams& p, const SmallWs& w, const int64_t* frame_off, int ncellp, int S, int n_frames,
+template <typename TO, int DS, int NR>
+static int launch_finish(const VoxParams& p, const SmallWs& w, const int64_t* frame_off, int S, int n_frames,
                          int64_t rows_per_frame, const int32_t* voxel_num, const int32_t* voxel_base, int64_t cap_rows,
                          void* voxels, float* decorated, int32_t* coors, int coors_cols, int32_t* num_points,
                          int32_t* point_slot, int32_t* cell_voxel, cudaStream_t st) {
-    const int P = p.max_points;
-    const size_t smem = (size_t)kFinishRows * P * DS * sizeof(float);
-    auto kern = vox_finish_kernel<TO, DS>;
-    int per_sm = 0;
-    PP_CHECK_ARG(smem <= 200 * 1024, "pp_voxelize_dev: max_points too large for the finish pass");
-    PP_TRY_RC(kernel_config(reinterpret_cast<const void*>(kern), kFinishWarps * 32, smem, &per_sm));
     const dim3 g((unsigned)ceil_div(rows_per_frame, kFinishRows), (unsigned)n_frames);
     PP_TIMED("vox_finish", st);
-    kern<<<g, kFinishWarps * 32, smem, st>>>(
-        frame_off, p, FastDiv((unsigned)P), ncellp, w.rowinfo, voxel_num, voxel_base, w.cutoff, cap_rows, w.sidx, w.crec,
-        w.ctag, w.nvalid, S, static_cast<TO*>(voxels), decorated, coors, coors_cols, num_points, point_slot, cell_voxel);
+    vox_finish_kernel<TO, DS, NR><<<g, kFinishWarps * 32, 0, st>>>(
+        frame_off, p, w.rowinfo, voxel_num, voxel_base, w.cutoff, cap_rows, w.sidx, w.crec, w.ctag, w.nvalid, S,
+        static_cast<TO*>(voxels), decorated, coors, coors_cols, num_points, point_slot, cell_voxel);
     PP_LAUNCHED();
     return PP_OK;
 }
@@ -835,7 +773,7 @@ int vox_small_run(const pp_voxel_cfg* cfg, const VoxParams& p, const void* point
     const int64_t ncell = p.ncell;
     const int ncellp = (int)align_up((size_t)ncell, 16);
     const int S = chunks_of(max_frame_points);
-    const SmallWs w = carve_small(workspace, cfg, ncell, n_frames, total_points, max_frame_points, D, out_dtype);
+    const SmallWs w = carve_small(workspace, ncell, n_frames, total_points, max_frame_points, D, out_dtype);
     if (w.total > workspace_bytes) {
         set_error("pp_voxelize_dev: workspace %zu < required %zu", workspace_bytes, w.total);
         return PP_E_WORKSPACE;
@@ -857,27 +795,34 @@ int vox_small_run(const pp_voxel_cfg* cfg, const VoxParams& p, const void* point
     {
         const dim3 g((unsigned)ceil_div(ncell, kPrefixThreads), (unsigned)n_frames);
         PP_TIMED("vox_prefix", st);
-        vox_prefix_kernel<<<g, kPrefixThreads, 0, st>>>(frame_offsets, S, (int)ncell, ncellp, P, w.hist, w.base8, w.cellinfo,
-                                                        w.newcount, cfg->max_voxels, n_frames, voxel_num, voxel_base,
-                                                        w.done_counter, w.frame_done);
+        vox_prefix_kernel<<<g, kPrefixThreads, 0, st>>>(frame_offsets, S, (int)ncell, ncellp, P, w.hist, w.base8, w.cellcnt,
+                                                        w.cellinfo, w.newcount, cfg->max_voxels, n_frames, voxel_num,
+                                                        voxel_base, w.tile_base, kFinishRows, w.done_counter,
+                                                        w.frame_done);
         PP_LAUNCHED();
     }
     if (cap_rows <= 0) return PP_OK;
     {
+        int cell_bits = 1;  // bits of a cell id
+        while ((1 << cell_bits) < ncell) ++cell_bits;
         const size_t smem = (size_t)ncellp;
+        int per_sm = 0;
+        PP_TRY_RC(kernel_config(reinterpret_cast<const void*>(vox_place_kernel), 32, smem, &per_sm));
         const dim3 g((unsigned)S, (unsigned)n_frames);
         PP_TIMED("vox_place", st);
         vox_place_kernel<<<g, 32, smem, st>>>(frame_offsets, S, (int)ncell, ncellp, P, cfg->max_voxels, w.ctag, w.base8, w.cellinfo,
-                                              w.nvalid, w.newcount, w.sidx, w.rowinfo, w.cutoff);
+                                              w.nvalid, w.newcount, w.sidx, w.rowinfo, w.cutoff, cell_bits);
         PP_LAUNCHED();
     }
     const int64_t rows_per_frame = cfg->max_voxels < ncell ? cfg->max_voxels : ncell;
     if (rows_per_frame <= 0) return PP_OK;
-#define PP_FINISH(TO, DS)                                                                                            \
-    launch_finish<TO, DS>(p, w, frame_offsets, ncellp, S, n_frames, rows_per_frame, voxel_num, voxel_base, cap_rows,  \
-                          voxels, decorated, coors, coors_cols, num_points, point_slot, cell_voxel, st)
-    if (out_dtype == PP_F64) rc = D == 3 ? PP_FINISH(double, 3) : PP_FINISH(double, 4);
-    else rc = D == 3 ? PP_FINISH(float, 3) : PP_FINISH(float, 4);
+#define PP_FINISH(TO, DS, NR)                                                                                           \
+    launch_finish<TO, DS, NR>(p, w, frame_offsets, S, n_frames, rows_per_frame, voxel_num, voxel_base, cap_rows, voxels, \
+                              decorated, coors, coors_cols, num_points, point_slot, cell_voxel, st)
+#define PP_FINISH_P(TO, DS) (P <= 64 ? PP_FINISH(TO, DS, 2) : P <= 128 ? PP_FINISH(TO, DS, 4) : PP_FINISH(TO, DS, 8))
+    if (out_dtype == PP_F64) rc = D == 3 ? PP_FINISH_P(double, 3) : PP_FINISH_P(double, 4);
+    else rc = D == 3 ? PP_FINISH_P(float, 3) : PP_FINISH_P(float, 4);
+#undef PP_FINISH_P
 #undef PP_FINISH
     return rc;
 }

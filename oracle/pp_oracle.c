@@ -632,14 +632,25 @@ PPO_API void ppo_anchor_cells(const float* anchors /*[A,7]*/, int64_t A, const d
         const float rb[5] = {a[0], a[1], a[3], a[4], a[6]};
         float bv[4];
         ppo_rbbox2d_to_near_bbox(rb, 1, bv);
-        int32_t c0 = (int32_t)floor(((double)bv[0] - coors_range[0]) / voxel_size[0]);
-        int32_t c1 = (int32_t)floor(((double)bv[1] - coors_range[1]) / voxel_size[1]);
-        int32_t c2 = (int32_t)floor(((double)bv[2] - coors_range[0]) / voxel_size[0]);
-        int32_t c3 = (int32_t)floor(((double)bv[3] - coors_range[1]) / voxel_size[1]);
-        cells[4 * i + 0] = c0 > 0 ? c0 : 0;
-        cells[4 * i + 1] = c1 > 0 ? c1 : 0;
-        cells[4 * i + 2] = c2 < grid_xyz[0] - 1 ? c2 : grid_xyz[0] - 1;
-        cells[4 * i + 3] = c3 < grid_xyz[1] - 1 ? c3 : grid_xyz[1] - 1;
+        /* load_data.py:569-580.  One side of each index is clipped; an index that stays negative wraps around
+         * once (numba negative indexing).  Indices the reference cannot form or that fall outside dense_map
+         * (NaN / infinite / far-off anchors: undefined behaviour there) are DEFINED here as the rectangle
+         * (-1,-1,-1,-1) = area 0. */
+        const double v[4] = {floor(((double)bv[0] - coors_range[0]) / voxel_size[0]), floor(((double)bv[1] - coors_range[1]) / voxel_size[1]),
+                             floor(((double)bv[2] - coors_range[0]) / voxel_size[0]), floor(((double)bv[3] - coors_range[1]) / voxel_size[1])};
+        int32_t* c = cells + 4 * i;
+        c[0] = c[1] = c[2] = c[3] = -1;
+        if (fabs(v[0]) < 2.0e9 && fabs(v[1]) < 2.0e9 && fabs(v[2]) < 2.0e9 && fabs(v[3]) < 2.0e9) {
+            const int32_t nx = grid_xyz[0], ny = grid_xyz[1];
+            int32_t c0 = (int32_t)v[0], c1 = (int32_t)v[1], c2 = (int32_t)v[2], c3 = (int32_t)v[3];
+            c0 = c0 > 0 ? c0 : 0;
+            c1 = c1 > 0 ? c1 : 0;
+            c2 = c2 < nx - 1 ? c2 : nx - 1;
+            c3 = c3 < ny - 1 ? c3 : ny - 1;
+            if (c2 < 0) c2 += nx;
+            if (c3 < 0) c3 += ny;
+            if (c0 < nx && c1 < ny && c2 >= 0 && c3 >= 0) { c[0] = c0; c[1] = c1; c[2] = c2; c[3] = c3; }
+        }
     }
 }
 
@@ -654,9 +665,12 @@ PPO_API void ppo_anchors_mask(const int32_t* coors, int64_t M, int ny, int nx, c
         for (int x = 1; x < nx; ++x) map[(size_t)y * nx + x] += map[(size_t)y * nx + x - 1];
     for (int64_t i = 0; i < A; ++i) {
         const int32_t* c = cells + 4 * i;
-        const float ID = map[(size_t)c[3] * nx + c[2]], IA = map[(size_t)c[1] * nx + c[0]];
-        const float IB = map[(size_t)c[3] * nx + c[0]], IC = map[(size_t)c[1] * nx + c[2]];
-        const float v = ID - IB - IC + IA;
+        float v = 0.f;
+        if (c[0] >= 0) {
+            const float ID = map[(size_t)c[3] * nx + c[2]], IA = map[(size_t)c[1] * nx + c[0]];
+            const float IB = map[(size_t)c[3] * nx + c[0]], IC = map[(size_t)c[1] * nx + c[2]];
+            v = ID - IB - IC + IA;
+        }
         area[i] = v;
         mask[i] = v > threshold;
     }

@@ -281,6 +281,31 @@ def test_anchor_mask(pp, oracle, synth):
     assert not a.any() and not m.any()
 
 
+def test_anchor_mask_off_grid_anchors(pp, oracle, synth):
+    """Anchors left / right / above / below the grid, NaN and 1e20 coordinates: one-sided clipping as in
+    load_data.py:577-580, one wraparound of an index that stays negative (numba), area 0 where the reference
+    would index outside dense_map.  No out-of-bounds read through the ABI."""
+    cfg = synth.D435
+    vs, pcr = np.array(cfg["voxel_size"]), np.array(cfg["point_cloud_range"])
+    _, c, _ = oracle.points_to_voxel(synth.d435_cloud(3), vs, pcr, cfg["max_points"], True, cfg["max_voxels"])
+    base = synth.anchors_stride(cfg)[:64].copy()
+    an = np.concatenate([base] * 10)
+    an[64:128, 0] -= 8.0        # wholly left of x_min: both x indices negative -> wraparound of the upper one
+    an[128:192, 0] += 9.0       # wholly right: lower index >= nx -> outside the map
+    an[192:256, 1] -= 7.0       # below y_min
+    an[256:320, 1] += 7.0       # above y_max
+    an[320:384, 0] = np.nan
+    an[384:448, 1] = 1e20
+    an[448:512, 0] = -1e20
+    an[512:576, 0] -= 1000.0    # more than one grid width to the left: no single wraparound reaches the map
+    an[576:640, 3:5] = np.inf
+    for thr in (1, 0, -1):
+        got = pp.anchors_mask(c, an, vs, pcr, thr)
+        want = oracle.anchors_mask(c, an, vs, pcr, thr)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    assert got[0][:64].any() and not got[0][320:576].any()
+
+
 def test_nms_ignores_minus_inf_scores(pp, oracle, synth):
     """Masked-out anchors carry score -inf and must behave as if gathered away (model/voxelnet.py:1119-1137)."""
     d = synth.rotated_boxes(3000, 31, clustered=True)
