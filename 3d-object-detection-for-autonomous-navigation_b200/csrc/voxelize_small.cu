@@ -45,9 +45,11 @@ constexpr int kMaxCellsSmall = 16384;              // cell ids are 14-bit in the
 constexpr int kMaxFramePointsSmall = kMaxChunks * kChunk;
 constexpr int kMaxPointsSmall = 254;               // uint8 counts saturate at 255
 constexpr int kPlaceUnroll = 4;
+constexpr int kSub = 4;                            // quarters of a chunk that the place pass walks independently
+constexpr int kSubTiles = kChunk / kScanTile / kSub;  // scan tiles per quarter
 constexpr int kNoCut = 0x7fffffff;
 
-static_assert(kChunk % kScanTile == 0 && kChunk <= 65536, "chunk size");
+static_assert(kChunk % (kScanTile * kSub) == 0 && kChunk <= 65536, "chunk size");
 
 __device__ __forceinline__ unsigned long long l2_evict_first_policy() {
     unsigned long long pol;
@@ -84,7 +86,7 @@ vox_scan_kernel(const T* __restrict__ points, const int64_t* __restrict__ frame_
                 int aligned16, int S, int ncellp, uint4* __restrict__ crec, unsigned* __restrict__ ctag,
                 unsigned* __restrict__ hist_out, int* __restrict__ nvalid, int* __restrict__ newcount,
                 int* __restrict__ cutoff, int* __restrict__ point_slot, int* __restrict__ done_counter,
-                int* __restrict__ frame_done) {
+                unsigned* __restrict__ snap, int* __restrict__ subv) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) unsigned long long s_bar[kScanStages];
     __shared__ int s_wtot[kScanWarps];
@@ -96,7 +98,7 @@ vox_scan_kernel(const T* __restrict__ points, const int64_t* __restrict__ frame_
     const int b = blockIdx.y, s = blockIdx.x;
     if (tid == 0) {
         newcount[b * S + s] = 0;
-        if (s == 0) { cutoff[b] = kNoCut; frame_done[b] = 0; }
+        if (s == 0) cutoff[b] = kNoCut;
         if (b == 0 && s == 0) *done_counter = 0;
     }
     const int64_t f0 = frame_off[b];
@@ -148,6 +150,18 @@ vox_scan_kernel(const T* __restrict__ points, const int64_t* __restrict__ frame_
     for (int j = 0; j < ntiles; ++j) {
         const int stg = j % kScanStages;
         issue(j + kScanStages - 1);  // its stage was released by the barrier that ended tile j-1
+        if (j % kSubTiles == 0 && j > 0) {
+            // quarter boundary: the counts so far (saturated to uint8) and the number of records so far let the
+            // place pass start a walk here, independently of the quarters before
+            const int q = j / kSubTiles;
+            unsigned* dst = snap + (((size_t)b * S + s) * (kSub - 1) + (q - 1)) * (size_t)(ncellp >> 2);
+            for (int k = tid; k < (ncellp >> 2); k += kScanThreads) {
+                const unsigned lo = hist32[2 * k], hi = hist32[2 * k + 1];
+                dst[k] = min(lo & 0xffffu, 255u) | (min(lo >> 16, 255u) << 8) | (min(hi & 0xffffu, 255u) << 16) | (min(hi >> 16, 255u) << 24);
+            }
+            if (tid == 0) subv[(b * S + s) * kSub + q] = crun;
+            __syncthreads();  // before the next tile's atomics change the counts
+        }
         unsigned char* buf = smem + (size_t)stg * stage_bytes;
         const int base = j * kScanTile;  // first point of the tile, relative to the chunk
         const int m = min(kScanTile, cn - base);
@@ -226,26 +240,27 @@ vox_scan_kernel(const T* __restrict__ points, const int64_t* __restrict__ frame_
     // the chunk's counts (uint16 pairs, as they lie in shared memory)
     const size_t tb = ((size_t)b * S + s) * (size_t)(ncellp >> 1);
     for (int k = tid; k < (ncellp >> 1); k += kScanThreads) hist_out[tb + k] = hist32[k];
-    if (tid == 0) nvalid[b * S + s] = crun;
+    if (tid == 0) {
+        nvalid[b * S + s] = crun;
+        subv[(b * S + s) * kSub] = 0;
+        for (int q = (ntiles + kSubTiles - 1) / kSubTiles; q < kSub; ++q) subv[(b * S + s) * kSub + q] = crun;  // empty quarters
+    }
 }
 
 
 // ---------------------------------------------------------------------------------------------
 // Pass 2: one thread per cell.  base8[s][cell] = min(255, points of the cell in chunks < s) = the slot of the
-// cell's first record of chunk s; a cell is counted as a new voxel of the first chunk that holds it.  The last
-// CTA of a frame lays the cells' runs of min(points, max_points) entries back to back in the frame's slot table
-// (cellinfo = {start, length}); the last CTA of the grid turns the per-chunk voxel counts into voxel_num,
-// voxel_base (rows of a batch are packed back to back, merge_second_batch layout) and the finish pass's tile list.
+// cell's first record of chunk s; min(points, max_points) goes to the last word of the cell's row of the slot table;
+// a cell is counted as a new voxel of the first chunk that holds it.  The last CTA of the grid turns the per-chunk voxel counts into voxel_num and
+// voxel_base (rows of a batch are packed back to back, merge_second_batch layout).
 __global__ void __launch_bounds__(kPrefixThreads)
 vox_prefix_kernel(const int64_t* __restrict__ frame_off, int S, int ncell, int ncellp, int P,
                   const unsigned short* __restrict__ hist, unsigned char* __restrict__ base8,
-                  unsigned* __restrict__ cellcnt, uint2* __restrict__ cellinfo, int* __restrict__ newcount,
-                  int max_voxels, int B, int* __restrict__ voxel_num, int* __restrict__ voxel_base,
-                  int* __restrict__ tile_base, int tile_rows, int* __restrict__ done_counter,
-                  int* __restrict__ frame_done) {
+                  unsigned* __restrict__ sidx, int* __restrict__ newcount, int max_voxels, int B,
+                  int* __restrict__ voxel_num, int* __restrict__ voxel_base, int* __restrict__ done_counter) {
     __shared__ int s_new[kMaxChunks];
     __shared__ int sm[33];
-    __shared__ int s_last, s_flast;
+    __shared__ int s_last;
     const int tid = threadIdx.x;
     const int b = blockIdx.y;
     const int cell = blockIdx.x * kPrefixThreads + tid;
@@ -269,42 +284,18 @@ vox_prefix_kernel(const int64_t* __restrict__ frame_off, int S, int ncell, int n
                 }
             }
         }
-        cellcnt[(size_t)b * ncellp + cell] = (unsigned)min(run, P);
+        sidx[((size_t)b * ncell + cell) * (size_t)(P + 1) + P] = (unsigned)min(run, P);
         if (first >= 0) atomicAdd(&s_new[first], 1);
-    } else if (cell < ncellp) {
-        cellcnt[(size_t)b * ncellp + cell] = 0u;
     }
     __syncthreads();
     if (tid < Sb && s_new[tid]) atomicAdd(&newcount[b * S + tid], s_new[tid]);
     __threadfence();
     __syncthreads();
-    if (tid == 0) {
-        s_flast = (atomicAdd(&frame_done[b], 1) == (int)gridDim.x - 1);
-        s_last = (atomicAdd(done_counter, 1) == (int)(gridDim.x * gridDim.y) - 1);
-    }
+    if (tid == 0) s_last = (atomicAdd(done_counter, 1) == (int)(gridDim.x * gridDim.y) - 1);
     __syncthreads();
-    if (s_flast) {
-        // exclusive prefix of the run lengths over the frame's cells, four cells per thread and round
-        __threadfence();
-        const uint4* cc = reinterpret_cast<const uint4*>(cellcnt + (size_t)b * ncellp);
-        uint4* ci = reinterpret_cast<uint4*>(cellinfo + (size_t)b * ncellp);
-        int running = 0;
-        for (int c0 = 0; c0 < ncellp; c0 += kPrefixThreads * 4) {
-            const int c = c0 + tid * 4;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (c < ncellp) v = __ldcg(&cc[c >> 2]);
-            int tot;
-            const unsigned e = (unsigned)(running + block_excl_scan((int)(v.x + v.y + v.z + v.w), &tot, sm));
-            if (c < ncellp) {
-                ci[c >> 1] = make_uint4(e, v.x, e + v.x, v.y);
-                ci[(c >> 1) + 1] = make_uint4(e + v.x + v.y, v.z, e + v.x + v.y + v.z, v.w);
-            }
-            running += tot;
-        }
-    }
     if (!s_last) return;
     __threadfence();
-    int running = 0, trun = 0;
+    int running = 0;
     for (int b0 = 0; b0 < B; b0 += kPrefixThreads) {
         const int i = b0 + tid;
         int v = 0;
@@ -317,101 +308,114 @@ vox_prefix_kernel(const int64_t* __restrict__ frame_off, int S, int ncell, int n
         const int e = running + block_excl_scan(v, &tot, sm);
         if (i < B) voxel_base[i] = e;
         running += tot;
-        // tiles of tile_rows consecutive pillars, frame by frame
-        const int te = trun + block_excl_scan((v + tile_rows - 1) / tile_rows, &tot, sm);
-        if (i < B) tile_base[i] = te;
-        trun += tot;
     }
     if (tid == 0) {
         voxel_base[B] = running;
-        tile_base[B] = trun;
         *done_counter = 0;
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Pass 3: one warp per (frame, chunk) walks the chunk's record tags in index order, 32 per step, with the chunk's
-// running per-cell counts (uint8, starting at the chunk base) in shared memory: slot = count[cell] + rank among
-// the step's earlier records of the same cell.  On a depth image 32 consecutive in-range points share a handful
-// of y/z bins, so two of them in the same cell is the rule (birthday collisions over ~80 x bins) and match_any
-// -- ~11 cycles per DISTINCT value, 300 per step here -- would sit on the walk's dependent chain; the lanes that
-// share a cell are found with one ballot per cell-id bit instead (14 independent votes, ~50 cycles).  A record
-// that finds count 0 opens its cell: the walk is in index order, so the running number of such records IS the
-// voxel id (order of first touch), and the record that would open voxel number max_voxels is the reference's
-// `break` position (load_data.py:630-634).  The record's position goes to entry `slot` of the cell's run in the
-// frame's slot table (4 bytes per kept point, L2 resident).  The walk is one dependent chain per chunk, so
-// nothing on it may wait for global memory: tags are fetched three groups ahead, the cells' {run start, run
-// length} one group ahead.  No atomic, no block barrier; every chunk of a 64-frame batch has its warp resident
-// at the same time.
+// Pass 3: one warp per (frame, chunk, quarter) walks the quarter's record tags in index order, 32 per step, with
+// the running per-cell counts (uint8) in shared memory: slot = count[cell] + rank among the step's earlier
+// records of the same cell.  The counts start at the chunk base plus the chunk's own counts at the
+// quarter boundary, which the scan pass snapshotted -- so the four quarters of a chunk are walked independently,
+// and a 64-frame batch has 6 400 short dependent chains in flight instead of 1 600 long ones (the walk is bound
+// by per-warp instruction latency, not by bandwidth).  A record that finds count 0 opens its cell: the walk is in
+// index order, so the running number of such records IS the voxel id (order of first touch), and the record
+// that would open voxel number max_voxels is the reference's `break` position (load_data.py:630-634).  The
+// record's position goes to entry (cell, slot) of the frame's slot table (4 bytes per kept point, L2 resident;
+// max_points entries per cell, so the address needs no lookup: the pass is bound by its scattered sector
+// accesses, one store per record).  Tags are fetched two groups ahead.  No atomic, no block barrier.
 constexpr unsigned kNone = 0xffffffffu;
-
-// lanes of the warp whose `c` equals this lane's (c < 2^nbits)
-__device__ __forceinline__ unsigned peers_by_bits(const unsigned c, const int nbits) {
-    unsigned peers = 0xffffffffu;
-#pragma unroll
-    for (int bit = 0; bit < 17; ++bit) {
-        if (bit < nbits) {  // uniform
-            const unsigned bal = __ballot_sync(0xffffffffu, (c >> bit) & 1u);
-            peers &= ((c >> bit) & 1u) ? bal : ~bal;
-        }
-    }
-    return peers;
-}
+constexpr int kPlaceScratch = 1024;  // words of the per-warp peer table (a power of two)
 
 __global__ void __launch_bounds__(32)
 vox_place_kernel(const int64_t* __restrict__ frame_off, int S, int ncell, int ncellp, int P, int max_voxels,
                  const unsigned* __restrict__ ctag, const unsigned char* __restrict__ base8,
-                 const uint2* __restrict__ cellinfo, const int* __restrict__ nvalid,
-                 const int* __restrict__ newcount, unsigned* __restrict__ sidx, uint4* __restrict__ rowinfo,
-                 int* __restrict__ cutoff, int cell_bits) {
+                 const int* __restrict__ nvalid,
+                 const int* __restrict__ newcount, unsigned* __restrict__ sidx, unsigned* __restrict__ rowinfo,
+                 int* __restrict__ cutoff, const unsigned char* __restrict__ snap, const int* __restrict__ subv) {
     extern __shared__ __align__(16) unsigned char tbl[];  // [ncellp] running counts
+    __shared__ unsigned scr[kPlaceScratch];                // lanes of the current step, keyed by cell (all zero between steps)
     constexpr int U = kPlaceUnroll;
     const int lane = lane_id();
+    for (int k = lane; k < kPlaceScratch; k += 32) scr[k] = 0u;
     // frames in reverse order: the scan pass wrote the last frames' tags last, so they are still in L2
-    const int b = (int)gridDim.y - 1 - (int)blockIdx.y, s = blockIdx.x;
+    const int b = (int)gridDim.y - 1 - (int)blockIdx.y, s = blockIdx.x / kSub, q = blockIdx.x % kSub;
     const int64_t f0 = frame_off[b];
     const int n = (int)(frame_off[b + 1] - f0);
     const int Sb = (n + kChunk - 1) >> kChunkShift;
     if (s >= Sb) return;
-    const int nval = nvalid[b * S + s];
-    if (nval <= 0) return;
+    // the quarter's records
+    const int rec0 = subv[(b * S + s) * kSub + q];
+    const int nval = q + 1 < kSub ? subv[(b * S + s) * kSub + q + 1] : nvalid[b * S + s];
+    if (nval <= rec0) return;
     // voxels opened by the earlier chunks of the frame
     int newrun = 0;
     for (int k = lane; k < s; k += 32) newrun += newcount[b * S + k];
+    {
+        // counts at the start of the quarter = chunk base + the chunk's counts at the quarter boundary; a cell
+        // that the chunk base does not hold but the boundary counts do was opened by an earlier quarter
+        const uint4* srcb = reinterpret_cast<const uint4*>(base8 + ((size_t)b * S + s) * ncellp);
+        const uint4* srcs = reinterpret_cast<const uint4*>(snap + (((size_t)b * S + s) * (kSub - 1) + (q ? q - 1 : 0)) * (size_t)ncellp);
+        uint4* dst = reinterpret_cast<uint4*>(tbl);
+        constexpr int kB = 5;  // 16-byte units per lane and batch: all loads of a batch are in flight together
+        const int nu = ncellp >> 4;
+        for (int k0 = lane; k0 < nu; k0 += 32 * kB) {
+            uint4 a[kB], c[kB];
+#pragma unroll
+            for (int i = 0; i < kB; ++i) {
+                const int k = min(k0 + 32 * i, nu - 1);
+                a[i] = __ldcg(&srcb[k]);
+                c[i] = q ? __ldcs(&srcs[k]) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int i = 0; i < kB; ++i) {
+                if (k0 + 32 * i >= nu) break;
+                newrun += (__popc(__vcmpeq4(a[i].x, 0u) & __vcmpne4(c[i].x, 0u)) + __popc(__vcmpeq4(a[i].y, 0u) & __vcmpne4(c[i].y, 0u)) +
+                           __popc(__vcmpeq4(a[i].z, 0u) & __vcmpne4(c[i].z, 0u)) + __popc(__vcmpeq4(a[i].w, 0u) & __vcmpne4(c[i].w, 0u))) >> 3;
+                dst[k0 + 32 * i] = make_uint4(__vaddus4(a[i].x, c[i].x), __vaddus4(a[i].y, c[i].y), __vaddus4(a[i].z, c[i].z),
+                                              __vaddus4(a[i].w, c[i].w));
+            }
+        }
+    }
 #pragma unroll
     for (int o = 16; o; o >>= 1) newrun += __shfl_xor_sync(0xffffffffu, newrun, o);
-    {
-        const uint4* srcb = reinterpret_cast<const uint4*>(base8 + ((size_t)b * S + s) * ncellp);
-        uint4* dst = reinterpret_cast<uint4*>(tbl);
-        for (int k = lane; k < (ncellp >> 4); k += 32) dst[k] = __ldcg(&srcb[k]);
-    }
     __syncwarp();
     const unsigned* tags = ctag + f0 + (int64_t)s * kChunk;
     const size_t cellrow0 = (size_t)b * ncell;
-    const uint2* ci_b = cellinfo + (size_t)b * ncellp;
-    unsigned* sidx_b = sidx + f0;  // the frame's slot table: the cells' runs back to back
+    unsigned* sidx_b = sidx + cellrow0 * (size_t)(P + 1);  // the frame's slot table: max_points entries (+ the count) per cell
 
     struct Tags { unsigned tg[U]; };
-    struct Info { uint2 ci[U]; };
     // unconditional loads (index clamped to the last record): a predicated load makes the compiler merge the
     // loaded registers with their old contents right behind the load, which waits for it and defeats the prefetch
     auto fetch_tags = [&](Tags& t, int g) {
 #pragma unroll
         for (int u = 0; u < U; ++u) t.tg[u] = __ldcs(&tags[max(0, min(g + u * 32 + lane, nval - 1))]);
     };
-    auto fetch_info = [&](Info& in, const Tags& t) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) in.ci[u] = __ldg(&ci_b[t.tg[u] & 0xffffu]);
-    };
-    auto process = [&](const Tags& cur, const Info& in, int g) {
+    auto process = [&](const Tags& cur, int g) {
         if (g >= nval) return;  // uniform
         int c[U], rk[U], npeer[U];
-        // independent of the table, so the votes of the group's steps overlap
+        // Lanes of a step that share a cell: every lane ORs its bit into a shared-memory word keyed by the low
+        // bits of its cell and reads the word back -- 4.4 cycles per step and SM where match_any takes 60 (it
+        // costs ~2 cycles per distinct value on a unit the SM's warps share: tools/micro/match_tput.cu).  Two
+        // different cells under one key are caught by comparing with the word's first lane; such a step (rare:
+        // neighbouring points differ in the low bits) is redone with match_any.
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const bool act = g + u * 32 + lane < nval;
             c[u] = (int)(cur.tg[u] & 0xffffu);
-            const unsigned peers = peers_by_bits((unsigned)c[u], cell_bits) & __ballot_sync(0xffffffffu, act);
+            unsigned* slot = scr + (c[u] & (kPlaceScratch - 1));
+            if (act) atomicOr(slot, 1u << lane);
+            __syncwarp();
+            unsigned peers = act ? *slot : 1u << lane;
+            __syncwarp();
+            if (act) *slot = 0u;
+            const int first = __shfl_sync(0xffffffffu, c[u], __ffs(peers) - 1);
+            if (__any_sync(0xffffffffu, act && first != c[u]))
+                peers = __match_any_sync(0xffffffffu, act ? c[u] : (0x10000 | lane));
+            __syncwarp();
             rk[u] = act ? __popc(peers & lanemask_lt()) : -1;  // rk 0: first record of its cell in the step
             npeer[u] = __popc(peers);
         }
@@ -430,37 +434,31 @@ vox_place_kernel(const int64_t* __restrict__ frame_off, int S, int ncell, int nc
             const unsigned cp = (unsigned)((s << kChunkShift) + g + u * 32 + lane);
             if (opener) {
                 const int rank = newrun + __popc(opens & lanemask_lt());
-                // the finish pass finds cell, run and run length of a voxel in one 16-byte word
-                if (rank < max_voxels) rowinfo[cellrow0 + rank] = make_uint4((unsigned)c[u], in.ci[u].x, in.ci[u].y, cp);
+                // the finish pass finds cell and point count of a voxel in one word
+                if (rank < max_voxels) rowinfo[cellrow0 + rank] = (unsigned)c[u];
                 else if (rank == max_voxels) cutoff[b] = (int)cp;  // the reference's break position
             }
             newrun += __popc(opens);
             const int slot = cnt + rk[u];
-            if (rk[u] >= 0 && slot < P) sidx_b[in.ci[u].x + slot] = cp;
+            if (rk[u] >= 0 && slot < P) sidx_b[c[u] * (P + 1) + slot] = cp;
         }
     };
     // register buffers used in rotation (no copies: a register move of a load that is still in flight would
-    // wait for it): tags of group i+3 and cell info of group i+1 are requested before group i is processed
+    // wait for it): the tags of group i+3 are requested before group i is processed
     constexpr int GS = U * 32;
     Tags t0, t1, t2, t3;
-    Info i0, i1;
-    fetch_tags(t0, 0);
-    fetch_tags(t1, GS);
-    fetch_tags(t2, 2 * GS);
-    fetch_info(i0, t0);
-    for (int g = 0; g < nval; g += 4 * GS) {
+    fetch_tags(t0, rec0);
+    fetch_tags(t1, rec0 + GS);
+    fetch_tags(t2, rec0 + 2 * GS);
+    for (int g = rec0; g < nval; g += 4 * GS) {
         fetch_tags(t3, g + 3 * GS);
-        fetch_info(i1, t1);
-        process(t0, i0, g);
+        process(t0, g);
         fetch_tags(t0, g + 4 * GS);
-        fetch_info(i0, t2);
-        process(t1, i1, g + GS);
+        process(t1, g + GS);
         fetch_tags(t1, g + 5 * GS);
-        fetch_info(i1, t3);
-        process(t2, i0, g + 2 * GS);
+        process(t2, g + 2 * GS);
         fetch_tags(t2, g + 6 * GS);
-        fetch_info(i0, t0);
-        process(t3, i1, g + 3 * GS);
+        process(t3, g + 3 * GS);
     }
 }
 
@@ -487,7 +485,7 @@ constexpr int kFinishRows = 2 * kFinishWarps;
 
 template <typename TO, int DS, int NR>
 __global__ void __launch_bounds__(kFinishWarps * 32)
-vox_finish_kernel(const int64_t* __restrict__ frame_off, VoxParams p, const uint4* __restrict__ rowinfo,
+vox_finish_kernel(const int64_t* __restrict__ frame_off, VoxParams p, const unsigned* __restrict__ rowinfo,
                   const int* __restrict__ voxel_num, const int* __restrict__ voxel_base,
                   const int* __restrict__ cutoff, int64_t cap_rows, const unsigned* __restrict__ sidx,
                   const uint4* __restrict__ crec, const unsigned* __restrict__ ctag, const int* __restrict__ nvalid,
@@ -526,23 +524,28 @@ vox_finish_kernel(const int64_t* __restrict__ frame_off, VoxParams p, const uint
     if (lr0 >= nrows) return;  // uniform per warp
     const bool two = lr0 + 1 < nrows;
     const int64_t row0 = (int64_t)vb + r0 + lr0;  // output row of the warp's first pillar
-    // ---- loads: row words -> slot entries -> records
-    uint4 info[2];
+    // ---- loads: cells -> rows of the slot table (entries + count, requested together) -> records
+    unsigned cellk[2];
     {
-        const uint4* ri = rowinfo + (size_t)b * p.ncell + r0 + lr0;
-        info[0] = __ldg(&ri[0]);
-        info[1] = two ? __ldg(&ri[1]) : make_uint4(0u, 0u, 0u, 0u);
+        const unsigned* ri = rowinfo + (size_t)b * p.ncell + r0 + lr0;
+        cellk[0] = __ldg(&ri[0]);
+        cellk[1] = two ? __ldg(&ri[1]) : cellk[0];
     }
     unsigned key[2][NR];
+    int len[2];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-        const unsigned* run = sidx + f0 + info[k].y + lane;
-        const int len = (int)info[k].z - lane;
+        const unsigned* run = sidx + ((size_t)b * p.ncell + cellk[k]) * (size_t)(P + 1);
+        len[k] = (int)__ldcg(&run[P]);
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            key[k][r] = kNone;
-            if (r * 32 < len) key[k][r] = __ldcg(&run[r * 32]);
-        }
+        for (int r = 0; r < NR; ++r) key[k][r] = __ldcg(&run[min(r * 32 + lane, P)]);  // entries past the count are not used
+    }
+    if (!two) len[1] = 0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r)
+            if (r * 32 + lane >= len[k]) key[k][r] = kNone;
     }
     uint4 rv[2][NR][rec16];
     {
@@ -619,7 +622,7 @@ vox_finish_kernel(const int64_t* __restrict__ frame_off, VoxParams p, const uint
         }
     }
     const int n_mine = h ? nsel[1] : nsel[0];
-    const int cell = (int)(h ? info[1].x : info[0].x);
+    const int cell = (int)(h ? cellk[1] : cellk[0]);
     const float nf = (float)n_mine;
     mx = __fdiv_rn(mx, nf); my = __fdiv_rn(my, nf); mz = __fdiv_rn(mz, nf);
     const int cz = p.div_nxny.div(cell);
@@ -675,16 +678,14 @@ struct SmallWs {
     unsigned* ctag;           // [total_points + 1] cell | index in chunk << 16, same positions
     unsigned short* hist;     // [B*S*ncellp]  chunk counts
     unsigned char* base8;     // [B*S*ncellp]  chunk bases
-    unsigned* cellcnt;        // [B*ncellp]    min(points of the cell, max_points) = length of its run
-    uint2* cellinfo;          // [B*ncellp]    {start, length} of the cell's run in the frame's slot table
-    int* tile_base;           // [B+1] first tile of every frame in the finish pass's tile list
-    int* frame_done;          // [B]
+    unsigned char* snap;      // [B*S][kSub-1][ncellp] chunk counts at the quarter boundaries, saturated
+    int* subv;                // [B*S][kSub] records of the chunk before each quarter
     int* nvalid;              // [B*S] records per chunk
     int* newcount;            // [B*S] voxels opened per chunk
-    uint4* rowinfo;           // [B*ncell] voxel id in frame -> {cell, run start, run length, first record}
+    unsigned* rowinfo;        // [B*ncell] voxel id in frame -> cell
     int* cutoff;              // [B] break position (record position in frame) or kNoCut
     int* done_counter;        // [1]
-    unsigned* sidx;           // [total_points + 1] slot tables: a frame's cells' runs back to back -> record position in frame
+    unsigned* sidx;           // [B][ncell][max_points + 1] slot table -> record position in frame; last word: min(points, max_points)
     size_t total;
 };
 
@@ -692,7 +693,7 @@ static int rec_bytes_of(int D, int out_dtype) { return (int)(((size_t)D * (out_d
 static int chunks_of(int64_t max_frame_points) { return (int)(max_frame_points > 0 ? ceil_div(max_frame_points, kChunk) : 1); }
 
 static SmallWs carve_small(void* ws, int64_t ncell, int n_frames, int64_t total_points, int64_t max_frame_points, int D,
-                           int out_dtype) {
+                           int out_dtype, int P) {
     SmallWs w;
     Carver c(ws);
     const int S = chunks_of(max_frame_points);
@@ -702,16 +703,14 @@ static SmallWs carve_small(void* ws, int64_t ncell, int n_frames, int64_t total_
     w.ctag = c.take<unsigned>((size_t)total_points + 1);
     w.hist = c.take<unsigned short>((size_t)n_frames * S * ncellp);
     w.base8 = c.take<unsigned char>((size_t)n_frames * S * ncellp);
-    w.cellcnt = c.take<unsigned>((size_t)n_frames * ncellp);
-    w.cellinfo = c.take<uint2>((size_t)n_frames * ncellp);
-    w.tile_base = c.take<int>((size_t)n_frames + 1);
-    w.frame_done = c.take<int>(n_frames);
+    w.snap = c.take<unsigned char>((size_t)n_frames * S * (kSub - 1) * ncellp);
+    w.subv = c.take<int>((size_t)n_frames * S * kSub);
     w.nvalid = c.take<int>((size_t)n_frames * S);
     w.newcount = c.take<int>((size_t)n_frames * S);
-    w.rowinfo = c.take<uint4>((size_t)n_frames * ncell);
+    w.rowinfo = c.take<unsigned>((size_t)n_frames * ncell);
     w.cutoff = c.take<int>(n_frames);
     w.done_counter = c.take<int>(1);
-    w.sidx = c.take<unsigned>((size_t)total_points + 1);
+    w.sidx = c.take<unsigned>((size_t)n_frames * ncell * (size_t)(P + 1));
     w.total = c.used();
     return w;
 }
@@ -723,7 +722,8 @@ bool vox_small_eligible(const pp_voxel_cfg* cfg, int64_t ncell, int n_frames, in
     // the per-chunk tables must stay small next to the points themselves (callers that do not know the largest
     // frame pass the batch total, which sizes one table set per 16 384 points for every frame)
     const double ncellp = (double)align_up((size_t)ncell, 16);
-    const double tables = (double)n_frames * chunks_of(max_frame_points) * ncellp * 3.0 + (double)n_frames * ncellp * 24.0;
+    const double tables = (double)n_frames * chunks_of(max_frame_points) * ncellp * (3.0 + kSub - 1) +
+                          (double)n_frames * (double)ncell * (cfg->max_points * 4.0 + 8.0);
     const double budget = 64.0 * (double)total_points + (double)(256 << 20);
     return tables <= budget;
 }
@@ -731,7 +731,7 @@ bool vox_small_eligible(const pp_voxel_cfg* cfg, int64_t ncell, int n_frames, in
 size_t vox_small_workspace_bytes(const pp_voxel_cfg* cfg, int64_t ncell, int n_frames, int64_t total_points,
                                  int64_t max_frame_points, int D, int out_dtype) {
     (void)cfg;
-    return carve_small(nullptr, ncell, n_frames, total_points, max_frame_points, D, out_dtype).total;
+    return carve_small(nullptr, ncell, n_frames, total_points, max_frame_points, D, out_dtype, cfg->max_points).total;
 }
 
 template <typename T, bool A32, bool FAST, typename TO, int DS>
@@ -745,7 +745,8 @@ static int launch_scan(const VoxParams& p, const SmallWs& w, const void* points,
     PP_TIMED("vox_scan", st);
     kern<<<dim3((unsigned)S, (unsigned)n_frames), kScanThreads, smem, st>>>(
         static_cast<const T*>(points), frame_off, p, total_points, aligned16, S, ncellp, w.crec, w.ctag,
-        reinterpret_cast<unsigned*>(w.hist), w.nvalid, w.newcount, w.cutoff, point_slot, w.done_counter, w.frame_done);
+        reinterpret_cast<unsigned*>(w.hist), w.nvalid, w.newcount, w.cutoff, point_slot, w.done_counter,
+        reinterpret_cast<unsigned*>(w.snap), w.subv);
     PP_LAUNCHED();
     return PP_OK;
 }
@@ -773,7 +774,7 @@ int vox_small_run(const pp_voxel_cfg* cfg, const VoxParams& p, const void* point
     const int64_t ncell = p.ncell;
     const int ncellp = (int)align_up((size_t)ncell, 16);
     const int S = chunks_of(max_frame_points);
-    const SmallWs w = carve_small(workspace, ncell, n_frames, total_points, max_frame_points, D, out_dtype);
+    const SmallWs w = carve_small(workspace, ncell, n_frames, total_points, max_frame_points, D, out_dtype, P);
     if (w.total > workspace_bytes) {
         set_error("pp_voxelize_dev: workspace %zu < required %zu", workspace_bytes, w.total);
         return PP_E_WORKSPACE;
@@ -795,23 +796,20 @@ int vox_small_run(const pp_voxel_cfg* cfg, const VoxParams& p, const void* point
     {
         const dim3 g((unsigned)ceil_div(ncell, kPrefixThreads), (unsigned)n_frames);
         PP_TIMED("vox_prefix", st);
-        vox_prefix_kernel<<<g, kPrefixThreads, 0, st>>>(frame_offsets, S, (int)ncell, ncellp, P, w.hist, w.base8, w.cellcnt,
-                                                        w.cellinfo, w.newcount, cfg->max_voxels, n_frames, voxel_num,
-                                                        voxel_base, w.tile_base, kFinishRows, w.done_counter,
-                                                        w.frame_done);
+        vox_prefix_kernel<<<g, kPrefixThreads, 0, st>>>(frame_offsets, S, (int)ncell, ncellp, P, w.hist, w.base8, w.sidx,
+                                                        w.newcount, cfg->max_voxels, n_frames, voxel_num, voxel_base,
+                                                        w.done_counter);
         PP_LAUNCHED();
     }
     if (cap_rows <= 0) return PP_OK;
     {
-        int cell_bits = 1;  // bits of a cell id
-        while ((1 << cell_bits) < ncell) ++cell_bits;
         const size_t smem = (size_t)ncellp;
         int per_sm = 0;
         PP_TRY_RC(kernel_config(reinterpret_cast<const void*>(vox_place_kernel), 32, smem, &per_sm));
-        const dim3 g((unsigned)S, (unsigned)n_frames);
+        const dim3 g((unsigned)(S * kSub), (unsigned)n_frames);
         PP_TIMED("vox_place", st);
-        vox_place_kernel<<<g, 32, smem, st>>>(frame_offsets, S, (int)ncell, ncellp, P, cfg->max_voxels, w.ctag, w.base8, w.cellinfo,
-                                              w.nvalid, w.newcount, w.sidx, w.rowinfo, w.cutoff, cell_bits);
+        vox_place_kernel<<<g, 32, smem, st>>>(frame_offsets, S, (int)ncell, ncellp, P, cfg->max_voxels, w.ctag, w.base8, w.nvalid,
+                                              w.newcount, w.sidx, w.rowinfo, w.cutoff, w.snap, w.subv);
         PP_LAUNCHED();
     }
     const int64_t rows_per_frame = cfg->max_voxels < ncell ? cfg->max_voxels : ncell;
