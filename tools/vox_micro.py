@@ -10,9 +10,15 @@ pts = torch.from_numpy(np.concatenate([fr[i % 4] for i in range(F)])).cuda()
 off = (torch.arange(F + 1, dtype=torch.int64) * n).cuda()
 pipe = pipeline.FramePipeline(cfg, max_frames=F, max_total_points=F * n, max_frame_points=n)
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-for _ in range(3): pipe.voxelize(pts, off, F, F * n, n, st)
-torch.cuda.synchronize(); _lib.profile_start()
-for _ in range(3): pipe.voxelize(pts, off, F, F * n, n, st)
-acc = {}
-for k, v in _lib.profile_stop(): acc.setdefault(k, []).append(v)
-print({k: round(1000 * float(np.mean(v))) for k, v in acc.items()})
+for _once in (0,):
+    for _ in range(3): pipe.voxelize(pts, off, F, F * n, n, st)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(10): pipe.voxelize(pts, off, F, F * n, n, st)
+    e1.record(); torch.cuda.synchronize()
+    whole = e0.elapsed_time(e1) / 10 * 1000
+    _lib.profile_start()
+    for _ in range(3): pipe.voxelize(pts, off, F, F * n, n, st)
+    acc = {}
+    for k, v in _lib.profile_stop(): acc.setdefault(k, []).append(v)
+    print("whole call %.0f us;" % whole, "per launch:", {k: round(1000 * float(np.mean(v))) for k, v in acc.items()})
