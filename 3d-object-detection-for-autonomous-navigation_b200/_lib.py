@@ -32,6 +32,17 @@ class PredictCfg(C.Structure):
                 ("anchors_per_frame", C.c_int32)]
 
 
+class StreamCfg(C.Structure):
+    _fields_ = [("vox", VoxelCfg), ("D", C.c_int32), ("point_dtype", C.c_int32), ("C", C.c_int32), ("layout", C.c_int32),
+                ("nms_kind", C.c_int32), ("pre_max", C.c_int32), ("post_max", C.c_int32), ("iou_threshold", C.c_float),
+                ("max_frames", C.c_int32), ("keep_voxels", C.c_int32), ("max_frame_points", C.c_int64)]
+
+
+class StreamTensors(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("voxels", "decorated", "coors", "num_points", "voxel_num", "voxel_base", "canvas",
+                                          "dets", "keep_count", "compute_stream")]
+
+
 _vp, _i32, _i64, _f32, _f64, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_size_t
 _cfgp = C.POINTER(VoxelCfg)
 _pcfgp = C.POINTER(PredictCfg)
@@ -90,6 +101,14 @@ SIGNATURES = {
     "pp_anchors_mask_host": (C.c_int, [_vp, _vp, _i64, _vp, _i64, C.POINTER(_f64), C.POINTER(_f64), _f32, _vp, _vp]),
     "pp_d3_box_overlap_host": (C.c_int, [_vp, _vp, _i64, _vp, _i64, C.c_int, _vp]),
     "pp_rotate_iou_host": (C.c_int, [_vp, _vp, _i64, _vp, _i64, C.c_int, _vp]),
+    "pp_stream_create": (C.c_int, [C.c_int, C.POINTER(StreamCfg), _vp, _i64, C.POINTER(_vp)]),
+    "pp_stream_destroy": (None, [_vp]),
+    "pp_stream_cap_rows": (_i64, [_vp]),
+    "pp_stream_anchor_count": (_i64, [_vp]),
+    "pp_stream_bind": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "pp_stream_submit": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp, C.POINTER(_i64)]),
+    "pp_stream_wait": (C.c_int, [_vp, _i64]),
+    "pp_stream_view": (C.c_int, [_vp, C.POINTER(StreamTensors)]),
 }
 
 _lib = None

@@ -37,7 +37,11 @@ constexpr int kChunkShift = PP_CHUNK_SHIFT;  // points per chunk = 2^shift; posi
 constexpr int kChunk = 1 << kChunkShift;
 constexpr int kScanThreads = 256;
 constexpr int kScanWarps = kScanThreads / 32;
-constexpr int kScanPPT = 4;
+#ifndef PP_SCAN_PPT
+#define PP_SCAN_PPT 4
+#endif
+constexpr int kScanPPT = PP_SCAN_PPT;  // points per thread and tile
+constexpr int kWarpPts = 32 * kScanPPT;  // consecutive points of a tile that one warp owns
 constexpr int kScanTile = kScanThreads * kScanPPT;
 constexpr int kPrefixThreads = 256;
 constexpr int kMaxChunks = 64;                     // per frame: max_frame_points <= 2^20
@@ -72,7 +76,7 @@ template <typename TO, int DS> struct RecFmt {
 };
 
 // ---------------------------------------------------------------------------------------------
-// Pass 1.  Warp w of a tile owns its points [128 w, 128 w + 128); round r of lane l is point 128 w + 32 r + l,
+// Pass 1.  Warp w of a tile owns kWarpPts consecutive points; round r of lane l is point kWarpPts w + 32 r + l,
 // so (warp, round, lane) enumerates the tile in index order and shared-memory row reads are conflict free.
 // kScanStages shared-memory stages: with two, the TMA bulk copy of tile j+1 is in flight while tile j is processed.
 #ifndef PP_SCAN_STAGES
@@ -188,14 +192,14 @@ vox_scan_kernel(const T* __restrict__ points, const int64_t* __restrict__ frame_
                 reinterpret_cast<T*>(buf)[k] = points[(gbase + base) * DS + k];
             __syncthreads();
         }
-        const unsigned char* rows = buf + shift + (size_t)(w * 128 + lane) * row_bytes;
+        const unsigned char* rows = buf + shift + (size_t)(w * kWarpPts + lane) * row_bytes;
 
         int cell[kScanPPT];
         unsigned bal[kScanPPT];
         int wtot = 0;
 #pragma unroll
         for (int r = 0; r < kScanPPT; ++r) {
-            const int t = w * 128 + r * 32 + lane;
+            const int t = w * kWarpPts + r * 32 + lane;
             const T* q = reinterpret_cast<const T*>(rows + (size_t)r * 32 * row_bytes);
             cell[r] = -1;
             if (t < m) cell[r] = FAST ? cell_of_fast20<T>(q, p) : cell_of<T, A32>(q, p);
@@ -218,7 +222,7 @@ vox_scan_kernel(const T* __restrict__ points, const int64_t* __restrict__ frame_
         int pos = crun + woff;
 #pragma unroll
         for (int r = 0; r < kScanPPT; ++r) {
-            const int t = w * 128 + r * 32 + lane;
+            const int t = w * kWarpPts + r * 32 + lane;
             if (cell[r] >= 0) {
                 const T* q = reinterpret_cast<const T*>(rows + (size_t)r * 32 * row_bytes);
                 const int64_t gi = gbase + pos + __popc(bal[r] & lanemask_lt());
@@ -360,7 +364,10 @@ vox_place_kernel(const int64_t* __restrict__ frame_off, int S, int ncell, int nc
         const uint4* srcb = reinterpret_cast<const uint4*>(base8 + ((size_t)b * S + s) * ncellp);
         const uint4* srcs = reinterpret_cast<const uint4*>(snap + (((size_t)b * S + s) * (kSub - 1) + (q ? q - 1 : 0)) * (size_t)ncellp);
         uint4* dst = reinterpret_cast<uint4*>(tbl);
-        constexpr int kB = 5;  // 16-byte units per lane and batch: all loads of a batch are in flight together
+#ifndef PP_PLACE_KB
+#define PP_PLACE_KB 5
+#endif
+        constexpr int kB = PP_PLACE_KB;  // 16-byte units per lane and batch: all loads of a batch are in flight together
         const int nu = ncellp >> 4;
         for (int k0 = lane; k0 < nu; k0 += 32 * kB) {
             uint4 a[kB], c[kB];
@@ -483,8 +490,11 @@ __device__ __forceinline__ void st_global_256_cs(void* ptr, const float4& a, con
 constexpr int kFinishWarps = 4;
 constexpr int kFinishRows = 2 * kFinishWarps;
 
+#ifndef PP_FINISH_MINB
+#define PP_FINISH_MINB 1
+#endif
 template <typename TO, int DS, int NR>
-__global__ void __launch_bounds__(kFinishWarps * 32)
+__global__ void __launch_bounds__(kFinishWarps * 32, PP_FINISH_MINB)
 vox_finish_kernel(const int64_t* __restrict__ frame_off, VoxParams p, const unsigned* __restrict__ rowinfo,
                   const int* __restrict__ voxel_num, const int* __restrict__ voxel_base,
                   const int* __restrict__ cutoff, int64_t cap_rows, const unsigned* __restrict__ sidx,

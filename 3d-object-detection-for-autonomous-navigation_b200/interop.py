@@ -41,21 +41,10 @@ def _stream(t):
     return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
-class _Scratch:
-    """Grow-only per-device workspaces (the C ABI never allocates)."""
-
-    def __init__(self):
-        self.buf = {}
-
-    def get(self, device, name, nbytes):
-        key = (device, name)
-        b = self.buf.get(key)
-        if b is None or b.numel() < nbytes:
-            b = self.buf[key] = torch.empty((max(int(nbytes), 256),), dtype=torch.uint8, device=device)
-        return b
-
-
-_scratch = _Scratch()
+def _workspace(device, nbytes):
+    """Workspace of one call, from torch's caching allocator: the block is stream-ordered (it is handed out again only
+    to work queued behind this call on the same stream), so calls on different streams or threads never share one."""
+    return torch.empty((max(int(nbytes), 256),), dtype=torch.uint8, device=device)
 
 
 def points_to_voxel(points, voxel_size, coors_range, max_points, reverse_index, max_voxels, frame_offsets=None,
@@ -94,12 +83,13 @@ def points_to_voxel(points, voxel_size, coors_range, max_points, reverse_index, 
     if decorate:
         out["decorated"] = torch.empty((cap, max_points, D + 5), dtype=torch.float32, device=dev)
     ws_bytes = int(L.pp_voxelize_workspace_bytes(C.byref(cfg), N, B, max_frame, D, _lib.PP_F64 if f64_out else _lib.PP_F32))
-    ws = _scratch.get(dev, "vox", ws_bytes)
-    _lib.check(L.pp_voxelize_dev(
-        C.byref(cfg), _p(pts), _lib.PP_F64 if pts.dtype == torch.float64 else _lib.PP_F32, D, _p(off), B, N, max_frame,
-        _lib.PP_F64 if f64_out else _lib.PP_F32, _p(out["voxels"]), _p(out.get("decorated")), _p(out["coors"]), 4,
-        _p(out["num_points"]), cap, _p(out["voxel_num"]), _p(out["voxel_base"]), None, None, _p(ws), ws_bytes,
-        _stream(pts)))
+    ws = _workspace(dev, ws_bytes)
+    with torch.cuda.device(dev):
+        _lib.check(L.pp_voxelize_dev(
+            C.byref(cfg), _p(pts), _lib.PP_F64 if pts.dtype == torch.float64 else _lib.PP_F32, D, _p(off), B, N, max_frame,
+            _lib.PP_F64 if f64_out else _lib.PP_F32, _p(out["voxels"]), _p(out.get("decorated")), _p(out["coors"]), 4,
+            _p(out["num_points"]), cap, _p(out["voxel_num"]), _p(out["voxel_base"]), None, None, _p(ws), ws_bytes,
+            _stream(pts)))
     return out
 
 
@@ -110,8 +100,9 @@ def pillar_decorate(voxels, num_points, coors, vx, vy, x_offset, y_offset):
     c = as_device_tensor(coors)
     M, P, D = v.shape
     out = torch.empty((M, P, D + 5), dtype=torch.float32, device=v.device)
-    _lib.check(_lib.lib().pp_decorate_dev(_p(v), _p(n), _p(c), M, P, D, float(vx), float(vy), float(x_offset),
-                                          float(y_offset), _p(out), _stream(v)))
+    with torch.cuda.device(v.device):
+        _lib.check(_lib.lib().pp_decorate_dev(_p(v), _p(n), _p(c), M, P, D, float(vx), float(vy), float(x_offset),
+                                              float(y_offset), _p(out), _stream(v)))
     return out
 
 
@@ -125,10 +116,11 @@ def scatter(voxel_features, coords, batch_size, ny, nx, layout="NCHW", num_rows=
     out = torch.empty((batch_size, ny, nx, Cc) if nhwc else (batch_size, Cc, ny, nx), dtype=torch.float32, device=f.device)
     L = _lib.lib()
     ws_bytes = int(L.pp_scatter_workspace_bytes(batch_size, ny, nx, M))
-    ws = _scratch.get(f.device, "scatter", ws_bytes)
-    _lib.check(L.pp_scatter_dev(_p(f), _p(c), M, _p(as_device_tensor(num_rows)) if num_rows is not None else None, Cc,
-                                batch_size, ny, nx, _lib.PP_LAYOUT_NHWC if nhwc else _lib.PP_LAYOUT_NCHW, _p(out), _p(ws),
-                                ws_bytes, _stream(f)))
+    ws = _workspace(f.device, ws_bytes)
+    with torch.cuda.device(f.device):
+        _lib.check(L.pp_scatter_dev(_p(f), _p(c), M, _p(as_device_tensor(num_rows)) if num_rows is not None else None, Cc,
+                                    batch_size, ny, nx, _lib.PP_LAYOUT_NHWC if nhwc else _lib.PP_LAYOUT_NCHW, _p(out), _p(ws),
+                                    ws_bytes, _stream(f)))
     return out
 
 
@@ -139,7 +131,8 @@ def second_box_decode(box_encodings, anchors):
     n = e.numel() // 7
     period = a.numel() // 7 if a.numel() != e.numel() else 0
     out = torch.empty_like(e)
-    _lib.check(_lib.lib().pp_box_decode_dev(_p(e), _p(a), n, period, _p(out), _stream(e)))
+    with torch.cuda.device(e.device):
+        _lib.check(_lib.lib().pp_box_decode_dev(_p(e), _p(a), n, period, _p(out), _stream(e)))
     return out
 
 
@@ -159,9 +152,10 @@ def nms(boxes, scores, pre_max_size=None, post_max_size=None, iou_threshold=0.5,
     cnt = torch.empty((B,), dtype=torch.int32, device=b.device)
     L = _lib.lib()
     ws_bytes = int(L.pp_nms_workspace_bytes(kind, B, N, pre))
-    ws = _scratch.get(b.device, "nms", ws_bytes)
-    _lib.check(L.pp_nms_dev(kind, _p(b), stride, _p(s), None, B, N, pre, post, float(iou_threshold), _p(keep), K, _p(cnt),
-                            _p(ws), ws_bytes, _stream(b)))
+    ws = _workspace(b.device, ws_bytes)
+    with torch.cuda.device(b.device):
+        _lib.check(L.pp_nms_dev(kind, _p(b), stride, _p(s), None, B, N, pre, post, float(iou_threshold), _p(keep), K, _p(cnt),
+                                _p(ws), ws_bytes, _stream(b)))
     return keep, cnt
 
 
@@ -171,7 +165,8 @@ def rotate_iou(boxes, query_boxes, criterion=-1):
     q = as_device_tensor(query_boxes).to(torch.float32)
     out = torch.zeros((b.shape[0], q.shape[0]), dtype=torch.float32, device=b.device)
     if b.shape[0] and q.shape[0]:
-        _lib.check(_lib.lib().pp_rotate_iou_dev(_p(b), b.shape[0], _p(q), q.shape[0], int(criterion), _p(out), _stream(b)))
+        with torch.cuda.device(b.device):
+            _lib.check(_lib.lib().pp_rotate_iou_dev(_p(b), b.shape[0], _p(q), q.shape[0], int(criterion), _p(out), _stream(b)))
     return out
 
 

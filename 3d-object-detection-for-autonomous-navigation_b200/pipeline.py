@@ -259,6 +259,72 @@ class FramePipeline:
         return self.dets_host, self.keep_count_host
 
 
+class FrameStream:
+    """pp_stream (include/pp_b200.h): batches of frames from HOST clouds to HOST detections through one C-ABI call per
+    batch; the copy of the next batch overlaps the processing of the current one inside the library.
+
+    The reference's call sites on this boundary: points_to_voxel on the tf.data thread (load_data.py:2966) and the
+    numpy detections VoxelNet.predict returns (model/voxelnet.py:1259-1326)."""
+
+    def __init__(self, cfg, device=0, max_frames=64, max_frame_points=410_000, rotated_nms=True, layout="NCHW",
+                 keep_voxels=True, anchors=None):
+        L = _lib.lib()
+        sc = _lib.StreamCfg()
+        sc.vox = _lib.make_cfg(cfg["voxel_size"], cfg["point_cloud_range"], cfg["max_points"], cfg["max_voxels"], True, False)
+        sc.D = cfg["num_point_features"]
+        sc.point_dtype = _lib.PP_F64 if cfg["point_dtype"] == "float64" else _lib.PP_F32
+        sc.C = cfg["num_filters"]
+        sc.layout = _lib.PP_LAYOUT_NCHW if layout == "NCHW" else _lib.PP_LAYOUT_NHWC
+        sc.nms_kind = _lib.PP_NMS_ROTATED if rotated_nms else _lib.PP_NMS_STANDUP
+        sc.pre_max, sc.post_max = cfg["nms_pre_max_size"], cfg["nms_post_max_size"]
+        sc.iou_threshold = cfg["nms_iou_threshold"]
+        sc.max_frames, sc.keep_voxels, sc.max_frame_points = int(max_frames), int(keep_voxels), int(max_frame_points)
+        an = np.ascontiguousarray(_synth.anchors_stride(cfg) if anchors is None else anchors, np.float32)
+        h = C.c_void_p()
+        _lib.check(L.pp_stream_create(int(device), C.byref(sc), _lib.ptr(an), an.shape[0], C.byref(h)))
+        self.handle, self.cfg, self.sc = h, cfg, sc
+        self.A, self.post = an.shape[0], sc.post_max
+        self.cap_rows = int(L.pp_stream_cap_rows(h))
+        self.D = sc.D
+        self.dtype = np.float64 if sc.point_dtype == _lib.PP_F64 else np.float32
+
+    def bind(self, pfn_feats, box_enc, scores):
+        """Device tensors of the host framework (torch tensors or raw pointers): PFN output [cap_rows, C], RPN box
+        encodings [max_frames, A, 7], scores [max_frames, A]."""
+        self._bound = (pfn_feats, box_enc, scores)  # keep them alive
+        _lib.check(_lib.lib().pp_stream_bind(self.handle, _p(pfn_feats), _p(box_enc), _p(scores)))
+
+    def submit(self, points, frame_offsets, dets_out, counts_out):
+        """points: numpy [N, D] (pinned: direct DMA); frame_offsets: numpy int64 [n+1]; dets_out [n, post, 8] float32,
+        counts_out [n] int32 numpy arrays that are filled when wait() returns.  -> ticket"""
+        n = frame_offsets.shape[0] - 1
+        assert points.dtype == self.dtype and points.flags.c_contiguous and frame_offsets.dtype == np.int64
+        assert dets_out.dtype == np.float32 and dets_out.shape[0] >= n and counts_out.dtype == np.int32
+        t = C.c_int64()
+        _lib.check(_lib.lib().pp_stream_submit(self.handle, _lib.ptr(points), _lib.ptr(frame_offsets), n, _lib.ptr(dets_out),
+                                               _lib.ptr(counts_out), C.byref(t)))
+        return int(t.value)
+
+    def wait(self, ticket=-1):
+        _lib.check(_lib.lib().pp_stream_wait(self.handle, int(ticket)))
+
+    def view(self):
+        v = _lib.StreamTensors()
+        _lib.check(_lib.lib().pp_stream_view(self.handle, C.byref(v)))
+        return v
+
+    def close(self):
+        if self.handle:
+            _lib.lib().pp_stream_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
 def capture_graph(step, device=None, warmup=3):
     """Capture `step()` (a closure that only issues pipeline stages on the current stream: kernel launches,
     memsets, event fork/join -- no host synchronisation) into a CUDA graph and return it; `graph.replay()`

@@ -325,6 +325,61 @@ PP_API int pp_predict_host(pp_ctx* ctx, const pp_predict_cfg* cfg, const float* 
                     const float* Trv2c, int B, int64_t A, int K, float* box3d_lidar, double* box3d_camera,
                     float* scores, int32_t* label_preds, int32_t* anchor_index, int32_t* count);
 
+/* ---- batches of frames from host memory -------------------------------------------------------------------
+ * The reference hands numpy clouds to points_to_voxel on the tf.data thread (load_data.py:2966), merges the samples
+ * of a batch (merge_second_batch, load_data.py:2164-2224) and takes numpy detections out of VoxelNet.predict
+ * (model/voxelnet.py:1259-1326).  pp_stream is that boundary for a batch: clouds in host memory in, detections in
+ * host memory out, with voxelize + decorate -> scatter -> decode + NMS chained on the device in between.  The clouds
+ * of batch k+1 are copied into a second device staging buffer on a copy stream while batch k is processed.
+ * Page-locked caller memory (pp_host_alloc, cudaHostAlloc / cudaHostRegister, torch pinned tensors) is handed to the
+ * copy engine directly; pageable memory is staged through pinned buffers of the stream (one extra host copy).
+ * The host framework's layers between the stages stay outside: their output tensors are bound as device pointers.
+ * One producer thread per pp_stream; different pp_streams are independent. */
+typedef struct pp_stream pp_stream;
+typedef struct pp_stream_cfg {
+    pp_voxel_cfg vox;
+    int32_t D;                /* values per point (3 or 4) */
+    int32_t point_dtype;      /* PP_F32 / PP_F64: dtype of the host clouds */
+    int32_t C;                /* PFN output channels = canvas channels */
+    int32_t layout;           /* PP_LAYOUT_NCHW (the reference's canvas) / PP_LAYOUT_NHWC */
+    int32_t nms_kind;         /* PP_NMS_ROTATED / PP_NMS_STANDUP */
+    int32_t pre_max, post_max;
+    float iou_threshold;
+    int32_t max_frames;       /* frames per batch */
+    int32_t keep_voxels;      /* 1: also materialise the raw voxel rows [rows, max_points, D] */
+    int64_t max_frame_points; /* points per frame */
+} pp_stream_cfg;
+typedef struct pp_stream_tensors {   /* device tensors of the last batch (pp_stream_view) */
+    const float* voxels;      /* [rows, max_points, D] or NULL */
+    const float* decorated;   /* [rows, max_points, D+5]: the PFN's input */
+    const int32_t* coors;     /* [rows, 4] (frame, z, y, x) */
+    const int32_t* num_points;
+    const int32_t* voxel_num; /* [max_frames] */
+    const int32_t* voxel_base;/* [max_frames + 1] */
+    const float* canvas;      /* [max_frames, C, ny, nx] or NHWC: the RPN's input */
+    const float* dets;        /* [max_frames, post_max, 8] box7 + score */
+    const int32_t* keep_count;
+    void* compute_stream;     /* the stream these tensors are produced on */
+} pp_stream_tensors;
+/* anchors: HOST [A,7] float32 (one set for every frame). */
+PP_API int pp_stream_create(int device, const pp_stream_cfg* cfg, const float* anchors, int64_t A, pp_stream** out);
+PP_API void pp_stream_destroy(pp_stream* s);
+PP_API int64_t pp_stream_cap_rows(pp_stream* s);     /* rows of pfn_feats the scatter stage may read */
+PP_API int64_t pp_stream_anchor_count(pp_stream* s);
+/* DEVICE tensors of the host framework: PFN output [cap_rows, C], RPN box encodings [max_frames, A, 7] and scores
+ * [max_frames, A]; they must stay valid while batches are in flight. */
+PP_API int pp_stream_bind(pp_stream* s, const float* pfn_feats, const float* box_encodings, const float* scores);
+/* One batch.  points: HOST [frame_offsets[n_frames], D] of cfg.point_dtype, frames concatenated; frame_offsets: HOST
+ * int64 [n_frames + 1] starting at 0; dets: HOST [n_frames, post_max, 8] float32 (box7 + score, zero padded); counts:
+ * HOST [n_frames] int32.  Returns after the work has been enqueued (at most two batches are in flight: the call
+ * first waits for the batch before the previous one); `points` may be reused as soon as pp_stream_wait returns for
+ * this ticket (pageable memory: as soon as this call returns); dets / counts are valid after pp_stream_wait. */
+PP_API int pp_stream_submit(pp_stream* s, const void* points, const int64_t* frame_offsets, int n_frames,
+                     float* dets, int32_t* counts, int64_t* ticket);
+/* ticket < 0: every batch in flight. */
+PP_API int pp_stream_wait(pp_stream* s, int64_t ticket);
+PP_API int pp_stream_view(pp_stream* s, pp_stream_tensors* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,3 +64,36 @@ def test_dlpack_device_path_matches_oracle(oracle, synth):
     np.testing.assert_allclose(iou.cpu().numpy(), oracle.rotate_iou_gpu_eval(dets[:50, :5], dets[:20, :5]), atol=1e-5)
     with pytest.raises(ValueError):
         iop.points_to_voxel(torch.from_numpy(pts), vs, pcr, 40, True, 9000)  # host tensor: no silent CPU path
+
+
+def test_tf_adaptor_with_torch_standing_in_for_tensorflow(oracle, synth):
+    """The TF shim (model/voxelnet.py:867, 881 call sites) exchanges tensors through
+    `tf.experimental.dlpack.to_dlpack / from_dlpack`; TensorFlow is not installed here, so a namespace with the same
+    two functions backed by torch's DLPack stands in for it.  Results must be the device path's (== the oracle's)."""
+    import types
+    import torch
+    tfa = importlib.import_module(PKG + ".tf_adaptor")
+    fake_tf = types.SimpleNamespace(experimental=types.SimpleNamespace(dlpack=types.SimpleNamespace(
+        to_dlpack=lambda t: torch.utils.dlpack.to_dlpack(t), from_dlpack=lambda c: torch.utils.dlpack.from_dlpack(c))))
+    tfa.use_tf_module(fake_tf)
+    cfg = synth.D435
+    vs, pcr = np.array(cfg["voxel_size"]), np.array(cfg["point_cloud_range"])
+    v, c, n = oracle.points_to_voxel(synth.d435_cloud(4, subsample=True), vs, pcr, cfg["max_points"], True, cfg["max_voxels"])
+    v = v.astype(np.float32)
+    c4 = np.concatenate([np.zeros((c.shape[0], 1), np.int32), c], axis=1)
+    vx, vy = cfg["voxel_size"][:2]
+    xo, yo = vx / 2 + pcr[0], vy / 2 + pcr[1]
+    dev = torch.device("cuda", 0)
+    tv, tn, tc = torch.from_numpy(v).to(dev), torch.from_numpy(n).to(dev), torch.from_numpy(c4).to(dev)
+    dec = tfa.pillar_decorate(tv, tn, tc, vx, vy, xo, yo)
+    want = oracle.decorate(v, n, c4, vx, vy, xo, yo)
+    np.testing.assert_allclose(dec.cpu().numpy(), want, rtol=1e-5, atol=1e-5 * (float(np.abs(v).max()) + 1))
+    nx, ny, _ = synth.grid_size(cfg)
+    feats = synth.pfn_standin(c4.shape[0], cfg["num_filters"], 1)
+    config = {"model": {"second": {"voxel_feature_extractor": {"num_filters": cfg["num_filters"]},
+                                   "voxel_generator": {"voxel_size": cfg["voxel_size"], "point_cloud_range": cfg["point_cloud_range"]}}},
+              "train_input_reader": {"batch_size": 2}, "eval_input_reader": {"batch_size": 1}}
+    layer = tfa.PointPillarsScatter(config, training=False)
+    assert (layer.batch_size, layer.ny, layer.nx, layer.nchannels) == (1, ny, nx, cfg["num_filters"])
+    canvas = layer(torch.from_numpy(feats).to(dev), tc)
+    assert np.array_equal(canvas.cpu().numpy(), oracle.scatter(feats, c4, 1, ny, nx))

@@ -315,3 +315,114 @@ def test_production_chain_empty_and_tiny_frames(synth, oracle):
             assert k == want["box3d_lidar"].shape[0]
             assert np.array_equal(pipe.det_index[b, :k].cpu().numpy(), want["anchor_index"])
     assert n_in[2] == 10 and 0 < vnum[2] <= 10
+
+
+def test_host_stream_matches_oracle(pp, synth, oracle):
+    """pp_stream (the host-buffer batch entry point): host clouds in, host detections out through one C-ABI call per
+    batch, pinned and pageable memory, three batches so that both staging slots are reused.  Reference boundary:
+    load_data.py:2966 (clouds in) / model/voxelnet.py:1259-1326 (detections out)."""
+    import torch
+    pipeline = importlib.import_module(PKG + ".pipeline")
+    _lib = importlib.import_module(PKG + "._lib")
+    cfg = synth.D435
+    B = 3
+    fs = pipeline.FrameStream(cfg, device=0, max_frames=B, max_frame_points=110_000)
+    A, post = fs.A, fs.post
+    dev = torch.device("cuda", 0)
+    box = np.stack([synth.rpn_standin(A, 80 + i)[0] for i in range(B)])
+    sco = np.stack([synth.rpn_standin(A, 80 + i)[1] for i in range(B)])
+    feats = synth.pfn_standin(fs.cap_rows, cfg["num_filters"], 3)
+    t_feats, t_box, t_sco = (torch.from_numpy(a).to(dev) for a in (feats, box, sco))
+    fs.bind(t_feats, t_box, t_sco)
+    batches = [[synth.d435_cloud(60 + 3 * j + i, subsample=True)[: 101_760 - 7000 * i] for i in range(B)] for j in range(3)]
+    batches[1][1] = np.zeros((0, 3), np.float64)  # an empty frame
+    batches[2] = batches[2][:2]                   # a short batch
+    outs = []
+    for j, frames in enumerate(batches):
+        n = len(frames)
+        pts = np.concatenate(frames)
+        off = np.cumsum([0] + [f.shape[0] for f in frames]).astype(np.int64)
+        if j != 1:  # pinned clouds and results: direct DMA
+            hp = _lib.pinned_empty(pts.shape, np.float64); hp[...] = pts
+            dets, cnt = _lib.pinned_empty((n, post, 8), np.float32), _lib.pinned_empty((n,), np.int32)
+        else:       # pageable numpy arrays: staged inside the library
+            hp, dets, cnt = pts.copy(), np.empty((n, post, 8), np.float32), np.empty((n,), np.int32)
+        outs.append((fs.submit(hp, off, dets, cnt), hp, dets, cnt, frames))
+    fs.wait()
+    vs, pcr = np.array(cfg["voxel_size"]), np.array(cfg["point_cloud_range"])
+    an = synth.anchors_stride(cfg)
+    for _, _, dets, cnt, frames in outs:
+        for b in range(len(frames)):
+            boxes = oracle.second_box_decode(box[b], an)
+            d = np.concatenate([boxes[:, [0, 1, 3, 4, 6]], sco[b][:, None]], axis=1)
+            keep = oracle.rotate_nms_gpu(d, cfg["nms_iou_threshold"], cfg["nms_pre_max_size"], cfg["nms_post_max_size"])
+            assert int(cnt[b]) == len(keep)
+            np.testing.assert_allclose(dets[b, :len(keep), :7], boxes[keep], rtol=1e-5, atol=1e-6)
+            assert np.array_equal(dets[b, :len(keep), 7], sco[b][keep]) and not dets[b, len(keep):].any()
+    # the device tensors of the last batch are the voxelizer's / scatter's results for that batch
+    v = fs.view()
+    frames = batches[2]
+    n = len(frames)
+    torch.cuda.synchronize()
+
+    class _Raw:  # a raw device pointer as a __cuda_array_interface__ object
+        def __init__(self, ptr, shape, typestr):
+            self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (int(ptr), False), "version": 3}
+    vbase = torch.as_tensor(_Raw(v.voxel_base, (n + 1,), "<i4"), device="cuda").cpu().numpy()
+    M = int(vbase[n])
+    coors = torch.as_tensor(_Raw(v.coors, (M, 4), "<i4"), device="cuda").cpu().numpy()
+    num = torch.as_tensor(_Raw(v.num_points, (M,), "<i4"), device="cuda").cpu().numpy()
+    for b, f in enumerate(frames):
+        _, oc, on = oracle.points_to_voxel(f, vs, pcr, cfg["max_points"], True, cfg["max_voxels"])
+        lo, hi = int(vbase[b]), int(vbase[b + 1])
+        assert hi - lo == oc.shape[0] and np.array_equal(coors[lo:hi, 1:], oc) and np.array_equal(num[lo:hi], on)
+    with pytest.raises(_lib.PPError):
+        fs.submit(np.zeros((200_000, 3)), np.array([0, 200_000], np.int64), np.empty((1, post, 8), np.float32), np.empty(1, np.int32))
+    fs.close()
+
+
+def test_two_threads_voxelizer_and_nms(pp, synth, oracle):
+    """SURVEY 8(b) concurrency contract: the reference runs points_to_voxel on the tf.data generator thread
+    (load_data.py:2339, 2389-2392, 2966) while the main thread is inside nms (model/voxelnet.py:1259).  Two python
+    threads, each with its own per-thread context, 200 calls each, must reproduce the serial results bit for bit."""
+    import threading
+    cfg = synth.D435
+    vs, pcr = np.array(cfg["voxel_size"]), np.array(cfg["point_cloud_range"])
+    clouds = [synth.d435_cloud(90 + i, subsample=True)[: 30_000 + 5000 * i] for i in range(4)]
+    an = synth.anchors_stride(cfg)
+    dets = []
+    for i in range(4):
+        be, sc = synth.rpn_standin(an.shape[0], 90 + i)
+        boxes = pp.second_box_decode(be, an)
+        dets.append((pp.rbox_to_standup(boxes[:, [0, 1, 3, 4, 6]]), sc))
+    want_v = [pp.points_to_voxel(c, vs, pcr, cfg["max_points"], True, cfg["max_voxels"]) for c in clouds]
+    want_k = [pp.nms(b, s, cfg["nms_pre_max_size"], cfg["nms_post_max_size"], cfg["nms_iou_threshold"]) for b, s in dets]
+    for (v, c, n), cl in zip(want_v, clouds):  # the serial results are the oracle's
+        ov, oc, on = oracle.points_to_voxel(cl, vs, pcr, cfg["max_points"], True, cfg["max_voxels"])
+        assert np.array_equal(v, ov) and np.array_equal(c, oc) and np.array_equal(n, on)
+    errors = []
+
+    def voxel_loop():
+        try:
+            for it in range(200):
+                i = it % 4
+                v, c, n = pp.points_to_voxel(clouds[i], vs, pcr, cfg["max_points"], True, cfg["max_voxels"])
+                assert np.array_equal(v, want_v[i][0]) and np.array_equal(c, want_v[i][1]) and np.array_equal(n, want_v[i][2])
+        except BaseException as e:  # noqa: BLE001
+            errors.append(("voxelizer thread", e))
+
+    def nms_loop():
+        try:
+            for it in range(200):
+                i = it % 4
+                k = pp.nms(dets[i][0], dets[i][1], cfg["nms_pre_max_size"], cfg["nms_post_max_size"], cfg["nms_iou_threshold"])
+                assert (k is None and want_k[i] is None) or np.array_equal(k, want_k[i])
+        except BaseException as e:  # noqa: BLE001
+            errors.append(("nms thread", e))
+
+    ts = [threading.Thread(target=voxel_loop), threading.Thread(target=nms_loop)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
