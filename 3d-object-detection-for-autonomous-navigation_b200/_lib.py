@@ -58,6 +58,7 @@ SIGNATURES = {
     "pp_voxelize_workspace_bytes": (_sz, [_cfgp, _i64, C.c_int, _i64, C.c_int, C.c_int]),
     "pp_voxelize_dev": (C.c_int, [_cfgp, _vp, C.c_int, C.c_int, _vp, C.c_int, _i64, _i64, C.c_int, _vp, _vp,
                                   _vp, C.c_int, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pp_voxelize_set_small_path_min_points": (C.c_int, [_i64]),
     "pp_decorate_dev": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int, C.c_int, _f64, _f64, _f64, _f64, _vp, _vp]),
     "pp_scatter_workspace_bytes": (_sz, [C.c_int, C.c_int, C.c_int, _i64]),
     "pp_scatter_dev": (C.c_int, [_vp, _vp, _i64, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _sz, _vp]),

@@ -20,4 +20,6 @@ int vox_small_run(const pp_voxel_cfg* cfg, const VoxParams& p, const void* point
                   int64_t cap_rows, int32_t* voxel_num, int32_t* voxel_base, int32_t* point_slot, int32_t* cell_voxel,
                   void* workspace, size_t workspace_bytes, cudaStream_t st);
 
+void vox_small_set_min_points(int64_t n);
+
 }  // namespace pp

@@ -1001,3 +1001,9 @@ extern "C" int pp_voxelize_dev(const pp_voxel_cfg* cfg, const void* points, int 
     }
     return PP_OK;
 }
+
+extern "C" int pp_voxelize_set_small_path_min_points(int64_t n) {
+    PP_CHECK_ARG(n >= 0, "pp_voxelize_set_small_path_min_points: n < 0");
+    pp::vox_small_set_min_points(n);
+    return PP_OK;
+}

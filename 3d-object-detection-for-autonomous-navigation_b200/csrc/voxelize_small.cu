@@ -52,6 +52,11 @@ constexpr int kPlaceUnroll = 4;
 constexpr int kSub = 4;                            // quarters of a chunk that the place pass walks independently
 constexpr int kSubTiles = kChunk / kScanTile / kSub;  // scan tiles per quarter
 constexpr int kNoCut = 0x7fffffff;
+#ifndef PP_SMALL_MIN_POINTS
+#define PP_SMALL_MIN_POINTS 1000000
+#endif
+// batches below this many points take the any-grid path (process-wide, pp_voxelize_set_small_path_min_points)
+static int64_t g_small_min_points = PP_SMALL_MIN_POINTS;
 
 static_assert(kChunk % (kScanTile * kSub) == 0 && kChunk <= 65536, "chunk size");
 
@@ -725,10 +730,13 @@ static SmallWs carve_small(void* ws, int64_t ncell, int n_frames, int64_t total_
     return w;
 }
 
+void vox_small_set_min_points(int64_t n) { g_small_min_points = n; }
+
 bool vox_small_eligible(const pp_voxel_cfg* cfg, int64_t ncell, int n_frames, int64_t total_points,
                         int64_t max_frame_points, int D) {
     if (ncell > kMaxCellsSmall || D > 4 || max_frame_points > kMaxFramePointsSmall || cfg->max_points > kMaxPointsSmall)
         return false;
+    if (total_points < g_small_min_points) return false;  // a frame or two: the any-grid path has the shorter launch chain
     // the per-chunk tables must stay small next to the points themselves (callers that do not know the largest
     // frame pass the batch total, which sizes one table set per 16 384 points for every frame)
     const double ncellp = (double)align_up((size_t)ncell, 16);

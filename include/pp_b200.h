@@ -116,6 +116,12 @@ PP_API int pp_voxelize_dev(const pp_voxel_cfg* cfg, const void* points, int poin
                     int32_t* voxel_num, int32_t* voxel_base, int32_t* point_slot,
                     int32_t* cell_voxel, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Two bit-identical implementations sit behind pp_voxelize_dev: grids of at most 16 384 cells (the d435i grid) have a
+ * path that keeps its per-cell tables in shared memory, which wins for batches and loses to the any-grid path for a
+ * frame or two (its launch chain is longer).  Batches of fewer than `n` points take the any-grid path; default
+ * 1 000 000, 0 = always the shared-memory path when the grid allows it.  Process-wide; size workspaces after setting it. */
+PP_API int pp_voxelize_set_small_path_min_points(int64_t n);
+
 /* ---- pillar decoration ------------------------------------------------------------------
  * Replaces lines 143-203 of PillarFeatureNet.call (model/pointpillars.py), constants 121-124,
  * mask 23-49.  voxels [M,P,D] f32, num_points [M], coors [M,4] (batch,z,y,x) ->

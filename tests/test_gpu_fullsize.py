@@ -162,3 +162,46 @@ def test_stripe_nms_thresholds(pp, oracle, synth, thr):
     assert got[:len(prefix)] == prefix
     want = [int(top[i]) for i in oracle.rotate_nms_gpu(d[top[:3000]], thr)]
     assert got[:len(want)] == want
+
+
+@pytest.mark.parametrize("rotated", [True, False])
+def test_nms_stress_batched(pp, synth, rotated):
+    """BASELINE configs[3] is a BATCH of 100k-box frames (nms_gpu.py:455-490 once per frame in the reference): eight
+    distinct frames in ONE pp_nms_dev call -- per-frame cursors, kept counts and bins of the large-N path -- must give
+    exactly the eight single-frame results, with and without post_max, for the rotated and the standup kind."""
+    import torch
+    _lib = importlib.import_module(PKG + "._lib")
+    oracle = importlib.import_module("oracle")
+    B, N = 8, 100_000
+    frames = [synth.rotated_boxes(N, 700 + i, clustered=bool(i & 1)) for i in range(B)]
+    if rotated:
+        boxes = np.stack([f[:, :5] for f in frames])
+    else:
+        boxes = np.stack([oracle.rbox_to_standup(f[:, :5]) * np.float32(10) for f in frames])
+    scores = np.stack([f[:, 5] for f in frames])
+    kind = _lib.PP_NMS_ROTATED if rotated else _lib.PP_NMS_STANDUP
+    dev = torch.device("cuda", 0)
+    L = _lib.lib()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def run(bx, sc, post):
+        b, n = sc.shape
+        K = n if post <= 0 else post
+        tb, ts = torch.from_numpy(np.ascontiguousarray(bx)).to(dev), torch.from_numpy(np.ascontiguousarray(sc)).to(dev)
+        keep = torch.full((b, K), -1, dtype=torch.int32, device=dev)
+        cnt = torch.zeros((b,), dtype=torch.int32, device=dev)
+        wsb = int(L.pp_nms_workspace_bytes(kind, b, n, -1))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        _lib.check(L.pp_nms_dev(kind, C.c_void_p(tb.data_ptr()), bx.shape[2], C.c_void_p(ts.data_ptr()), None, b, n, -1, post, 0.5,
+                                C.c_void_p(keep.data_ptr()), K, C.c_void_p(cnt.data_ptr()), C.c_void_p(ws.data_ptr()), wsb, st))
+        torch.cuda.synchronize()
+        c = cnt.cpu().numpy()
+        k = keep.cpu().numpy()
+        return [k[i, :c[i]].tolist() for i in range(b)]
+    for post in (-1, 777):
+        batched = run(boxes, scores, post)
+        for i in range(B):
+            single = run(boxes[i:i + 1], scores[i:i + 1], post)[0]
+            assert len(single) > 100 and batched[i] == single, f"frame {i}, post_max {post}"
+        if post > 0:
+            assert all(len(k) == post for k in batched)

@@ -8,7 +8,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("seed", range(24))
-def test_voxelizer_random_config(pp, oracle, seed):
+def test_voxelizer_random_config(pp, oracle, seed, vox_path):
     rng = np.random.default_rng(1000 + seed)
     D = int(rng.integers(3, 7))
     dt = np.float64 if rng.random() < 0.5 else np.float32

@@ -24,7 +24,7 @@ def voxel_args(g):
 
 
 @pytest.mark.parametrize("case", VOXEL_CASES)
-def test_voxelizer_golden(pp, oracle, case):
+def test_voxelizer_golden(pp, oracle, case, vox_path):
     g = golden(case)
     args = voxel_args(g)
     v, c, n, slots = pp.points_to_voxel(*args, return_point_slots=True)
@@ -41,7 +41,7 @@ def _cfg_args(cfg):
 
 
 @pytest.mark.parametrize("name", ["d435_full", "d435_sub", "d435_f32", "kitti_ring", "kitti_shuf", "kitti_uniform"])
-def test_voxelizer_full_size_vs_oracle(pp, oracle, synth, name):
+def test_voxelizer_full_size_vs_oracle(pp, oracle, synth, name, vox_path):
     if name.startswith("d435"):
         cfg = synth.D435
         pts = synth.d435_cloud(3, subsample=(name == "d435_sub"))
@@ -58,7 +58,7 @@ def test_voxelizer_full_size_vs_oracle(pp, oracle, synth, name):
         assert a.dtype == b.dtype and np.array_equal(a, b)
 
 
-def test_voxelizer_edge_cases(pp, oracle, synth):
+def test_voxelizer_edge_cases(pp, oracle, synth, vox_path):
     cfg = synth.KITTI
     vs, pcr = np.array(cfg["voxel_size"]), np.array(cfg["point_cloud_range"])
     rng = np.random.default_rng(0)
@@ -86,7 +86,7 @@ def test_voxelizer_edge_cases(pp, oracle, synth):
         assert np.array_equal(a, b)
 
 
-def test_voxelizer_cell_boundaries(pp, oracle, synth):
+def test_voxelizer_cell_boundaries(pp, oracle, synth, vox_path):
     """Points exactly on / one ulp around cell boundaries: floor((p-lo)/vs) must match the
     reference's IEEE division in float64 and in float32 arithmetic."""
     rng = np.random.default_rng(11)
@@ -470,7 +470,7 @@ def test_ingest_bit_exact(pp, oracle):
                                rtol=0, atol=1e-14)
 
 
-def test_ingest_feeds_voxelizer(pp, oracle, synth):
+def test_ingest_feeds_voxelizer(pp, oracle, synth, vox_path):
     """Sensor cloud -> ingest -> points_to_voxel equals the reference sequence on the host."""
     cfg = synth.D435
     xyz = _sensor_cloud(120000, 21, 0.15)

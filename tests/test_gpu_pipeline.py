@@ -125,16 +125,20 @@ def test_pipeline_with_anchor_mask(synth, oracle):
 def test_profiler_and_launch_count(pp, synth):
     _lib = importlib.import_module(PKG + "._lib")
     pts = synth.d435_cloud(1, subsample=True)
-    pp.launch_count(reset=True)
-    _lib.profile_start()
-    pp.points_to_voxel(pts, np.array(synth.D435["voxel_size"]), np.array(synth.D435["point_cloud_range"]), 50, True, 12000)
-    rec = _lib.profile_stop()
-    names = [n for n, _ in rec]
-    # the d435i grid (10 240 cells) takes the shared-memory path: four launches, no memset
-    kernels = ["vox_scan", "vox_prefix", "vox_place", "vox_finish"]
-    assert names == kernels
-    assert all(t >= 0 for _, t in rec)
-    assert pp.launch_count() == len(kernels)
+    vs, pcr = np.array(synth.D435["voxel_size"]), np.array(synth.D435["point_cloud_range"])
+    # the d435i grid (10 240 cells) has the shared-memory table path: four launches, no memset.  Batches of fewer than a
+    # million points (this 101 760-point frame) take the any-grid path unless the threshold is lowered.
+    small = ["vox_scan", "vox_prefix", "vox_place", "vox_finish"]
+    anygrid = ["vox_mark", "vox_cell", "vox_rank", "vox_rowmap", "vox_bucket", "vox_gather"]
+    for thr, kernels, memset in ((0, small, []), (1_000_000, anygrid, ["vox_memset"])):
+        _lib.check(_lib.lib().pp_voxelize_set_small_path_min_points(thr))
+        pp.launch_count(reset=True)
+        _lib.profile_start()
+        pp.points_to_voxel(pts, vs, pcr, 50, True, 12000)
+        rec = _lib.profile_stop()
+        assert [n for n, _ in rec] == memset + kernels
+        assert all(t >= 0 for _, t in rec)
+        assert pp.launch_count() == len(kernels)
     # a KITTI-sized grid (214 272 cells) takes the any-grid path
     kp = synth.kitti_cloud(0)
     pp.launch_count(reset=True)
