@@ -352,7 +352,6 @@ def main():
     for _ in range(3):
         step_serial()
     ms_serial = timed(step_serial, args.steps)
-    del pipe_serial
 
     # ---- e2e: pinned host points in, host detections out, every step, through pp_stream ---------------
     for _ in range(3):
@@ -721,7 +720,7 @@ def main():
         torch.cuda.synchronize()
         _lib.profile_start()
         for _ in range(args.profile_steps):
-            step_resident()
+            step_serial()   # one stream: per-kernel times without the forked post stage running beside them
         for name, t in _lib.profile_stop():
             per_kernel.setdefault(name, []).append(t)
     kern_ms = {k: float(np.mean(v)) for k, v in per_kernel.items()}
