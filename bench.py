@@ -469,6 +469,7 @@ def main():
             return float(np.median(ts) * 1e3)
         vs_h, pcr_h = np.array(cfg["voxel_size"]), np.array(cfg["point_cloud_range"])
         cloud = distinct[0]
+        cloud_pin = pp.pinned_empty(cloud.shape, cloud.dtype); cloud_pin[:] = cloud   # page-locked: direct DMA both ways
         v_, c_, n_ = pp.points_to_voxel(cloud, vs_h, pcr_h, cfg["max_points"], True, cfg["max_voxels"])
         c4_ = np.concatenate([np.zeros((c_.shape[0], 1), np.int32), c_], axis=1)
         f_ = synth.pfn_standin(c_.shape[0], cfg["num_filters"], 0)
@@ -479,11 +480,15 @@ def main():
         dropin = {
             "points_to_voxel_ms": med_ms(lambda: pp.points_to_voxel(cloud, vs_h, pcr_h, cfg["max_points"], True, cfg["max_voxels"])),
             "points_to_voxel_bytes": {"h2d": int(cloud.nbytes), "d2h": int(v_.nbytes + c_.nbytes + n_.nbytes)},
+            "points_to_voxel_pinned_ms": med_ms(lambda: pp.points_to_voxel(cloud_pin, vs_h, pcr_h, cfg["max_points"], True,
+                                                                           cfg["max_voxels"], out="pinned")),
+            "points_to_voxel_pcie_floor_ms": (cloud.nbytes + v_.nbytes) / 55e9 * 1e3,
             "scatter_ms": med_ms(lambda: pp.scatter(f_, c4_, 1, grid[1], grid[0])),
             "nms_100_boxes_ms": med_ms(lambda: pp.nms(sb_, sco[0][order], cfg["nms_pre_max_size"], cfg["nms_post_max_size"],
                                                       cfg["nms_iou_threshold"])),
             "second_box_decode_ms": med_ms(lambda: pp.second_box_decode(box[0], an_h)),
-            "note": "one call each, numpy arrays in and out (pageable memory, staged through the context's pinned ring), "
+            "note": "one call each, numpy arrays in and out (pageable memory, staged through the context's pinned ring; `_pinned_`: "
+                    "page-locked input and output, the copy engine works on caller memory), "
                     "median of 15; reference call sites load_data.py:2966, model/pointpillars.py:285, model/voxelnet.py:1227,1259"}
 
     # ---- BASELINE configs[1] literally: ONE frame per step (latency-bound; reported beside the batched number) ----

@@ -20,7 +20,7 @@ def test_voxelizer_random_config(pp, oracle, seed, vox_path):
     hi = lo + (grid + extra) * vs
     pcr = np.concatenate([lo, hi])
     N = int(rng.choice([0, 1, 31, 32, 33, 1000, 5000, 20000]))
-    P = int(rng.choice([1, 2, 5, 31, 32, 33, 64, 65, 100]))
+    P = int(rng.choice([1, 2, 5, 31, 32, 33, 64, 65, 100, 129, 254]))
     cap = int(rng.choice([0, 1, 7, 100, 5000]))
     # clustered points so that some cells overflow max_points and the cap binds
     centers = rng.uniform(lo - 0.2 * (hi - lo), hi + 0.2 * (hi - lo), size=(max(1, N // 50), 3))
