@@ -6,24 +6,26 @@
 //   scan    (frame, chunk of 16 384 points)  rows staged by TMA bulk copies, four points per thread; cell id in
 //           the reference's arithmetic; in-range points are compacted IN INDEX ORDER into 16/32-byte records
 //           (coordinates in the output type) and 4-byte tags {cell | index in chunk}; the chunk's per-cell counts
-//           live in SHARED memory (ATOMS) and are written out once per chunk.
+//           live in SHARED memory (ATOMS) and are written out once per chunk, plus a saturated snapshot of them at
+//           the three quarter boundaries of the chunk.
 //   prefix  (frame, 256 cells)  per cell: exclusive prefix of the chunk counts = the slot base of every chunk
-//           (uint8, saturated: a base >= max_points means "full"); the chunk in which a cell first appears is
-//           counted, which gives every chunk the number of voxels opened before it; the cells' runs of
-//           min(points, max_points) entries are laid back to back in a per-frame slot table.
-//   place   (frame, chunk)  ONE WARP walks the chunk's record tags in order, 32 per step, with the chunk's running
-//           per-cell counts in shared memory: slot = count[cell] + rank among the step's earlier records of the
-//           cell (match_any, only in steps where a one-byte scratch table saw a cell repeat).  A record that finds
-//           count 0 opens its cell: because the walk is in index order, the running number of such records IS
-//           the voxel id (order of first touch), and the record that would open voxel number max_voxels is the
-//           reference's `break` position (load_data.py:630-634).  The record's position goes to entry `slot` of
-//           the cell's run in the slot table (4 bytes per kept point, 0.9 MB per d435i frame: it stays in L2,
-//           where scattering the 16-byte records themselves was measured DRAM-random-write bound: 384 us against
-//           158 us without the stores); no barrier, no atomic.
-//   finish  (pillar)  32 pillars per CTA: the records a pillar's run points at (before the break position) ->
-//           zero-padded voxel rows and the fused PillarFeatureNet decoration (model/pointpillars.py:143-203),
-//           both assembled in shared memory and written as two TMA bulk stores per CTA (the rows of consecutive
-//           pillars are contiguous in global memory); num_points, coors, point->slot map.
+//           (uint8, saturated: a base >= max_points means "full"); min(points, max_points) goes to the tail word
+//           of the cell's row of the slot table; the chunk in which a cell first appears is counted, which gives
+//           every chunk the number of voxels opened before it.
+//   place   (frame, quarter chunk)  ONE WARP walks the quarter's record tags in order, 32 per step, with the
+//           running per-cell counts (chunk base + quarter snapshot) in shared memory: slot = count[cell] + rank
+//           among the step's earlier records of the cell.  The step's peers are found through a shared-memory
+//           atomicOr table keyed by the cell (match_any costs 60 cycles per step and SM on scattered cells, the table
+//           4.4: tools/micro/match_tput.cu).  A record that finds count 0 opens its cell: because the walk is in index
+//           order, the running number of such records IS the voxel id (order of first touch), and the record that
+//           would open voxel number max_voxels is the reference's `break` position (load_data.py:630-634).  The
+//           record's position goes to entry `slot` of the cell's row of the slot table (max_points + 1 words per
+//           cell, L2 resident; scattering the 16-byte records themselves was measured DRAM-random-write bound).
+//   finish  (pillar)  one warp per two pillars, lane = slot: cell -> slot row -> records (before the break position);
+//           every lane owns its slot of the output rows whether or not a point sits in it, so the zero-padded voxel
+//           rows and the fused PillarFeatureNet decoration (model/pointpillars.py:143-203) leave as dense coalesced
+//           stores straight from registers; num_points, coors, point->slot map.  (Staging the rows in shared memory
+//           for TMA bulk stores was measured slower: profiles/r02_notes.md.)
 #include "pp_common.cuh"
 #include "vox_common.cuh"
 #include "vox_internal.h"

@@ -5,7 +5,7 @@
  * krullgit/3D-Object-Detection-for-autonomous-navigation.  Each entry point names the
  * reference interface it stands in for (paths relative to the reference checkout).
  *
- * Two layers, both plain C (pointers + sizes, no framework types):
+ * Three layers, all plain C (pointers + sizes, no framework types):
  *
  *   *_dev   device pointers in, device pointers out, asynchronous on the caller's stream,
  *           caller-provided workspace.  This is what a DLPack / __cuda_array_interface__
@@ -15,11 +15,14 @@
  *           in pieces so that the host copy overlaps the transfer).  Synchronous, like the
  *           reference's numpy functions.
  *           This is what the reference's call sites bind through ctypes.
+ *   pp_stream  a batch of host clouds in, host detections out per call; the copy of the next batch
+ *           overlaps the kernels of the current one inside the library (end of this header).
  *
  * Conventions
  *   - Every function returns 0 on success, <0 on error (PP_E_*); pp_last_error_string() gives the
  *     thread-local message.  Nothing throws or exits across this boundary.
- *   - The library never frees or retains caller memory.  The only state is inside pp_ctx.
+ *   - The library never frees or retains caller memory.  State lives in pp_ctx / pp_stream objects; process-wide are
+ *     only the kernel launch-configuration cache and pp_voxelize_set_small_path_min_points.
  *   - A pp_ctx must not be used from two threads at once; create one per thread (the reference
  *     calls the voxelizer on the tf.data thread and NMS on the main thread).
  *   - `stream` is a cudaStream_t passed as void*.  The legacy default stream is never used
