@@ -76,7 +76,7 @@ SIGNATURES = {
     "pp_anchor_mask_workspace_bytes": (_sz, [C.c_int, C.c_int, C.c_int]),
     "pp_anchor_mask_dev": (C.c_int, [_vp, C.c_int, _i64, _vp, C.c_int, C.c_int, C.c_int, _vp, _i64, _f32, _vp, _vp, _vp,
                                      _vp, _vp, _sz, _vp]),
-    "pp_predict_workspace_bytes": (_sz, [C.c_int, _i64]),
+    "pp_predict_workspace_bytes": (_sz, [_pcfgp, C.c_int, _i64, C.c_int]),
     "pp_predict_dev": (C.c_int, [_pcfgp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _i64, C.c_int, _vp, _vp, _vp, _vp,
                                  _vp, _vp, _vp, _sz, _vp]),
     "pp_predict_host": (C.c_int, [_vp, _pcfgp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _i64, C.c_int, _vp, _vp, _vp,

@@ -540,7 +540,7 @@ extern "C" int pp_predict_host(pp_ctx* c, const pp_predict_cfg* cfg, const float
     PP_CHECK_ARG(cfg && B > 0 && A >= 0 && K > 0 && box3d_lidar && count, "pp_predict_host: bad argument");
     const size_t nbox = (size_t)B * A;
     const size_t n_anch = cfg->anchors_per_frame ? nbox : (size_t)A;
-    const size_t ws_bytes = pp_predict_workspace_bytes(B, A);
+    const size_t ws_bytes = pp_predict_workspace_bytes(cfg, B, A, K);
     void *d_bp, *d_cls, *d_dir = nullptr, *d_an, *d_mask = nullptr, *d_rect = nullptr, *d_trv = nullptr, *d_ws, *d_out;
     PP_TRY(c->get(0, nbox * 28, &d_bp));
     PP_TRY(c->get(1, nbox * 4 * cfg->num_class, &d_cls));

@@ -30,10 +30,8 @@ nms_topk_kernel(const float* __restrict__ scores, const int* __restrict__ n_vali
     const int b = blockIdx.x;
     const float* sc = scores + (int64_t)b * N;
     const int nv = n_valid ? max(0, min(n_valid[b], (int)N)) : (int)N;
-    const int kk = min(k, block_count_present(sc, nv));
+    const int kk = block_topk(sc, nv, k, skey);
     if (threadIdx.x == 0) n_sorted[b] = kk;
-    if (kk == 0) return;
-    block_topk(sc, nv, kk, skey);
     for (int i = threadIdx.x; i < kk; i += kSortThreads)
         order[(int64_t)b * order_stride + i] = (int)(skey[i] & 0xffffffffu);
 }
@@ -992,29 +990,35 @@ __global__ void nms_stripe_finish_kernel(const int* __restrict__ kept_cnt, int l
 }
 
 // ---------------------------------------------------------------------------------------------
-// Whole NMS of one frame in one CTA when at most kSmallN boxes survive pre_max_size (the live
-// path: pre_max_size = 100, configs/train.yaml:176): top-k, per-box prep, all pairs spread over
-// the block with the mask in shared memory, sweep by one thread.  One launch instead of four and
-// no global intermediates.
+// Whole NMS of one frame in one launch when at most kSmallN boxes survive pre_max_size (the live
+// path: pre_max_size = 100, configs/train.yaml:176): top-k, per-box prep, all pairs with the mask in
+// shared memory, sweep by one thread.  One launch instead of four and no global intermediates.
+// A frame is a thread-block CLUSTER of `csize` CTAs (1, 2, 4 or 8; as many as fit one wave of the batch):
+// every CTA selects and prepares the same <= 128 boxes (identical results, no exchange needed), takes every
+// csize-th pair of the i < j triangle, and ORs its suppression bits into the mask of CTA 0 through
+// distributed shared memory; CTA 0 sweeps.  A single frame on 8 SMs tests one pair per thread instead of five.
 constexpr int kSmallN = 128;
 template <bool ROTATED>
 __global__ void __launch_bounds__(kSortThreads)
 nms_small_kernel(BoxSrc bs, const float* __restrict__ scores,
                  const int* __restrict__ n_valid, int64_t N, int k, int post_max, float thresh,
                  int* __restrict__ keep, int64_t keep_stride, int* __restrict__ keep_count) {
+    namespace cg = cooperative_groups;
     using BoxG = typename std::conditional<ROTATED, RBoxG, float4>::type;
     __shared__ unsigned long long skey[kSelectMaxK];
     __shared__ BoxG s_box[kSmallN];
     __shared__ unsigned long long s_mask[kSmallN][2];
-    const int b = blockIdx.x;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int csize = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int b = blockIdx.x / csize;
     const float* sc = scores + (int64_t)b * N;
     const int nv = n_valid ? max(0, min(n_valid[b], (int)N)) : (int)N;
-    const int n = min(min(k, kSmallN), block_count_present(sc, nv));
-    if (n == 0) {
-        if (threadIdx.x == 0) keep_count[b] = 0;
+    const int n = block_topk(sc, nv, min(k, kSmallN), skey);
+    if (n == 0) {  // the same in every CTA of the cluster
+        if (threadIdx.x == 0 && rank == 0) keep_count[b] = 0;
         return;
     }
-    block_topk(sc, nv, n, skey);
     if (threadIdx.x < n) {
         const int64_t row = (int64_t)b * N + (int)(skey[threadIdx.x] & 0xffffffffu);
         if constexpr (ROTATED) {
@@ -1032,11 +1036,19 @@ nms_small_kernel(BoxSrc bs, const float* __restrict__ scores,
         s_mask[threadIdx.x][0] = 0ull;
         s_mask[threadIdx.x][1] = 0ull;
     }
-    __syncthreads();
+    if (csize > 1) cluster.sync(); else __syncthreads();
+    // 32-bit ORs: native shared-memory atomics, also from the other CTAs of the cluster (a 64-bit OR is a
+    // compare-and-swap loop on local shared memory and loses bits against remote updates)
+    unsigned* own = reinterpret_cast<unsigned*>(&s_mask[0][0]);
+    unsigned* mask0 = csize > 1 ? cluster.map_shared_rank(own, 0) : own;
     const double th = (double)thresh;
-    for (int idx = threadIdx.x; idx < n * n; idx += kSortThreads) {
-        const int i = idx / n, j = idx - i * n;
-        if (j <= i) continue;
+    const int npairs = n * (n - 1) / 2;
+    for (int p = rank + csize * (int)threadIdx.x; p < npairs; p += csize * kSortThreads) {
+        // pair p of the triangle, column-major: p = j (j - 1) / 2 + i with i < j
+        int j = (int)((1.f + sqrtf(1.f + 8.f * (float)p)) * 0.5f);
+        while (j * (j - 1) / 2 > p) --j;
+        while ((j + 1) * j / 2 <= p) ++j;
+        const int i = p - j * (j - 1) / 2;
         bool sup;
         if constexpr (ROTATED) {
             RBox a, c;
@@ -1046,10 +1058,10 @@ nms_small_kernel(BoxSrc bs, const float* __restrict__ scores,
         } else {
             sup = standup_iou(s_box[i], s_box[j]) > th;
         }
-        if (sup) atomicOr(&s_mask[i][j >> 6], 1ull << (j & 63));
+        if (sup) atomicOr(&mask0[4 * i + (j >> 5)], 1u << (j & 31));
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    if (csize > 1) cluster.sync(); else __syncthreads();
+    if (threadIdx.x == 0 && rank == 0) {
         unsigned long long rm0 = 0ull, rm1 = 0ull;
         const int limit = (int)min((int64_t)(post_max > 0 ? post_max : n), keep_stride);
         int nk = 0;
@@ -1064,6 +1076,36 @@ nms_small_kernel(BoxSrc bs, const float* __restrict__ scores,
         }
         keep_count[b] = nk;
     }
+}
+
+// Cluster size of nms_small for a batch of B frames: the largest of 8, 4, 2, 1 that keeps the batch in one wave of
+// one CTA per SM.  A cluster lives inside one GPC (18-20 SMs on B200), so clusters of 8 pack two per GPC: 16 frames
+// as 16 x 8 CTAs measured 62 us against 40 us for 32 frames as 32 x 4.
+static int nms_small_cluster(int B) {
+#ifdef PP_NMS_SMALL_CLUSTER
+    return PP_NMS_SMALL_CLUSTER;
+#endif
+    const int sms = num_sms();
+    if (B * 16 <= sms) return 8;
+    if (B * 4 <= sms) return 4;
+    if (B * 2 <= sms) return 2;
+    return 1;
+}
+
+template <typename... Args>
+static cudaError_t launch_clustered(void (*kernel)(Args...), unsigned grid, unsigned block, int csize, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid);
+    lc.blockDim = dim3(block);
+    lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)csize;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    lc.attrs = at;
+    lc.numAttrs = 1;
+    return cudaLaunchKernelEx(&lc, kernel, args...);
 }
 
 // final detections: out[b,k,:] = (boxes[b, keep[b,k], 0:box_dim], scores[b, keep[b,k]]), zero padded
@@ -1258,12 +1300,10 @@ static int nms_run(int kind, const float* boxes, int box_stride, const float* an
     PP_CHECK_ARG(w.cb_cap * 8 <= 200 * 1024, "pp_nms_dev: more than 1.6M boxes per frame after pre_max_size");
     if (w.n_cap <= kSmallN) {
         PP_TIMED("nms_small", st);
-        if (kind == PP_NMS_ROTATED)
-            nms_small_kernel<true><<<B, kSortThreads, 0, st>>>(bsrc, scores, n_valid, N, (int)w.n_cap,
-                                                              post_max_size, thresh, keep, keep_stride, keep_count);
-        else
-            nms_small_kernel<false><<<B, kSortThreads, 0, st>>>(bsrc, scores, n_valid, N, (int)w.n_cap,
-                                                               post_max_size, thresh, keep, keep_stride, keep_count);
+        const int csize = nms_small_cluster(B);
+        PP_CUDA(launch_clustered(kind == PP_NMS_ROTATED ? nms_small_kernel<true> : nms_small_kernel<false>, (unsigned)(B * csize),
+                                 (unsigned)kSortThreads, csize, st, bsrc, scores, n_valid, N, (int)w.n_cap, post_max_size, thresh,
+                                 keep, keep_stride, keep_count));
         PP_LAUNCHED();
         return PP_OK;
     }

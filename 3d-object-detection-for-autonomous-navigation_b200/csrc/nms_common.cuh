@@ -65,40 +65,93 @@ __device__ __forceinline__ void select_digit(const unsigned* hist, unsigned rem,
     }
 }
 
-// Block-wide: the kk (<= kSelectMaxK) best of sc[0..nv) by (score desc, index desc), sorted, as
-// (key<<32 | index) in skey[0..kk).  All kSortThreads threads of the block must call it.
-__device__ __forceinline__ void block_topk(const float* __restrict__ sc, int nv, int kk,
-                                           unsigned long long* skey /*[kSelectMaxK]*/) {
-    __shared__ unsigned hist[256];
-    __shared__ unsigned s_prefix, s_remaining, s_count, s_scratch;
+// One histogram pass of the radix select over `count` elements: element e has key key_of(e) and takes part when
+// in(key); bins are the byte at `shift`.  Warp-aggregated: scores cluster in a few top-byte bins, a plain atomicAdd
+// would serialise the whole block on one shared-memory word.  All threads of the block must call it.
+template <typename KeyOf, typename In>
+__device__ __forceinline__ void topk_hist_pass(unsigned* hist, int count, int shift, KeyOf key_of, In in) {
+    for (int e0 = 0; e0 < count; e0 += kSortThreads) {
+        const int e = e0 + threadIdx.x;
+        int d = -1;
+        if (e < count) {
+            const unsigned key = key_of(e);
+            if (in(key)) d = (int)((key >> shift) & 255u);
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        if (d >= 0 && (int)lane_id() == __ffs(peers) - 1) atomicAdd(&hist[d], (unsigned)__popc(peers));
+    }
+}
 
+// Block-wide: the n = min(kmax, present scores) best of sc[0..nv) by (score desc, index desc), sorted, as
+// (key<<32 | index) in skey[0..n); returns n (kmax <= kSelectMaxK).  All kSortThreads threads of the block must call it.
+//   pass 1   byte histogram of all keys + count of absent (-inf) scores
+//   as soon as the keys that can still be selected (larger prefix, or inside the chosen bin) number <= kTopkCand, their
+//   indices are compacted into a shared-memory list and the remaining passes, the tie pass and the collection walk
+//   that list instead of the whole frame (d435i: 10 240 scores -> ~1 900 after the first byte)
+constexpr int kTopkCand = 4096;
+__device__ __forceinline__ int block_topk(const float* __restrict__ sc, int nv, int kmax,
+                                          unsigned long long* skey /*[kSelectMaxK]*/) {
+    __shared__ unsigned hist[256];
+    __shared__ unsigned cand[kTopkCand];
+    __shared__ unsigned s_prefix, s_remaining, s_count, s_scratch, s_absent, s_ncand;
+
+    if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) { s_absent = 0; s_ncand = 0; s_prefix = 0; }
+    __syncthreads();
+    // ---- pass 1 over the frame: top byte + absent count
+    for (int i0 = 0; i0 < nv; i0 += kSortThreads) {
+        const int i = i0 + threadIdx.x;
+        int d = -1;
+        bool absent = false;
+        if (i < nv) {
+            const float v = sc[i];
+            absent = v == -INFINITY;
+            d = (int)(score_key(v) >> 24);
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        if (d >= 0 && (int)lane_id() == __ffs(peers) - 1) atomicAdd(&hist[d], (unsigned)__popc(peers));
+        const unsigned ab = __ballot_sync(0xffffffffu, absent);
+        if (ab && lane_id() == 0) atomicAdd(&s_absent, (unsigned)__popc(ab));
+    }
+    __syncthreads();
+    const int kk = min(kmax, nv - (int)s_absent);
+    if (kk <= 0) return 0;
     unsigned T = 0, Tidx = 0;
+    int ncand = -1;  // < 0: the frame itself is the element list
+    auto key_at = [&](int e) { return score_key(sc[ncand < 0 ? e : (int)cand[e]]); };
+    auto idx_at = [&](int e) { return ncand < 0 ? (unsigned)e : cand[e]; };
     if (kk < nv) {
         // ---- k-th largest key
-        if (threadIdx.x == 0) { s_prefix = 0; s_remaining = (unsigned)kk; }
         for (int shift = 24; shift >= 0; shift -= 8) {
-            if (threadIdx.x < 256) hist[threadIdx.x] = 0;
-            __syncthreads();
             const unsigned prefix = s_prefix;
-            // warp-aggregated histogram: scores cluster in a few top-byte bins, a plain atomicAdd
-            // would serialise the whole block on one shared-memory word
-            for (int i0 = 0; i0 < nv; i0 += kSortThreads) {
-                const int i = i0 + threadIdx.x;
-                int d = -1;
-                if (i < nv) {
-                    const unsigned key = score_key(sc[i]);
-                    if (shift == 24 || ((key ^ prefix) >> (shift + 8)) == 0) d = (int)((key >> shift) & 255u);
-                }
-                const unsigned peers = __match_any_sync(0xffffffffu, d);
-                if (d >= 0 && (int)lane_id() == __ffs(peers) - 1) atomicAdd(&hist[d], (unsigned)__popc(peers));
+            if (shift != 24) {
+                if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+                __syncthreads();
+                topk_hist_pass(hist, ncand < 0 ? nv : ncand, shift, key_at,
+                               [&](unsigned key) { return ((key ^ prefix) >> (shift + 8)) == 0; });
+                __syncthreads();
             }
-            __syncthreads();
             if (threadIdx.x < 32) {
-                const unsigned rem = s_remaining;
+                const unsigned rem = shift == 24 ? (unsigned)kk : s_remaining;
                 __syncwarp();
                 select_digit(hist, rem, prefix, shift, &s_prefix, &s_remaining, &s_count);
             }
             __syncthreads();
+            // keys that can still be selected: larger prefix (kk - remaining of them) or inside the chosen bin
+            if (ncand < 0 && shift > 0 && (unsigned)kk - s_remaining + s_count <= (unsigned)kTopkCand) {
+                const unsigned floor_key = s_prefix;
+                for (int i0 = 0; i0 < nv; i0 += kSortThreads) {
+                    const int i = i0 + threadIdx.x;
+                    const bool take = i < nv && (score_key(sc[i]) >> shift) >= (floor_key >> shift);
+                    const unsigned bal = __ballot_sync(0xffffffffu, take);
+                    unsigned base = 0;
+                    if (lane_id() == 0 && bal) base = atomicAdd(&s_ncand, (unsigned)__popc(bal));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (take) cand[base + __popc(bal & ((1u << lane_id()) - 1u))] = (unsigned)i;
+                }
+                __syncthreads();
+                ncand = (int)s_ncand;
+            }
         }
         T = s_prefix;
         const unsigned need_eq = s_remaining, have_eq = s_count;
@@ -110,9 +163,10 @@ __device__ __forceinline__ void block_topk(const float* __restrict__ sc, int nv,
                 if (threadIdx.x < 256) hist[threadIdx.x] = 0;
                 __syncthreads();
                 const unsigned prefix = s_prefix;
-                for (int i = threadIdx.x; i < nv; i += kSortThreads) {
-                    if (score_key(sc[i]) != T) continue;
-                    const unsigned key = (unsigned)i;
+                const int count = ncand < 0 ? nv : ncand;
+                for (int e = threadIdx.x; e < count; e += kSortThreads) {
+                    if (key_at(e) != T) continue;
+                    const unsigned key = idx_at(e);
                     if (shift == 24 || ((key ^ prefix) >> (shift + 8)) == 0) atomicAdd(&hist[(key >> shift) & 255u], 1u);
                 }
                 __syncthreads();
@@ -127,17 +181,20 @@ __device__ __forceinline__ void block_topk(const float* __restrict__ sc, int nv,
             __syncthreads();
         }
     }
-    // ---- compaction (arbitrary order) + bitonic sort, descending on (key, index)
+    // ---- collection (arbitrary order) + bitonic sort, descending on (key, index)
     if (threadIdx.x == 0) s_count = 0;
     int np2 = 1;
     while (np2 < kk) np2 <<= 1;
     for (int i = threadIdx.x; i < np2; i += kSortThreads) skey[i] = 0ull;
     __syncthreads();
-    for (int i = threadIdx.x; i < nv; i += kSortThreads) {
-        const unsigned key = score_key(sc[i]);
-        if (kk == nv || key > T || (key == T && (unsigned)i >= Tidx)) {
-            const unsigned pos = atomicAdd(&s_count, 1u);
-            if (pos < (unsigned)kSelectMaxK) skey[pos] = ((unsigned long long)key << 32) | (unsigned)i;
+    {
+        const int count = ncand < 0 ? nv : ncand;
+        for (int e = threadIdx.x; e < count; e += kSortThreads) {
+            const unsigned key = key_at(e), i = idx_at(e);
+            if (kk == nv || key > T || (key == T && i >= Tidx)) {
+                const unsigned pos = atomicAdd(&s_count, 1u);
+                if (pos < (unsigned)kSelectMaxK) skey[pos] = ((unsigned long long)key << 32) | i;
+            }
         }
     }
     __syncthreads();
@@ -153,6 +210,7 @@ __device__ __forceinline__ void block_topk(const float* __restrict__ sc, int nv,
             __syncthreads();
         }
     }
+    return kk;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -124,7 +124,7 @@ class FramePipeline:
                 self.ws_in_bytes = int(L.pp_ingest_workspace_bytes(B, self.n_sensor))
                 self.ws_in = torch.empty((self.ws_in_bytes,), dtype=torch.uint8, **e)
                 self.pcfg = _make_predict_cfg(1, True, 100, self.pre, self.post, self.thr, 0.0, rotated_nms, False)
-                self.ws_pr_bytes = int(L.pp_predict_workspace_bytes(B, self.A))
+                self.ws_pr_bytes = int(L.pp_predict_workspace_bytes(C.byref(self.pcfg), B, self.A, self.post))
                 self.ws_pr = torch.empty((self.ws_pr_bytes,), dtype=torch.uint8, **e)
                 self.box3d_lidar = torch.empty((B, self.post, 7), dtype=torch.float32, **e)
                 self.box3d_camera = torch.empty((B, self.post, 7), dtype=torch.float64, **e)

@@ -72,7 +72,7 @@ def predict_arrays(box_preds, cls_preds, dir_preds, anchors, anchors_mask=None, 
     cfg = make_cfg(num_class, use_direction_classifier, top_k, nms_pre_max_size, nms_post_max_size, nms_iou_threshold,
                    nms_score_threshold, rotated, per_frame)
     n_max = cfg.top_k if cfg.nms_pre_max_size <= 0 else min(cfg.top_k, cfg.nms_pre_max_size)
-    K = max(1, n_max if cfg.nms_post_max_size <= 0 else min(n_max, cfg.nms_post_max_size))
+    K = max(1, min(A, n_max if cfg.nms_post_max_size <= 0 else min(n_max, cfg.nms_post_max_size)))
     lid = np.empty((B, K, 7), np.float32)
     cam = np.empty((B, K, 7), np.float64) if rc is not None else None
     sc = np.empty((B, K), np.float32)

@@ -236,8 +236,10 @@ PP_API int pp_anchor_mask_dev(const int32_t* coors, int coors_cols, int64_t M, c
  * threshold (1190-1198), top-k by score (hard-coded 100, 1207), second_box_decode of the selected
  * boxes (1227), standup boxes (1233-1249) and nms (1259-1265) -- or rotated NMS when nms_kind is
  * PP_NMS_ROTATED --, `box_preds[selected]` (1281-1287), direction flip (1301-1306) and
- * box_lidar_to_camera (1319, load_data.py:1511-1523).  One launch for the scores, one CTA per frame for
- * the rest; min(top_k, nms_pre_max_size) must be <= 128.
+ * box_lidar_to_camera (1319, load_data.py:1511-1523).  One launch for the scores, then one CTA per frame for
+ * the rest when min(top_k, nms_pre_max_size) <= 128 (the reference's 100); larger selections (the reference's
+ * code has no limit) run pp_decode_nms_dev on the same scores plus one launch for the per-detection tail.
+ * Workspace: pp_predict_workspace_bytes(cfg, B, A, K).
  *   box_preds [B,A,7], cls_preds [B,A,num_class], dir_preds [B,A,2] (NULL without direction classifier),
  *   anchors [A,7] shared (anchors_per_frame 0) or [B,A,7], anchors_mask [B,A] uint8 or NULL,
  *   rect, Trv2c [B,4,4] float32 or both NULL (then box3d_camera is not written)
@@ -256,7 +258,7 @@ typedef struct pp_predict_cfg {
     float nms_score_threshold;        /* <= 0: off */
     int32_t anchors_per_frame;
 } pp_predict_cfg;
-PP_API size_t pp_predict_workspace_bytes(int B, int64_t A);
+PP_API size_t pp_predict_workspace_bytes(const pp_predict_cfg* cfg, int B, int64_t A, int K);
 PP_API int pp_predict_dev(const pp_predict_cfg* cfg, const float* box_preds, const float* cls_preds,
                    const float* dir_preds, const float* anchors, const uint8_t* anchors_mask, const float* rect,
                    const float* Trv2c, int B, int64_t A, int K, float* box3d_lidar, double* box3d_camera,

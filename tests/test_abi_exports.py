@@ -77,8 +77,10 @@ def test_argument_validation_needs_no_gpu(pp):
     # "next" rows: predict glue and sensor ingest
     pc = _lib.PredictCfg(1, 1, 100, 100, 50, 0, 0.5, 0.0, 1)
     pargs = [C.byref(pc), one, one, one, one, None, None, None, 2, 100, 50, one, None, one, one, one, one, one, 1 << 20, None]
-    bad = list(pargs); bad[0] = C.byref(_lib.PredictCfg(1, 1, 500, -1, 50, 0, 0.5, 0.0, 1))   # 500 boxes into the fused NMS
-    assert L.pp_predict_dev(*bad) == -1 and b"exceeds 128" in L.pp_last_error_string()
+    big = _lib.PredictCfg(1, 1, 500, -1, 50, 0, 0.5, 0.0, 1)                                    # 500 boxes: the general NMS path
+    assert L.pp_predict_workspace_bytes(C.byref(big), 2, 100000, 50) > L.pp_predict_workspace_bytes(C.byref(pc), 2, 100000, 50) >= 800000
+    bad = list(pargs); bad[0] = C.byref(big); bad[9] = 100000; bad[18] = L.pp_predict_workspace_bytes(C.byref(pc), 2, 100000, 50)
+    assert L.pp_predict_dev(*bad) == -3
     bad = list(pargs); bad[6] = one                                                             # rect without Trv2c
     assert L.pp_predict_dev(*bad) == -1
     bad = list(pargs); bad[18] = 16

@@ -99,6 +99,47 @@ def test_predict_fuzz(pp, oracle, synth, seed):
         np.testing.assert_allclose(sc[b, :k], want["scores"], rtol=1e-6, atol=0)
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_predict_large_selection(pp, oracle, synth, seed):
+    """N2 with min(top_k, nms_pre_max_size) > 128 (KITTI-style 1000 / 300): the general decode + NMS path behind the same call."""
+    rng = np.random.default_rng(7000 + seed)
+    A = int(rng.choice([150, 3000, 10240, 40000]))
+    B = int(rng.integers(1, 4))
+    nc = int(rng.integers(1, 4))
+    base = synth.anchors_stride(synth.D435)
+    an = base[rng.choice(10240, A, replace=A > 10240)]
+    per_frame = bool(seed % 3 == 2)
+    if per_frame:
+        an = np.stack([an[rng.permutation(A)] for _ in range(B)])
+    bp = rng.normal(0, 0.2, (B, A, 7)).astype(np.float32)
+    cl = rng.normal(-1, 1.5, (B, A, nc)).astype(np.float32)
+    dr = rng.normal(0, 1, (B, A, 2)).astype(np.float32)
+    mask = (rng.random((B, A)) < rng.uniform(0.05, 1.0)).astype(np.uint8) if rng.random() < 0.6 else None
+    rect = rng.normal(0, 1, (B, 4, 4)).astype(np.float32)
+    trv = rng.normal(0, 1, (B, 4, 4)).astype(np.float32)
+    top_k = int(rng.choice([129, 500, 1000, 1025, 3000]))
+    pre = int(rng.choice([-1, 129, 1000, 2000]))
+    post = int(rng.choice([-1, 50, 300]))
+    opts = dict(top_k=top_k, nms_pre_max_size=pre, nms_post_max_size=post, nms_iou_threshold=float(rng.uniform(0.05, 0.8)),
+                nms_score_threshold=float(rng.choice([0.0, 0.05, 0.3])), rotated=bool(seed % 2))
+    lid, cam, sc, lab, idx, cnt = pp.predict_arrays(bp, cl, dr, an, mask, rect, trv, num_class=nc, **opts)
+    for b in range(B):
+        want = oracle.predict_frame(bp[b], cl[b], dr[b], an[b] if per_frame else an, None if mask is None else mask[b], rect[b],
+                                    trv[b], top_k=top_k, pre_max_size=pre, post_max_size=post,
+                                    iou_threshold=opts["nms_iou_threshold"], score_threshold=opts["nms_score_threshold"],
+                                    rotated=opts["rotated"])
+        k = int(cnt[b])
+        if want["box3d_lidar"] is None:
+            assert k == 0
+            continue
+        assert np.array_equal(idx[b, :k], want["anchor_index"]), (seed, b, opts)
+        assert np.array_equal(lab[b, :k], want["label_preds"])
+        np.testing.assert_allclose(lid[b, :k], want["box3d_lidar"], rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(cam[b, :k], want["box3d_camera"], rtol=1e-5, atol=1e-4)
+        np.testing.assert_allclose(sc[b, :k], want["scores"], rtol=1e-6, atol=0)
+        assert np.all(idx[b, k:] == -1) and not lid[b, k:].any()
+
+
 @pytest.mark.parametrize("seed", range(4))
 def test_ingest_fuzz(pp, oracle, seed):
     """N3: random record layouts, slices and NaN patterns; reference matrices => bit-identical."""

@@ -434,8 +434,16 @@ def test_predict_options(pp, oracle, synth):
     want = oracle.predict_frame(bp[0], cl[0, :, :1], None, an, None, None, None, use_direction_classifier=False)
     assert cam2 is None and np.array_equal(idx2[0, :cnt2[0]], want["anchor_index"])
     np.testing.assert_allclose(lid2[0, :cnt2[0]], want["box3d_lidar"], rtol=1e-5, atol=1e-6)
-    with pytest.raises(pp.PPError):
-        pp.predict_arrays(bp, cl, dr, an, None, rect, trv, num_class=3, top_k=500, nms_pre_max_size=None)
+    # more than 128 boxes into NMS (no limit in the reference): the general decode + NMS path behind the same call
+    lid3, cam3, sc3, lab3, idx3, cnt3 = pp.predict_arrays(bp, cl, dr, an, None, rect, trv, num_class=3, top_k=500, nms_pre_max_size=None,
+                                                          nms_post_max_size=None, nms_iou_threshold=0.3)
+    for b in range(B):
+        want = oracle.predict_frame(bp[b], cl[b], dr[b], an, None, rect[b], trv[b], top_k=500, pre_max_size=None, post_max_size=None,
+                                    iou_threshold=0.3)
+        k = int(cnt3[b])
+        assert k > 0 and np.array_equal(idx3[b, :k], want["anchor_index"]) and np.array_equal(lab3[b, :k], want["label_preds"])
+        np.testing.assert_allclose(lid3[b, :k], want["box3d_lidar"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(cam3[b, :k], want["box3d_camera"], rtol=1e-5, atol=1e-6)
 
 
 def _sensor_cloud(n, seed, nan_frac=0.2):
