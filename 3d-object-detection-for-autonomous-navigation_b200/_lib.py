@@ -62,6 +62,7 @@ SIGNATURES = {
     "pp_decorate_dev": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int, C.c_int, _f64, _f64, _f64, _f64, _vp, _vp]),
     "pp_scatter_workspace_bytes": (_sz, [C.c_int, C.c_int, C.c_int, _i64]),
     "pp_scatter_dev": (C.c_int, [_vp, _vp, _i64, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _sz, _vp]),
+    "pp_scatter_cells_dev": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "pp_box_decode_dev": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "pp_rbox_to_standup_dev": (C.c_int, [_vp, C.c_int, _i64, _vp, _vp]),
     "pp_nms_workspace_bytes": (_sz, [C.c_int, C.c_int, _i64, C.c_int]),

@@ -1002,12 +1002,14 @@ template <bool ROTATED>
 __global__ void __launch_bounds__(kSortThreads)
 nms_small_kernel(BoxSrc bs, const float* __restrict__ scores,
                  const int* __restrict__ n_valid, int64_t N, int k, int post_max, float thresh,
-                 int* __restrict__ keep, int64_t keep_stride, int* __restrict__ keep_count) {
+                 int* __restrict__ keep, int64_t keep_stride, int* __restrict__ keep_count, float* __restrict__ dets, int K) {
     namespace cg = cooperative_groups;
     using BoxG = typename std::conditional<ROTATED, RBoxG, float4>::type;
     __shared__ unsigned long long skey[kSelectMaxK];
     __shared__ BoxG s_box[kSmallN];
     __shared__ unsigned long long s_mask[kSmallN][2];
+    __shared__ int s_kept[kSmallN];
+    __shared__ int s_nk;
     cg::cluster_group cluster = cg::this_cluster();
     const int csize = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
@@ -1016,7 +1018,12 @@ nms_small_kernel(BoxSrc bs, const float* __restrict__ scores,
     const int nv = n_valid ? max(0, min(n_valid[b], (int)N)) : (int)N;
     const int n = block_topk(sc, nv, min(k, kSmallN), skey);
     if (n == 0) {  // the same in every CTA of the cluster
-        if (threadIdx.x == 0 && rank == 0) keep_count[b] = 0;
+        if (rank == 0) {
+            if (threadIdx.x == 0) keep_count[b] = 0;
+            if (dets)
+                for (int i = threadIdx.x; i < K * 2; i += kSortThreads)
+                    reinterpret_cast<float4*>(dets + (int64_t)b * K * 8)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         return;
     }
     if (threadIdx.x < n) {
@@ -1061,7 +1068,8 @@ nms_small_kernel(BoxSrc bs, const float* __restrict__ scores,
         if (sup) atomicOr(&mask0[4 * i + (j >> 5)], 1u << (j & 31));
     }
     if (csize > 1) cluster.sync(); else __syncthreads();
-    if (threadIdx.x == 0 && rank == 0) {
+    if (rank != 0) return;
+    if (threadIdx.x == 0) {
         unsigned long long rm0 = 0ull, rm1 = 0ull;
         const int limit = (int)min((int64_t)(post_max > 0 ? post_max : n), keep_stride);
         int nk = 0;
@@ -1069,12 +1077,30 @@ nms_small_kernel(BoxSrc bs, const float* __restrict__ scores,
         for (int i = 0; i < n && nk < limit; ++i) {
             const unsigned long long rm = i < 64 ? rm0 : rm1;
             if (!((rm >> (i & 63)) & 1ull)) {
-                kp[nk++] = (int)(skey[i] & 0xffffffffu);
+                const int a = (int)(skey[i] & 0xffffffffu);
+                s_kept[nk] = a;
+                kp[nk++] = a;
                 rm0 |= s_mask[i][0];
                 rm1 |= s_mask[i][1];
             }
         }
         keep_count[b] = nk;
+        s_nk = nk;
+    }
+    if (!dets) return;
+    // final detections of the frame (what gather_dets does for the longer lists): decoded box + score, zero padded
+    __syncthreads();
+    const int nk = min(s_nk, K);
+    for (int kq = threadIdx.x; kq < K; kq += kSortThreads) {
+        float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (kq < nk) {
+            const int64_t row = (int64_t)b * N + s_kept[kq];
+            src_decoded(bs, row, o);
+            o[7] = scores[row];
+        }
+        float4* dst = reinterpret_cast<float4*>(dets + ((int64_t)b * K + kq) * 8);
+        dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_float4(o[4], o[5], o[6], o[7]);
     }
 }
 
@@ -1279,7 +1305,7 @@ extern "C" size_t pp_nms_workspace_bytes(int kind, int B, int64_t N, int pre_max
 static int nms_run(int kind, const float* boxes, int box_stride, const float* anchors, int64_t anchor_period,
                    const float* scores, const int32_t* n_valid, int B, int64_t N, int pre_max_size, int post_max_size,
                    float thresh, int32_t* keep, int64_t keep_stride, int32_t* keep_count, void* workspace,
-                   size_t workspace_bytes, void* stream) {
+                   size_t workspace_bytes, void* stream, float* dets = nullptr, int K = 0, bool* dets_done = nullptr) {
     const BoxSrc bsrc{boxes, box_stride, anchors, anchor_period};
     PP_CHECK_ARG(kind == PP_NMS_STANDUP || kind == PP_NMS_ROTATED, "pp_nms_dev: bad kind");
     PP_CHECK_ARG(B > 0 && B <= 65535 && N >= 0 && N < ((int64_t)1 << 31), "pp_nms_dev: bad B/N");
@@ -1303,8 +1329,9 @@ static int nms_run(int kind, const float* boxes, int box_stride, const float* an
         const int csize = nms_small_cluster(B);
         PP_CUDA(launch_clustered(kind == PP_NMS_ROTATED ? nms_small_kernel<true> : nms_small_kernel<false>, (unsigned)(B * csize),
                                  (unsigned)kSortThreads, csize, st, bsrc, scores, n_valid, N, (int)w.n_cap, post_max_size, thresh,
-                                 keep, keep_stride, keep_count));
+                                 keep, keep_stride, keep_count, dets, K));
         PP_LAUNCHED();
+        if (dets_done) *dets_done = true;
         return PP_OK;
     }
     if (w.full_sort) {
@@ -1421,9 +1448,10 @@ extern "C" int pp_decode_nms_dev(int kind, const float* box_encodings, const flo
     PP_CHECK_ARG(N == 0 || anchors, "pp_decode_nms_dev: null anchors");
     PP_CHECK_ARG(anchor_period >= 0, "pp_decode_nms_dev: bad anchor_period");
     PP_CHECK_ARG(!dets || (K > 0 && (reinterpret_cast<uintptr_t>(dets) & 15) == 0), "pp_decode_nms_dev: dets needs K > 0 and 16-byte alignment");
+    bool dets_done = false;  // the one-launch path for <= 128 boxes writes the detections itself
     const int rc = nms_run(kind, box_encodings, 7, anchors, anchor_period, scores, n_valid, B, N, pre_max_size, post_max_size,
-                           thresh, keep, keep_stride, keep_count, workspace, workspace_bytes, stream);
-    if (rc || !dets) return rc;
+                           thresh, keep, keep_stride, keep_count, workspace, workspace_bytes, stream, dets, K, &dets_done);
+    if (rc || !dets || dets_done) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (N == 0) {
         PP_CUDA(cudaMemsetAsync(dets, 0, (size_t)B * K * 8 * sizeof(float), st));

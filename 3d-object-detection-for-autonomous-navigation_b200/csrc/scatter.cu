@@ -37,10 +37,12 @@ scatter_link_kernel(const int* __restrict__ coords, int64_t M, const int* __rest
     }
 }
 
-template <bool NHWC, int kScThreads>
+// CELLMAP: `head` is the voxelizer's cell -> row map [B][nz][ny][nx] (pp_voxelize_dev's cell_voxel) and the chain of a
+// canvas cell is read straight from its nz <= kChainMax slabs -- no link pass, no list walk (pp_scatter_cells_dev).
+template <bool NHWC, int kScThreads, bool CELLMAP>
 __global__ void __launch_bounds__(kScThreads)
 scatter_canvas_kernel(const float* __restrict__ feats, const int* __restrict__ head,
-                      const int* __restrict__ next, const unsigned char* __restrict__ multi, int C, int ny, int nx,
+                      const int* __restrict__ next, const unsigned char* __restrict__ multi, int nz, int C, int ny, int nx,
                       float* __restrict__ out) {
     extern __shared__ float tile[];  // [C][33]
     __shared__ int s_chain[kTileX][kChainMax];
@@ -54,7 +56,26 @@ scatter_canvas_kernel(const float* __restrict__ feats, const int* __restrict__ h
     int any = 0;
     if (threadIdx.x < kTileX) {
         int len = 0;
-        if (threadIdx.x < wx) {
+        if (CELLMAP) {
+            if (threadIdx.x < wx) {
+                int rows[kChainMax];
+#pragma unroll
+                for (int z = 0; z < kChainMax; ++z)
+                    rows[z] = z < nz ? __ldg(&head[(((int64_t)b * nz + z) * ny + y) * nx + x0 + threadIdx.x]) : -1;
+#pragma unroll
+                for (int z = 0; z < kChainMax; ++z) {
+                    const int m = rows[z];
+                    if (m < 0) continue;
+                    int j = len;
+                    while (j > 0 && s_chain[threadIdx.x][j - 1] > m) {
+                        s_chain[threadIdx.x][j] = s_chain[threadIdx.x][j - 1];
+                        --j;
+                    }
+                    s_chain[threadIdx.x][j] = m;
+                    ++len;
+                }
+            }
+        } else if (threadIdx.x < wx) {
             int m = head[cellbase + threadIdx.x];
             if (m >= 0 && !multi[cellbase + threadIdx.x]) {
                 // the usual case, one pillar on the cell: no dependent next[] round trip
@@ -244,10 +265,38 @@ extern "C" int pp_scatter_dev(const float* feats, const int32_t* coords, int64_t
     PP_TIMED("scatter_canvas", st);
 #define PP_CANVAS(NHWC_, T_)                                                                                          \
     do {                                                                                                              \
-        auto k = scatter_canvas_kernel<NHWC_, T_>;                                                                    \
+        auto k = scatter_canvas_kernel<NHWC_, T_, false>;                                                             \
         int per_sm__ = 0;                                                                                             \
         PP_TRY_RC(kernel_config(reinterpret_cast<const void*>(k), T_, smem, &per_sm__));                              \
-        k<<<g, T_, smem, st>>>(feats, head, next, multi, C, ny, nx, out);                                             \
+        k<<<g, T_, smem, st>>>(feats, head, next, multi, 1, C, ny, nx, out);                                          \
+    } while (0)
+    const bool nhwc = layout == PP_LAYOUT_NHWC;
+    if (C <= 64) { if (nhwc) PP_CANVAS(true, kScThreadsNarrow); else PP_CANVAS(false, kScThreadsNarrow); }
+    else { if (nhwc) PP_CANVAS(true, kScThreadsWide); else PP_CANVAS(false, kScThreadsWide); }
+#undef PP_CANVAS
+    PP_LAUNCHED();
+    return PP_OK;
+}
+
+extern "C" int pp_scatter_cells_dev(const float* feats, const int32_t* cell_voxel, int nz, int C, int B, int ny, int nx,
+                                    int layout, float* out, void* stream) {
+    PP_CHECK_ARG(B > 0 && ny > 0 && nx > 0 && C > 0, "pp_scatter_cells_dev: bad shape");
+    PP_CHECK_ARG(B <= 65535 && ny <= 65535, "pp_scatter_cells_dev: B and ny must be <= 65535");
+    PP_CHECK_ARG(nz >= 1 && nz <= kChainMax, "pp_scatter_cells_dev: nz=%d, at most %d slabs (use pp_scatter_dev)", nz, kChainMax);
+    PP_CHECK_ARG(layout == PP_LAYOUT_NCHW || layout == PP_LAYOUT_NHWC, "pp_scatter_cells_dev: bad layout");
+    PP_CHECK_ARG(out && feats && cell_voxel, "pp_scatter_cells_dev: null argument");
+    PP_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "pp_scatter_cells_dev: out must be 16-byte aligned");
+    const size_t smem = (size_t)C * 33 * sizeof(float);
+    PP_CHECK_ARG(smem <= 200 * 1024, "pp_scatter_cells_dev: C=%d too large", C);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const dim3 g((unsigned)ceil_div(nx, kTileX), ny, B);
+    PP_TIMED("scatter_canvas", st);
+#define PP_CANVAS(NHWC_, T_)                                                                                          \
+    do {                                                                                                              \
+        auto k = scatter_canvas_kernel<NHWC_, T_, true>;                                                              \
+        int per_sm__ = 0;                                                                                             \
+        PP_TRY_RC(kernel_config(reinterpret_cast<const void*>(k), T_, smem, &per_sm__));                              \
+        k<<<g, T_, smem, st>>>(feats, cell_voxel, nullptr, nullptr, nz, C, ny, nx, out);                              \
     } while (0)
     const bool nhwc = layout == PP_LAYOUT_NHWC;
     if (C <= 64) { if (nhwc) PP_CANVAS(true, kScThreadsNarrow); else PP_CANVAS(false, kScThreadsNarrow); }

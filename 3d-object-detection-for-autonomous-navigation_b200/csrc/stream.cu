@@ -32,6 +32,7 @@ struct pp_stream {
     int64_t* d_off[kSlots] = {};
     float *d_anchors = nullptr, *d_voxels = nullptr, *d_decorated = nullptr, *d_canvas = nullptr, *d_dets = nullptr;
     int32_t *d_coors = nullptr, *d_num = nullptr, *d_vnum = nullptr, *d_vbase = nullptr, *d_keep = nullptr, *d_kcnt = nullptr;
+    int32_t* d_cellrow = nullptr;  // the voxelizer's cell -> row map, read by the scatter (grids of at most 4 z slabs)
     void *ws_vox = nullptr, *ws_sc = nullptr, *ws_nms = nullptr;
     size_t ws_vox_bytes = 0, ws_sc_bytes = 0, ws_nms_bytes = 0;
     // host (pinned)
@@ -68,7 +69,7 @@ extern "C" void pp_stream_destroy(pp_stream* s) {
         if (s->ev_done[k]) cudaEventDestroy(s->ev_done[k]);
     }
     cudaFree(s->d_anchors); cudaFree(s->d_voxels); cudaFree(s->d_decorated); cudaFree(s->d_canvas); cudaFree(s->d_dets);
-    cudaFree(s->d_coors); cudaFree(s->d_num); cudaFree(s->d_vnum); cudaFree(s->d_vbase); cudaFree(s->d_keep); cudaFree(s->d_kcnt);
+    cudaFree(s->d_cellrow); cudaFree(s->d_coors); cudaFree(s->d_num); cudaFree(s->d_vnum); cudaFree(s->d_vbase); cudaFree(s->d_keep); cudaFree(s->d_kcnt);
     cudaFree(s->ws_vox); cudaFree(s->ws_sc); cudaFree(s->ws_nms);
     if (s->compute) cudaStreamDestroy(s->compute);
     if (s->copy) cudaStreamDestroy(s->copy);
@@ -106,6 +107,7 @@ static int stream_init(pp_stream* s, const float* anchors_host) {
     PP_CUDA(cudaMalloc(&s->d_num, (size_t)s->cap_rows * 4));
     PP_CUDA(cudaMalloc(&s->d_vnum, (size_t)B * 4));
     PP_CUDA(cudaMalloc(&s->d_vbase, (size_t)(B + 1) * 4));
+    if (s->nz <= 4) PP_CUDA(cudaMalloc(&s->d_cellrow, (size_t)B * s->nx * s->ny * s->nz * 4));
     PP_CUDA(cudaMalloc(&s->d_canvas, (size_t)B * c.C * s->ny * s->nx * 4));
     PP_CUDA(cudaMalloc(&s->d_keep, (size_t)B * c.post_max * 4));
     PP_CUDA(cudaMalloc(&s->d_kcnt, (size_t)B * 4));
@@ -205,9 +207,12 @@ extern "C" int pp_stream_submit(pp_stream* s, const void* points, const int64_t*
     PP_CUDA(cudaStreamWaitEvent(st, s->ev_copied[k], 0));
     PP_TRY_RC(pp_voxelize_dev(&c.vox, s->d_points[k], c.point_dtype, c.D, s->d_off[k], n_frames, total, maxf, PP_F32,
                               s->d_voxels, s->d_decorated, s->d_coors, 4, s->d_num, s->cap_rows, s->d_vnum, s->d_vbase,
-                              nullptr, nullptr, s->ws_vox, s->ws_vox_bytes, st));
+                              nullptr, s->d_cellrow, s->ws_vox, s->ws_vox_bytes, st));
     PP_CUDA(cudaEventRecord(s->ev_consumed[k], st));
-    PP_TRY_RC(pp_scatter_dev(s->pfn_feats, s->d_coors, s->cap_rows, s->d_vbase + n_frames, c.C, n_frames, s->ny, s->nx,
+    if (s->d_cellrow)
+        PP_TRY_RC(pp_scatter_cells_dev(s->pfn_feats, s->d_cellrow, s->nz, c.C, n_frames, s->ny, s->nx, c.layout, s->d_canvas, st));
+    else
+        PP_TRY_RC(pp_scatter_dev(s->pfn_feats, s->d_coors, s->cap_rows, s->d_vbase + n_frames, c.C, n_frames, s->ny, s->nx,
                              c.layout, s->d_canvas, s->ws_sc, s->ws_sc_bytes, st));
     PP_TRY_RC(pp_decode_nms_dev(c.nms_kind, s->box_enc, s->d_anchors, s->A, s->scores, nullptr, n_frames, s->A, c.pre_max,
                                 c.post_max, c.iou_threshold, s->d_keep, c.post_max, s->d_kcnt, s->d_dets, c.post_max,

@@ -1003,7 +1003,6 @@ extern "C" int pp_voxelize_dev(const pp_voxel_cfg* cfg, const void* points, int 
 }
 
 extern "C" int pp_voxelize_set_small_path_min_points(int64_t n) {
-    PP_CHECK_ARG(n >= 0, "pp_voxelize_set_small_path_min_points: n < 0");
-    pp::vox_small_set_min_points(n);
+    pp::vox_small_set_min_points(n);  // n < 0: back to the default
     return PP_OK;
 }

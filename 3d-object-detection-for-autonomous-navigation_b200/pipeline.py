@@ -31,7 +31,7 @@ class FramePipeline:
     def __init__(self, cfg, device=0, max_frames=64, max_total_points=None, rotated_nms=True,
                  layout="NCHW", fused_decorate=True, keep_voxels=True, anchors=None, overlap_post=True,
                  anchor_area_threshold=None, production=False, sensor_points=None, fused_post=True,
-                 max_frame_points=None):
+                 max_frame_points=None, scatter_from_cells=True):
         self.cfg = cfg
         self.fused_post = fused_post
         self.dev = torch.device("cuda", device)
@@ -77,6 +77,10 @@ class FramePipeline:
             self.num_points = torch.empty((self.cap_rows,), dtype=torch.int32, **e)
             self.voxel_num = torch.zeros((B,), dtype=torch.int32, **e)
             self.voxel_base = torch.zeros((B + 1,), dtype=torch.int32, **e)
+            # the voxelizer's cell -> row map feeds the scatter directly (pp_scatter_cells_dev: no link pass); grids with
+            # more than 4 z slabs go through coors (pp_scatter_dev), as do callers that ask for it
+            self.cell_voxel = (torch.empty((B * self.nx * self.ny * self.nz,), dtype=torch.int32, **e)
+                               if scatter_from_cells and self.nz <= 4 else None)
             self.canvas = torch.empty((B, Cc, self.ny, self.nx) if layout == "NCHW" else (B, self.ny, self.nx, Cc),
                                       dtype=torch.float32, **e)
             # all-anchor decoded / standup tensors exist only on the unfused path (decode -> standup -> NMS -> gather)
@@ -147,13 +151,18 @@ class FramePipeline:
             _p(frame_off), n_frames, total_points, max_frame_points, _lib.PP_F32,
             _p(self.voxels) if self.keep_voxels else None, _p(self.decorated) if self.fused else None,
             _p(self.coors), 4, _p(self.num_points), self.cap_rows, _p(self.voxel_num), _p(self.voxel_base),
-            None, None, _p(self.ws_vox), self.ws_vox_bytes, stream))
+            None, _p(self.cell_voxel) if self.cell_voxel is not None else None, _p(self.ws_vox), self.ws_vox_bytes, stream))
         if not self.fused:
             # M is only known on the device: decorate the capacity (rows past M are scratch)
             raise NotImplementedError("unfused decoration needs the host to know M; use fused_decorate=True")
 
     def scatter(self, pfn_feats, n_frames, stream):
         L = _lib.lib()
+        if self.cell_voxel is not None:
+            _lib.check(L.pp_scatter_cells_dev(_p(pfn_feats), _p(self.cell_voxel), self.nz, self.C, n_frames, self.ny, self.nx,
+                                              _lib.PP_LAYOUT_NCHW if self.layout == "NCHW" else _lib.PP_LAYOUT_NHWC,
+                                              _p(self.canvas), stream))
+            return
         _lib.check(L.pp_scatter_dev(_p(pfn_feats), _p(self.coors), min(pfn_feats.shape[0], self.cap_rows),
                                     C.c_void_p(self.voxel_base.data_ptr() + 4 * n_frames), self.C, n_frames, self.ny,
                                     self.nx, _lib.PP_LAYOUT_NCHW if self.layout == "NCHW" else _lib.PP_LAYOUT_NHWC,

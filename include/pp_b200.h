@@ -120,9 +120,10 @@ PP_API int pp_voxelize_dev(const pp_voxel_cfg* cfg, const void* points, int poin
                     int32_t* cell_voxel, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Two bit-identical implementations sit behind pp_voxelize_dev: grids of at most 16 384 cells (the d435i grid) have a
- * path that keeps its per-cell tables in shared memory, which wins for batches and loses to the any-grid path for a
- * frame or two (its launch chain is longer).  Batches of fewer than `n` points take the any-grid path; default
- * 1 000 000, 0 = always the shared-memory path when the grid allows it.  Process-wide; size workspaces after setting it. */
+ * path that keeps its per-cell tables in shared memory (chunks of 4 096 points for a few frames, of 16 384 for batches);
+ * below ~150 000 points it has no advantage over the any-grid path (measured: profiles/r02_notes.md).  Batches of fewer
+ * than `n` points take the any-grid path; default 150 000, 0 = always the shared-memory path when the grid allows it,
+ * n < 0 = back to the default.  Process-wide; size workspaces after setting it. */
 PP_API int pp_voxelize_set_small_path_min_points(int64_t n);
 
 /* ---- pillar decoration ------------------------------------------------------------------
@@ -144,6 +145,13 @@ PP_API size_t pp_scatter_workspace_bytes(int B, int ny, int nx, int64_t M);
 PP_API int pp_scatter_dev(const float* feats, const int32_t* coords, int64_t M, const int32_t* M_dev, int C,
                    int B, int ny, int nx, int layout, float* out, void* workspace,
                    size_t workspace_bytes, void* stream);
+/* The same canvas straight from the voxelizer's cell -> row map (pp_voxelize_dev's cell_voxel, [B][nz][ny][nx], nz <= 4):
+ * for coords that come from pp_voxelize_dev the result is identical to pp_scatter_dev (rows of the z slabs of one
+ * (y, x) are added in ascending row order, as the reference's scatter_nd does, model/pointpillars.py:302-317), without
+ * the link pass and its workspace.  What the chained pipeline (pp_stream, FramePipeline) uses between its own stages. */
+PP_API int pp_scatter_cells_dev(const float* features, const int32_t* cell_voxel, int nz, int C, int B, int ny, int nx,
+                         int layout, float* out, void* stream);
+
 
 /* ---- box decode -------------------------------------------------------------------------
  * Replaces second_box_decode (default flags), libraries/eval_helper_functions.py:388-461

@@ -38,12 +38,12 @@ def oracle():
 def vox_path(request):
     """Both implementations behind pp_voxelize_dev must pass the voxelizer tests: the shared-memory table path (forced
     for every batch size the grid allows) and the any-grid path (forced for every batch); the default threshold between
-    them (1 000 000 points) is restored afterwards."""
+    them is restored afterwards."""
     _lib = importlib.import_module(PKG + "._lib")
     n = 0 if request.param == "table_path" else 1 << 62
     _lib.check(_lib.lib().pp_voxelize_set_small_path_min_points(n))
     yield request.param
-    _lib.check(_lib.lib().pp_voxelize_set_small_path_min_points(1_000_000))
+    _lib.check(_lib.lib().pp_voxelize_set_small_path_min_points(-1))
 
 
 def golden(name):

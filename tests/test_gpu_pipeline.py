@@ -10,7 +10,7 @@ from conftest import PKG
 pytestmark = pytest.mark.gpu
 
 
-def _run(synth, oracle, cfg, frames, rotated, layout):
+def _run(synth, oracle, cfg, frames, rotated, layout, scatter_from_cells=True, max_voxels=None):
     import torch
     pipeline = importlib.import_module(PKG + ".pipeline")
     B = len(frames)
@@ -18,8 +18,11 @@ def _run(synth, oracle, cfg, frames, rotated, layout):
     tdtype = torch.float64 if cfg["point_dtype"] == "float64" else torch.float32
     pts = np.concatenate(frames)
     off = np.cumsum([0] + [f.shape[0] for f in frames]).astype(np.int64)
+    if max_voxels is not None:
+        cfg = dict(cfg, max_voxels=max_voxels)
     pipe = pipeline.FramePipeline(cfg, device=0, max_frames=B, max_total_points=pts.shape[0], rotated_nms=rotated,
-                                  layout=layout)
+                                  layout=layout, scatter_from_cells=scatter_from_cells)
+    assert (pipe.cell_voxel is not None) == scatter_from_cells
     A = pipe.A
     box = np.stack([synth.rpn_standin(A, 50 + i)[0] for i in range(B)])
     sco = np.stack([synth.rpn_standin(A, 50 + i)[1] for i in range(B)])
@@ -79,6 +82,18 @@ def test_pipeline_d435_batched_ragged(synth, oracle):
     _run(synth, oracle, cfg, frames[:2], rotated=False, layout="NHWC")
 
 
+def test_pipeline_scatter_paths(synth, oracle, vox_path):
+    """The canvas from the voxelizer's cell -> row map (pp_scatter_cells_dev) and from coors (pp_scatter_dev), on both
+    voxelizer implementations; with the max_voxels cap binding, cells past the cap must stay empty on the canvas."""
+    frames = [synth.d435_cloud(24), synth.d435_cloud(25)[::5], np.zeros((0, 3), np.float64), synth.d435_cloud(26)[:300000]]
+    for cells in (True, False):
+        _run(synth, oracle, synth.D435, frames, rotated=True, layout="NCHW", scatter_from_cells=cells)
+    _run(synth, oracle, synth.D435, frames, rotated=True, layout="NHWC", scatter_from_cells=True, max_voxels=700)
+    _run(synth, oracle, synth.D435, frames[:1], rotated=True, layout="NCHW", scatter_from_cells=True)
+    kitti = [synth.kitti_cloud(33), synth.uniform_cloud(30000, synth.KITTI, 34)]
+    _run(synth, oracle, dict(synth.KITTI), kitti, rotated=False, layout="NCHW", scatter_from_cells=False)
+
+
 def test_pipeline_kitti_batched(synth, oracle):
     cfg = dict(synth.KITTI)
     frames = [synth.kitti_cloud(30), synth.kitti_cloud(31, shuffled=True), synth.uniform_cloud(50000, cfg, 32)]
@@ -126,11 +141,11 @@ def test_profiler_and_launch_count(pp, synth):
     _lib = importlib.import_module(PKG + "._lib")
     pts = synth.d435_cloud(1, subsample=True)
     vs, pcr = np.array(synth.D435["voxel_size"]), np.array(synth.D435["point_cloud_range"])
-    # the d435i grid (10 240 cells) has the shared-memory table path: four launches, no memset.  Batches of fewer than a
-    # million points (this 101 760-point frame) take the any-grid path unless the threshold is lowered.
+    # the d435i grid (10 240 cells) has the shared-memory table path: four launches, no memset.  Batches of fewer than
+    # 150 000 points (this 101 760-point frame) take the any-grid path unless the threshold is lowered.
     small = ["vox_scan", "vox_prefix", "vox_place", "vox_finish"]
     anygrid = ["vox_mark", "vox_cell", "vox_rank", "vox_rowmap", "vox_bucket", "vox_gather"]
-    for thr, kernels, memset in ((0, small, []), (1_000_000, anygrid, ["vox_memset"])):
+    for thr, kernels, memset in ((0, small, []), (-1, anygrid, ["vox_memset"])):
         _lib.check(_lib.lib().pp_voxelize_set_small_path_min_points(thr))
         pp.launch_count(reset=True)
         _lib.profile_start()
