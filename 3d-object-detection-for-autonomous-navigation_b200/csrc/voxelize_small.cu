@@ -37,10 +37,14 @@
 #define PP_VS_NS vs14
 #define PP_VS_SHIFT 14
 #define PP_VS_SUB 4
+#define PP_VS_STAGES 2
+#define PP_VS_KB 5
 #include "voxelize_small_impl.cuh"
 #undef PP_VS_NS
 #undef PP_VS_SHIFT
 #undef PP_VS_SUB
+#undef PP_VS_STAGES
+#undef PP_VS_KB
 #ifndef PP_SHORT_SHIFT
 #define PP_SHORT_SHIFT 12
 #endif
@@ -53,10 +57,20 @@
 #else
 #define PP_VS_SUB 1
 #endif
+#ifndef PP_SHORT_STAGES
+#define PP_SHORT_STAGES 2
+#endif
+#ifndef PP_SHORT_KB
+#define PP_SHORT_KB 5
+#endif
+#define PP_VS_STAGES PP_SHORT_STAGES
+#define PP_VS_KB PP_SHORT_KB
 #include "voxelize_small_impl.cuh"
 #undef PP_VS_NS
 #undef PP_VS_SHIFT
 #undef PP_VS_SUB
+#undef PP_VS_STAGES
+#undef PP_VS_KB
 
 namespace pp {
 

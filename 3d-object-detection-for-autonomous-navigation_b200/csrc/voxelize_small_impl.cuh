@@ -1,6 +1,8 @@
 // Body of the table path (see voxelize_small.cu), compiled once per chunk size:
 //   PP_VS_NS     namespace of this instance
 //   PP_VS_SHIFT  log2 of the points per chunk
+//   PP_VS_STAGES shared-memory stages of the scan pass (tiles in flight)
+//   PP_VS_KB     16-byte table units per lane that the place pass loads per round trip
 //   PP_VS_SUB    parts of a chunk that the place pass walks independently (a part is a whole number of scan tiles)
 namespace pp {
 namespace PP_VS_NS {
@@ -58,10 +60,7 @@ template <typename TO, int DS> struct RecFmt {
 // Pass 1.  Warp w of a tile owns kWarpPts consecutive points; round r of lane l is point kWarpPts w + 32 r + l,
 // so (warp, round, lane) enumerates the tile in index order and shared-memory row reads are conflict free.
 // kScanStages shared-memory stages: with two, the TMA bulk copy of tile j+1 is in flight while tile j is processed.
-#ifndef PP_SCAN_STAGES
-#define PP_SCAN_STAGES 2
-#endif
-constexpr int kScanStages = PP_SCAN_STAGES;
+constexpr int kScanStages = PP_VS_STAGES;
 
 template <typename T, bool A32, bool FAST, typename TO, int DS>
 __global__ void __launch_bounds__(kScanThreads)
@@ -259,12 +258,12 @@ vox_prefix_kernel(const int64_t* __restrict__ frame_off, int S, int ncell, int n
     const size_t t0 = (size_t)b * S * ncellp + cell;
     int sum = 0;
     if (kPrefixParts > 1 && cell < ncell) {
-        for (int s0 = s_lo; s0 < s_hi; s0 += 8) {
-            int h[8];
+        for (int s0 = s_lo; s0 < s_hi; s0 += 16) {
+            int h[16];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) h[k] = s0 + k < s_hi ? (int)__ldcg(&hist[t0 + (size_t)(s0 + k) * ncellp]) : 0;
+            for (int k = 0; k < 16; ++k) h[k] = s0 + k < s_hi ? (int)__ldcg(&hist[t0 + (size_t)(s0 + k) * ncellp]) : 0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) sum += h[k];
+            for (int k = 0; k < 16; ++k) sum += h[k];
         }
     }
     s_part[part][lane] = sum;
@@ -273,6 +272,7 @@ vox_prefix_kernel(const int64_t* __restrict__ frame_off, int S, int ncell, int n
         if (cell_voxel && part == 0) cell_voxel[(size_t)b * ncell + cell] = -1;  // the finish pass fills in the cells that get a row
         int run = 0, first = -1;
         for (int q = 0; q < part; ++q) run += s_part[q][lane];
+        // eight loads in flight per round trip (32 at once, a whole d435i frame of 25 chunks, costs occupancy: 46 -> 62 us)
         for (int s0 = s_lo; s0 < s_hi; s0 += 8) {
             int h[8];
 #pragma unroll
@@ -367,10 +367,7 @@ vox_place_kernel(const int64_t* __restrict__ frame_off, int S, int ncell, int nc
         const uint4* srcb = reinterpret_cast<const uint4*>(base8 + ((size_t)b * S + s) * ncellp);
         const uint4* srcs = reinterpret_cast<const uint4*>(snap + (((size_t)b * S + s) * (kSub - 1) + (q ? q - 1 : 0)) * (size_t)ncellp);
         uint4* dst = reinterpret_cast<uint4*>(tbl);
-#ifndef PP_PLACE_KB
-#define PP_PLACE_KB 5
-#endif
-        constexpr int kB = PP_PLACE_KB;  // 16-byte units per lane and batch: all loads of a batch are in flight together
+        constexpr int kB = PP_VS_KB;  // 16-byte units per lane and batch: all loads of a batch are in flight together
         const int nu = ncellp >> 4;
         for (int k0 = lane; k0 < nu; k0 += 32 * kB) {
             uint4 a[kB], c[kB];
