@@ -8,7 +8,7 @@
 //           (coordinates in the output type) and 4-byte tags {cell | index in chunk}; the chunk's per-cell counts
 //           live in SHARED memory (ATOMS) and are written out once per chunk, plus a saturated snapshot of them at
 //           the three quarter boundaries of the chunk.
-//   prefix  (frame, 256 cells)  per cell: exclusive prefix of the chunk counts = the slot base of every chunk
+//   prefix  (frame, 256 cells; short batches: 32 cells x 8 ranges of the frame's chunks)  per cell: exclusive prefix of the chunk counts = the slot base of every chunk
 //           (uint8, saturated: a base >= max_points means "full"); min(points, max_points) goes to the tail word
 //           of the cell's row of the slot table; the chunk in which a cell first appears is counted, which gives
 //           every chunk the number of voxels opened before it.
