@@ -39,7 +39,9 @@
 #define PP_VS_SUB 4
 #define PP_VS_STAGES 2
 #define PP_VS_KB 5
+#define PP_VS_PPT 4
 #include "voxelize_small_impl.cuh"
+#undef PP_VS_PPT
 #undef PP_VS_NS
 #undef PP_VS_SHIFT
 #undef PP_VS_SUB
@@ -50,7 +52,9 @@
 #endif
 #define PP_VS_NS vs12
 #define PP_VS_SHIFT PP_SHORT_SHIFT
-#if PP_SHORT_SHIFT >= 12
+#ifdef PP_SHORT_SUB
+#define PP_VS_SUB PP_SHORT_SUB
+#elif PP_SHORT_SHIFT >= 12
 #define PP_VS_SUB 4
 #elif PP_SHORT_SHIFT == 11
 #define PP_VS_SUB 2
@@ -63,9 +67,14 @@
 #ifndef PP_SHORT_KB
 #define PP_SHORT_KB 5
 #endif
+#ifndef PP_SHORT_PPT
+#define PP_SHORT_PPT 4
+#endif
 #define PP_VS_STAGES PP_SHORT_STAGES
 #define PP_VS_KB PP_SHORT_KB
+#define PP_VS_PPT PP_SHORT_PPT
 #include "voxelize_small_impl.cuh"
+#undef PP_VS_PPT
 #undef PP_VS_NS
 #undef PP_VS_SHIFT
 #undef PP_VS_SUB

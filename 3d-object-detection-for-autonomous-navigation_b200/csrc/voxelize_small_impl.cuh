@@ -1,6 +1,7 @@
 // Body of the table path (see voxelize_small.cu), compiled once per chunk size:
 //   PP_VS_NS     namespace of this instance
 //   PP_VS_SHIFT  log2 of the points per chunk
+//   PP_VS_PPT    points per thread and scan tile (tile = 256 threads x this)
 //   PP_VS_STAGES shared-memory stages of the scan pass (tiles in flight)
 //   PP_VS_KB     16-byte table units per lane that the place pass loads per round trip
 //   PP_VS_SUB    parts of a chunk that the place pass walks independently (a part is a whole number of scan tiles)
@@ -12,10 +13,7 @@ constexpr int kChunkShift = PP_VS_SHIFT;  // points per chunk = 2^shift; positio
 constexpr int kChunk = 1 << kChunkShift;
 constexpr int kScanThreads = 256;
 constexpr int kScanWarps = kScanThreads / 32;
-#ifndef PP_SCAN_PPT
-#define PP_SCAN_PPT 4
-#endif
-constexpr int kScanPPT = PP_SCAN_PPT;  // points per thread and tile
+constexpr int kScanPPT = PP_VS_PPT;  // points per thread and tile
 constexpr int kWarpPts = 32 * kScanPPT;  // consecutive points of a tile that one warp owns
 constexpr int kScanTile = kScanThreads * kScanPPT;
 constexpr int kPrefixThreads = 256;
