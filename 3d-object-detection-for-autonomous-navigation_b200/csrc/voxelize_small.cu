@@ -40,7 +40,9 @@
 #define PP_VS_STAGES 2
 #define PP_VS_KB 5
 #define PP_VS_PPT 4
+#define PP_VS_PLACE_THREADS 32
 #include "voxelize_small_impl.cuh"
+#undef PP_VS_PLACE_THREADS
 #undef PP_VS_PPT
 #undef PP_VS_NS
 #undef PP_VS_SHIFT
@@ -72,8 +74,13 @@
 #endif
 #define PP_VS_STAGES PP_SHORT_STAGES
 #define PP_VS_KB PP_SHORT_KB
+#ifndef PP_SHORT_PLACE_THREADS
+#define PP_SHORT_PLACE_THREADS 128
+#endif
 #define PP_VS_PPT PP_SHORT_PPT
+#define PP_VS_PLACE_THREADS PP_SHORT_PLACE_THREADS
 #include "voxelize_small_impl.cuh"
+#undef PP_VS_PLACE_THREADS
 #undef PP_VS_PPT
 #undef PP_VS_NS
 #undef PP_VS_SHIFT

@@ -3,6 +3,7 @@
 //   PP_VS_SHIFT  log2 of the points per chunk
 //   PP_VS_PPT    points per thread and scan tile (tile = 256 threads x this)
 //   PP_VS_STAGES shared-memory stages of the scan pass (tiles in flight)
+//   PP_VS_PLACE_THREADS  threads of a place CTA (one warp walks, the others only help with the prologue)
 //   PP_VS_KB     16-byte table units per lane that the place pass loads per round trip
 //   PP_VS_SUB    parts of a chunk that the place pass walks independently (a part is a whole number of scan tiles)
 namespace pp {
@@ -334,8 +335,12 @@ vox_prefix_kernel(const int64_t* __restrict__ frame_off, int S, int ncell, int n
 // accesses, one store per record).  Tags are fetched two groups ahead.  No atomic, no block barrier.
 constexpr unsigned kNone = 0xffffffffu;
 constexpr int kPlaceScratch = 1024;  // words of the per-warp peer table (a power of two)
+// Threads of a place CTA.  ONE warp walks; in the short-batch instance (a few hundred walks on 148 SMs) three more warps
+// help with the prologue, the 20 KB of chunk tables the walk starts from -- ncu had 45 % of the pass's samples of a single
+// frame waiting for those loads with one warp's worth in flight -- and leave.  Batches fill every SM with one-warp CTAs anyway.
+constexpr int kPlaceThreads = PP_VS_PLACE_THREADS;
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(kPlaceThreads)
 vox_place_kernel(const int64_t* __restrict__ frame_off, int S, int ncell, int ncellp, int P, int max_voxels,
                  const unsigned* __restrict__ ctag, const unsigned char* __restrict__ base8,
                  const int* __restrict__ nvalid,
@@ -343,9 +348,10 @@ vox_place_kernel(const int64_t* __restrict__ frame_off, int S, int ncell, int nc
                  int* __restrict__ cutoff, const unsigned char* __restrict__ snap, const int* __restrict__ subv) {
     extern __shared__ __align__(16) unsigned char tbl[];  // [ncellp] running counts
     __shared__ unsigned scr[kPlaceScratch];                // lanes of the current step, keyed by cell (all zero between steps)
+    __shared__ int s_run[kPlaceThreads / 32];
     constexpr int U = kPlaceUnroll;
-    const int lane = lane_id();
-    for (int k = lane; k < kPlaceScratch; k += 32) scr[k] = 0u;
+    const int lane = lane_id(), tid = threadIdx.x, nthr = blockDim.x;  // 32, or up to kPlaceThreads when the launch has few walks
+    for (int k = tid; k < kPlaceScratch; k += nthr) scr[k] = 0u;
     // frames in reverse order: the scan pass wrote the last frames' tags last, so they are still in L2
     const int b = (int)gridDim.y - 1 - (int)blockIdx.y, s = blockIdx.x / kSub, q = blockIdx.x % kSub;
     const int64_t f0 = frame_off[b];
@@ -358,7 +364,7 @@ vox_place_kernel(const int64_t* __restrict__ frame_off, int S, int ncell, int nc
     if (nval <= rec0) return;
     // voxels opened by the earlier chunks of the frame
     int newrun = 0;
-    for (int k = lane; k < s; k += 32) newrun += newcount[b * S + k];
+    for (int k = tid; k < s; k += nthr) newrun += newcount[b * S + k];
     {
         // counts at the start of the quarter = chunk base + the chunk's counts at the quarter boundary; a cell
         // that the chunk base does not hold but the boundary counts do was opened by an earlier quarter
@@ -367,26 +373,33 @@ vox_place_kernel(const int64_t* __restrict__ frame_off, int S, int ncell, int nc
         uint4* dst = reinterpret_cast<uint4*>(tbl);
         constexpr int kB = PP_VS_KB;  // 16-byte units per lane and batch: all loads of a batch are in flight together
         const int nu = ncellp >> 4;
-        for (int k0 = lane; k0 < nu; k0 += 32 * kB) {
+        for (int k0 = tid; k0 < nu; k0 += nthr * kB) {
             uint4 a[kB], c[kB];
 #pragma unroll
             for (int i = 0; i < kB; ++i) {
-                const int k = min(k0 + 32 * i, nu - 1);
+                const int k = min(k0 + nthr * i, nu - 1);
                 a[i] = __ldcg(&srcb[k]);
                 c[i] = q ? __ldcs(&srcs[k]) : make_uint4(0u, 0u, 0u, 0u);
             }
 #pragma unroll
             for (int i = 0; i < kB; ++i) {
-                if (k0 + 32 * i >= nu) break;
+                if (k0 + nthr * i >= nu) break;
                 newrun += (__popc(__vcmpeq4(a[i].x, 0u) & __vcmpne4(c[i].x, 0u)) + __popc(__vcmpeq4(a[i].y, 0u) & __vcmpne4(c[i].y, 0u)) +
                            __popc(__vcmpeq4(a[i].z, 0u) & __vcmpne4(c[i].z, 0u)) + __popc(__vcmpeq4(a[i].w, 0u) & __vcmpne4(c[i].w, 0u))) >> 3;
-                dst[k0 + 32 * i] = make_uint4(__vaddus4(a[i].x, c[i].x), __vaddus4(a[i].y, c[i].y), __vaddus4(a[i].z, c[i].z),
+                dst[k0 + nthr * i] = make_uint4(__vaddus4(a[i].x, c[i].x), __vaddus4(a[i].y, c[i].y), __vaddus4(a[i].z, c[i].z),
                                               __vaddus4(a[i].w, c[i].w));
             }
         }
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) newrun += __shfl_xor_sync(0xffffffffu, newrun, o);
+    if (kPlaceThreads > 32 && nthr > 32) {
+        if (lane == 0) s_run[tid >> 5] = newrun;
+        __syncthreads();
+        if (tid >= 32) return;  // the helpers of the prologue are done
+        newrun = 0;
+        for (int k = 0; k < (nthr >> 5); ++k) newrun += s_run[k];
+    }
     __syncwarp();
     const unsigned* tags = ctag + f0 + (int64_t)s * kChunk;
     const size_t cellrow0 = (size_t)b * ncell;
@@ -811,10 +824,12 @@ int run(const pp_voxel_cfg* cfg, const VoxParams& p, const void* points, int poi
     {
         const size_t smem = (size_t)ncellp;
         int per_sm = 0;
-        PP_TRY_RC(kernel_config(reinterpret_cast<const void*>(vox_place_kernel), 32, smem, &per_sm));
+        PP_TRY_RC(kernel_config(reinterpret_cast<const void*>(vox_place_kernel), kPlaceThreads, smem, &per_sm));
         const dim3 g((unsigned)(S * kSub), (unsigned)n_frames);
         PP_TIMED("vox_place", st);
-        vox_place_kernel<<<g, 32, smem, st>>>(frame_offsets, S, (int)ncell, ncellp, P, cfg->max_voxels, w.ctag, w.base8, w.nvalid,
+        // helpers for the prologue only while the launch leaves SMs idle (at most ~4 walks per SM)
+        const int pthreads = (int64_t)S * kSub * n_frames <= 4 * (int64_t)num_sms() ? kPlaceThreads : 32;
+        vox_place_kernel<<<g, pthreads, smem, st>>>(frame_offsets, S, (int)ncell, ncellp, P, cfg->max_voxels, w.ctag, w.base8, w.nvalid,
                                               w.newcount, w.sidx, w.rowinfo, w.cutoff, w.snap, w.subv);
         PP_LAUNCHED();
     }
