@@ -40,7 +40,10 @@
 #define PP_VS_STAGES 2
 #define PP_VS_KB 5
 #define PP_VS_PPT 4
-#define PP_VS_PLACE_THREADS 32
+#ifndef PP_BATCH_PLACE_THREADS
+#define PP_BATCH_PLACE_THREADS 128
+#endif
+#define PP_VS_PLACE_THREADS PP_BATCH_PLACE_THREADS
 #include "voxelize_small_impl.cuh"
 #undef PP_VS_PLACE_THREADS
 #undef PP_VS_PPT

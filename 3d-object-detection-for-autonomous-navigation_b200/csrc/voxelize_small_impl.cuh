@@ -335,9 +335,9 @@ vox_prefix_kernel(const int64_t* __restrict__ frame_off, int S, int ncell, int n
 // accesses, one store per record).  Tags are fetched two groups ahead.  No atomic, no block barrier.
 constexpr unsigned kNone = 0xffffffffu;
 constexpr int kPlaceScratch = 1024;  // words of the per-warp peer table (a power of two)
-// Threads of a place CTA.  ONE warp walks; in the short-batch instance (a few hundred walks on 148 SMs) three more warps
-// help with the prologue, the 20 KB of chunk tables the walk starts from -- ncu had 45 % of the pass's samples of a single
-// frame waiting for those loads with one warp's worth in flight -- and leave.  Batches fill every SM with one-warp CTAs anyway.
+// Threads of a place CTA.  ONE warp walks; three more warps help with the prologue, the 20 KB of chunk tables the walk
+// starts from, and leave -- ncu had 45 % of the pass's samples of a single frame (20 % for a 64-frame batch) waiting for
+// those loads with one warp's worth in flight.
 constexpr int kPlaceThreads = PP_VS_PLACE_THREADS;
 
 __global__ void __launch_bounds__(kPlaceThreads)
@@ -827,8 +827,9 @@ int run(const pp_voxel_cfg* cfg, const VoxParams& p, const void* points, int poi
         PP_TRY_RC(kernel_config(reinterpret_cast<const void*>(vox_place_kernel), kPlaceThreads, smem, &per_sm));
         const dim3 g((unsigned)(S * kSub), (unsigned)n_frames);
         PP_TIMED("vox_place", st);
-        // helpers for the prologue only while the launch leaves SMs idle (at most ~4 walks per SM)
-        const int pthreads = (int64_t)S * kSub * n_frames <= 4 * (int64_t)num_sms() ? kPlaceThreads : 32;
+        // helper warps for the prologue: always in the batch instance (64 frames: 160 -> 153 us), in the short-batch instance
+        // while the launch leaves SMs idle (one frame: 20 -> 15 us; 1 600 walks of four frames: 21 -> 23 us with them)
+        const int pthreads = (kChunkShift >= 14 || (int64_t)S * kSub * n_frames <= 4 * (int64_t)num_sms()) ? kPlaceThreads : 32;
         vox_place_kernel<<<g, pthreads, smem, st>>>(frame_offsets, S, (int)ncell, ncellp, P, cfg->max_voxels, w.ctag, w.base8, w.nvalid,
                                               w.newcount, w.sidx, w.rowinfo, w.cutoff, w.snap, w.subv);
         PP_LAUNCHED();
