@@ -137,7 +137,10 @@ extern "C" int pp_profile_stop(char* names, size_t names_cap, float* ms, int max
 // instead of preceding it (a pageable cudaMemcpyAsync does the same inside the driver with one thread).
 constexpr size_t kPiece = (size_t)2 << 20;   // bytes per staged piece
 constexpr int kRing = 4;                      // pieces in flight
-constexpr int kCopyThreads = 8;                // measured on a 16-core host, 407 040 f64 points in / 9.9 MB out: 2 threads 1.04 ms, 4: 1.02, 8: 0.75
+#ifndef PP_COPY_THREADS
+#define PP_COPY_THREADS 12
+#endif
+constexpr int kCopyThreads = PP_COPY_THREADS;                // 407 040 f64 points in / 9.9 MB out on the 32-vCPU host of the GPU box: 2 threads 1.04 ms, 4: 1.02, 8: 0.75, 12: 0.69, 16: 0.69
 
 static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
     if (bytes < ((size_t)256 << 10)) { memcpy(dst, src, bytes); return; }
