@@ -73,6 +73,8 @@ def test_argument_validation_needs_no_gpu(pp):
     assert L.pp_voxelize_dev(*bad) == -3 and b"workspace" in L.pp_last_error_string()
     assert L.pp_scatter_dev(one, one, 10, None, 64, 0, 4, 4, 0, one, one, 1 << 20, None) == -1
     assert L.pp_nms_dev(7, one, 5, one, None, 1, 10, -1, -1, 0.5, one, 10, one, one, 1 << 20, None) == -1
+    assert L.pp_scatter_cells_dev(one, one, 5, 64, 1, 4, 4, 0, one, None) == -1 and b"slabs" in L.pp_last_error_string()   # nz > 4
+    assert L.pp_scatter_cells_dev(one, None, 1, 64, 1, 4, 4, 0, one, None) == -1                                           # no cell map
     assert L.pp_rotate_iou_dev(one, 4, one, 4, 9, one, None) == -1
     # "next" rows: predict glue and sensor ingest
     pc = _lib.PredictCfg(1, 1, 100, 100, 50, 0, 0.5, 0.0, 1)

@@ -283,6 +283,43 @@ def test_decode_nms_fused_equals_decode_then_nms(synth, name, rotated):
     assert np.array_equal(d0, d1)
 
 
+@pytest.mark.parametrize("rotated", [True, False])
+def test_small_nms_every_cluster_size(synth, rotated):
+    """nms_small runs a frame on a thread-block cluster of 8 / 4 / 2 / 1 CTAs depending on the batch size (B <= 9 / 37 / 74 /
+    above on 148 SMs): the same frames must give the same keep lists and detections at every size, frame by frame
+    (batch 1 is the configuration the per-frame oracle tests pin)."""
+    import torch
+    pipeline = importlib.import_module(PKG + ".pipeline")
+    cfg = synth.D435
+    dev = torch.device("cuda", 0)
+    Bmax = 80
+    an = synth.anchors_stride(cfg)
+    A = an.shape[0]
+    box_h = np.stack([synth.rpn_standin(A, 300 + (i % 7))[0] for i in range(Bmax)])
+    sco_h = np.stack([synth.rpn_standin(A, 300 + (i % 7))[1] for i in range(Bmax)])
+    sco_h[5, ::2] = -np.inf      # a frame with absent anchors
+    sco_h[6, :] = -np.inf        # a frame with none at all
+    sco_h[7, 100:] = -np.inf     # fewer present boxes than pre_max_size
+    box, sco = torch.from_numpy(box_h).to(dev), torch.from_numpy(sco_h).to(dev)
+    out = {}
+    for B in (1, 9, 10, 37, 38, 74, 80):
+        pipe = pipeline.FramePipeline(cfg, device=0, max_frames=B, max_total_points=1000, rotated_nms=rotated)
+        pipe.postprocess(box[:B].contiguous(), sco[:B].contiguous(), B, C_void(torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        out[B] = (pipe.keep_count[:B].cpu().numpy().copy(), pipe.keep[:B].cpu().numpy().copy(), pipe.dets[:B].cpu().numpy().copy())
+    cnt80, keep80, dets80 = out[80]   # one CTA per frame
+    assert cnt80[6] == 0 and not dets80[6].any() and 0 < cnt80[7] <= 50 and cnt80[0] > 0
+    for B, (cnt, keep, dets) in out.items():
+        assert np.array_equal(cnt, cnt80[:B]) and np.array_equal(dets, dets80[:B]), B
+        for f in range(B):
+            assert np.array_equal(keep[f, :cnt[f]], keep80[f, :cnt80[f]]), (B, f)
+    # frames repeat with period 7 (apart from the three edited ones): equal inputs, equal outputs
+    for f in range(8, 80):
+        a = f % 7
+        if a in (5, 6):
+            continue
+        assert cnt80[f] == cnt80[a] and np.array_equal(keep80[f, :cnt80[f]], keep80[a, :cnt80[a]]) and np.array_equal(dets80[f], dets80[a])
+
 def C_void(x):
     import ctypes
     return ctypes.c_void_p(x)
