@@ -44,6 +44,7 @@ nms_topk_kernel(const float* __restrict__ scores, const int* __restrict__ n_vali
 // (key, index) pairs are appended to the rank-0 CTA's shared-memory list with DSMEM atomics and sorted
 // there.  Same total order and tie rule as block_topk (descending score, then descending index).
 constexpr int kTopkCluster = 8;
+constexpr int64_t kLongScores = kLongScoreList;  // score lists from this length on are selected by the cluster kernel
 // 256 threads per CTA: at 64 registers a 1024-thread CTA owns a whole SM's register file, i.e. 16 clusters in flight
 // on the chip and four waves for 64 frames (198 us); with 256 threads 74 clusters are resident and 64 frames are one wave
 #ifndef PP_TOPK_THREADS
@@ -1002,7 +1003,8 @@ template <bool ROTATED>
 __global__ void __launch_bounds__(kSortThreads)
 nms_small_kernel(BoxSrc bs, const float* __restrict__ scores,
                  const int* __restrict__ n_valid, int64_t N, int k, int post_max, float thresh,
-                 int* __restrict__ keep, int64_t keep_stride, int* __restrict__ keep_count, float* __restrict__ dets, int K) {
+                 int* __restrict__ keep, int64_t keep_stride, int* __restrict__ keep_count, float* __restrict__ dets, int K,
+                 const int* __restrict__ order, int64_t order_stride, const int* __restrict__ n_sorted) {
     namespace cg = cooperative_groups;
     using BoxG = typename std::conditional<ROTATED, RBoxG, float4>::type;
     __shared__ unsigned long long skey[kSelectMaxK];
@@ -1016,7 +1018,18 @@ nms_small_kernel(BoxSrc bs, const float* __restrict__ scores,
     const int b = blockIdx.x / csize;
     const float* sc = scores + (int64_t)b * N;
     const int nv = n_valid ? max(0, min(n_valid[b], (int)N)) : (int)N;
-    const int n = block_topk(sc, nv, min(k, kSmallN), skey);
+    int n;
+    if (order) {
+        // long score lists (KITTI: 107 k anchors) are selected by the 8-CTA cluster top-k beforehand: same order, same tie rule
+        n = min(n_sorted[b], kSmallN);
+        if ((int)threadIdx.x < n) {
+            const int a = order[(int64_t)b * order_stride + threadIdx.x];
+            skey[threadIdx.x] = ((unsigned long long)score_key(sc[a]) << 32) | (unsigned)a;
+        }
+        __syncthreads();
+    } else {
+        n = block_topk(sc, nv, min(k, kSmallN), skey);
+    }
     if (n == 0) {  // the same in every CTA of the cluster
         if (rank == 0) {
             if (threadIdx.x == 0) keep_count[b] = 0;
@@ -1297,6 +1310,14 @@ NmsWs nms_carve(void* ws, int kind, int B, int64_t N, int pre_max) {
 }
 }  // namespace
 
+// Top-k of long score lists for other translation units (predict.cu): order [B][order_stride], n_sorted [B].
+int nms_topk_long_dev(const float* scores, int B, int64_t N, int k, int* order, int64_t order_stride, int* n_sorted, cudaStream_t st) {
+    PP_TIMED("nms_topk", st);
+    pp::nms_topk_cluster_kernel<<<B * pp::kTopkCluster, pp::kTopkThreads, 0, st>>>(scores, nullptr, N, k, order, order_stride, n_sorted);
+    PP_LAUNCHED();
+    return PP_OK;
+}
+
 extern "C" size_t pp_nms_workspace_bytes(int kind, int B, int64_t N, int pre_max_size) {
     if (B <= 0 || N < 0) return 0;
     return nms_carve(nullptr, kind, B, N > 0 ? N : 1, pre_max_size).total + 256;
@@ -1325,11 +1346,18 @@ static int nms_run(int kind, const float* boxes, int box_stride, const float* an
     }
     PP_CHECK_ARG(w.cb_cap * 8 <= 200 * 1024, "pp_nms_dev: more than 1.6M boxes per frame after pre_max_size");
     if (w.n_cap <= kSmallN) {
+        const int* order = nullptr;
+        if (N >= kLongScores) {  // one CTA walking 100 k scores five times costs more than the rest of the frame
+            PP_TIMED("nms_topk", st);
+            nms_topk_cluster_kernel<<<B * kTopkCluster, kTopkThreads, 0, st>>>(scores, n_valid, N, (int)w.n_cap, w.order, w.n_cap, w.n_sorted);
+            PP_LAUNCHED();
+            order = w.order;
+        }
         PP_TIMED("nms_small", st);
         const int csize = nms_small_cluster(B);
         PP_CUDA(launch_clustered(kind == PP_NMS_ROTATED ? nms_small_kernel<true> : nms_small_kernel<false>, (unsigned)(B * csize),
                                  (unsigned)kSortThreads, csize, st, bsrc, scores, n_valid, N, (int)w.n_cap, post_max_size, thresh,
-                                 keep, keep_stride, keep_count, dets, K));
+                                 keep, keep_stride, keep_count, dets, K, order, (int64_t)w.n_cap, (const int*)w.n_sorted));
         PP_LAUNCHED();
         if (dets_done) *dets_done = true;
         return PP_OK;
@@ -1341,7 +1369,7 @@ static int nms_run(int kind, const float* boxes, int box_stride, const float* an
     } else {
         const int k = (int)w.n_cap;
         PP_TIMED("nms_topk", st);
-        if (N >= 16384)  // long score lists: one 8-CTA cluster per frame (DSMEM histograms)
+        if (N >= kLongScores)  // long score lists: one 8-CTA cluster per frame (DSMEM histograms)
             nms_topk_cluster_kernel<<<B * kTopkCluster, kTopkThreads, 0, st>>>(scores, n_valid, N, k, w.order, w.n_cap, w.n_sorted);
         else
             nms_topk_kernel<<<B, kSortThreads, 0, st>>>(scores, n_valid, N, k, w.order, w.n_cap, w.n_sorted);

@@ -240,3 +240,8 @@ __device__ __forceinline__ double standup_iou(const float4& a, const float4& b) 
 }
 
 }  // namespace pp
+
+// nms.cu: top-k of long score lists (>= 16 384 per frame) by one 8-CTA cluster per frame; order [B][order_stride]
+// (descending score, then descending index), n_sorted [B].
+int nms_topk_long_dev(const float* scores, int B, int64_t N, int k, int* order, int64_t order_stride, int* n_sorted, cudaStream_t st);
+constexpr int64_t kLongScoreList = 16384;

@@ -113,7 +113,8 @@ predict_frame_kernel(const float* __restrict__ box_preds, const float* __restric
                      const float* __restrict__ trv2c, const float* __restrict__ scores, int64_t A, int NC, int n_max,
                      int post_max, float thresh, int K, float* __restrict__ box3d_lidar,
                      double* __restrict__ box3d_camera, float* __restrict__ out_scores, int* __restrict__ out_labels,
-                     int* __restrict__ out_index, int* __restrict__ out_count) {
+                     int* __restrict__ out_index, int* __restrict__ out_count, const int* __restrict__ order,
+                     const int* __restrict__ n_sorted) {
     using BoxG = typename std::conditional<ROTATED, RBoxG, float4>::type;
     __shared__ unsigned long long skey[kSelectMaxK];
     __shared__ BoxG s_box[kPredictMaxSel];
@@ -124,7 +125,17 @@ predict_frame_kernel(const float* __restrict__ box_preds, const float* __restric
     __shared__ float s_M[12];
     const int b = blockIdx.x;
     const float* sc = scores + (int64_t)b * A;
-    const int n = block_topk(sc, (int)A, n_max, skey);
+    int n;
+    if (order) {  // long score lists: selected beforehand by the cluster top-k of nms.cu (same order, same tie rule)
+        n = min(n_sorted[b], n_max);
+        if ((int)threadIdx.x < n) {
+            const int a = order[(int64_t)b * kPredictMaxSel + threadIdx.x];
+            skey[threadIdx.x] = ((unsigned long long)score_key(sc[a]) << 32) | (unsigned)a;
+        }
+        __syncthreads();
+    } else {
+        n = block_topk(sc, (int)A, n_max, skey);
+    }
     if (n > 0) {
         if (threadIdx.x < n) {
             const int a = (int)(skey[threadIdx.x] & 0xffffffffu);
@@ -235,6 +246,10 @@ extern "C" size_t pp_predict_workspace_bytes(const pp_predict_cfg* cfg, int B, i
     Carver c(nullptr);
     c.take<float>((size_t)B * A + 1);
     const int n_max = predict_n_max(cfg);
+    if (n_max <= kPredictMaxSel && A >= kLongScoreList) {
+        c.take<int32_t>((size_t)B * kPredictMaxSel);
+        c.take<int32_t>((size_t)B);
+    }
     if (n_max > kPredictMaxSel) {
         c.take<int32_t>((size_t)B * K);
         c.take<int32_t>((size_t)B);
@@ -288,18 +303,24 @@ extern "C" int pp_predict_dev(const pp_predict_cfg* cfg, const float* box_preds,
         PP_LAUNCHED();
         return PP_OK;
     }
+    int32_t *order = nullptr, *n_sorted = nullptr;
+    if (A >= kLongScoreList) {  // KITTI heads (107 k anchors): one CTA walking the scores five times was 3/4 of the call
+        order = c.take<int32_t>((size_t)B * kPredictMaxSel);
+        n_sorted = c.take<int32_t>((size_t)B);
+        PP_TRY_RC(nms_topk_long_dev(sc, B, A, n_max, order, kPredictMaxSel, n_sorted, st));
+    }
     {
         PP_TIMED("predict_frame", st);
         if (cfg->nms_kind == PP_NMS_ROTATED)
             predict_frame_kernel<true><<<B, kSortThreads, 0, st>>>(box_preds, cls_preds, dir, anchors, astride, rect, Trv2c, sc, A,
                                                                    cfg->num_class, n_max, cfg->nms_post_max_size,
                                                                    cfg->nms_iou_threshold, K, box3d_lidar, box3d_camera,
-                                                                   scores, label_preds, anchor_index, count);
+                                                                   scores, label_preds, anchor_index, count, order, n_sorted);
         else
             predict_frame_kernel<false><<<B, kSortThreads, 0, st>>>(box_preds, cls_preds, dir, anchors, astride, rect, Trv2c, sc, A,
                                                                     cfg->num_class, n_max, cfg->nms_post_max_size,
                                                                     cfg->nms_iou_threshold, K, box3d_lidar, box3d_camera,
-                                                                    scores, label_preds, anchor_index, count);
+                                                                    scores, label_preds, anchor_index, count, order, n_sorted);
         PP_LAUNCHED();
     }
     return PP_OK;

@@ -140,6 +140,43 @@ def test_predict_large_selection(pp, oracle, synth, seed):
         assert np.all(idx[b, k:] == -1) and not lid[b, k:].any()
 
 
+@pytest.mark.parametrize("seed", range(3))
+def test_long_score_lists_small_selection(pp, oracle, synth, seed):
+    """>= 16 384 scores per frame with <= 128 boxes into NMS (KITTI heads with the reference's top-100): the selection comes
+    from the cluster top-k, the rest from the one-launch NMS / the predict kernel; ties and absent anchors included."""
+    rng = np.random.default_rng(8000 + seed)
+    n = int(rng.choice([16384, 30000, 107136]))
+    d = synth.rotated_boxes(n, 8100 + seed, clustered=bool(seed & 1))
+    d[:, 5] = np.round(d[:, 5], 2)            # many tied scores: the tie rule (descending index) decides the selection
+    thr = float(rng.choice([0.1, 0.5]))
+    pre, post = int(rng.choice([100, 128])), int(rng.choice([50, 128]))
+    got = pp.rotate_nms_gpu(d, thr, pre_max_size=pre, post_max_size=post)
+    want = oracle.rotate_nms_gpu(d, thr, pre, post)
+    assert_keep_lists_agree(got, want, d, thr, oracle, tol=1e-6, pre_max_size=pre, post_max_size=post)
+    sb = oracle.rbox_to_standup(d[:, :5])
+    g2, w2 = pp.nms(sb, d[:, 5], pre, post, thr), oracle.nms(sb, d[:, 5], pre, post, thr)
+    assert g2.tolist() == w2.tolist()
+    # predict glue on the same number of anchors
+    A, B, nc = n, 2, 1
+    an = synth.anchors_stride(synth.D435)[rng.choice(10240, A, replace=True)]
+    bp = rng.normal(0, 0.2, (B, A, 7)).astype(np.float32)
+    cl = np.round(rng.normal(-1, 1.5, (B, A, nc)), 1).astype(np.float32)
+    dr = rng.normal(0, 1, (B, A, 2)).astype(np.float32)
+    mask = (rng.random((B, A)) < 0.5).astype(np.uint8)
+    rect = rng.normal(0, 1, (B, 4, 4)).astype(np.float32)
+    trv = rng.normal(0, 1, (B, 4, 4)).astype(np.float32)
+    for rotated in (False, True):
+        lid, cam, sc, lab, idx, cnt = pp.predict_arrays(bp, cl, dr, an, mask, rect, trv, num_class=nc, top_k=100, nms_pre_max_size=pre,
+                                                        nms_post_max_size=post, nms_iou_threshold=thr, rotated=rotated)
+        for b in range(B):
+            w = oracle.predict_frame(bp[b], cl[b], dr[b], an, mask[b], rect[b], trv[b], top_k=100, pre_max_size=pre, post_max_size=post,
+                                     iou_threshold=thr, rotated=rotated)
+            k = int(cnt[b])
+            assert k > 0 and np.array_equal(idx[b, :k], w["anchor_index"]), (seed, b, rotated)
+            np.testing.assert_allclose(lid[b, :k], w["box3d_lidar"], rtol=1e-5, atol=1e-5)
+            np.testing.assert_allclose(sc[b, :k], w["scores"], rtol=1e-6, atol=0)
+
+
 @pytest.mark.parametrize("seed", range(4))
 def test_ingest_fuzz(pp, oracle, seed):
     """N3: random record layouts, slices and NaN patterns; reference matrices => bit-identical."""
