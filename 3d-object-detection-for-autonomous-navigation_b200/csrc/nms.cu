@@ -52,7 +52,8 @@ constexpr int64_t kLongScores = kLongScoreList;  // score lists from this length
 #endif
 constexpr int kTopkThreads = PP_TOPK_THREADS;
 
-__global__ void __cluster_dims__(kTopkCluster, 1, 1) __launch_bounds__(kTopkThreads)
+template <int kT>
+__global__ void __cluster_dims__(kTopkCluster, 1, 1) __launch_bounds__(kT)
 nms_topk_cluster_kernel(const float* __restrict__ scores, const int* __restrict__ n_valid, int64_t N, int k,
                         int* __restrict__ order, int64_t order_stride, int* __restrict__ n_sorted) {
     namespace cg = cooperative_groups;
@@ -93,7 +94,7 @@ nms_topk_cluster_kernel(const float* __restrict__ scores, const int* __restrict_
     {
         int c = 0;
 #pragma unroll 4
-        for (int i = lo + threadIdx.x; i < hi; i += kTopkThreads) c += sc[i] != -INFINITY;
+        for (int i = lo + threadIdx.x; i < hi; i += kT) c += sc[i] != -INFINITY;
 #pragma unroll
         for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
         if (lane_id() == 0 && c) atomicAdd(&hist[0], (unsigned)c);
@@ -121,16 +122,16 @@ nms_topk_cluster_kernel(const float* __restrict__ scores, const int* __restrict_
             __syncthreads();
             const unsigned prefix = s_prefix;
             // four independent loads per trip: the scan is bound by the L2 latency of its one dependent load otherwise
-            for (int i0 = lo; i0 < hi; i0 += 4 * kTopkThreads) {
+            for (int i0 = lo; i0 < hi; i0 += 4 * kT) {
                 float v[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int i = i0 + u * kTopkThreads + threadIdx.x;
+                    const int i = i0 + u * kT + threadIdx.x;
                     v[u] = i < hi ? sc[i] : 0.f;
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int i = i0 + u * kTopkThreads + threadIdx.x;
+                    const int i = i0 + u * kT + threadIdx.x;
                     int d = -1;
                     if (i < hi) {
                         const unsigned key = score_key(v[u]);
@@ -153,7 +154,7 @@ nms_topk_cluster_kernel(const float* __restrict__ scores, const int* __restrict_
                 if (threadIdx.x < 256) hist[threadIdx.x] = 0;
                 __syncthreads();
                 const unsigned prefix = s_prefix;
-                for (int i = lo + threadIdx.x; i < hi; i += kTopkThreads) {
+                for (int i = lo + threadIdx.x; i < hi; i += kT) {
                     if (score_key(sc[i]) != T) continue;
                     const unsigned key = (unsigned)i;
                     if (shift == 24 || ((key ^ prefix) >> (shift + 8)) == 0) atomicAdd(&hist[(key >> shift) & 255u], 1u);
@@ -170,22 +171,22 @@ nms_topk_cluster_kernel(const float* __restrict__ scores, const int* __restrict_
     while (np2 < kk) np2 <<= 1;
     if (rank == 0) {
         if (threadIdx.x == 0) s_fill = 0;
-        for (int i = threadIdx.x; i < np2; i += kTopkThreads) skey[i] = 0ull;
+        for (int i = threadIdx.x; i < np2; i += kT) skey[i] = 0ull;
     }
     cluster.sync();
     {
         unsigned long long* rkey = cluster.map_shared_rank(skey, 0);
         unsigned* rfill = cluster.map_shared_rank(&s_fill, 0);
-        for (int i0 = lo; i0 < hi; i0 += 4 * kTopkThreads) {
+        for (int i0 = lo; i0 < hi; i0 += 4 * kT) {
             float v[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * kTopkThreads + threadIdx.x;
+                const int i = i0 + u * kT + threadIdx.x;
                 v[u] = i < hi ? sc[i] : 0.f;
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * kTopkThreads + threadIdx.x;
+                const int i = i0 + u * kT + threadIdx.x;
                 if (i >= hi) continue;
                 const unsigned key = score_key(v[u]);
                 if (kk == nv || key > T || (key == T && (unsigned)i >= Tidx)) {
@@ -199,7 +200,7 @@ nms_topk_cluster_kernel(const float* __restrict__ scores, const int* __restrict_
     if (rank != 0) return;
     for (int size = 2; size <= np2; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int t = threadIdx.x; t < (np2 >> 1); t += kTopkThreads) {
+            for (int t = threadIdx.x; t < (np2 >> 1); t += kT) {
                 const int l = 2 * t - (t & (stride - 1));
                 const int h = l + stride;
                 const bool desc = ((l & size) == 0);
@@ -210,8 +211,19 @@ nms_topk_cluster_kernel(const float* __restrict__ scores, const int* __restrict_
         }
     }
     if (threadIdx.x == 0) n_sorted[b] = kk;
-    for (int i = threadIdx.x; i < kk; i += kTopkThreads)
+    for (int i = threadIdx.x; i < kk; i += kT)
         order[(int64_t)b * order_stride + i] = (int)(skey[i] & 0xffffffffu);
+}
+
+// 256-thread CTAs keep 64 clusters in one wave; a few frames have the SMs to themselves and take 1024-thread CTAs
+static int nms_topk_cluster_launch(const float* scores, const int* n_valid, int B, int64_t N, int k, int* order, int64_t order_stride,
+                                   int* n_sorted, cudaStream_t st) {
+    if ((int64_t)B * kTopkCluster <= num_sms())
+        nms_topk_cluster_kernel<1024><<<B * kTopkCluster, 1024, 0, st>>>(scores, n_valid, N, k, order, order_stride, n_sorted);
+    else
+        nms_topk_cluster_kernel<kTopkThreads><<<B * kTopkCluster, kTopkThreads, 0, st>>>(scores, n_valid, N, k, order, order_stride, n_sorted);
+    PP_LAUNCHED();
+    return PP_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1313,9 +1325,7 @@ NmsWs nms_carve(void* ws, int kind, int B, int64_t N, int pre_max) {
 // Top-k of long score lists for other translation units (predict.cu): order [B][order_stride], n_sorted [B].
 int nms_topk_long_dev(const float* scores, int B, int64_t N, int k, int* order, int64_t order_stride, int* n_sorted, cudaStream_t st) {
     PP_TIMED("nms_topk", st);
-    pp::nms_topk_cluster_kernel<<<B * pp::kTopkCluster, pp::kTopkThreads, 0, st>>>(scores, nullptr, N, k, order, order_stride, n_sorted);
-    PP_LAUNCHED();
-    return PP_OK;
+    return pp::nms_topk_cluster_launch(scores, nullptr, B, N, k, order, order_stride, n_sorted, st);
 }
 
 extern "C" size_t pp_nms_workspace_bytes(int kind, int B, int64_t N, int pre_max_size) {
@@ -1349,8 +1359,7 @@ static int nms_run(int kind, const float* boxes, int box_stride, const float* an
         const int* order = nullptr;
         if (N >= kLongScores) {  // one CTA walking 100 k scores five times costs more than the rest of the frame
             PP_TIMED("nms_topk", st);
-            nms_topk_cluster_kernel<<<B * kTopkCluster, kTopkThreads, 0, st>>>(scores, n_valid, N, (int)w.n_cap, w.order, w.n_cap, w.n_sorted);
-            PP_LAUNCHED();
+            PP_TRY_RC(nms_topk_cluster_launch(scores, n_valid, B, N, (int)w.n_cap, w.order, w.n_cap, w.n_sorted, st));
             order = w.order;
         }
         PP_TIMED("nms_small", st);
@@ -1369,12 +1378,14 @@ static int nms_run(int kind, const float* boxes, int box_stride, const float* an
     } else {
         const int k = (int)w.n_cap;
         PP_TIMED("nms_topk", st);
-        if (N >= kLongScores)  // long score lists: one 8-CTA cluster per frame (DSMEM histograms)
-            nms_topk_cluster_kernel<<<B * kTopkCluster, kTopkThreads, 0, st>>>(scores, n_valid, N, k, w.order, w.n_cap, w.n_sorted);
-        else
+        if (N >= kLongScores) {  // long score lists: one 8-CTA cluster per frame (DSMEM histograms)
+            PP_TRY_RC(nms_topk_cluster_launch(scores, n_valid, B, N, k, w.order, w.n_cap, w.n_sorted, st));
+        } else {
             nms_topk_kernel<<<B, kSortThreads, 0, st>>>(scores, n_valid, N, k, w.order, w.n_cap, w.n_sorted);
+            PP_LAUNCHED();
+        }
     }
-    PP_LAUNCHED();
+    if (w.full_sort) PP_LAUNCHED();
     {
         const dim3 g((unsigned)ceil_div(w.n_cap, 256), B);
         PP_TIMED("nms_prep", st);
