@@ -121,3 +121,25 @@ def test_header_is_plain_c_and_exports_match():
     out = subprocess.run(["nm", "-D", "--defined-only", build.build()], capture_output=True, text=True).stdout
     exported = sorted({ln.split()[-1] for ln in out.splitlines() if ln.split() and ln.split()[-1].startswith("pp_")})
     assert exported == header_symbols()
+
+
+def test_voxelizer_workspace_covers_smaller_batches(pp, synth):
+    """A workspace sized for the largest batch must serve every smaller one: the table path picks its chunk size (4 096 or
+    16 384 points) from the batch it is handed, and pp_voxelize_dev falls back to the any-grid path when the bytes it is
+    given do not cover the instance it would pick -- silently slower, so the sizing function has to be monotone."""
+    import ctypes as C
+    _lib = importlib.import_module(PKG + "._lib")
+    L = _lib.lib()
+    for c, n in ((synth.D435, 407040),     # 10 240 cells: table path eligible
+                 (synth.KITTI, 120000)):   # 214 272 cells: any-grid path only
+        cfg = _lib.make_cfg(c["voxel_size"], c["point_cloud_range"], c["max_points"], c["max_voxels"], True, False)
+        big = L.pp_voxelize_workspace_bytes(C.byref(cfg), 64 * n, 64, n, 3, 0)
+        assert big > 0
+        prev = 0
+        for k in (1, 2, 3, 6, 7, 8, 16, 33, 64):
+            ws = L.pp_voxelize_workspace_bytes(C.byref(cfg), k * n, k, n, 3, 0)
+            assert 0 < ws <= big, (k, ws, big)
+            assert ws >= prev, (k, ws, prev)     # monotone in the batch size
+            prev = ws
+        # smaller frames inside the same capacity
+        assert L.pp_voxelize_workspace_bytes(C.byref(cfg), 64 * 1000, 64, 1000, 3, 0) <= big
